@@ -1,0 +1,592 @@
+// C-ABI of the streaming block-FIR engine (include/afp.h): context, stage planning, launches.
+//
+// A context owns, per GPU: the stage list of one processing chain, the ping-pong history buffers of
+// every stage (the device-side replacement of the reference's sliding `input_buffer`,
+// stream_process.py:45-46,97-98), f32 intermediates between stages, and the dither sample counter.
+// Device I/O buffers belong to the caller.  Nothing here falls back to the CPU: every failure is a
+// status code + message.
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/afp.h"
+#include "afp_fir_kernel.cuh"
+
+using afp::FirParams;
+
+namespace {
+
+std::string g_create_error;
+
+constexpr int kMaxSmem = 227 * 1024;
+constexpr uint32_t kStateMagic = 0x41465031u;  // "AFP1"
+
+enum StageKind { ST_INTERP = 0, ST_EQ = 1, ST_MAIN = 2 };
+
+struct Geometry {
+    int nt = 0, tg_log2 = 0, smem = 0, grid = 0, segs_per_stream = 0;
+};
+
+struct Stage {
+    int kind = ST_MAIN;
+    bool active = false;
+    int U = 1;                      // phases this stage computes
+    int T = 16;                     // chunk size = base positions per thread
+    int n_taps = 0;
+    int kq_pad = 0;                 // padded taps per phase (history length in base samples)
+    int n_chunks = 0;
+    std::vector<double> taps;       // as given
+    std::vector<float> table;       // natural order, zero padded to U*kq_pad
+    float* hist[2] = {nullptr, nullptr};
+    long long hist_pitch = 0;
+    int cur = 0;
+    Geometry geo;
+};
+
+typedef void (*kern_t)(const FirParams);
+
+template <int U, int T>
+kern_t pick_nt(int nt) {
+    return nt == 256 ? (kern_t)afp::fir_stream_kernel<U, T, 256> : (kern_t)afp::fir_stream_kernel<U, T, 128>;
+}
+int tile_for(int U) { return U == 1 ? 16 : (U == 2 ? 8 : 4); }
+kern_t kernel_for(int U, int nt) {
+    switch (U) {
+        case 1: return pick_nt<1, 16>(nt);
+        case 2: return pick_nt<2, 8>(nt);
+        case 3: return pick_nt<3, 4>(nt);
+        case 4: return pick_nt<4, 4>(nt);
+    }
+    return nullptr;
+}
+
+}  // namespace
+
+struct afp_ctx {
+    afp_config cfg{};
+    std::string err;
+    Stage up, eq, mainf;
+    std::vector<std::vector<double>> bands;
+    std::vector<double> gains;
+    float* tmp_a = nullptr;          // interp output  [S][max_frames*U]
+    float* tmp_b = nullptr;          // EQ output      [S][pitch_b]
+    long long pitch_a = 0, pitch_b = 0;
+    unsigned long long out_samples = 0;   // kept output samples per stream since reset
+    long long launches = 0;
+    // afp_process_host staging
+    float* d_in = nullptr;
+    void* d_out = nullptr;
+    cudaStream_t own_stream = nullptr;
+};
+
+namespace {
+
+int fail(afp_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+int cuda_fail(afp_ctx* c, cudaError_t e, const char* what) {
+    return fail(c, AFP_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define AFP_CUDA(c, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail((c), e__, #call); } while (0)
+
+int rate_of(const afp_ctx* c) {   // processing rate / base rate
+    return c->cfg.upsample;
+}
+
+void free_stage(Stage& s) {
+    for (int i = 0; i < 2; ++i) { if (s.hist[i]) cudaFree(s.hist[i]); s.hist[i] = nullptr; }
+    s.active = false;
+}
+
+// (re)build one stage from double taps: pad, convert to float32, allocate + zero the history
+int build_stage(afp_ctx* c, Stage& s, int kind, int U, const double* taps, int n) {
+    if (n < 1) return fail(c, AFP_ERR_INVALID, "filter needs at least one tap");
+    for (int i = 0; i < n; ++i)
+        if (!std::isfinite(taps[i])) return fail(c, AFP_ERR_INVALID, "non-finite filter tap");
+    const int T = tile_for(U);
+    const int kq = (n + U - 1) / U;
+    const int n_chunks = (kq + T - 1) / T;
+    if ((long long)n_chunks * T * U > afp::MAX_TAPS)
+        return fail(c, AFP_ERR_INVALID, "filter too long for the per-launch tap table (max 4096 padded taps)");
+    free_stage(s);
+    s.kind = kind; s.U = U; s.T = T; s.n_taps = n;
+    s.n_chunks = n_chunks; s.kq_pad = n_chunks * T;
+    s.taps.assign(taps, taps + n);
+    s.table.assign((size_t)s.kq_pad * U, 0.f);
+    for (int i = 0; i < n; ++i) s.table[i] = (float)taps[i];
+    s.hist_pitch = s.kq_pad;
+    const size_t bytes = (size_t)c->cfg.n_streams * s.hist_pitch * sizeof(float);
+    for (int i = 0; i < 2; ++i) {
+        AFP_CUDA(c, cudaMalloc(&s.hist[i], bytes));
+        AFP_CUDA(c, cudaMemset(s.hist[i], 0, bytes));
+    }
+    s.cur = 0;
+    s.active = true;
+    return AFP_OK;
+}
+
+// CTA geometry for n_q base positions per stream with a halo of kq_pad
+Geometry pick_geometry(int T, int kq_pad, int n_q, int n_streams) {
+    Geometry best;
+    double best_score = -1;
+    for (int nt = 256; nt >= 128; nt >>= 1) {
+        int tg_log2 = 3;
+        while ((1 << tg_log2) * T < n_q && (1 << tg_log2) < nt) ++tg_log2;
+        for (;; ++tg_log2) {
+            const int tg = 1 << tg_log2, slots = nt / tg;
+            const int smem = slots * afp::region_granules(kq_pad + tg * T) * 16;
+            if (smem <= kMaxSmem) {
+                const int max_cta = nt == 256 ? 2 : 4;
+                int cta = kMaxSmem / (smem + 1024);
+                if (cta > max_cta) cta = max_cta;
+                if (cta < 1) cta = 1;
+                const int segs = (n_q + tg * T - 1) / (tg * T);
+                const double useful = (double)n_q / ((double)segs * tg * T);   // masked-lane waste
+                const double score = cta * nt * useful + (nt == 256 ? 1 : 0);
+                if (score > best_score) {
+                    best_score = score;
+                    best.nt = nt; best.tg_log2 = tg_log2; best.smem = smem; best.segs_per_stream = segs;
+                    const long long pairs = ((long long)n_streams * segs + 1) / 2;
+                    best.grid = (int)((pairs + slots - 1) / slots);
+                }
+                break;
+            }
+            if (tg >= nt) break;   // cannot fit even one segment per CTA
+        }
+    }
+    return best;
+}
+
+struct StageIO {
+    const float* src0 = nullptr; long long pitch0 = 0; int len0 = 0;
+    const float* src1 = nullptr; long long pitch1 = 0; int len1 = 0;
+    int q_begin = 0, n_q = 0;
+    void* out = nullptr; long long out_pitch = 0;
+    int fmt = AFP_FMT_F32, dither = AFP_DITHER_NONE, decim = 1;
+    unsigned long long sample_base = 0;
+    float* hist_out = nullptr; long long hist_pitch = 0; int hist_len = 0, hist_from = 0;
+};
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int launch_stage(afp_ctx* c, Stage& s, const StageIO& io, cudaStream_t stream) {
+    const int S = c->cfg.n_streams;
+    Geometry g = pick_geometry(s.T, s.kq_pad, io.n_q, S);
+    if (g.nt == 0) return fail(c, AFP_ERR_INVALID, "filter/block combination does not fit in shared memory");
+    s.geo = g;
+    static FirParams P;   // 16 KB: keep it off the stack; contexts are single-owner, launches serialised per process call
+    P.src0 = io.src0; P.src1 = io.src1; P.pitch0 = io.pitch0; P.pitch1 = io.pitch1;
+    P.len0 = io.len0; P.len1 = io.len1;
+    P.q_begin = io.q_begin; P.n_q = io.n_q;
+    P.tg_log2 = g.tg_log2; P.segs_per_stream = g.segs_per_stream;
+    P.n_seg_total = S * g.segs_per_stream;
+    P.n_chunks = s.n_chunks;
+    P.out = io.out; P.out_pitch = io.out_pitch;
+    P.decim = io.decim; P.fmt = io.fmt; P.dither = io.dither;
+    P.seed = c->cfg.seed; P.sample_base = io.sample_base; P.stream_id0 = c->cfg.first_stream_id;
+    P.hist_out = io.hist_out; P.hist_pitch = io.hist_pitch; P.hist_len = io.hist_len; P.hist_from = io.hist_from;
+    P.gain = 1.0f;
+    const int start0 = io.q_begin - s.kq_pad;   // logical index of the first pair of segment 0's region
+    const int lq = (1 << g.tg_log2) * s.T;
+    const bool n_al = (start0 % 4 == 0) && (lq % 4 == 0);
+    P.fast0 = (io.len0 > 0 && n_al && aligned16(io.src0) && io.pitch0 % 4 == 0) ? 1 : 0;
+    P.fast1 = (io.len1 > 0 && n_al && aligned16(io.src1) && io.pitch1 % 4 == 0 && io.len0 % 4 == 0) ? 1 : 0;
+    P.fast_hist = (io.hist_out && n_al && aligned16(io.hist_out) && io.hist_pitch % 4 == 0 && io.hist_from % 4 == 0) ? 1 : 0;
+    const int eb = io.fmt == AFP_FMT_I16 ? 2 : (io.fmt == AFP_FMT_I24_PACKED ? 3 : 4);
+    P.fast_out = (aligned16(io.out) && (io.out_pitch * eb) % 16 == 0) ? 1 : 0;
+    std::memset(P.taps, 0, sizeof(P.taps));
+    std::memcpy(P.taps, s.table.data(), s.table.size() * sizeof(float));
+    kern_t k = kernel_for(s.U, g.nt);
+    k<<<g.grid, g.nt, g.smem, stream>>>(P);
+    AFP_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    return AFP_OK;
+}
+
+// streaming launch: history | new block, outputs for the new block, history rolled forward
+int run_streaming(afp_ctx* c, Stage& s, const float* in, long long in_pitch, int len,
+                  void* out, long long out_pitch, int fmt, int dither, int decim,
+                  unsigned long long sample_base, cudaStream_t stream) {
+    StageIO io;
+    io.src0 = s.hist[s.cur]; io.pitch0 = s.hist_pitch; io.len0 = s.kq_pad;
+    io.src1 = in; io.pitch1 = in_pitch; io.len1 = len;
+    io.q_begin = s.kq_pad; io.n_q = len;
+    io.out = out; io.out_pitch = out_pitch; io.fmt = fmt; io.dither = dither; io.decim = decim;
+    io.sample_base = sample_base;
+    io.hist_out = s.hist[s.cur ^ 1]; io.hist_pitch = s.hist_pitch; io.hist_len = s.kq_pad; io.hist_from = len;
+    int rc = launch_stage(c, s, io, stream);
+    if (rc == AFP_OK) s.cur ^= 1;
+    return rc;
+}
+
+int rebuild_eq(afp_ctx* c, bool reset_state) {
+    if (c->bands.empty()) { free_stage(c->eq); return AFP_OK; }
+    // taps-domain sum, centre aligned (stream_process_EQ_GUI.py:86-90)
+    size_t nmax = 0;
+    for (auto& b : c->bands) nmax = b.size() > nmax ? b.size() : nmax;
+    std::vector<double> comb(nmax, 0.0);
+    for (size_t i = 0; i < c->bands.size(); ++i) {
+        const size_t off = (nmax - c->bands[i].size()) / 2;
+        for (size_t k = 0; k < c->bands[i].size(); ++k) comb[off + k] += c->gains[i] * c->bands[i][k];
+    }
+    if (reset_state || !c->eq.active || c->eq.n_taps != (int)nmax) {
+        return build_stage(c, c->eq, ST_EQ, 1, comb.data(), (int)nmax);
+    }
+    // gains only: swap the table, keep the carried state (filter_lock swap, stream_process_EQ_GUI.py:380-385)
+    c->eq.taps = comb;
+    for (size_t i = 0; i < nmax; ++i) c->eq.table[i] = (float)comb[i];
+    return AFP_OK;
+}
+
+int ensure_tmp(afp_ctx* c) {
+    const int S = c->cfg.n_streams, U = c->cfg.upsample;
+    const long long need = (long long)c->cfg.max_frames * U;
+    const bool need_a = (c->cfg.chain == AFP_CHAIN_REFERENCE && U > 1);
+    const bool need_b = c->eq.active;
+    if (need_a && !c->tmp_a) {
+        c->pitch_a = (need + 3) / 4 * 4;
+        AFP_CUDA(c, cudaMalloc(&c->tmp_a, (size_t)S * c->pitch_a * sizeof(float)));
+    }
+    if (need_b && !c->tmp_b) {
+        c->pitch_b = (need + 3) / 4 * 4;
+        AFP_CUDA(c, cudaMalloc(&c->tmp_b, (size_t)S * c->pitch_b * sizeof(float)));
+    }
+    return AFP_OK;
+}
+
+template <int N>
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* out, const float* in, int iters, long long* cyc) {
+    float2 acc[N], w[2 * N];
+    float h[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) acc[i] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 2 * N; ++i) w[i] = make_float2(in[threadIdx.x + i], in[threadIdx.x + i + 64]);
+#pragma unroll
+    for (int j = 0; j < N; ++j) h[j] = in[j + 32];
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 4; ++rep)
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+#pragma unroll
+                for (int i = 0; i < N; ++i) afp::ffma2(acc[i], w[i + N - j], h[j]);
+    }
+    const long long t1 = clock64();
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) s += acc[i].x + acc[i].y;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* afp_version(void) { return "afp-b200 0.1 (sm_100a)"; }
+
+const char* afp_last_error(const afp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int afp_create(const afp_config* cfg, afp_ctx** out_ctx) {
+    if (!cfg || !out_ctx) return fail(nullptr, AFP_ERR_INVALID, "null argument");
+    *out_ctx = nullptr;
+    if (cfg->n_streams < 1) return fail(nullptr, AFP_ERR_INVALID, "n_streams must be >= 1");
+    if (cfg->max_frames < 1) return fail(nullptr, AFP_ERR_INVALID, "max_frames must be >= 1");
+    if (cfg->upsample < 1 || cfg->upsample > 4) return fail(nullptr, AFP_ERR_INVALID, "upsample must be 1..4");
+    if (cfg->chain != AFP_CHAIN_DAC && cfg->chain != AFP_CHAIN_REFERENCE) return fail(nullptr, AFP_ERR_INVALID, "unknown chain");
+    if (cfg->out_format < 0 || cfg->out_format > 3) return fail(nullptr, AFP_ERR_INVALID, "unknown out_format");
+    if (cfg->dither < 0 || cfg->dither > 2) return fail(nullptr, AFP_ERR_INVALID, "unknown dither mode");
+    if (cfg->eq_mode < 0 || cfg->eq_mode > 3) return fail(nullptr, AFP_ERR_INVALID, "unknown eq_mode");
+    if (cfg->eq_mode != AFP_EQ_NONE && cfg->chain == AFP_CHAIN_DAC && cfg->upsample > 1)
+        return fail(nullptr, AFP_ERR_INVALID, "EQ runs at the processing rate: use AFP_CHAIN_REFERENCE with upsample > 1");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceCount");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, AFP_ERR_INVALID, "no such CUDA device");
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, cfg->device);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+    if (prop.major != 10) return fail(nullptr, AFP_ERR_INVALID, "this library is built for sm_100a (B200) only");
+    for (int U = 1; U <= 4; ++U)
+        for (int nt = 128; nt <= 256; nt <<= 1) {
+            e = cudaFuncSetAttribute((const void*)kernel_for(U, nt), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+            if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem)");
+        }
+    afp_ctx* c = new (std::nothrow) afp_ctx();
+    if (!c) return fail(nullptr, AFP_ERR_NOMEM, "out of host memory");
+    c->cfg = *cfg;
+    e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return cuda_fail(nullptr, e, "cudaStreamCreate"); }
+    *out_ctx = c;
+    return AFP_OK;
+}
+
+int afp_destroy(afp_ctx* c) {
+    if (!c) return AFP_OK;
+    cudaSetDevice(c->cfg.device);
+    free_stage(c->up); free_stage(c->eq); free_stage(c->mainf);
+    if (c->tmp_a) cudaFree(c->tmp_a);
+    if (c->tmp_b) cudaFree(c->tmp_b);
+    if (c->d_in) cudaFree(c->d_in);
+    if (c->d_out) cudaFree(c->d_out);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return AFP_OK;
+}
+
+int afp_set_taps(afp_ctx* c, const double* taps, int32_t n) {
+    if (!c || !taps) return fail(c, AFP_ERR_INVALID, "null argument");
+    AFP_CUDA(c, cudaSetDevice(c->cfg.device));
+    const int U = c->cfg.chain == AFP_CHAIN_DAC ? c->cfg.upsample : 1;
+    return build_stage(c, c->mainf, ST_MAIN, U, taps, n);
+}
+
+int afp_set_upsampler(afp_ctx* c, const double* taps, int32_t n) {
+    if (!c || !taps) return fail(c, AFP_ERR_INVALID, "null argument");
+    if (c->cfg.chain != AFP_CHAIN_REFERENCE || c->cfg.upsample < 2)
+        return fail(c, AFP_ERR_STATE, "an up-sampler prototype is only used by AFP_CHAIN_REFERENCE with upsample > 1");
+    AFP_CUDA(c, cudaSetDevice(c->cfg.device));
+    return build_stage(c, c->up, ST_INTERP, c->cfg.upsample, taps, n);
+}
+
+int afp_set_eq(afp_ctx* c, const double* band_taps, const int32_t* band_len, int32_t n_bands, const double* gains) {
+    if (!c) return fail(c, AFP_ERR_INVALID, "null argument");
+    if (c->cfg.eq_mode == AFP_EQ_NONE) return fail(c, AFP_ERR_STATE, "context was created with eq_mode = AFP_EQ_NONE");
+    if (n_bands < 0 || (n_bands > 0 && (!band_taps || !band_len))) return fail(c, AFP_ERR_INVALID, "bad EQ bank");
+    AFP_CUDA(c, cudaSetDevice(c->cfg.device));
+    c->bands.clear(); c->gains.clear();
+    const double* p = band_taps;
+    for (int b = 0; b < n_bands; ++b) {
+        if (band_len[b] < 1) return fail(c, AFP_ERR_INVALID, "EQ band needs at least one tap");
+        c->bands.emplace_back(p, p + band_len[b]);
+        p += band_len[b];
+        c->gains.push_back(gains ? gains[b] : 1.0);
+    }
+    return rebuild_eq(c, true);
+}
+
+int afp_set_gains(afp_ctx* c, const double* gains, int32_t n_bands) {
+    if (!c || !gains) return fail(c, AFP_ERR_INVALID, "null argument");
+    if ((size_t)n_bands != c->bands.size()) return fail(c, AFP_ERR_INVALID, "gain count does not match the EQ bank");
+    AFP_CUDA(c, cudaSetDevice(c->cfg.device));
+    for (int b = 0; b < n_bands; ++b) {
+        if (!std::isfinite(gains[b])) return fail(c, AFP_ERR_INVALID, "non-finite gain");
+        c->gains[b] = gains[b];
+    }
+    return rebuild_eq(c, false);
+}
+
+int32_t afp_out_frames(const afp_ctx* c, int32_t frames) {
+    if (!c) return 0;
+    return c->cfg.chain == AFP_CHAIN_DAC ? frames * c->cfg.upsample : frames;
+}
+
+int32_t afp_out_elem_bytes(const afp_ctx* c) {
+    if (!c) return 0;
+    return c->cfg.out_format == AFP_FMT_I16 ? 2 : (c->cfg.out_format == AFP_FMT_I24_PACKED ? 3 : 4);
+}
+
+int afp_process(afp_ctx* c, const float* in, int64_t in_pitch, void* out, int64_t out_pitch, int32_t frames, void* cuda_stream) {
+    if (!c) return AFP_ERR_INVALID;
+    if (!in || !out) return fail(c, AFP_ERR_INVALID, "null buffer");
+    if (frames < 0 || frames > c->cfg.max_frames) return fail(c, AFP_ERR_INVALID, "frames outside 0..max_frames");
+    if (!c->mainf.active) return fail(c, AFP_ERR_STATE, "afp_set_taps has not been called");
+    if (frames == 0) return AFP_OK;
+    const int U = c->cfg.upsample;
+    const bool ref = c->cfg.chain == AFP_CHAIN_REFERENCE;
+    if (ref && U > 1 && !c->up.active) return fail(c, AFP_ERR_STATE, "afp_set_upsampler has not been called");
+    if (c->cfg.eq_mode != AFP_EQ_NONE && !c->eq.active) return fail(c, AFP_ERR_STATE, "afp_set_eq has not been called");
+    if (in_pitch < frames) return fail(c, AFP_ERR_INVALID, "in_pitch smaller than frames");
+    const int out_n = afp_out_frames(c, frames);
+    if (out_pitch < (int64_t)out_n * (c->cfg.out_format == AFP_FMT_I24_PACKED ? 3 : 1))
+        return fail(c, AFP_ERR_INVALID, "out_pitch smaller than the output row");
+    AFP_CUDA(c, cudaSetDevice(c->cfg.device));
+    int rc = ensure_tmp(c);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+
+    const float* cur = in; long long cur_pitch = in_pitch; int cur_len = frames;
+    if (ref && U > 1) {   // interpolate to the processing rate (replaces soxr.resample, stream_process.py:66-77)
+        rc = run_streaming(c, c->up, cur, cur_pitch, cur_len, c->tmp_a, c->pitch_a, AFP_FMT_F32, AFP_DITHER_NONE, 1, 0, st);
+        if (rc) return rc;
+        cur = c->tmp_a; cur_pitch = c->pitch_a; cur_len = frames * U;
+    }
+    if (c->eq.active) {
+        if (c->cfg.eq_mode == AFP_EQ_BUFFER_SAME || c->cfg.eq_mode == AFP_EQ_PER_BAND)
+            return fail(c, AFP_ERR_INVALID, "eq_mode not implemented yet in this build");
+        rc = run_streaming(c, c->eq, cur, cur_pitch, cur_len, c->tmp_b, c->pitch_b, AFP_FMT_F32, AFP_DITHER_NONE, 1, 0, st);
+        if (rc) return rc;
+        cur = c->tmp_b; cur_pitch = c->pitch_b;
+    }
+    const int decim = ref ? U : 1;
+    const long long opitch = c->cfg.out_format == AFP_FMT_I24_PACKED ? out_pitch / 3 : out_pitch;
+    rc = run_streaming(c, c->mainf, cur, cur_pitch, cur_len, out, opitch, c->cfg.out_format, c->cfg.dither, decim,
+                       c->out_samples, st);
+    if (rc) return rc;
+    c->out_samples += (unsigned long long)out_n;
+    return AFP_OK;
+}
+
+int afp_process_host(afp_ctx* c, const float* in, void* out, int32_t frames) {
+    if (!c) return AFP_ERR_INVALID;
+    if (!in || !out) return fail(c, AFP_ERR_INVALID, "null buffer");
+    if (frames < 0 || frames > c->cfg.max_frames) return fail(c, AFP_ERR_INVALID, "frames outside 0..max_frames");
+    if (frames == 0) return AFP_OK;
+    AFP_CUDA(c, cudaSetDevice(c->cfg.device));
+    const int S = c->cfg.n_streams;
+    const int eb = afp_out_elem_bytes(c);
+    const long long max_out = (long long)afp_out_frames(c, c->cfg.max_frames);
+    if (!c->d_in) AFP_CUDA(c, cudaMalloc(&c->d_in, (size_t)S * c->cfg.max_frames * sizeof(float)));
+    if (!c->d_out) AFP_CUDA(c, cudaMalloc(&c->d_out, (size_t)S * max_out * eb));
+    const int out_n = afp_out_frames(c, frames);
+    AFP_CUDA(c, cudaMemcpyAsync(c->d_in, in, (size_t)S * frames * sizeof(float), cudaMemcpyHostToDevice, c->own_stream));
+    int rc = afp_process(c, c->d_in, frames, c->d_out, (int64_t)out_n * (eb == 3 ? 3 : 1), frames, c->own_stream);
+    if (rc) return rc;
+    AFP_CUDA(c, cudaMemcpyAsync(out, c->d_out, (size_t)S * out_n * eb, cudaMemcpyDeviceToHost, c->own_stream));
+    AFP_CUDA(c, cudaStreamSynchronize(c->own_stream));
+    return AFP_OK;
+}
+
+int afp_reset(afp_ctx* c) {
+    if (!c) return AFP_ERR_INVALID;
+    AFP_CUDA(c, cudaSetDevice(c->cfg.device));
+    AFP_CUDA(c, cudaDeviceSynchronize());
+    Stage* st[3] = {&c->up, &c->eq, &c->mainf};
+    for (Stage* s : st)
+        if (s->active)
+            for (int i = 0; i < 2; ++i)
+                AFP_CUDA(c, cudaMemset(s->hist[i], 0, (size_t)c->cfg.n_streams * s->hist_pitch * sizeof(float)));
+    c->out_samples = 0;
+    return AFP_OK;
+}
+
+int afp_state_size(const afp_ctx* c, size_t* bytes) {
+    if (!c || !bytes) return AFP_ERR_INVALID;
+    size_t n = 4 * sizeof(uint64_t);
+    const Stage* st[3] = {&c->up, &c->eq, &c->mainf};
+    for (const Stage* s : st)
+        if (s->active) n += (size_t)c->cfg.n_streams * s->hist_pitch * sizeof(float);
+    *bytes = n;
+    return AFP_OK;
+}
+
+int afp_get_state(afp_ctx* c, void* buf, size_t bytes) {
+    if (!c || !buf) return fail(c, AFP_ERR_INVALID, "null argument");
+    size_t need = 0; afp_state_size(c, &need);
+    if (bytes < need) return fail(c, AFP_ERR_INVALID, "state buffer too small");
+    AFP_CUDA(c, cudaSetDevice(c->cfg.device));
+    AFP_CUDA(c, cudaDeviceSynchronize());
+    uint64_t* hdr = static_cast<uint64_t*>(buf);
+    hdr[0] = kStateMagic; hdr[1] = need; hdr[2] = c->out_samples; hdr[3] = 0;
+    unsigned char* p = static_cast<unsigned char*>(buf) + 4 * sizeof(uint64_t);
+    Stage* st[3] = {&c->up, &c->eq, &c->mainf};
+    for (Stage* s : st)
+        if (s->active) {
+            const size_t n = (size_t)c->cfg.n_streams * s->hist_pitch * sizeof(float);
+            AFP_CUDA(c, cudaMemcpy(p, s->hist[s->cur], n, cudaMemcpyDeviceToHost));
+            p += n;
+        }
+    return AFP_OK;
+}
+
+int afp_set_state(afp_ctx* c, const void* buf, size_t bytes) {
+    if (!c || !buf) return fail(c, AFP_ERR_INVALID, "null argument");
+    size_t need = 0; afp_state_size(c, &need);
+    const uint64_t* hdr = static_cast<const uint64_t*>(buf);
+    if (bytes < need || hdr[0] != kStateMagic || hdr[1] != need)
+        return fail(c, AFP_ERR_INVALID, "state blob does not match this context's filters");
+    AFP_CUDA(c, cudaSetDevice(c->cfg.device));
+    AFP_CUDA(c, cudaDeviceSynchronize());
+    c->out_samples = hdr[2];
+    const unsigned char* p = static_cast<const unsigned char*>(buf) + 4 * sizeof(uint64_t);
+    Stage* st[3] = {&c->up, &c->eq, &c->mainf};
+    for (Stage* s : st)
+        if (s->active) {
+            const size_t n = (size_t)c->cfg.n_streams * s->hist_pitch * sizeof(float);
+            AFP_CUDA(c, cudaMemcpy(s->hist[s->cur], p, n, cudaMemcpyHostToDevice));
+            p += n;
+        }
+    return AFP_OK;
+}
+
+int afp_get_stage_info(const afp_ctx* c, int32_t stage, afp_stage_info* info) {
+    if (!c || !info) return AFP_ERR_INVALID;
+    const Stage* st[3] = {&c->up, &c->eq, &c->mainf};
+    int k = 0;
+    for (const Stage* s : st) {
+        if (!s->active) continue;
+        if (k++ != stage) continue;
+        info->kind = s->kind; info->upsample = s->U; info->n_taps = s->n_taps;
+        info->taps_per_phase_padded = s->kq_pad; info->tile_taps = s->T;
+        info->threads = s->geo.nt; info->threads_per_segment = s->geo.nt ? (1 << s->geo.tg_log2) : 0;
+        info->smem_bytes = s->geo.smem; info->grid = s->geo.grid; info->history = s->kq_pad;
+        return AFP_OK;
+    }
+    return AFP_ERR_INVALID;
+}
+
+int64_t afp_kernel_launches(const afp_ctx* c) { return c ? c->launches : 0; }
+
+int afp_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return AFP_ERR_INVALID;
+    cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaHostAlloc");
+    return AFP_OK;
+}
+
+int afp_host_free(void* ptr) {
+    if (!ptr) return AFP_OK;
+    cudaError_t e = cudaFreeHost(ptr);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFreeHost");
+    return AFP_OK;
+}
+
+int afp_measure_fma_peak(int32_t device, double* tflops, double* sm_mhz) {
+    if (!tflops || !sm_mhz) return AFP_ERR_INVALID;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+    const int grid = prop.multiProcessorCount * 2, threads = 256, iters = 4000;
+    float *out = nullptr, *in = nullptr; long long* cyc = nullptr;
+    if (cudaMalloc(&out, sizeof(float) * grid * threads) != cudaSuccess ||
+        cudaMalloc(&in, sizeof(float) * 4096) != cudaSuccess ||
+        cudaMalloc(&cyc, sizeof(long long) * grid) != cudaSuccess)
+        return fail(nullptr, AFP_ERR_NOMEM, "cudaMalloc failed in afp_measure_fma_peak");
+    cudaMemset(in, 0, sizeof(float) * 4096);
+    fma_peak_kernel<8><<<grid, threads>>>(out, in, 100, cyc);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        fma_peak_kernel<8><<<grid, threads>>>(out, in, iters, cyc);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    e = cudaGetLastError();
+    std::vector<long long> hc(grid);
+    cudaMemcpy(hc.data(), cyc, sizeof(long long) * grid, cudaMemcpyDeviceToHost);
+    long long cmax = 0;
+    for (long long v : hc) cmax = v > cmax ? v : cmax;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out); cudaFree(in); cudaFree(cyc);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "fma_peak_kernel");
+    const double fma = 2.0 * 4 * 8 * 8 * (double)iters * threads * grid;   // FMAs (2 per FFMA2 lane)
+    *tflops = 2.0 * fma / (best * 1e-3) / 1e12;
+    *sm_mhz = (double)cmax / (best * 1e-3) / 1e6;
+    return AFP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,406 @@
+// Batched streaming FIR / polyphase-interpolator kernel for sm_100a (kernels 1-5 of the north star).
+//
+// What it replaces in the reference (file:line under /root/reference):
+//   * sliding float32 buffer + oaconvolve(buffer, h, 'valid')          stream_process.py:45-46,97-102
+//   * per-band / fused EQ 'same' convolution over that buffer          stream_process_EQ.py:124-129,
+//                                                                      stream_process_EQ_GUI.py:86-90
+//   * zero-stuff + anti-imaging filter (soxr.resample per block)       stream_process.py:66-77
+//   * processed[::U] decimation                                        stream_process.py:106
+//   * apply_dither                                                     stream_process.py:61-64
+//
+// Formulation.  Per stream the kernel sees a logical base-rate sequence
+//       X = [ src0 (len0 samples) | src1 (len1 samples) | zeros ... ],   X[n<0] = 0
+// (streaming: src0 = carried history, src1 = the new block) and computes, for base positions
+// q in [q_begin, q_begin+n_q) and phases p in [0,U):
+//       y[(q-q_begin)*U + p] = sum_j  h[j*U + p] * X[q - j]
+// i.e. a direct-form FIR for U = 1 and a polyphase interpolator that touches only the non-zero
+// products for U > 1 (taps are passed in their natural order h[k], zero-padded to U*T*n_chunks).
+//
+// Mapping to the SM (design notes, see DESIGN.md for the measurements behind them):
+//   * Packed FP32: the inner product is issued as FFMA2 (fma.rn.f32x2), two FMAs per lane per
+//     instruction, which reaches 128 FMA/clk/SM with half the issue slots of scalar FFMA, so the
+//     LDS / address / loop instructions ride in the free slots.  The two halves of every pair are
+//     two different rows (row A, row B = two segments that share the same taps); the shared-memory
+//     tile stores them interleaved as (A[n], B[n]) so one LDS.128 yields two ready operand pairs.
+//   * The tap is the scalar-broadcast operand of FFMA2 and lives in a uniform register loaded
+//     straight from the kernel-parameter constant bank (LDCU): taps cost no vector register, no
+//     shared memory bandwidth and one issue slot per 2-4 taps.
+//   * Register blocking: each thread owns T consecutive base positions (x U phases) of both rows and
+//     walks the taps in chunks of T with a 2T-deep register window -> one shared-memory word per
+//     U*T FMAs.
+//   * Shared-memory layout: 16-byte granules (2 pairs) with one pad granule per 8, which makes the
+//     per-thread-contiguous LDS.128 pattern (lane stride T/2 granules) bank-conflict free.
+//   * Outputs leave from registers as 16-byte stores; dither/quantisation is applied on the way.
+//   * The history for the next block (last hist_len samples of [src0|src1]) is written by the
+//     loader while the tile is in registers - no second pass, no extra launch.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "afp_philox.cuh"
+
+namespace afp {
+
+constexpr int MAX_TAPS = 4096;   // floats in the per-launch tap table (all phases, zero padded)
+
+struct FirParams {
+    const float* src0;           // [n_streams][pitch0]  first len0 logical samples
+    const float* src1;           // [n_streams][pitch1]  next len1 logical samples
+    long long pitch0, pitch1;
+    int len0, len1;
+    int q_begin, n_q;            // base positions computed per stream
+    int tg_log2;                 // log2(threads per segment); a segment is (1<<tg_log2)*T positions
+    int segs_per_stream;
+    int n_seg_total;             // n_streams * segs_per_stream
+    int n_chunks;                // padded taps per phase / T
+    void* out;                   // [n_streams][out_pitch] elements of the output format
+    long long out_pitch;
+    int decim;                   // keep output samples whose index % decim == 0
+    int fmt, dither;
+    unsigned long long seed;
+    unsigned long long sample_base;   // absolute index (per stream) of this call's first kept output
+    int stream_id0;              // global id of stream 0 (Philox counter word 2)
+    float* hist_out;             // [n_streams][hist_pitch]; hist_out[s][i] = X[hist_from + i]
+    long long hist_pitch;
+    int hist_len, hist_from;
+    int fast0, fast1, fast_hist, fast_out;   // 16-byte alignment guarantees, computed on the host
+    float gain;                  // applied to the accumulators before the epilogue (1.0 = none)
+    alignas(16) float taps[MAX_TAPS];
+};
+
+__device__ __forceinline__ unsigned long long as_u64(const float2& v) {
+    return *reinterpret_cast<const unsigned long long*>(&v);
+}
+__device__ __forceinline__ void ffma2(float2& acc, const float2& x, float h) {
+    unsigned long long d = as_u64(acc);
+    const float2 hh = make_float2(h, h);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(as_u64(x)), "l"(as_u64(hh)));
+    acc = *reinterpret_cast<float2*>(&d);
+}
+
+// physical granule (16 B) index: one pad granule per 8
+__device__ __forceinline__ int phys_granule(int g) { return g + (g >> 3); }
+__host__ __device__ constexpr int region_granules(int pairs) { return (pairs / 2) + (pairs / 16) + 2; }
+
+template <int T>
+__device__ __forceinline__ void load_block(float2 (&w)[T], const float4* __restrict__ region, int block) {
+    const int g = block * (T / 2);
+    const float4* p = region + phys_granule(g);
+#pragma unroll
+    for (int m = 0; m < T / 2; ++m) {
+        const float4 v = p[m];
+        w[2 * m] = make_float2(v.x, v.y);
+        w[2 * m + 1] = make_float2(v.z, v.w);
+    }
+}
+
+// One chunk of T taps: hi holds X[q0 .. q0+T-1] relative to the chunk origin, lo the T samples below.
+template <int U, int T>
+__device__ __forceinline__ void chunk_fma(float2 (&acc)[U][T], const float2 (&lo)[T], const float2 (&hi)[T],
+                                          const float* __restrict__ taps) {
+#pragma unroll
+    for (int j = 0; j < T; ++j) {
+#pragma unroll
+        for (int p = 0; p < U; ++p) {
+            const float h = taps[j * U + p];
+#pragma unroll
+            for (int r = 0; r < T; ++r) {
+                if (r >= j) ffma2(acc[p][r], hi[r - j], h);
+                else        ffma2(acc[p][r], lo[T + r - j], h);
+            }
+        }
+    }
+}
+
+struct RowSrc {
+    const float* r0;
+    const float* r1;
+    bool valid;
+};
+
+__device__ __forceinline__ float4 fetch4(const FirParams& P, const RowSrc& rs, int n) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!rs.valid) return v;
+    const int L = P.len0 + P.len1;
+    if (P.fast0 && n >= 0 && n + 4 <= P.len0) {
+        v = __ldg(reinterpret_cast<const float4*>(rs.r0 + n));
+    } else if (P.fast1 && n >= P.len0 && n + 4 <= L) {
+        v = __ldg(reinterpret_cast<const float4*>(rs.r1 + (n - P.len0)));
+    } else if (n + 4 > 0 && n < L) {
+        float e[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int m = n + i;
+            e[i] = (m < 0 || m >= L) ? 0.f : (m < P.len0 ? __ldg(rs.r0 + m) : __ldg(rs.r1 + (m - P.len0)));
+        }
+        v = make_float4(e[0], e[1], e[2], e[3]);
+    }
+    return v;
+}
+
+__device__ __forceinline__ void hist_store4(const FirParams& P, float* hrow, int n, const float4& v, int own_from) {
+    // logical samples n..n+3; keep those >= own_from that fall in [hist_from, hist_from + hist_len)
+    const int lo = max(P.hist_from, own_from), hi = P.hist_from + P.hist_len;
+    if (n + 4 <= lo || n >= hi) return;
+    if (P.fast_hist && n >= lo && n + 4 <= hi) {
+        *reinterpret_cast<float4*>(hrow + (n - P.hist_from)) = v;
+    } else {
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (n + i >= lo && n + i < hi) hrow[n + i - P.hist_from] = e[i];
+    }
+}
+
+// ---- epilogue ---------------------------------------------------------------------------------
+template <int NOUT, int MODE>
+__device__ __forceinline__ void dither_values(float (&d)[NOUT], const FirParams& P, int stream, unsigned long long idx0) {
+    const uint32_t k0 = (uint32_t)P.seed, k1 = (uint32_t)(P.seed >> 32);
+    const uint32_t sid = (uint32_t)(P.stream_id0 + stream);
+    if ((idx0 & 1ull) == 0) {
+#pragma unroll
+        for (int i = 0; i < NOUT; i += 2) {
+            const unsigned long long c = (idx0 + i) >> 1;
+            const Philox4 w = philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), sid, 0u, k0, k1);
+            d[i] = dither_lsb<MODE>(w.w[0], w.w[1]);
+            if (i + 1 < NOUT) d[i + 1] = dither_lsb<MODE>(w.w[2], w.w[3]);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NOUT; ++i) {
+            const unsigned long long idx = idx0 + i, c = idx >> 1;
+            const Philox4 w = philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), sid, 0u, k0, k1);
+            d[i] = (idx & 1ull) ? dither_lsb<MODE>(w.w[2], w.w[3]) : dither_lsb<MODE>(w.w[0], w.w[1]);
+        }
+    }
+}
+
+template <int NB>
+__device__ __forceinline__ void store_words(void* dst, const uint32_t (&w)[NB]) {
+    // NB 32-bit words to a destination whose alignment matches the widest vector dividing NB*4
+    if (NB % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < NB / 4; ++i)
+            reinterpret_cast<uint4*>(dst)[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+    } else if (NB % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < NB / 2; ++i) reinterpret_cast<uint2*>(dst)[i] = make_uint2(w[2 * i], w[2 * i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < NB; ++i) reinterpret_cast<uint32_t*>(dst)[i] = w[i];
+    }
+}
+
+__device__ __forceinline__ int elem_bytes(int fmt) {
+    return fmt == FMT_I16 ? 2 : (fmt == FMT_I24_PACKED ? 3 : 4);
+}
+
+// y[NOUT]: consecutive output samples o_base .. o_base+NOUT-1 (pre-decimation) of one stream row.
+template <int NOUT>
+__device__ __forceinline__ void store_row(const FirParams& P, float (&y)[NOUT], int stream, long long o_base, int n_valid) {
+    if (n_valid <= 0) return;
+    if (P.gain != 1.0f) {
+#pragma unroll
+        for (int i = 0; i < NOUT; ++i) y[i] = __fmul_rn(y[i], P.gain);
+    }
+    unsigned char* row = reinterpret_cast<unsigned char*>(P.out) + (long long)stream * P.out_pitch * elem_bytes(P.fmt);
+    if (P.decim == 1) {
+        float d[NOUT];
+        const unsigned long long idx0 = P.sample_base + (unsigned long long)o_base;
+        if (P.dither == DITHER_TPDF) dither_values<NOUT, DITHER_TPDF>(d, P, stream, idx0);
+        else if (P.dither == DITHER_RPDF) dither_values<NOUT, DITHER_RPDF>(d, P, stream, idx0);
+        else {
+#pragma unroll
+            for (int i = 0; i < NOUT; ++i) d[i] = 0.f;
+        }
+        const bool full = P.fast_out && n_valid == NOUT;
+        if (P.fmt == FMT_F32) {
+            if (P.dither != DITHER_NONE) {
+#pragma unroll
+                for (int i = 0; i < NOUT; ++i) y[i] = dither_float(y[i], d[i]);
+            }
+            float* o = reinterpret_cast<float*>(row) + o_base;
+            if (full) {
+                uint32_t w[NOUT];
+#pragma unroll
+                for (int i = 0; i < NOUT; ++i) w[i] = __float_as_uint(y[i]);
+                store_words<NOUT>(o, w);
+            } else {
+#pragma unroll
+                for (int i = 0; i < NOUT; ++i) if (i < n_valid) o[i] = y[i];
+            }
+        } else if (P.fmt == FMT_I16) {
+            int q[NOUT];
+#pragma unroll
+            for (int i = 0; i < NOUT; ++i) q[i] = quantise<16>(y[i], d[i]);
+            short* o = reinterpret_cast<short*>(row) + o_base;
+            if (full) {
+                uint32_t w[NOUT / 2];
+#pragma unroll
+                for (int i = 0; i < NOUT / 2; ++i) w[i] = ((uint32_t)q[2 * i] & 0xFFFFu) | ((uint32_t)q[2 * i + 1] << 16);
+                store_words<NOUT / 2>(o, w);
+            } else {
+#pragma unroll
+                for (int i = 0; i < NOUT; ++i) if (i < n_valid) o[i] = (short)q[i];
+            }
+        } else {
+            int q[NOUT];
+#pragma unroll
+            for (int i = 0; i < NOUT; ++i) q[i] = quantise<24>(y[i], d[i]);
+            if (P.fmt == FMT_I24_IN_I32) {
+                int* o = reinterpret_cast<int*>(row) + o_base;
+                if (full) {
+                    uint32_t w[NOUT];
+#pragma unroll
+                    for (int i = 0; i < NOUT; ++i) w[i] = (uint32_t)q[i];
+                    store_words<NOUT>(o, w);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NOUT; ++i) if (i < n_valid) o[i] = q[i];
+                }
+            } else {  // packed little-endian 3-byte samples
+                unsigned char* o = row + o_base * 3;
+                if (full) {
+                    uint32_t w[NOUT * 3 / 4];
+#pragma unroll
+                    for (int i = 0; i < NOUT / 4; ++i) {
+                        const uint32_t a = (uint32_t)q[4 * i] & 0xFFFFFFu, b = (uint32_t)q[4 * i + 1] & 0xFFFFFFu;
+                        const uint32_t c = (uint32_t)q[4 * i + 2] & 0xFFFFFFu, e = (uint32_t)q[4 * i + 3] & 0xFFFFFFu;
+                        w[3 * i] = a | (b << 24);
+                        w[3 * i + 1] = (b >> 8) | (c << 16);
+                        w[3 * i + 2] = (c >> 16) | (e << 8);
+                    }
+                    store_words<NOUT * 3 / 4>(o, w);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NOUT; ++i) if (i < n_valid) {
+                        o[3 * i] = (unsigned char)(q[i] & 0xFF);
+                        o[3 * i + 1] = (unsigned char)((q[i] >> 8) & 0xFF);
+                        o[3 * i + 2] = (unsigned char)((q[i] >> 16) & 0xFF);
+                    }
+                }
+            }
+        }
+    } else {
+        // decimating store (reference chain, stream_process.py:106): element-wise, parity path
+        const uint32_t k0 = (uint32_t)P.seed, k1 = (uint32_t)(P.seed >> 32);
+        const uint32_t sid = (uint32_t)(P.stream_id0 + stream);
+#pragma unroll
+        for (int i = 0; i < NOUT; ++i) {
+            const long long o = o_base + i;
+            if (i >= n_valid || (o % P.decim) != 0) continue;
+            const long long od = o / P.decim;
+            float d = 0.f;
+            if (P.dither != DITHER_NONE) {
+                const unsigned long long idx = P.sample_base + (unsigned long long)od, c = idx >> 1;
+                const Philox4 w = philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), sid, 0u, k0, k1);
+                const uint32_t wa = (idx & 1ull) ? w.w[2] : w.w[0], wb = (idx & 1ull) ? w.w[3] : w.w[1];
+                d = (P.dither == DITHER_TPDF) ? dither_lsb<DITHER_TPDF>(wa, wb) : dither_lsb<DITHER_RPDF>(wa, wb);
+            }
+            if (P.fmt == FMT_F32) {
+                reinterpret_cast<float*>(row)[od] = (P.dither != DITHER_NONE) ? dither_float(y[i], d) : y[i];
+            } else if (P.fmt == FMT_I16) {
+                reinterpret_cast<short*>(row)[od] = (short)quantise<16>(y[i], d);
+            } else {
+                const int q = quantise<24>(y[i], d);
+                if (P.fmt == FMT_I24_IN_I32) reinterpret_cast<int*>(row)[od] = q;
+                else {
+                    row[3 * od] = (unsigned char)(q & 0xFF);
+                    row[3 * od + 1] = (unsigned char)((q >> 8) & 0xFF);
+                    row[3 * od + 2] = (unsigned char)((q >> 16) & 0xFF);
+                }
+            }
+        }
+    }
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------
+template <int U, int T, int NT>
+__global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 4))
+fir_stream_kernel(const __grid_constant__ FirParams P) {
+    extern __shared__ float4 smem[];
+    const int tid = threadIdx.x;
+    const int tg = 1 << P.tg_log2;                 // threads per segment
+    const int slots = NT >> P.tg_log2;             // segment pairs per CTA
+    const int lq = tg * T;                         // base positions per segment
+    const int kq = P.n_chunks * T;                 // padded taps per phase = halo
+    const int region_pairs = kq + lq;
+    const int region_g = region_granules(region_pairs);
+
+    // ---- load phase: global -> (row A, row B) interleaved pairs in shared memory, history out
+    for (int slot = 0; slot < slots; ++slot) {
+        const int pair_idx = blockIdx.x * slots + slot;
+        const int segA = 2 * pair_idx, segB = segA + 1;
+        RowSrc ra, rb;
+        int sA = 0, sB = 0, gA = 0, gB = 0;
+        ra.valid = segA < P.n_seg_total;
+        rb.valid = segB < P.n_seg_total;
+        if (ra.valid) { sA = segA / P.segs_per_stream; gA = segA - sA * P.segs_per_stream; }
+        if (rb.valid) { sB = segB / P.segs_per_stream; gB = segB - sB * P.segs_per_stream; }
+        ra.r0 = P.src0 + (long long)sA * P.pitch0; ra.r1 = P.src1 + (long long)sA * P.pitch1;
+        rb.r0 = P.src0 + (long long)sB * P.pitch0; rb.r1 = P.src1 + (long long)sB * P.pitch1;
+        const int startA = P.q_begin + gA * lq - kq;      // logical index of pair 0 of the region
+        const int startB = P.q_begin + gB * lq - kq;
+        float* hA = P.hist_out ? P.hist_out + (long long)sA * P.hist_pitch : nullptr;
+        float* hB = P.hist_out ? P.hist_out + (long long)sB * P.hist_pitch : nullptr;
+        const int ownA = gA == 0 ? INT_MIN : startA + kq;
+        const int ownB = gB == 0 ? INT_MIN : startB + kq;
+        float4* region = smem + slot * region_g;
+        const int n4 = region_pairs >> 2;
+#pragma unroll 2
+        for (int i4 = tid; i4 < n4; i4 += NT) {
+            const float4 a = fetch4(P, ra, startA + 4 * i4);
+            const float4 b = fetch4(P, rb, startB + 4 * i4);
+            const int g = phys_granule(2 * i4);
+            region[g] = make_float4(a.x, b.x, a.y, b.y);
+            region[g + 1] = make_float4(a.z, b.z, a.w, b.w);
+            if (hA && ra.valid) hist_store4(P, hA, startA + 4 * i4, a, ownA);
+            if (hB && rb.valid) hist_store4(P, hB, startB + 4 * i4, b, ownB);
+        }
+    }
+    __syncthreads();
+
+    // ---- compute phase
+    const int slot = tid >> P.tg_log2;
+    const int lt = tid & (tg - 1);
+    const float4* region = smem + slot * region_g;
+    const int b0 = P.n_chunks + lt;               // block holding this thread's own T positions
+
+    float2 acc[U][T];
+#pragma unroll
+    for (int p = 0; p < U; ++p)
+#pragma unroll
+        for (int r = 0; r < T; ++r) acc[p][r] = make_float2(0.f, 0.f);
+
+    float2 wa[T], wb[T];
+    load_block<T>(wb, region, b0);
+    int c = 0;
+    for (; c + 2 <= P.n_chunks; c += 2) {
+        load_block<T>(wa, region, b0 - c - 1);
+        chunk_fma<U, T>(acc, wa, wb, P.taps + c * (T * U));
+        load_block<T>(wb, region, b0 - c - 2);
+        chunk_fma<U, T>(acc, wb, wa, P.taps + (c + 1) * (T * U));
+    }
+    if (c < P.n_chunks) {
+        load_block<T>(wa, region, b0 - c - 1);
+        chunk_fma<U, T>(acc, wa, wb, P.taps + c * (T * U));
+    }
+
+    // ---- epilogue: registers -> global, dither / quantise on the way
+    const int pair_idx = blockIdx.x * slots + slot;
+#pragma unroll
+    for (int row = 0; row < 2; ++row) {
+        const int seg = 2 * pair_idx + row;
+        if (seg >= P.n_seg_total) continue;
+        const int s = seg / P.segs_per_stream, gi = seg - s * P.segs_per_stream;
+        const int q_local = gi * lq + lt * T;               // first base position (relative to q_begin)
+        const int nv = min(max(P.n_q - q_local, 0), T) * U;
+        float y[U * T];
+#pragma unroll
+        for (int r = 0; r < T; ++r)
+#pragma unroll
+            for (int p = 0; p < U; ++p) y[r * U + p] = row == 0 ? acc[p][r].x : acc[p][r].y;
+        store_row<U * T>(P, y, s, (long long)q_local * U, nv);
+    }
+}
+
+}  // namespace afp

@@ -1,0 +1,62 @@
+// Dither + quantise epilogue (kernel 5): Philox4x32-10 counter RNG, TPDF/RPDF dither, int16/int24.
+//
+// The reference's apply_dither (stream_process.py:61-64) adds +-1/2 LSB *float* noise from the
+// unseeded numpy RNG and never quantises, so this stage is build-defined.  The
+// arithmetic contract (bit for bit) is written down in oracle/dither_quant.py:
+//   key     = (seed lo, seed hi)
+//   counter = (c lo, c hi, stream_id, 0),  c = absolute_output_sample_index >> 1
+//   even samples use words (0,1) of the block, odd samples words (2,3); k = word >> 8
+//   TPDF d = float(k1 + k2 - (2^24-1)) * 2^-24      RPDF d = float(2*k1 + 1 - 2^24) * 2^-25
+//   q = clip(rint(fl32(fl32(y*2^(bits-1)) + d)), -2^(bits-1), 2^(bits-1)-1)   (no fused multiply-add)
+#pragma once
+#include <cstdint>
+
+namespace afp {
+
+enum : int { FMT_F32 = 0, FMT_I16 = 1, FMT_I24_IN_I32 = 2, FMT_I24_PACKED = 3 };
+enum : int { DITHER_NONE = 0, DITHER_TPDF = 1, DITHER_RPDF = 2 };
+
+struct Philox4 { uint32_t w[4]; };
+
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    Philox4 o;
+    o.w[0] = c0; o.w[1] = c1; o.w[2] = c2; o.w[3] = c3;
+    return o;
+}
+
+// Dither value in LSB units from two 32-bit words.
+template <int MODE>
+__device__ __forceinline__ float dither_lsb(uint32_t wa, uint32_t wb) {
+    const int a = (int)(wa >> 8), b = (int)(wb >> 8);
+    if (MODE == DITHER_TPDF) return __fmul_rn((float)(a + b - ((1 << 24) - 1)), 5.9604644775390625e-08f);
+    return __fmul_rn((float)(2 * a + 1 - (1 << 24)), 2.98023223876953125e-08f);
+}
+
+// float sample -> integer code of a BITS-bit signed format, d in LSB units.
+template <int BITS>
+__device__ __forceinline__ int quantise(float y, float d) {
+    constexpr float scale = (float)(1 << (BITS - 1));
+    float v = __fadd_rn(__fmul_rn(y, scale), d);
+    v = fminf(fmaxf(rintf(v), -scale), scale - 1.0f);   // fmaxf/fminf drop NaN -> -scale, fixed below
+    int q = __float2int_rn(v);
+    return (y != y) ? 0 : q;
+}
+
+// Reference-style float dither at 24-bit scale: y + d * 2^-23, both steps rounded to float32.
+__device__ __forceinline__ float dither_float(float y, float d) {
+    return __fadd_rn(y, __fmul_rn(d, 1.1920928955078125e-07f));
+}
+
+}  // namespace afp

@@ -1,0 +1,182 @@
+"""BatchFirEngine - the host-side operator over the C-ABI (one engine = one GPU = one chain).
+
+It batches S independent streams (channel x session) through the reference's per-block chain
+
+    [interpolate xU] -> [EQ bank] -> FIR with carried state -> [decimate] -> [dither / quantise]
+
+(stream_process.py:79-120, stream_process_EQ.py:99-166) with all arithmetic in the sm_100a kernels
+of csrc/.  Taps come from ``design.create_fir_filter`` exactly as in the reference
+(stream_process.py:33-40: designed at ``samplerate * upsample``).  torch is used only to hold
+device buffers and to pick the CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+_TORCH_DTYPE = {0: "float32", 1: "int16", 2: "int32", 3: "uint8"}
+_NP_DTYPE = {0: np.float32, 1: np.int16, 2: np.int32, 3: np.uint8}
+
+
+def _dbl(a):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64).ravel())
+    return a, a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class BatchFirEngine:
+    """Streaming block-FIR over ``n_streams`` independent streams on one B200.
+
+    chain='dac'        out[S, frames*U]: the designed filter *is* the interpolation filter
+                       (polyphase, only non-zero products are computed).
+    chain='reference'  out[S, frames]: interpolate with ``upsampler_taps`` -> [EQ] -> FIR -> keep
+                       every U-th sample, the structure of stream_process.py:89-107.
+    out_format         'f32' | 'i16' | 'i24' (int32 container) | 'i24_packed' (3-byte little endian)
+    dither             'none' | 'tpdf' | 'rpdf'  (Philox4x32-10 keyed by seed/stream/sample index)
+    eq_mode            'none' | 'fused' (taps-domain sum, stream_process_EQ_GUI.py:86-90)
+    """
+
+    def __init__(self, taps, n_streams=1, max_frames=1024, upsample=1, chain="dac", out_format="f32",
+                 dither="none", seed=0, device=0, upsampler_taps=None, eq_bands=None, eq_gains=None,
+                 eq_mode="none", first_stream_id=0):
+        self._lib = _lib.load()
+        self._ctx = C.c_void_p()
+        if eq_bands is not None and eq_mode in ("none", None):
+            eq_mode = "fused"
+        cfg = _lib.Config(device=int(device), n_streams=int(n_streams), max_frames=int(max_frames),
+                          upsample=int(upsample), chain=_lib.CHAIN[chain],
+                          out_format=_lib.FMT[out_format], dither=_lib.DITHER[dither],
+                          eq_mode=_lib.EQ_MODE[eq_mode], seed=int(seed) & (2 ** 64 - 1),
+                          first_stream_id=int(first_stream_id), reserved=0)
+        _lib.check(self._lib.afp_create(C.byref(cfg), C.byref(self._ctx)))
+        self.cfg = cfg
+        self.n_streams, self.max_frames, self.upsample = int(n_streams), int(max_frames), int(upsample)
+        self.device = int(device)
+        self.fmt = cfg.out_format
+        self.taps = None
+        try:
+            self.set_taps(taps)
+            if upsampler_taps is not None:
+                self.set_upsampler(upsampler_taps)
+            if eq_bands is not None:
+                self.set_eq(eq_bands, eq_gains)
+        except Exception:
+            self.close()
+            raise
+
+    # -- filter tables -----------------------------------------------------------------------
+    def set_taps(self, taps):
+        a, p = _dbl(taps)
+        _lib.check(self._lib.afp_set_taps(self._ctx, p, len(a)), self._ctx)
+        self.taps = a
+
+    def set_upsampler(self, taps):
+        a, p = _dbl(taps)
+        _lib.check(self._lib.afp_set_upsampler(self._ctx, p, len(a)), self._ctx)
+
+    def set_eq(self, bands, gains=None):
+        bands = [np.asarray(b, dtype=np.float64).ravel() for b in bands]
+        lens = (C.c_int32 * len(bands))(*[len(b) for b in bands])
+        flat, fp = _dbl(np.concatenate(bands) if bands else np.zeros(0))
+        gp = None
+        if gains is not None:
+            g, gp = _dbl(gains)
+        _lib.check(self._lib.afp_set_eq(self._ctx, fp, lens, len(bands), gp), self._ctx)
+
+    def set_gains(self, gains):
+        g, gp = _dbl(gains)
+        _lib.check(self._lib.afp_set_gains(self._ctx, gp, len(g)), self._ctx)
+
+    # -- processing --------------------------------------------------------------------------
+    def out_frames(self, frames):
+        return int(self._lib.afp_out_frames(self._ctx, int(frames)))
+
+    def _out_cols(self, frames):
+        n = self.out_frames(frames)
+        return n * 3 if self.fmt == 3 else n
+
+    def process(self, x, out=None):
+        """One block for all streams on device tensors: ``x`` float32 cuda [S, frames] (row stride
+        arbitrary, unit column stride).  Asynchronous on torch's current stream."""
+        import torch
+        if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2 or x.shape[0] != self.n_streams:
+            raise ValueError("x must be a float32 CUDA tensor of shape [n_streams, frames]")
+        if x.stride(1) != 1:
+            x = x.contiguous()
+        frames = x.shape[1]
+        if out is None:
+            out = torch.empty((self.n_streams, self._out_cols(frames)),
+                              dtype=getattr(torch, _TORCH_DTYPE[self.fmt]), device=x.device)
+        elif out.stride(1) != 1 or out.shape[0] != self.n_streams or out.shape[1] < self._out_cols(frames):
+            raise ValueError("out has the wrong shape / stride")
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(self._lib.afp_process(self._ctx, x.data_ptr(), x.stride(0), out.data_ptr(),
+                                         out.stride(0), frames, stream), self._ctx)
+        return out
+
+    def process_host(self, x, out=None):
+        """One block with host arrays (numpy float32 [S, frames]); returns a numpy array."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim != 2 or x.shape[0] != self.n_streams:
+            raise ValueError("x must have shape [n_streams, frames]")
+        frames = x.shape[1]
+        if out is None:
+            out = np.empty((self.n_streams, self._out_cols(frames)), dtype=_NP_DTYPE[self.fmt])
+        _lib.check(self._lib.afp_process_host(self._ctx, x.ctypes.data, out.ctypes.data, frames), self._ctx)
+        return out
+
+    # -- state -------------------------------------------------------------------------------
+    def reset(self):
+        _lib.check(self._lib.afp_reset(self._ctx), self._ctx)
+
+    def get_state(self):
+        n = C.c_size_t()
+        _lib.check(self._lib.afp_state_size(self._ctx, C.byref(n)), self._ctx)
+        buf = np.empty(n.value, dtype=np.uint8)
+        _lib.check(self._lib.afp_get_state(self._ctx, buf.ctypes.data, n.value), self._ctx)
+        return buf
+
+    def set_state(self, blob):
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        _lib.check(self._lib.afp_set_state(self._ctx, blob.ctypes.data, blob.size), self._ctx)
+
+    # -- introspection -----------------------------------------------------------------------
+    def stage_info(self):
+        out, i = [], 0
+        while True:
+            info = _lib.StageInfo()
+            if self._lib.afp_get_stage_info(self._ctx, i, C.byref(info)) != 0:
+                return out
+            out.append({n: getattr(info, n) for n, _ in info._fields_})
+            i += 1
+
+    @property
+    def kernel_launches(self):
+        return int(self._lib.afp_kernel_launches(self._ctx))
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self._lib.afp_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def measure_fma_peak(device=0):
+    """FP32 FMA roof of the device (TFLOP/s, SM MHz) from the packed-FFMA2 issue loop."""
+    lib = _lib.load()
+    t, m = C.c_double(), C.c_double()
+    _lib.check(lib.afp_measure_fma_peak(int(device), C.byref(t), C.byref(m)))
+    return t.value, m.value

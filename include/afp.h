@@ -1,0 +1,141 @@
+/* afp.h - C-ABI of the B200 streaming block-FIR engine.
+ *
+ * This is the boundary a maintainer of MrEstefano/Audio-Filtering-Pipeline binds (ctypes, see
+ * INTEGRATION.md) to move the per-block DSP of the sounddevice callback onto a B200.  Plain C:
+ * pointers, sizes and integer status codes only; no C++/torch types.  Every entry point returns
+ * AFP_OK (0) or a non-zero AFP_ERR_* code and never throws; afp_last_error() gives the message.
+ *
+ * Reference interfaces replaced (file:line under the reference checkout):
+ *   afp_set_taps / afp_process        sliding buffer + oaconvolve(buffer, fir_coeff, 'valid')
+ *                                     stream_process.py:45-46,96-107; OverlapAddFilter.process_block
+ *                                     stream_process_GUI_Presets.py:69-123
+ *   afp_set_upsampler                 safe_upsample -> soxr.resample     stream_process.py:66-77
+ *   afp_set_eq / afp_set_gains        EQ bank: per-band 'same' sum       stream_process_EQ.py:124-129
+ *                                     fused taps-domain sum              stream_process_EQ_GUI.py:86-90
+ *                                     filter swap under filter_lock      stream_process_EQ_GUI.py:380-385
+ *   out_format / dither in afp_config apply_dither                       stream_process.py:61-64
+ *   chain = AFP_CHAIN_REFERENCE       processed[::UPSAMPLE_FACTOR]       stream_process.py:106
+ *   afp_process_host                  the body of audio_callback(indata, outdata, frames, ...)
+ *                                     stream_process.py:79-120 (host buffers in, host buffers out)
+ *
+ * Data layout: planar, stream-major.  in[s*in_pitch + i] is frame i of stream s (float32 at the
+ * base rate); out[s*out_pitch + j] is output sample j of stream s in `out_format`.  A "stream" is
+ * one channel of one session; stereo is two streams.  Streams share taps and nothing else.
+ */
+#ifndef AFP_H
+#define AFP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AFP_OK 0
+#define AFP_ERR_INVALID 1   /* bad argument / configuration */
+#define AFP_ERR_CUDA 2      /* a CUDA runtime call failed; message has the CUDA error string */
+#define AFP_ERR_STATE 3     /* call made in the wrong state (e.g. process before set_taps) */
+#define AFP_ERR_NOMEM 4
+
+/* afp_config.chain */
+#define AFP_CHAIN_DAC 0        /* x -> [EQ] -> polyphase FIR(h, U) -> out at fs*U (the FIR is the interpolator) */
+#define AFP_CHAIN_REFERENCE 1  /* x -> interp(h_up, U) -> [EQ] -> FIR(h) -> [::U] -> out at fs (stream_process.py) */
+
+/* afp_config.out_format */
+#define AFP_FMT_F32 0
+#define AFP_FMT_I16 1
+#define AFP_FMT_I24_IN_I32 2   /* 24-bit code sign-extended in an int32 */
+#define AFP_FMT_I24_PACKED 3   /* little-endian 3-byte samples */
+
+/* afp_config.dither */
+#define AFP_DITHER_NONE 0
+#define AFP_DITHER_TPDF 1      /* triangular, (-1,1) LSB, Philox4x32-10 keyed (seed, stream, sample index) */
+#define AFP_DITHER_RPDF 2      /* rectangular +-1/2 LSB: the amplitude of the reference's apply_dither */
+
+/* afp_config.eq_mode */
+#define AFP_EQ_NONE 0
+#define AFP_EQ_FUSED 1         /* one FIR with taps sum_b g_b*h_b, state carried (stream_process_EQ_GUI.py:86-90) */
+#define AFP_EQ_PER_BAND 2      /* every band convolved separately and summed with its gain */
+#define AFP_EQ_BUFFER_SAME 3   /* parity mode: 'same' convolution over the [history|block] buffer,
+                                  zero-extended at both ends, recomputed every block
+                                  (stream_process_EQ.py:124-134) */
+
+typedef struct afp_ctx afp_ctx;
+
+typedef struct afp_config {
+    int32_t device;           /* CUDA device ordinal */
+    int32_t n_streams;        /* S */
+    int32_t max_frames;       /* largest `frames` a process call will pass (base rate, per stream) */
+    int32_t upsample;         /* U in 1..4 */
+    int32_t chain;            /* AFP_CHAIN_* */
+    int32_t out_format;       /* AFP_FMT_* */
+    int32_t dither;           /* AFP_DITHER_* */
+    int32_t eq_mode;          /* AFP_EQ_* */
+    uint64_t seed;            /* dither seed */
+    int32_t first_stream_id;  /* global id of stream 0 (keeps dither identical under multi-GPU sharding) */
+    int32_t reserved;
+} afp_config;
+
+typedef struct afp_stage_info {
+    int32_t kind;             /* 0 interp, 1 eq, 2 main */
+    int32_t upsample;         /* phases computed by this stage */
+    int32_t n_taps;           /* taps as given */
+    int32_t taps_per_phase_padded;
+    int32_t tile_taps;        /* T: taps per register-blocked chunk = base positions per thread */
+    int32_t threads;          /* CTA size chosen for the last launch */
+    int32_t threads_per_segment;
+    int32_t smem_bytes;
+    int32_t grid;
+    int32_t history;          /* carried samples per stream */
+} afp_stage_info;
+
+const char* afp_version(void);
+
+int afp_create(const afp_config* cfg, afp_ctx** out_ctx);
+int afp_destroy(afp_ctx* ctx);
+const char* afp_last_error(const afp_ctx* ctx);   /* ctx may be NULL: error of the last failed afp_create */
+
+/* Filter tables (host pointers, float64 as create_fir_filter returns them).  Each call resets the
+ * carried state of the stage it changes, like OverlapAddFilter.set_coefficients
+ * (stream_process_GUI_Presets.py:44-67); afp_set_gains does not. */
+int afp_set_taps(afp_ctx* ctx, const double* taps, int32_t n_taps);
+int afp_set_upsampler(afp_ctx* ctx, const double* taps, int32_t n_taps);
+int afp_set_eq(afp_ctx* ctx, const double* band_taps, const int32_t* band_len, int32_t n_bands,
+               const double* gains);
+int afp_set_gains(afp_ctx* ctx, const double* gains, int32_t n_bands);
+
+/* One block for all streams.  Device pointers are caller-owned; the call is asynchronous on
+ * `cuda_stream` (a cudaStream_t, NULL = the legacy default stream).  Pitches are in elements
+ * (bytes for AFP_FMT_I24_PACKED output).  Output samples per stream: afp_out_frames(). */
+int afp_process(afp_ctx* ctx, const float* in_dev, int64_t in_pitch, void* out_dev, int64_t out_pitch,
+                int32_t frames, void* cuda_stream);
+/* Same with host buffers (any host memory; pinned memory from afp_host_alloc is fastest).
+ * Copies in, runs, copies out and waits.  Dense layout: in[S][frames], out[S][afp_out_frames]. */
+int afp_process_host(afp_ctx* ctx, const float* in_host, void* out_host, int32_t frames);
+
+int32_t afp_out_frames(const afp_ctx* ctx, int32_t frames);
+int32_t afp_out_elem_bytes(const afp_ctx* ctx);
+
+/* State: zero it, or save / restore it (carried history of every stage + dither sample counter). */
+int afp_reset(afp_ctx* ctx);
+int afp_state_size(const afp_ctx* ctx, size_t* bytes);
+int afp_get_state(afp_ctx* ctx, void* host_buf, size_t bytes);
+int afp_set_state(afp_ctx* ctx, const void* host_buf, size_t bytes);
+
+/* Introspection for the benchmark harness and DESIGN.md tables. */
+int afp_get_stage_info(const afp_ctx* ctx, int32_t stage, afp_stage_info* info);   /* AFP_ERR_INVALID past the end */
+int64_t afp_kernel_launches(const afp_ctx* ctx);
+
+/* Pinned host memory for afp_process_host. */
+int afp_host_alloc(void** ptr, size_t bytes);
+int afp_host_free(void* ptr);
+
+/* FP32 FMA roof of the device, measured with a packed-FFMA2 issue loop (there is no
+ * FP32 entry in MEASURED_PEAKS.json).  Returns TFLOP/s and the SM clock seen during the loop. */
+int afp_measure_fma_peak(int32_t device, double* tflops, double* sm_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFP_H */
