@@ -19,7 +19,7 @@ EQ_MODE = {"none": 0, None: 0, "fused": 1, "per_band": 2, "buffer_same": 3}
 # every symbol include/afp.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "afp_version", "afp_create", "afp_destroy", "afp_last_error", "afp_set_taps", "afp_set_upsampler",
-    "afp_set_eq", "afp_set_gains", "afp_process", "afp_process_host", "afp_out_frames",
+    "afp_set_eq", "afp_set_gains", "afp_process", "afp_process_host", "afp_process_host_blocks", "afp_out_frames",
     "afp_out_elem_bytes", "afp_reset", "afp_state_size", "afp_get_state", "afp_set_state",
     "afp_get_stage_info", "afp_kernel_launches", "afp_host_alloc", "afp_host_free",
     "afp_measure_fma_peak",
@@ -74,6 +74,7 @@ def load():
     lib.afp_set_gains.argtypes = [vp, dp, i32]
     lib.afp_process.argtypes = [vp, vp, i64, vp, i64, i32, vp]
     lib.afp_process_host.argtypes = [vp, vp, vp, i32]
+    lib.afp_process_host_blocks.argtypes = [vp, vp, vp, i32, i32]
     lib.afp_out_frames.argtypes = [vp, i32]
     lib.afp_out_frames.restype = i32
     lib.afp_out_elem_bytes.argtypes = [vp]

@@ -76,10 +76,13 @@ struct afp_ctx {
     long long pitch_a = 0, pitch_b = 0;
     unsigned long long out_samples = 0;   // kept output samples per stream since reset
     long long launches = 0;
-    // afp_process_host staging
-    float* d_in = nullptr;
-    void* d_out = nullptr;
-    cudaStream_t own_stream = nullptr;
+    // afp_process_host staging: a ring of device slots fed by three streams (H2D, compute, D2H)
+    static constexpr int kSlots = 3;
+    float* d_in[kSlots] = {nullptr, nullptr, nullptr};
+    unsigned char* d_out[kSlots] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_in[kSlots] = {}, ev_k[kSlots] = {}, ev_out[kSlots] = {};
+    int slot_streams = 0;            // streams per staging slot
+    cudaStream_t own_stream = nullptr, s_in = nullptr, s_out = nullptr;
 };
 
 namespace {
@@ -169,17 +172,20 @@ struct StageIO {
     int fmt = AFP_FMT_F32, dither = AFP_DITHER_NONE, decim = 1;
     unsigned long long sample_base = 0;
     float* hist_out = nullptr; long long hist_pitch = 0; int hist_len = 0, hist_from = 0;
+    int s0 = 0, ns = 0;              // stream sub-range [s0, s0+ns) this launch covers
 };
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int launch_stage(afp_ctx* c, Stage& s, const StageIO& io, cudaStream_t stream) {
-    const int S = c->cfg.n_streams;
+    const int S = io.ns;
     Geometry g = pick_geometry(s.T, s.kq_pad, io.n_q, S);
     if (g.nt == 0) return fail(c, AFP_ERR_INVALID, "filter/block combination does not fit in shared memory");
     s.geo = g;
     static FirParams P;   // 16 KB: keep it off the stack; contexts are single-owner, launches serialised per process call
-    P.src0 = io.src0; P.src1 = io.src1; P.pitch0 = io.pitch0; P.pitch1 = io.pitch1;
+    const int eb = io.fmt == AFP_FMT_I16 ? 2 : (io.fmt == AFP_FMT_I24_PACKED ? 3 : 4);
+    P.src0 = io.src0; P.src1 = io.src1;     // all pointers arrive offset to stream s0
+    P.pitch0 = io.pitch0; P.pitch1 = io.pitch1;
     P.len0 = io.len0; P.len1 = io.len1;
     P.q_begin = io.q_begin; P.n_q = io.n_q;
     P.tg_log2 = g.tg_log2; P.segs_per_stream = g.segs_per_stream;
@@ -187,7 +193,7 @@ int launch_stage(afp_ctx* c, Stage& s, const StageIO& io, cudaStream_t stream) {
     P.n_chunks = s.n_chunks;
     P.out = io.out; P.out_pitch = io.out_pitch;
     P.decim = io.decim; P.fmt = io.fmt; P.dither = io.dither;
-    P.seed = c->cfg.seed; P.sample_base = io.sample_base; P.stream_id0 = c->cfg.first_stream_id;
+    P.seed = c->cfg.seed; P.sample_base = io.sample_base; P.stream_id0 = c->cfg.first_stream_id + io.s0;
     P.hist_out = io.hist_out; P.hist_pitch = io.hist_pitch; P.hist_len = io.hist_len; P.hist_from = io.hist_from;
     P.gain = 1.0f;
     const int start0 = io.q_begin - s.kq_pad;   // logical index of the first pair of segment 0's region
@@ -196,7 +202,6 @@ int launch_stage(afp_ctx* c, Stage& s, const StageIO& io, cudaStream_t stream) {
     P.fast0 = (io.len0 > 0 && n_al && aligned16(io.src0) && io.pitch0 % 4 == 0) ? 1 : 0;
     P.fast1 = (io.len1 > 0 && n_al && aligned16(io.src1) && io.pitch1 % 4 == 0 && io.len0 % 4 == 0) ? 1 : 0;
     P.fast_hist = (io.hist_out && n_al && aligned16(io.hist_out) && io.hist_pitch % 4 == 0 && io.hist_from % 4 == 0) ? 1 : 0;
-    const int eb = io.fmt == AFP_FMT_I16 ? 2 : (io.fmt == AFP_FMT_I24_PACKED ? 3 : 4);
     P.fast_out = (aligned16(io.out) && (io.out_pitch * eb) % 16 == 0) ? 1 : 0;
     std::memset(P.taps, 0, sizeof(P.taps));
     std::memcpy(P.taps, s.table.data(), s.table.size() * sizeof(float));
@@ -210,17 +215,16 @@ int launch_stage(afp_ctx* c, Stage& s, const StageIO& io, cudaStream_t stream) {
 // streaming launch: history | new block, outputs for the new block, history rolled forward
 int run_streaming(afp_ctx* c, Stage& s, const float* in, long long in_pitch, int len,
                   void* out, long long out_pitch, int fmt, int dither, int decim,
-                  unsigned long long sample_base, cudaStream_t stream) {
+                  unsigned long long sample_base, int s0, int ns, cudaStream_t stream) {
     StageIO io;
-    io.src0 = s.hist[s.cur]; io.pitch0 = s.hist_pitch; io.len0 = s.kq_pad;
+    io.s0 = s0; io.ns = ns;
+    io.src0 = s.hist[s.cur] + (long long)s0 * s.hist_pitch; io.pitch0 = s.hist_pitch; io.len0 = s.kq_pad;
     io.src1 = in; io.pitch1 = in_pitch; io.len1 = len;
     io.q_begin = s.kq_pad; io.n_q = len;
     io.out = out; io.out_pitch = out_pitch; io.fmt = fmt; io.dither = dither; io.decim = decim;
     io.sample_base = sample_base;
-    io.hist_out = s.hist[s.cur ^ 1]; io.hist_pitch = s.hist_pitch; io.hist_len = s.kq_pad; io.hist_from = len;
-    int rc = launch_stage(c, s, io, stream);
-    if (rc == AFP_OK) s.cur ^= 1;
-    return rc;
+    io.hist_out = s.hist[s.cur ^ 1] + (long long)s0 * s.hist_pitch; io.hist_pitch = s.hist_pitch; io.hist_len = s.kq_pad; io.hist_from = len;
+    return launch_stage(c, s, io, stream);   // the caller flips s.cur once the whole block is launched
 }
 
 int rebuild_eq(afp_ctx* c, bool reset_state) {
@@ -335,9 +339,16 @@ int afp_destroy(afp_ctx* c) {
     free_stage(c->up); free_stage(c->eq); free_stage(c->mainf);
     if (c->tmp_a) cudaFree(c->tmp_a);
     if (c->tmp_b) cudaFree(c->tmp_b);
-    if (c->d_in) cudaFree(c->d_in);
-    if (c->d_out) cudaFree(c->d_out);
+    for (int i = 0; i < afp_ctx::kSlots; ++i) {
+        if (c->d_in[i]) cudaFree(c->d_in[i]);
+        if (c->d_out[i]) cudaFree(c->d_out[i]);
+        if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+        if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
+        if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
+    }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
     delete c;
     return AFP_OK;
 }
@@ -394,65 +405,142 @@ int32_t afp_out_elem_bytes(const afp_ctx* c) {
     return c->cfg.out_format == AFP_FMT_I16 ? 2 : (c->cfg.out_format == AFP_FMT_I24_PACKED ? 3 : 4);
 }
 
+// One block for streams [s0, s0+ns); `in` / `out` point at stream s0.  Does not advance the state.
+static int process_block_range(afp_ctx* c, const float* in, int64_t in_pitch, void* out, int64_t out_pitch,
+                               int32_t frames, int s0, int ns, cudaStream_t st) {
+    const int U = c->cfg.upsample;
+    const bool ref = c->cfg.chain == AFP_CHAIN_REFERENCE;
+    int rc;
+    const float* cur = in; long long cur_pitch = in_pitch; int cur_len = frames;
+    if (ref && U > 1) {   // interpolate to the processing rate (replaces soxr.resample, stream_process.py:66-77)
+        float* ta = c->tmp_a + (long long)s0 * c->pitch_a;
+        rc = run_streaming(c, c->up, cur, cur_pitch, cur_len, ta, c->pitch_a, AFP_FMT_F32, AFP_DITHER_NONE, 1, 0, s0, ns, st);
+        if (rc) return rc;
+        cur = ta; cur_pitch = c->pitch_a; cur_len = frames * U;
+    }
+    if (c->eq.active) {
+        float* tb = c->tmp_b + (long long)s0 * c->pitch_b;
+        rc = run_streaming(c, c->eq, cur, cur_pitch, cur_len, tb, c->pitch_b, AFP_FMT_F32, AFP_DITHER_NONE, 1, 0, s0, ns, st);
+        if (rc) return rc;
+        cur = tb; cur_pitch = c->pitch_b;
+    }
+    const int decim = ref ? U : 1;
+    const long long opitch = c->cfg.out_format == AFP_FMT_I24_PACKED ? out_pitch / 3 : out_pitch;
+    return run_streaming(c, c->mainf, cur, cur_pitch, cur_len, out, opitch, c->cfg.out_format, c->cfg.dither, decim,
+                         c->out_samples, s0, ns, st);
+}
+
+// the whole block has been launched: roll the ping-pong histories and the dither counter
+static void finish_block(afp_ctx* c, int32_t frames) {
+    const bool ref = c->cfg.chain == AFP_CHAIN_REFERENCE;
+    if (ref && c->cfg.upsample > 1) c->up.cur ^= 1;
+    if (c->eq.active) c->eq.cur ^= 1;
+    c->mainf.cur ^= 1;
+    c->out_samples += (unsigned long long)afp_out_frames(c, frames);
+}
+
+static int check_ready(afp_ctx* c, int32_t frames) {
+    if (frames < 0 || frames > c->cfg.max_frames) return fail(c, AFP_ERR_INVALID, "frames outside 0..max_frames");
+    if (!c->mainf.active) return fail(c, AFP_ERR_STATE, "afp_set_taps has not been called");
+    if (c->cfg.chain == AFP_CHAIN_REFERENCE && c->cfg.upsample > 1 && !c->up.active)
+        return fail(c, AFP_ERR_STATE, "afp_set_upsampler has not been called");
+    if (c->cfg.eq_mode != AFP_EQ_NONE && !c->eq.active) return fail(c, AFP_ERR_STATE, "afp_set_eq has not been called");
+    if (c->cfg.eq_mode == AFP_EQ_BUFFER_SAME || c->cfg.eq_mode == AFP_EQ_PER_BAND)
+        return fail(c, AFP_ERR_INVALID, "eq_mode not implemented yet in this build");
+    return AFP_OK;
+}
+
 int afp_process(afp_ctx* c, const float* in, int64_t in_pitch, void* out, int64_t out_pitch, int32_t frames, void* cuda_stream) {
     if (!c) return AFP_ERR_INVALID;
     if (!in || !out) return fail(c, AFP_ERR_INVALID, "null buffer");
-    if (frames < 0 || frames > c->cfg.max_frames) return fail(c, AFP_ERR_INVALID, "frames outside 0..max_frames");
-    if (!c->mainf.active) return fail(c, AFP_ERR_STATE, "afp_set_taps has not been called");
+    int rc = check_ready(c, frames);
+    if (rc) return rc;
     if (frames == 0) return AFP_OK;
-    const int U = c->cfg.upsample;
-    const bool ref = c->cfg.chain == AFP_CHAIN_REFERENCE;
-    if (ref && U > 1 && !c->up.active) return fail(c, AFP_ERR_STATE, "afp_set_upsampler has not been called");
-    if (c->cfg.eq_mode != AFP_EQ_NONE && !c->eq.active) return fail(c, AFP_ERR_STATE, "afp_set_eq has not been called");
     if (in_pitch < frames) return fail(c, AFP_ERR_INVALID, "in_pitch smaller than frames");
     const int out_n = afp_out_frames(c, frames);
     if (out_pitch < (int64_t)out_n * (c->cfg.out_format == AFP_FMT_I24_PACKED ? 3 : 1))
         return fail(c, AFP_ERR_INVALID, "out_pitch smaller than the output row");
     AFP_CUDA(c, cudaSetDevice(c->cfg.device));
-    int rc = ensure_tmp(c);
+    rc = ensure_tmp(c);
     if (rc) return rc;
-    cudaStream_t st = (cudaStream_t)cuda_stream;
+    rc = process_block_range(c, in, in_pitch, out, out_pitch, frames, 0, c->cfg.n_streams, (cudaStream_t)cuda_stream);
+    if (rc) return rc;
+    finish_block(c, frames);
+    return AFP_OK;
+}
 
-    const float* cur = in; long long cur_pitch = in_pitch; int cur_len = frames;
-    if (ref && U > 1) {   // interpolate to the processing rate (replaces soxr.resample, stream_process.py:66-77)
-        rc = run_streaming(c, c->up, cur, cur_pitch, cur_len, c->tmp_a, c->pitch_a, AFP_FMT_F32, AFP_DITHER_NONE, 1, 0, st);
-        if (rc) return rc;
-        cur = c->tmp_a; cur_pitch = c->pitch_a; cur_len = frames * U;
+static int ensure_host_staging(afp_ctx* c) {
+    if (c->d_in[0]) return AFP_OK;
+    const int S = c->cfg.n_streams;
+    // stream chunks of >= 1 MiB of input so that copies in both directions overlap the kernels
+    int chunks = 1;
+    const long long in_bytes = (long long)S * c->cfg.max_frames * 4;
+    while (chunks < 8 && in_bytes / (chunks * 2) >= (1 << 20) && S / (chunks * 2) >= 64) chunks *= 2;
+    c->slot_streams = ((S + chunks - 1) / chunks + 1) & ~1;   // even: row pairs stay inside a chunk
+    const int eb = afp_out_elem_bytes(c);
+    const long long max_out = (long long)afp_out_frames(c, c->cfg.max_frames);
+    for (int i = 0; i < afp_ctx::kSlots; ++i) {
+        AFP_CUDA(c, cudaMalloc(&c->d_in[i], (size_t)c->slot_streams * c->cfg.max_frames * sizeof(float)));
+        AFP_CUDA(c, cudaMalloc(&c->d_out[i], (size_t)c->slot_streams * max_out * eb));
+        AFP_CUDA(c, cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+        AFP_CUDA(c, cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
+        AFP_CUDA(c, cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
     }
-    if (c->eq.active) {
-        if (c->cfg.eq_mode == AFP_EQ_BUFFER_SAME || c->cfg.eq_mode == AFP_EQ_PER_BAND)
-            return fail(c, AFP_ERR_INVALID, "eq_mode not implemented yet in this build");
-        rc = run_streaming(c, c->eq, cur, cur_pitch, cur_len, c->tmp_b, c->pitch_b, AFP_FMT_F32, AFP_DITHER_NONE, 1, 0, st);
-        if (rc) return rc;
-        cur = c->tmp_b; cur_pitch = c->pitch_b;
-    }
-    const int decim = ref ? U : 1;
-    const long long opitch = c->cfg.out_format == AFP_FMT_I24_PACKED ? out_pitch / 3 : out_pitch;
-    rc = run_streaming(c, c->mainf, cur, cur_pitch, cur_len, out, opitch, c->cfg.out_format, c->cfg.dither, decim,
-                       c->out_samples, st);
+    AFP_CUDA(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    AFP_CUDA(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    return AFP_OK;
+}
+
+int afp_process_host_blocks(afp_ctx* c, const float* in, void* out, int32_t frames, int32_t n_blocks) {
+    if (!c) return AFP_ERR_INVALID;
+    if (!in || !out) return fail(c, AFP_ERR_INVALID, "null buffer");
+    if (n_blocks < 0) return fail(c, AFP_ERR_INVALID, "negative block count");
+    int rc = check_ready(c, frames);
     if (rc) return rc;
-    c->out_samples += (unsigned long long)out_n;
+    if (frames == 0 || n_blocks == 0) return AFP_OK;
+    AFP_CUDA(c, cudaSetDevice(c->cfg.device));
+    rc = ensure_tmp(c);
+    if (rc) return rc;
+    rc = ensure_host_staging(c);
+    if (rc) return rc;
+    const int S = c->cfg.n_streams, eb = afp_out_elem_bytes(c);
+    const int out_n = afp_out_frames(c, frames);
+    const size_t in_row = (size_t)frames * sizeof(float), out_row = (size_t)out_n * eb;
+    const unsigned char* hin = reinterpret_cast<const unsigned char*>(in);
+    unsigned char* hout = static_cast<unsigned char*>(out);
+    long long unit = 0;
+    for (int b = 0; b < n_blocks; ++b) {
+        for (int s0 = 0; s0 < S; s0 += c->slot_streams, ++unit) {
+            const int ns = S - s0 < c->slot_streams ? S - s0 : c->slot_streams;
+            const int slot = (int)(unit % afp_ctx::kSlots);
+            const bool reused = unit >= afp_ctx::kSlots;
+            // H2D: the slot's previous kernel must have consumed its input
+            if (reused) AFP_CUDA(c, cudaStreamWaitEvent(c->s_in, c->ev_k[slot], 0));
+            AFP_CUDA(c, cudaMemcpyAsync(c->d_in[slot], hin + ((size_t)b * S + s0) * in_row, ns * in_row,
+                                        cudaMemcpyHostToDevice, c->s_in));
+            AFP_CUDA(c, cudaEventRecord(c->ev_in[slot], c->s_in));
+            // compute: input landed, and the slot's previous output has been copied out
+            AFP_CUDA(c, cudaStreamWaitEvent(c->own_stream, c->ev_in[slot], 0));
+            if (reused) AFP_CUDA(c, cudaStreamWaitEvent(c->own_stream, c->ev_out[slot], 0));
+            rc = process_block_range(c, c->d_in[slot], frames, c->d_out[slot], (int64_t)out_n * (eb == 3 ? 3 : 1),
+                                     frames, s0, ns, c->own_stream);
+            if (rc) return rc;
+            AFP_CUDA(c, cudaEventRecord(c->ev_k[slot], c->own_stream));
+            // D2H
+            AFP_CUDA(c, cudaStreamWaitEvent(c->s_out, c->ev_k[slot], 0));
+            AFP_CUDA(c, cudaMemcpyAsync(hout + ((size_t)b * S + s0) * out_row, c->d_out[slot], ns * out_row,
+                                        cudaMemcpyDeviceToHost, c->s_out));
+            AFP_CUDA(c, cudaEventRecord(c->ev_out[slot], c->s_out));
+        }
+        finish_block(c, frames);
+    }
+    AFP_CUDA(c, cudaStreamSynchronize(c->s_out));
+    AFP_CUDA(c, cudaStreamSynchronize(c->own_stream));
     return AFP_OK;
 }
 
 int afp_process_host(afp_ctx* c, const float* in, void* out, int32_t frames) {
-    if (!c) return AFP_ERR_INVALID;
-    if (!in || !out) return fail(c, AFP_ERR_INVALID, "null buffer");
-    if (frames < 0 || frames > c->cfg.max_frames) return fail(c, AFP_ERR_INVALID, "frames outside 0..max_frames");
-    if (frames == 0) return AFP_OK;
-    AFP_CUDA(c, cudaSetDevice(c->cfg.device));
-    const int S = c->cfg.n_streams;
-    const int eb = afp_out_elem_bytes(c);
-    const long long max_out = (long long)afp_out_frames(c, c->cfg.max_frames);
-    if (!c->d_in) AFP_CUDA(c, cudaMalloc(&c->d_in, (size_t)S * c->cfg.max_frames * sizeof(float)));
-    if (!c->d_out) AFP_CUDA(c, cudaMalloc(&c->d_out, (size_t)S * max_out * eb));
-    const int out_n = afp_out_frames(c, frames);
-    AFP_CUDA(c, cudaMemcpyAsync(c->d_in, in, (size_t)S * frames * sizeof(float), cudaMemcpyHostToDevice, c->own_stream));
-    int rc = afp_process(c, c->d_in, frames, c->d_out, (int64_t)out_n * (eb == 3 ? 3 : 1), frames, c->own_stream);
-    if (rc) return rc;
-    AFP_CUDA(c, cudaMemcpyAsync(out, c->d_out, (size_t)S * out_n * eb, cudaMemcpyDeviceToHost, c->own_stream));
-    AFP_CUDA(c, cudaStreamSynchronize(c->own_stream));
-    return AFP_OK;
+    return afp_process_host_blocks(c, in, out, frames, 1);
 }
 
 int afp_reset(afp_ctx* c) {

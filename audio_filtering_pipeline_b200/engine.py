@@ -127,6 +127,20 @@ class BatchFirEngine:
         _lib.check(self._lib.afp_process_host(self._ctx, x.ctypes.data, out.ctypes.data, frames), self._ctx)
         return out
 
+    def process_host_blocks(self, x, out=None):
+        """``n`` consecutive blocks with host arrays, block-major: x float32 [n, S, frames] ->
+        [n, S, out_cols].  Copies and kernels of successive blocks overlap (three CUDA streams);
+        pass pinned arrays (``pinned_empty``) for full PCIe speed."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim != 3 or x.shape[1] != self.n_streams:
+            raise ValueError("x must have shape [n_blocks, n_streams, frames]")
+        nb, _, frames = x.shape
+        if out is None:
+            out = np.empty((nb, self.n_streams, self._out_cols(frames)), dtype=_NP_DTYPE[self.fmt])
+        _lib.check(self._lib.afp_process_host_blocks(self._ctx, x.ctypes.data, out.ctypes.data, frames, nb),
+                   self._ctx)
+        return out
+
     # -- state -------------------------------------------------------------------------------
     def reset(self):
         _lib.check(self._lib.afp_reset(self._ctx), self._ctx)
@@ -172,6 +186,32 @@ class BatchFirEngine:
 
     def __exit__(self, *exc):
         self.close()
+
+
+class PinnedArray:
+    """Page-locked host memory from afp_host_alloc with a numpy view in ``.a`` (keep the object
+    alive while the view is in use; ``free()`` or garbage collection releases it)."""
+
+    def __init__(self, shape, dtype):
+        self._lib = _lib.load()
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape))
+        self._ptr = C.c_void_p()
+        _lib.check(self._lib.afp_host_alloc(C.byref(self._ptr), max(count * dtype.itemsize, 1)))
+        buf = (C.c_uint8 * max(count * dtype.itemsize, 1)).from_address(self._ptr.value)
+        self.a = np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+    def free(self):
+        if self._ptr:
+            self.a = None
+            self._lib.afp_host_free(self._ptr)
+            self._ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def measure_fma_peak(device=0):

@@ -113,6 +113,11 @@ int afp_process(afp_ctx* ctx, const float* in_dev, int64_t in_pitch, void* out_d
 /* Same with host buffers (any host memory; pinned memory from afp_host_alloc is fastest).
  * Copies in, runs, copies out and waits.  Dense layout: in[S][frames], out[S][afp_out_frames]. */
 int afp_process_host(afp_ctx* ctx, const float* in_host, void* out_host, int32_t frames);
+/* n_blocks consecutive blocks, block-major: in[n_blocks][S][frames] -> out[n_blocks][S][afp_out_frames]
+ * (the buffers of n_blocks consecutive callbacks back to back).  Host->device copies, kernels and
+ * device->host copies of successive blocks / stream chunks overlap on three CUDA streams. */
+int afp_process_host_blocks(afp_ctx* ctx, const float* in_host, void* out_host, int32_t frames,
+                            int32_t n_blocks);
 
 int32_t afp_out_frames(const afp_ctx* ctx, int32_t frames);
 int32_t afp_out_elem_bytes(const afp_ctx* ctx);

@@ -1,0 +1,73 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports every
+symbol include/afp.h declares; without a GPU the product path fails loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from audio_filtering_pipeline_b200 import _build, _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    _build.build()
+    return _lib.load()
+
+
+def test_header_and_binding_agree(lib):
+    hdr = open(os.path.join(ROOT, "include", "afp.h")).read()
+    declared = set(re.findall(r"\b(afp_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} not exported by libafp_b200.so"
+
+
+def test_struct_layout_matches_header():
+    assert C.sizeof(_lib.Config) == 48          # 8 x int32, uint64, 2 x int32
+    assert _lib.Config.seed.offset == 32
+    assert C.sizeof(_lib.StageInfo) == 40
+
+
+def test_version_string(lib):
+    assert b"sm_100a" in lib.afp_version()
+
+
+def test_no_cpu_fallback(lib):
+    """On a box without a CUDA device afp_create must fail with a message, not compute on the CPU."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("GPU present")
+    except ImportError:
+        pass
+    ctx = C.c_void_p()
+    cfg = _lib.Config(device=0, n_streams=1, max_frames=64, upsample=1)
+    rc = lib.afp_create(C.byref(cfg), C.byref(ctx))
+    assert rc != 0 and not ctx
+    assert lib.afp_last_error(None)
+    from audio_filtering_pipeline_b200.engine import BatchFirEngine
+    with pytest.raises(_lib.AfpError):
+        BatchFirEngine([1.0])
+
+
+def test_argument_validation_needs_no_gpu(lib):
+    ctx = C.c_void_p()
+    for bad in (dict(n_streams=0), dict(upsample=5), dict(out_format=9), dict(chain=3), dict(dither=4)):
+        kw = dict(device=0, n_streams=1, max_frames=64, upsample=1)
+        kw.update(bad)
+        cfg = _lib.Config(**kw)
+        assert lib.afp_create(C.byref(cfg), C.byref(ctx)) == _lib.ERR_INVALID
+    assert lib.afp_process(None, None, 0, None, 0, 0, None) == _lib.ERR_INVALID
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under the product package may import it."""
+    pkg = os.path.join(ROOT, "audio_filtering_pipeline_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
