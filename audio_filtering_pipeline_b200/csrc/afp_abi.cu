@@ -28,6 +28,7 @@ enum StageKind { ST_INTERP = 0, ST_EQ = 1, ST_MAIN = 2 };
 
 struct Geometry {
     int nt = 0, tg_log2 = 0, smem = 0, grid = 0, segs_per_stream = 0;
+    int key_nq = -1, key_ns = -1;   // launch shape this geometry was computed for
 };
 
 struct Stage {
@@ -76,6 +77,7 @@ struct afp_ctx {
     long long pitch_a = 0, pitch_b = 0;
     unsigned long long out_samples = 0;   // kept output samples per stream since reset
     long long launches = 0;
+    int n_sm = 148;
     // afp_process_host staging: a ring of device slots fed by three streams (H2D, compute, D2H)
     static constexpr int kSlots = 3;
     float* d_in[kSlots] = {nullptr, nullptr, nullptr};
@@ -128,6 +130,7 @@ int build_stage(afp_ctx* c, Stage& s, int kind, int U, const double* taps, int n
         AFP_CUDA(c, cudaMemset(s.hist[i], 0, bytes));
     }
     s.cur = 0;
+    s.geo = Geometry();
     s.active = true;
     return AFP_OK;
 }
@@ -179,9 +182,22 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 
 int launch_stage(afp_ctx* c, Stage& s, const StageIO& io, cudaStream_t stream) {
     const int S = io.ns;
-    Geometry g = pick_geometry(s.T, s.kq_pad, io.n_q, S);
-    if (g.nt == 0) return fail(c, AFP_ERR_INVALID, "filter/block combination does not fit in shared memory");
-    s.geo = g;
+    if (s.geo.key_nq != io.n_q || s.geo.key_ns != S) {
+        Geometry g = pick_geometry(s.T, s.kq_pad, io.n_q, S);
+        if (g.nt == 0) return fail(c, AFP_ERR_INVALID, "filter/block combination does not fit in shared memory");
+        // persistent grid: no more CTAs than fit on the device at once (items are dealt round-robin)
+        int per_sm = 0;
+        AFP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kernel_for(s.U, g.nt), g.nt, g.smem));
+        if (per_sm < 1) return fail(c, AFP_ERR_INVALID, "kernel does not fit on an SM with this geometry");
+        // ... and never fewer than min(resident, items): items are dealt CTA-first, so a small launch
+        // spreads over all SMs instead of filling every group of a few CTAs
+        const long long n_pairs = ((long long)S * g.segs_per_stream + 1) / 2;
+        const int resident = per_sm * c->n_sm;
+        g.grid = (int)(n_pairs < resident ? n_pairs : resident);
+        g.key_nq = io.n_q; g.key_ns = S;
+        s.geo = g;
+    }
+    const Geometry& g = s.geo;
     static FirParams P;   // 16 KB: keep it off the stack; contexts are single-owner, launches serialised per process call
     const int eb = io.fmt == AFP_FMT_I16 ? 2 : (io.fmt == AFP_FMT_I24_PACKED ? 3 : 4);
     P.src0 = io.src0; P.src1 = io.src1;     // all pointers arrive offset to stream s0
@@ -190,6 +206,7 @@ int launch_stage(afp_ctx* c, Stage& s, const StageIO& io, cudaStream_t stream) {
     P.q_begin = io.q_begin; P.n_q = io.n_q;
     P.tg_log2 = g.tg_log2; P.segs_per_stream = g.segs_per_stream;
     P.n_seg_total = S * g.segs_per_stream;
+    P.n_pairs = (P.n_seg_total + 1) / 2;
     P.n_chunks = s.n_chunks;
     P.out = io.out; P.out_pitch = io.out_pitch;
     P.decim = io.decim; P.fmt = io.fmt; P.dither = io.dither;
@@ -202,6 +219,10 @@ int launch_stage(afp_ctx* c, Stage& s, const StageIO& io, cudaStream_t stream) {
     P.fast0 = (io.len0 > 0 && n_al && aligned16(io.src0) && io.pitch0 % 4 == 0) ? 1 : 0;
     P.fast1 = (io.len1 > 0 && n_al && aligned16(io.src1) && io.pitch1 % 4 == 0 && io.len0 % 4 == 0) ? 1 : 0;
     P.fast_hist = (io.hist_out && n_al && aligned16(io.hist_out) && io.hist_pitch % 4 == 0 && io.hist_from % 4 == 0) ? 1 : 0;
+    // aligned fast loader: both sources vector-aligned, both lengths multiples of 4, history (if any) too
+    P.fast_all = (n_al && (io.len0 == 0 || P.fast0) && (io.len1 == 0 || (aligned16(io.src1) && io.pitch1 % 4 == 0))
+                  && io.len0 % 4 == 0 && io.len1 % 4 == 0
+                  && (!io.hist_out || (P.fast_hist && io.hist_len % 4 == 0))) ? 1 : 0;
     P.fast_out = (aligned16(io.out) && (io.out_pitch * eb) % 16 == 0) ? 1 : 0;
     std::memset(P.taps, 0, sizeof(P.taps));
     std::memcpy(P.taps, s.table.data(), s.table.size() * sizeof(float));
@@ -327,6 +348,7 @@ int afp_create(const afp_config* cfg, afp_ctx** out_ctx) {
     afp_ctx* c = new (std::nothrow) afp_ctx();
     if (!c) return fail(nullptr, AFP_ERR_NOMEM, "out of host memory");
     c->cfg = *cfg;
+    c->n_sm = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete c; return cuda_fail(nullptr, e, "cudaStreamCreate"); }
     *out_ctx = c;
@@ -472,16 +494,11 @@ int afp_process(afp_ctx* c, const float* in, int64_t in_pitch, void* out, int64_
 static int ensure_host_staging(afp_ctx* c) {
     if (c->d_in[0]) return AFP_OK;
     const int S = c->cfg.n_streams;
-    // stream chunks of >= 1 MiB of input so that copies in both directions overlap the kernels
-    int chunks = 1;
-    const long long in_bytes = (long long)S * c->cfg.max_frames * 4;
-    while (chunks < 8 && in_bytes / (chunks * 2) >= (1 << 20) && S / (chunks * 2) >= 64) chunks *= 2;
-    c->slot_streams = ((S + chunks - 1) / chunks + 1) & ~1;   // even: row pairs stay inside a chunk
     const int eb = afp_out_elem_bytes(c);
     const long long max_out = (long long)afp_out_frames(c, c->cfg.max_frames);
-    for (int i = 0; i < afp_ctx::kSlots; ++i) {
-        AFP_CUDA(c, cudaMalloc(&c->d_in[i], (size_t)c->slot_streams * c->cfg.max_frames * sizeof(float)));
-        AFP_CUDA(c, cudaMalloc(&c->d_out[i], (size_t)c->slot_streams * max_out * eb));
+    for (int i = 0; i < afp_ctx::kSlots; ++i) {   // each slot can hold one whole block of all streams
+        AFP_CUDA(c, cudaMalloc(&c->d_in[i], (size_t)S * c->cfg.max_frames * sizeof(float)));
+        AFP_CUDA(c, cudaMalloc(&c->d_out[i], (size_t)S * max_out * eb));
         AFP_CUDA(c, cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
         AFP_CUDA(c, cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
         AFP_CUDA(c, cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
@@ -489,6 +506,18 @@ static int ensure_host_staging(afp_ctx* c) {
     AFP_CUDA(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
     AFP_CUDA(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
     return AFP_OK;
+}
+
+// Pipeline unit = a chunk of streams of one block.  Few, large units keep the copy engines at
+// full PCIe rate and the launch/event overhead low; a single-block call is still cut into chunks
+// so that its own H2D, kernel and D2H overlap.
+static int pick_slot_streams(const afp_ctx* c, int frames, int n_blocks) {
+    const int S = c->cfg.n_streams;
+    int chunks = 1;
+    const long long in_bytes = (long long)S * frames * 4;
+    while (chunks * n_blocks < 8 && chunks < 8 && in_bytes / (chunks * 2) >= (1 << 20) && S / (chunks * 2) >= 64)
+        chunks *= 2;
+    return ((S + chunks - 1) / chunks + 1) & ~1;   // even: row pairs stay inside a chunk
 }
 
 int afp_process_host_blocks(afp_ctx* c, const float* in, void* out, int32_t frames, int32_t n_blocks) {
@@ -505,6 +534,7 @@ int afp_process_host_blocks(afp_ctx* c, const float* in, void* out, int32_t fram
     if (rc) return rc;
     const int S = c->cfg.n_streams, eb = afp_out_elem_bytes(c);
     const int out_n = afp_out_frames(c, frames);
+    c->slot_streams = pick_slot_streams(c, frames, n_blocks);
     const size_t in_row = (size_t)frames * sizeof(float), out_row = (size_t)out_n * eb;
     const unsigned char* hin = reinterpret_cast<const unsigned char*>(in);
     unsigned char* hout = static_cast<unsigned char*>(out);

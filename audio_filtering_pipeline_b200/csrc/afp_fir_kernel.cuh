@@ -51,6 +51,7 @@ struct FirParams {
     int tg_log2;                 // log2(threads per segment); a segment is (1<<tg_log2)*T positions
     int segs_per_stream;
     int n_seg_total;             // n_streams * segs_per_stream
+    int n_pairs;                 // work items: ceil(n_seg_total / 2)
     int n_chunks;                // padded taps per phase / T
     void* out;                   // [n_streams][out_pitch] elements of the output format
     long long out_pitch;
@@ -63,6 +64,7 @@ struct FirParams {
     long long hist_pitch;
     int hist_len, hist_from;
     int fast0, fast1, fast_hist, fast_out;   // 16-byte alignment guarantees, computed on the host
+    int fast_all;                // every 4-sample group of every region is aligned and lies in one source
     float gain;                  // applied to the accumulators before the epilogue (1.0 = none)
     alignas(16) float taps[MAX_TAPS];
 };
@@ -313,93 +315,175 @@ __device__ __forceinline__ void store_row(const FirParams& P, float (&y)[NOUT], 
     }
 }
 
+// L2 prefetch of the part of row `r` (element range [e0, e1)) an item will read: one bulk-prefetch
+// instruction, fire and forget.  Issued for the group's NEXT item while the current one computes, so
+// the HBM traffic of the load phases is spread over the FMA-bound phase instead of arriving as one
+// burst per round (all groups run in lock step: same taps, same item size).
+__device__ __forceinline__ void prefetch_row_l2(const float* r, int e0, int e1) {
+    if (e1 <= e0) return;
+    const unsigned long long a0 = reinterpret_cast<unsigned long long>(r + e0) & ~15ull;
+    const unsigned long long a1 = (reinterpret_cast<unsigned long long>(r + e1) + 15ull) & ~15ull;
+    // stay inside the row's own bytes: shrink to the aligned interior if rounding left it
+    const unsigned long long lo = reinterpret_cast<unsigned long long>(r + e0);
+    const unsigned long long hi = reinterpret_cast<unsigned long long>(r + e1);
+    const unsigned long long b0 = a0 < lo ? a0 + 16 : a0;
+    const unsigned long long b1 = a1 > hi ? a1 - 16 : a1;
+    if (b1 <= b0) return;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(b0), "r"((unsigned)(b1 - b0)) : "memory");
+}
+
 // ---- the kernel ---------------------------------------------------------------------------------
+template <int NT>
+__device__ __forceinline__ void group_sync(int tg, int slot) {
+    if (tg <= 32) __syncwarp();
+    else if (tg == NT) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "r"(tg) : "memory");
+}
+
+// Persistent over work items.  An item is one segment pair (row A, row B); it belongs to one thread
+// group (tg threads, one shared-memory region).  Items are dealt round-robin with the CTA index
+// varying fastest, so a partly filled last round leaves every SM with the same number of busy
+// groups instead of leaving whole SMs idle (the 1024-CTA one-shot grid of the first version ran 3.46
+// waves in the time of 4).
 template <int U, int T, int NT>
 __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 4))
 fir_stream_kernel(const __grid_constant__ FirParams P) {
     extern __shared__ float4 smem[];
     const int tid = threadIdx.x;
     const int tg = 1 << P.tg_log2;                 // threads per segment
-    const int slots = NT >> P.tg_log2;             // segment pairs per CTA
+    const int slots = NT >> P.tg_log2;             // thread groups per CTA
     const int lq = tg * T;                         // base positions per segment
     const int kq = P.n_chunks * T;                 // padded taps per phase = halo
     const int region_pairs = kq + lq;
     const int region_g = region_granules(region_pairs);
-
-    // ---- load phase: global -> (row A, row B) interleaved pairs in shared memory, history out
-    for (int slot = 0; slot < slots; ++slot) {
-        const int pair_idx = blockIdx.x * slots + slot;
-        const int segA = 2 * pair_idx, segB = segA + 1;
-        RowSrc ra, rb;
-        int sA = 0, sB = 0, gA = 0, gB = 0;
-        ra.valid = segA < P.n_seg_total;
-        rb.valid = segB < P.n_seg_total;
-        if (ra.valid) { sA = segA / P.segs_per_stream; gA = segA - sA * P.segs_per_stream; }
-        if (rb.valid) { sB = segB / P.segs_per_stream; gB = segB - sB * P.segs_per_stream; }
-        ra.r0 = P.src0 + (long long)sA * P.pitch0; ra.r1 = P.src1 + (long long)sA * P.pitch1;
-        rb.r0 = P.src0 + (long long)sB * P.pitch0; rb.r1 = P.src1 + (long long)sB * P.pitch1;
-        const int startA = P.q_begin + gA * lq - kq;      // logical index of pair 0 of the region
-        const int startB = P.q_begin + gB * lq - kq;
-        float* hA = P.hist_out ? P.hist_out + (long long)sA * P.hist_pitch : nullptr;
-        float* hB = P.hist_out ? P.hist_out + (long long)sB * P.hist_pitch : nullptr;
-        const int ownA = gA == 0 ? INT_MIN : startA + kq;
-        const int ownB = gB == 0 ? INT_MIN : startB + kq;
-        float4* region = smem + slot * region_g;
-        const int n4 = region_pairs >> 2;
-#pragma unroll 2
-        for (int i4 = tid; i4 < n4; i4 += NT) {
-            const float4 a = fetch4(P, ra, startA + 4 * i4);
-            const float4 b = fetch4(P, rb, startB + 4 * i4);
-            const int g = phys_granule(2 * i4);
-            region[g] = make_float4(a.x, b.x, a.y, b.y);
-            region[g + 1] = make_float4(a.z, b.z, a.w, b.w);
-            if (hA && ra.valid) hist_store4(P, hA, startA + 4 * i4, a, ownA);
-            if (hB && rb.valid) hist_store4(P, hB, startB + 4 * i4, b, ownB);
-        }
-    }
-    __syncthreads();
-
-    // ---- compute phase
     const int slot = tid >> P.tg_log2;
     const int lt = tid & (tg - 1);
-    const float4* region = smem + slot * region_g;
+    float4* region_w = smem + slot * region_g;
+    const float4* region = region_w;
     const int b0 = P.n_chunks + lt;               // block holding this thread's own T positions
+    const int stride = gridDim.x * slots;
 
-    float2 acc[U][T];
+    for (int pair_idx = slot * gridDim.x + blockIdx.x; pair_idx < P.n_pairs; pair_idx += stride) {
+        // ---- load phase: global -> (row A, row B) interleaved pairs in shared memory, history out.
+        // Every thread group loads and waits for its own region only, so groups drift apart and one
+        // group's load / epilogue hides behind the others' FMA work.
+        {
+            const int segA = 2 * pair_idx, segB = segA + 1;
+            RowSrc ra, rb;
+            int sA = 0, sB = 0, gA = 0, gB = 0;
+            ra.valid = segA < P.n_seg_total;
+            rb.valid = segB < P.n_seg_total;
+            if (ra.valid) { sA = segA / P.segs_per_stream; gA = segA - sA * P.segs_per_stream; }
+            if (rb.valid) { sB = segB / P.segs_per_stream; gB = segB - sB * P.segs_per_stream; }
+            ra.r0 = P.src0 + (long long)sA * P.pitch0; ra.r1 = P.src1 + (long long)sA * P.pitch1;
+            rb.r0 = P.src0 + (long long)sB * P.pitch0; rb.r1 = P.src1 + (long long)sB * P.pitch1;
+            const int startA = P.q_begin + gA * lq - kq;      // logical index of pair 0 of the region
+            const int startB = P.q_begin + gB * lq - kq;
+            float* hA = (P.hist_out && ra.valid) ? P.hist_out + (long long)sA * P.hist_pitch : nullptr;
+            float* hB = (P.hist_out && rb.valid) ? P.hist_out + (long long)sB * P.hist_pitch : nullptr;
+            const int ownA = gA == 0 ? INT_MIN : startA + kq;
+            const int ownB = gB == 0 ? INT_MIN : startB + kq;
+            const int n4 = region_pairs >> 2;
+            if (P.fast_all) {
+                // Aligned case: every 4-sample group lies wholly in src0, in src1 or outside, so a group
+                // is one predicated LDG.128.  LOAD_B groups per row are requested before any is used:
+                // 2*LOAD_B independent 16-byte loads in flight per thread, one memory round trip per
+                // batch (the branchy generic loader below cost ~15 dependent round trips per item).
+                constexpr int LOAD_B = 6;
+                const int L = P.len0 + P.len1;
+                for (int base = lt; base < n4; base += tg * LOAD_B) {
+                    float4 a[LOAD_B], b[LOAD_B];
 #pragma unroll
-    for (int p = 0; p < U; ++p)
+                    for (int k = 0; k < LOAD_B; ++k) {
+                        const int i4 = base + k * tg;
+                        const int nA = startA + 4 * i4, nB = startB + 4 * i4;
+                        a[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        b[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (i4 < n4 && ra.valid && nA >= 0 && nA < L)
+                            a[k] = __ldg(reinterpret_cast<const float4*>(nA < P.len0 ? ra.r0 + nA : ra.r1 + (nA - P.len0)));
+                        if (i4 < n4 && rb.valid && nB >= 0 && nB < L)
+                            b[k] = __ldg(reinterpret_cast<const float4*>(nB < P.len0 ? rb.r0 + nB : rb.r1 + (nB - P.len0)));
+                    }
 #pragma unroll
-        for (int r = 0; r < T; ++r) acc[p][r] = make_float2(0.f, 0.f);
+                    for (int k = 0; k < LOAD_B; ++k) {
+                        const int i4 = base + k * tg;
+                        if (i4 < n4) {
+                            const int g = phys_granule(2 * i4);
+                            region_w[g] = make_float4(a[k].x, b[k].x, a[k].y, b[k].y);
+                            region_w[g + 1] = make_float4(a[k].z, b[k].z, a[k].w, b[k].w);
+                            const int nA = startA + 4 * i4, nB = startB + 4 * i4;
+                            const int hlo = P.hist_from, hhi = P.hist_from + P.hist_len;
+                            if (hA && nA >= max(hlo, ownA) && nA < hhi)
+                                *reinterpret_cast<float4*>(hA + (nA - hlo)) = a[k];
+                            if (hB && nB >= max(hlo, ownB) && nB < hhi)
+                                *reinterpret_cast<float4*>(hB + (nB - hlo)) = b[k];
+                        }
+                    }
+                }
+            } else {
+#pragma unroll 2
+                for (int i4 = lt; i4 < n4; i4 += tg) {
+                    const float4 a = fetch4(P, ra, startA + 4 * i4);
+                    const float4 b = fetch4(P, rb, startB + 4 * i4);
+                    const int g = phys_granule(2 * i4);
+                    region_w[g] = make_float4(a.x, b.x, a.y, b.y);
+                    region_w[g + 1] = make_float4(a.z, b.z, a.w, b.w);
+                    if (hA) hist_store4(P, hA, startA + 4 * i4, a, ownA);
+                    if (hB) hist_store4(P, hB, startB + 4 * i4, b, ownB);
+                }
+            }
+        }
+        group_sync<NT>(tg, slot);
 
-    float2 wa[T], wb[T];
-    load_block<T>(wb, region, b0);
-    int c = 0;
-    for (; c + 2 <= P.n_chunks; c += 2) {
-        load_block<T>(wa, region, b0 - c - 1);
-        chunk_fma<U, T>(acc, wa, wb, P.taps + c * (T * U));
-        load_block<T>(wb, region, b0 - c - 2);
-        chunk_fma<U, T>(acc, wb, wa, P.taps + (c + 1) * (T * U));
-    }
-    if (c < P.n_chunks) {
-        load_block<T>(wa, region, b0 - c - 1);
-        chunk_fma<U, T>(acc, wa, wb, P.taps + c * (T * U));
-    }
+        // ---- L2 prefetch of the next item's rows (lanes 0..3 of the group: row A/B x src0/src1)
+        if (lt < 4 && pair_idx + stride < P.n_pairs) {
+            const int seg = 2 * (pair_idx + stride) + (lt >> 1);
+            if (seg < P.n_seg_total) {
+                const int s_ = seg / P.segs_per_stream, g_ = seg - s_ * P.segs_per_stream;
+                const int n0 = P.q_begin + g_ * lq - kq, n1 = n0 + region_pairs;   // logical range
+                if (lt & 1) prefetch_row_l2(P.src1 + (long long)s_ * P.pitch1, max(n0, P.len0) - P.len0,
+                                            min(n1, P.len0 + P.len1) - P.len0);
+                else        prefetch_row_l2(P.src0 + (long long)s_ * P.pitch0, max(n0, 0), min(n1, P.len0));
+            }
+        }
 
-    // ---- epilogue: registers -> global, dither / quantise on the way
-    const int pair_idx = blockIdx.x * slots + slot;
+        // ---- compute phase
+        float2 acc[U][T];
 #pragma unroll
-    for (int row = 0; row < 2; ++row) {
-        const int seg = 2 * pair_idx + row;
-        if (seg >= P.n_seg_total) continue;
-        const int s = seg / P.segs_per_stream, gi = seg - s * P.segs_per_stream;
-        const int q_local = gi * lq + lt * T;               // first base position (relative to q_begin)
-        const int nv = min(max(P.n_q - q_local, 0), T) * U;
-        float y[U * T];
+        for (int p = 0; p < U; ++p)
 #pragma unroll
-        for (int r = 0; r < T; ++r)
+            for (int r = 0; r < T; ++r) acc[p][r] = make_float2(0.f, 0.f);
+
+        float2 wa[T], wb[T];
+        load_block<T>(wb, region, b0);
+        int c = 0;
+        for (; c + 2 <= P.n_chunks; c += 2) {
+            load_block<T>(wa, region, b0 - c - 1);
+            chunk_fma<U, T>(acc, wa, wb, P.taps + c * (T * U));
+            load_block<T>(wb, region, b0 - c - 2);
+            chunk_fma<U, T>(acc, wb, wa, P.taps + (c + 1) * (T * U));
+        }
+        if (c < P.n_chunks) {
+            load_block<T>(wa, region, b0 - c - 1);
+            chunk_fma<U, T>(acc, wa, wb, P.taps + c * (T * U));
+        }
+        group_sync<NT>(tg, slot);      // the region may be overwritten by the next item's load
+
+        // ---- epilogue: registers -> global, dither / quantise on the way
 #pragma unroll
-            for (int p = 0; p < U; ++p) y[r * U + p] = row == 0 ? acc[p][r].x : acc[p][r].y;
-        store_row<U * T>(P, y, s, (long long)q_local * U, nv);
+        for (int row = 0; row < 2; ++row) {
+            const int seg = 2 * pair_idx + row;
+            if (seg >= P.n_seg_total) continue;
+            const int s = seg / P.segs_per_stream, gi = seg - s * P.segs_per_stream;
+            const int q_local = gi * lq + lt * T;               // first base position (relative to q_begin)
+            const int nv = min(max(P.n_q - q_local, 0), T) * U;
+            float y[U * T];
+#pragma unroll
+            for (int r = 0; r < T; ++r)
+#pragma unroll
+                for (int p = 0; p < U; ++p) y[r * U + p] = row == 0 ? acc[p][r].x : acc[p][r].y;
+            store_row<U * T>(P, y, s, (long long)q_local * U, nv);
+        }
     }
 }
 
