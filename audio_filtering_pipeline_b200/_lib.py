@@ -14,7 +14,8 @@ OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOMEM = 0, 1, 2, 3, 4
 CHAIN = {"dac": 0, "reference": 1}
 FMT = {"f32": 0, "i16": 1, "i24": 2, "i24_in_i32": 2, "i24_packed": 3}
 DITHER = {"none": 0, None: 0, False: 0, "tpdf": 1, True: 1, "rpdf": 2}
-EQ_MODE = {"none": 0, None: 0, "fused": 1, "per_band": 2, "buffer_same": 3}
+EQ_MODE = {"none": 0, None: 0, "fused": 1, "per_band": 2, "buffer_same": 3, "buffer_same_per_band": 4,
+           "stateless_same": 5}
 
 # every symbol include/afp.h declares (tests check that the library exports all of them)
 SYMBOLS = [
@@ -37,7 +38,8 @@ class Config(C.Structure):
         ("device", C.c_int32), ("n_streams", C.c_int32), ("max_frames", C.c_int32),
         ("upsample", C.c_int32), ("chain", C.c_int32), ("out_format", C.c_int32),
         ("dither", C.c_int32), ("eq_mode", C.c_int32), ("seed", C.c_uint64),
-        ("first_stream_id", C.c_int32), ("reserved", C.c_int32),
+        ("first_stream_id", C.c_int32), ("decimate", C.c_int32), ("dither_bits", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 

@@ -1,0 +1,233 @@
+"""Drop-in shapes of the reference's per-block API, backed by the CUDA engine.
+
+Same names, positional arguments and error behaviour as the reference so that a script such as
+stream_process.py keeps its structure and only swaps its imports:
+
+    make_audio_callback      <- audio_callback(indata, outdata, frames, time, status)
+                                stream_process.py:79-120, stream_process_GUI_Presets.py:617-686
+    OverlapAddFilter         <- stream_process_GUI_Presets.py:35-123
+    process_audio_block      <- stream_process_GUI_Presets.py:598-613
+    apply_dither             <- stream_process.py:61-64
+    safe_upsample            <- stream_process.py:66-77, stream_process_EQ_GUI.py:420-427
+    safe_downsample          <- stream_process_EQ_GUI.py:429-436
+
+All arithmetic runs on the GPU through BatchFirEngine; there is no numpy fallback - if the CUDA
+library or the device is missing, constructing any of these raises.  What the callback does on a
+*runtime* error is the reference's convention (never raise into PortAudio: replay the last good
+block, else silence).
+"""
+from __future__ import annotations
+
+from collections import deque
+
+import numpy as np
+
+from . import design
+from .engine import BatchFirEngine
+
+__all__ = ["make_audio_callback", "OverlapAddFilter", "process_audio_block", "apply_dither",
+           "safe_upsample", "safe_downsample", "StreamChain"]
+
+
+class StreamChain:
+    """The module-level state of stream_process.py (:19-51) as one object: design constants, the
+    engine that replaces ``input_buffer`` + ``oaconvolve``, and the last-good-block deque.
+
+    ``channels`` independent channels are batched as streams (the reference is mono, :22)."""
+
+    def __init__(self, samplerate=44100, upsample_factor=4, blocksize=4096, numtaps=301, cutoff=11000,
+                 window_type="hamming", filter_type="lowpass", method="window", channels=1,
+                 eq_bands=None, eq_gains=None, eq_numtaps=None, eq_mode="buffer_same_per_band",
+                 min_phase=False, dither=True, bit_depth=24, seed=0, device=0, upsampler_taps=None,
+                 fir_coeff=None):
+        self.samplerate, self.upsample_factor, self.blocksize = int(samplerate), int(upsample_factor), int(blocksize)
+        self.channels = int(channels)
+        up_rate = self.samplerate * self.upsample_factor                     # stream_process.py:20
+        if fir_coeff is None:
+            fir_coeff = design.create_fir_filter(method=method, cutoff=cutoff, numtaps=numtaps,   # :33-40
+                                                 window_type=window_type, filter_type=filter_type,
+                                                 samplerate=up_rate)
+        if min_phase:
+            fir_coeff = design.apply_min_phase(fir_coeff, up_rate)           # stream_process_EQ_GUI.py:377-379
+        self.fir_coeff = np.asarray(fir_coeff, dtype=np.float64)
+        bands = None
+        if eq_bands is not None:
+            n_eq = eq_numtaps or len(self.fir_coeff)
+            bands = [design.create_fir_filter(method="window", cutoff=list(b), numtaps=n_eq,
+                                              window_type="hamming", filter_type="bandpass",
+                                              samplerate=up_rate) for b in eq_bands]   # stream_process_EQ.py:40-42
+            if eq_gains is None:
+                eq_gains = [1.0] * len(bands)
+        if upsampler_taps is None and self.upsample_factor > 1:
+            upsampler_taps = design.design_upsampler(self.upsample_factor, self.samplerate)
+        self.engine = BatchFirEngine(
+            self.fir_coeff, n_streams=self.channels, max_frames=self.blocksize,
+            upsample=self.upsample_factor, chain="reference", out_format="f32",
+            dither="rpdf" if dither else "none", dither_bits=bit_depth, seed=seed, device=device,
+            upsampler_taps=upsampler_taps, eq_bands=bands, eq_gains=eq_gains,
+            eq_mode=eq_mode if bands is not None else "none")
+        self.audio_buffer = deque(maxlen=4)                                   # stream_process.py:50
+        self.silence_block = np.zeros((self.blocksize, self.channels), dtype=np.float32)
+        self._planar = np.zeros((self.channels, self.blocksize), dtype=np.float32)
+
+    def process(self, indata):
+        """indata float32 [frames, channels] (or [frames]) -> float32 [frames, channels]."""
+        x = np.asarray(indata, dtype=np.float32)
+        if x.ndim == 1:
+            x = x[:, None]
+        frames = x.shape[0]
+        planar = np.ascontiguousarray(x[:, :self.channels].T)
+        y = self.engine.process_host(planar)
+        return np.ascontiguousarray(y.T[:frames])
+
+    def close(self):
+        self.engine.close()
+
+
+def make_audio_callback(chain, verbose=True):
+    """Returns ``audio_callback(indata, outdata, frames, time, status)`` for ``sd.Stream(callback=...)``
+    with the reference's contract (stream_process.py:79-120): ``outdata`` is written in place, only
+    the first ``chain.channels`` columns are used, status flags are printed, and the function never
+    raises - on an error it replays the last good block, else writes silence."""
+
+    def audio_callback(indata, outdata, frames, time, status):
+        if status and verbose:
+            print(f"Audio status: {status}")                                   # :82-85
+        try:
+            y = chain.process(indata)                                          # :89-113
+            if y.shape[0] != frames:
+                y = np.resize(y, (frames, y.shape[1]))                         # :106-107
+            chain.audio_buffer.append(y.copy())                                # :110
+            outdata[:, :y.shape[1]] = y
+        except Exception as exc:                                               # noqa: BLE001 (:115-120)
+            if verbose:
+                print(f"Processing error: {exc}")
+            if len(chain.audio_buffer) > 0:
+                last = chain.audio_buffer[-1]
+                outdata[:, :last.shape[1]] = np.resize(last, (frames, last.shape[1]))
+            else:
+                outdata[:] = 0.0
+
+    return audio_callback
+
+
+class OverlapAddFilter:
+    """Stateful block FIR with the constructor, methods and attributes of the reference class
+    (stream_process_GUI_Presets.py:35-123).  The carried state is the engine's input history, so
+    unlike the reference it is also correct when ``len(coeffs) - 1 > block_size``."""
+
+    def __init__(self, filter_coeffs, block_size, device=0):
+        self._device = device
+        self._engine = None
+        self.set_coefficients(filter_coeffs, block_size)
+
+    def set_coefficients(self, filter_coeffs, block_size):
+        if len(filter_coeffs) == 0:                                            # :45-46
+            self.coeffs = np.array([1.0], dtype=np.float32)
+        else:
+            self.coeffs = np.array(filter_coeffs, dtype=np.float32)           # :48 (taps truncated to f32)
+        self.block_size = int(block_size)
+        self.filter_length = len(self.coeffs)
+        self.overlap_length = self.filter_length - 1
+        need = self.block_size + self.filter_length - 1
+        self.fft_length = int(2 ** np.ceil(np.log2(need)))                     # :56-57 (informational here)
+        if self._engine is not None:
+            self._engine.close()
+        self._engine = BatchFirEngine(self.coeffs.astype(np.float64), n_streams=1,
+                                      max_frames=self.block_size, device=self._device)
+        self._tail_x = np.zeros(self.overlap_length, dtype=np.float32)
+
+    def process_block(self, input_block):
+        L = self.block_size
+        x = np.asarray(input_block, dtype=np.float32).ravel()
+        if len(x) != L:                                                        # :71-76
+            x = np.pad(x, (0, L - len(x)), "constant") if len(x) < L else x[:L]
+        y = self._engine.process_host(x[None, :])[0]
+        if self.overlap_length:
+            self._tail_x = np.concatenate([self._tail_x, x])[-self.overlap_length:]
+        return y.astype(np.float32, copy=False)
+
+    @property
+    def overlap_buffer(self):
+        """The reference's carried tail (:115-121): what the samples seen so far still contribute to
+        the next ``N-1`` outputs.  Computed on request from the input history (GUI read-out only)."""
+        n = self.overlap_length
+        if n == 0:
+            return np.zeros(0, dtype=np.float32)
+        full = np.convolve(self._tail_x.astype(np.float64), self.coeffs.astype(np.float64))
+        return full[n:2 * n].astype(np.float32)
+
+    def close(self):
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None
+
+
+def process_audio_block(gui, upsampled_block):
+    """``fir(sum_b gain_b * eq_b(x))`` over the filter objects a GUI holds
+    (stream_process_GUI_Presets.py:598-613): ``gui.eq_filter_objects``, ``gui.eq_gains[i].get()``,
+    ``gui.fir_filter_object``."""
+    upsampled_block = np.asarray(upsampled_block, dtype=np.float32)
+    current_eq_sum = np.zeros_like(upsampled_block)
+    for eq_filter, gain_var in zip(gui.eq_filter_objects, gui.eq_gains):
+        current_eq_sum += gain_var.get() * eq_filter.process_block(upsampled_block)
+    if gui.fir_filter_object:
+        return gui.fir_filter_object.process_block(current_eq_sum)
+    return current_eq_sum
+
+
+# --- helper shims (module-level state like the reference's globals) --------------------------------
+_ENGINES = {}
+
+
+def _cached(key, factory):
+    eng = _ENGINES.get(key)
+    if eng is None:
+        eng = _ENGINES[key] = factory()
+    return eng
+
+
+def apply_dither(audio, bit_depth=24):
+    """``audio + uniform(-0.5, 0.5) LSB`` at LSB = 2/2**bit_depth (stream_process.py:61-64), drawn
+    from the engine's Philox stream instead of numpy's global RNG.  Returns float32."""
+    a = np.asarray(audio, dtype=np.float32)
+    flat = a.reshape(1, -1)
+    eng = _cached(("dither", flat.shape[1], int(bit_depth)), lambda: BatchFirEngine(
+        [1.0], n_streams=1, max_frames=flat.shape[1], dither="rpdf", dither_bits=int(bit_depth), seed=0x5EED))
+    return eng.process_host(flat).reshape(a.shape)
+
+
+def safe_upsample(data, sr=44100, upsr=176400):
+    """Interpolation by ``upsr/sr`` (1..4).  Streaming polyphase FIR with carried state in place of the
+    reference's one-shot ``soxr.resample`` per block; zeros on failure like :75-77."""
+    try:
+        x = np.asarray(data, dtype=np.float32)
+        x = x[:, 0] if x.ndim > 1 else x                                       # :70
+        if upsr == sr:
+            return x.astype(np.float32)                                        # stream_process_EQ_GUI.py:422-423
+        if upsr < sr:
+            return safe_downsample(x, sr, upsr, int(round(len(x) * upsr / sr)))
+        factor = int(round(upsr / sr))
+        eng = _cached(("up", factor, len(x), int(sr)), lambda: BatchFirEngine(
+            design.design_upsampler(factor, sr), n_streams=1, max_frames=len(x), upsample=factor, chain="dac"))
+        return eng.process_host(x[None, :])[0]
+    except Exception as exc:                                                   # noqa: BLE001
+        print(f"Upsample error: {exc}")
+        return np.zeros(int(len(data) * upsr / sr), dtype=np.float32)
+
+
+def safe_downsample(data, upsr, sr, expected_len):
+    """Anti-alias FIR + keep every ``upsr/sr``-th sample (stream_process_EQ_GUI.py:429-436)."""
+    try:
+        x = np.asarray(data, dtype=np.float32).ravel()
+        if upsr == sr:
+            return x
+        factor = int(round(upsr / sr))
+        eng = _cached(("down", factor, len(x), int(sr)), lambda: BatchFirEngine(
+            design.design_upsampler(factor, sr) / factor, n_streams=1, max_frames=len(x), upsample=1,
+            chain="dac", decimate=factor))
+        y = eng.process_host(x[None, :])[0]
+        return np.resize(y, expected_len) if len(y) != expected_len else y
+    except Exception as exc:                                                   # noqa: BLE001
+        print(f"Downsample error: {exc}")
+        return np.zeros(expected_len, dtype=np.float32)

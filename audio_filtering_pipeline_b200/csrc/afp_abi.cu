@@ -39,8 +39,9 @@ struct Stage {
     int n_taps = 0;
     int kq_pad = 0;                 // padded taps per phase (history length in base samples)
     int n_chunks = 0;
-    std::vector<double> taps;       // as given
-    std::vector<float> table;       // natural order, zero padded to U*kq_pad
+    int n_sub = 1;                  // passes over the tap axis (EQ bands in per-band form)
+    std::vector<double> taps;       // as given (EQ: the centre-aligned taps-domain sum)
+    std::vector<float> table;       // n_sub tables, natural order, each zero padded to U*kq_pad
     float* hist[2] = {nullptr, nullptr};
     long long hist_pitch = 0;
     int cur = 0;
@@ -75,9 +76,17 @@ struct afp_ctx {
     float* tmp_a = nullptr;          // interp output  [S][max_frames*U]
     float* tmp_b = nullptr;          // EQ output      [S][pitch_b]
     long long pitch_a = 0, pitch_b = 0;
+    // AFP_EQ_BUFFER_SAME*: the reference's sliding input_buffer minus the new block, i.e. the last
+    // N_main-1 processing-rate samples (stream_process_EQ.py:44-45,119-121), ping-pong
+    float* xhist[2] = {nullptr, nullptr};
+    long long xhist_pitch = 0;
+    int xhist_len = -1, xhist_cur = 0;
+    int eq_centre = 0;               // (N_eq-1)//2 of the widest band: 'same' centring
     unsigned long long out_samples = 0;   // kept output samples per stream since reset
     long long launches = 0;
     int n_sm = 148;
+    int decim = 1;                   // keep every decim-th sample of the main stage's output
+    int dither_bits = 24;            // LSB of the float-output dither
     // afp_process_host staging: a ring of device slots fed by three streams (H2D, compute, D2H)
     static constexpr int kSlots = 3;
     float* d_in[kSlots] = {nullptr, nullptr, nullptr};
@@ -107,30 +116,35 @@ void free_stage(Stage& s) {
     s.active = false;
 }
 
-// (re)build one stage from double taps: pad, convert to float32, allocate + zero the history
-int build_stage(afp_ctx* c, Stage& s, int kind, int U, const double* taps, int n) {
+// (re)build one stage: n_sub tables of n taps each (natural order, double), pad, convert to float32,
+// allocate + zero the carried history (kq_pad base-rate samples per stream)
+int build_stage(afp_ctx* c, Stage& s, int kind, int U, const double* taps, int n, int n_sub = 1,
+                bool keep_state = false) {
     if (n < 1) return fail(c, AFP_ERR_INVALID, "filter needs at least one tap");
-    for (int i = 0; i < n; ++i)
+    for (long long i = 0; i < (long long)n * n_sub; ++i)
         if (!std::isfinite(taps[i])) return fail(c, AFP_ERR_INVALID, "non-finite filter tap");
     const int T = tile_for(U);
     const int kq = (n + U - 1) / U;
     const int n_chunks = (kq + T - 1) / T;
-    if ((long long)n_chunks * T * U > afp::MAX_TAPS)
-        return fail(c, AFP_ERR_INVALID, "filter too long for the per-launch tap table (max 4096 padded taps)");
-    free_stage(s);
-    s.kind = kind; s.U = U; s.T = T; s.n_taps = n;
-    s.n_chunks = n_chunks; s.kq_pad = n_chunks * T;
-    s.taps.assign(taps, taps + n);
-    s.table.assign((size_t)s.kq_pad * U, 0.f);
-    for (int i = 0; i < n; ++i) s.table[i] = (float)taps[i];
-    s.hist_pitch = s.kq_pad;
-    const size_t bytes = (size_t)c->cfg.n_streams * s.hist_pitch * sizeof(float);
-    for (int i = 0; i < 2; ++i) {
-        AFP_CUDA(c, cudaMalloc(&s.hist[i], bytes));
-        AFP_CUDA(c, cudaMemset(s.hist[i], 0, bytes));
+    if ((long long)n_chunks * T * U * n_sub > afp::MAX_TAPS)
+        return fail(c, AFP_ERR_INVALID, "filter (x bands) too long for the per-launch tap table (max 6144 padded taps)");
+    const bool same_shape = s.active && s.kind == kind && s.U == U && s.n_chunks == n_chunks;
+    if (!(keep_state && same_shape)) {
+        free_stage(s);
+        s.hist_pitch = (long long)n_chunks * T;
+        const size_t bytes = (size_t)c->cfg.n_streams * s.hist_pitch * sizeof(float);
+        for (int i = 0; i < 2; ++i) {
+            AFP_CUDA(c, cudaMalloc(&s.hist[i], bytes));
+            AFP_CUDA(c, cudaMemset(s.hist[i], 0, bytes));
+        }
+        s.cur = 0;
+        s.geo = Geometry();
     }
-    s.cur = 0;
-    s.geo = Geometry();
+    s.kind = kind; s.U = U; s.T = T; s.n_taps = n; s.n_sub = n_sub;
+    s.n_chunks = n_chunks; s.kq_pad = n_chunks * T;
+    s.table.assign((size_t)s.kq_pad * U * n_sub, 0.f);
+    for (int b = 0; b < n_sub; ++b)
+        for (int i = 0; i < n; ++i) s.table[(size_t)b * s.kq_pad * U + i] = (float)taps[(size_t)b * n + i];
     s.active = true;
     return AFP_OK;
 }
@@ -207,12 +221,13 @@ int launch_stage(afp_ctx* c, Stage& s, const StageIO& io, cudaStream_t stream) {
     P.tg_log2 = g.tg_log2; P.segs_per_stream = g.segs_per_stream;
     P.n_seg_total = S * g.segs_per_stream;
     P.n_pairs = (P.n_seg_total + 1) / 2;
-    P.n_chunks = s.n_chunks;
+    P.n_chunks = s.n_chunks; P.n_sub = s.n_sub; P.sub_stride = s.kq_pad * s.U;
     P.out = io.out; P.out_pitch = io.out_pitch;
     P.decim = io.decim; P.fmt = io.fmt; P.dither = io.dither;
     P.seed = c->cfg.seed; P.sample_base = io.sample_base; P.stream_id0 = c->cfg.first_stream_id + io.s0;
     P.hist_out = io.hist_out; P.hist_pitch = io.hist_pitch; P.hist_len = io.hist_len; P.hist_from = io.hist_from;
     P.gain = 1.0f;
+    P.dither_lsb = std::ldexp(1.0f, -(c->dither_bits - 1));
     const int start0 = io.q_begin - s.kq_pad;   // logical index of the first pair of segment 0's region
     const int lq = (1 << g.tg_log2) * s.T;
     const bool n_al = (start0 % 4 == 0) && (lq % 4 == 0);
@@ -248,35 +263,58 @@ int run_streaming(afp_ctx* c, Stage& s, const float* in, long long in_pitch, int
     return launch_stage(c, s, io, stream);   // the caller flips s.cur once the whole block is launched
 }
 
+bool eq_is_per_band(const afp_ctx* c) {
+    return c->cfg.eq_mode == AFP_EQ_PER_BAND || c->cfg.eq_mode == AFP_EQ_BUFFER_SAME_PER_BAND;
+}
+bool eq_is_buffer_same(const afp_ctx* c) {
+    return c->cfg.eq_mode == AFP_EQ_BUFFER_SAME || c->cfg.eq_mode == AFP_EQ_BUFFER_SAME_PER_BAND;
+}
+
+// EQ tables.  Bands are aligned on their 'same' centres (N_b-1)//2, the way scipy centres each band's
+// output in stream_process_EQ.py:128; fused form: one table sum_b g_b*h_b (stream_process_EQ_GUI.py:
+// 86-90); per-band form: one table g_b*h_b per band, accumulated in the kernel.
 int rebuild_eq(afp_ctx* c, bool reset_state) {
     if (c->bands.empty()) { free_stage(c->eq); return AFP_OK; }
-    // taps-domain sum, centre aligned (stream_process_EQ_GUI.py:86-90)
-    size_t nmax = 0;
-    for (auto& b : c->bands) nmax = b.size() > nmax ? b.size() : nmax;
-    std::vector<double> comb(nmax, 0.0);
-    for (size_t i = 0; i < c->bands.size(); ++i) {
-        const size_t off = (nmax - c->bands[i].size()) / 2;
-        for (size_t k = 0; k < c->bands[i].size(); ++k) comb[off + k] += c->gains[i] * c->bands[i][k];
+    int cmax = 0;
+    for (auto& b : c->bands) cmax = std::max(cmax, ((int)b.size() - 1) / 2);
+    int nall = 0;
+    for (auto& b : c->bands) nall = std::max(nall, cmax - ((int)b.size() - 1) / 2 + (int)b.size());
+    const int nb = (int)c->bands.size();
+    const int n_sub = eq_is_per_band(c) ? nb : 1;
+    std::vector<double> tab((size_t)n_sub * nall, 0.0);
+    for (int i = 0; i < nb; ++i) {
+        const int off = cmax - ((int)c->bands[i].size() - 1) / 2;
+        double* dst = tab.data() + (size_t)(n_sub == 1 ? 0 : i) * nall;
+        for (size_t k = 0; k < c->bands[i].size(); ++k) dst[off + k] += c->gains[i] * c->bands[i][k];
     }
-    if (reset_state || !c->eq.active || c->eq.n_taps != (int)nmax) {
-        return build_stage(c, c->eq, ST_EQ, 1, comb.data(), (int)nmax);
-    }
-    // gains only: swap the table, keep the carried state (filter_lock swap, stream_process_EQ_GUI.py:380-385)
-    c->eq.taps = comb;
-    for (size_t i = 0; i < nmax; ++i) c->eq.table[i] = (float)comb[i];
-    return AFP_OK;
+    c->eq_centre = cmax;
+    return build_stage(c, c->eq, ST_EQ, 1, tab.data(), nall, n_sub, !reset_state);
 }
 
 int ensure_tmp(afp_ctx* c) {
     const int S = c->cfg.n_streams, U = c->cfg.upsample;
-    const long long need = (long long)c->cfg.max_frames * U;
-    const bool need_a = (c->cfg.chain == AFP_CHAIN_REFERENCE && U > 1);
-    const bool need_b = c->eq.active;
-    if (need_a && !c->tmp_a) {
-        c->pitch_a = (need + 3) / 4 * 4;
+    const bool ref = c->cfg.chain == AFP_CHAIN_REFERENCE;
+    const long long rate_len = (long long)c->cfg.max_frames * (ref ? U : 1);   // EQ-rate samples per block
+    if (ref && U > 1 && !c->tmp_a) {
+        c->pitch_a = (rate_len + 3) / 4 * 4;
         AFP_CUDA(c, cudaMalloc(&c->tmp_a, (size_t)S * c->pitch_a * sizeof(float)));
     }
-    if (need_b && !c->tmp_b) {
+    const bool stateless = c->cfg.eq_mode == AFP_EQ_STATELESS_SAME;
+    if (eq_is_buffer_same(c)) {
+        const int hm = c->mainf.n_taps - 1;
+        if (c->xhist_len != hm) {
+            for (int i = 0; i < 2; ++i) { if (c->xhist[i]) cudaFree(c->xhist[i]); c->xhist[i] = nullptr; }
+            c->xhist_pitch = (hm + 3) / 4 * 4 + 4;
+            for (int i = 0; i < 2; ++i) {
+                AFP_CUDA(c, cudaMalloc(&c->xhist[i], (size_t)S * c->xhist_pitch * sizeof(float)));
+                AFP_CUDA(c, cudaMemset(c->xhist[i], 0, (size_t)S * c->xhist_pitch * sizeof(float)));
+            }
+            c->xhist_len = hm; c->xhist_cur = 0;
+            if (c->tmp_b) { cudaFree(c->tmp_b); c->tmp_b = nullptr; }
+        }
+    }
+    if ((c->eq.active || stateless) && !c->tmp_b) {
+        const long long need = rate_len + (eq_is_buffer_same(c) ? c->xhist_len : 0);
         c->pitch_b = (need + 3) / 4 * 4;
         AFP_CUDA(c, cudaMalloc(&c->tmp_b, (size_t)S * c->pitch_b * sizeof(float)));
     }
@@ -327,7 +365,10 @@ int afp_create(const afp_config* cfg, afp_ctx** out_ctx) {
     if (cfg->chain != AFP_CHAIN_DAC && cfg->chain != AFP_CHAIN_REFERENCE) return fail(nullptr, AFP_ERR_INVALID, "unknown chain");
     if (cfg->out_format < 0 || cfg->out_format > 3) return fail(nullptr, AFP_ERR_INVALID, "unknown out_format");
     if (cfg->dither < 0 || cfg->dither > 2) return fail(nullptr, AFP_ERR_INVALID, "unknown dither mode");
-    if (cfg->eq_mode < 0 || cfg->eq_mode > 3) return fail(nullptr, AFP_ERR_INVALID, "unknown eq_mode");
+    if (cfg->eq_mode < 0 || cfg->eq_mode > 5) return fail(nullptr, AFP_ERR_INVALID, "unknown eq_mode");
+    if (cfg->decimate < 0 || cfg->decimate > 64) return fail(nullptr, AFP_ERR_INVALID, "decimate must be 0..64");
+    if (cfg->dither_bits != 0 && (cfg->dither_bits < 2 || cfg->dither_bits > 32))
+        return fail(nullptr, AFP_ERR_INVALID, "dither_bits must be 0 or 2..32");
     if (cfg->eq_mode != AFP_EQ_NONE && cfg->chain == AFP_CHAIN_DAC && cfg->upsample > 1)
         return fail(nullptr, AFP_ERR_INVALID, "EQ runs at the processing rate: use AFP_CHAIN_REFERENCE with upsample > 1");
     int ndev = 0;
@@ -349,6 +390,8 @@ int afp_create(const afp_config* cfg, afp_ctx** out_ctx) {
     if (!c) return fail(nullptr, AFP_ERR_NOMEM, "out of host memory");
     c->cfg = *cfg;
     c->n_sm = prop.multiProcessorCount;
+    c->decim = cfg->decimate > 0 ? cfg->decimate : (cfg->chain == AFP_CHAIN_REFERENCE ? cfg->upsample : 1);
+    c->dither_bits = cfg->dither_bits > 0 ? cfg->dither_bits : 24;
     e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete c; return cuda_fail(nullptr, e, "cudaStreamCreate"); }
     *out_ctx = c;
@@ -361,6 +404,7 @@ int afp_destroy(afp_ctx* c) {
     free_stage(c->up); free_stage(c->eq); free_stage(c->mainf);
     if (c->tmp_a) cudaFree(c->tmp_a);
     if (c->tmp_b) cudaFree(c->tmp_b);
+    for (int i = 0; i < 2; ++i) if (c->xhist[i]) cudaFree(c->xhist[i]);
     for (int i = 0; i < afp_ctx::kSlots; ++i) {
         if (c->d_in[i]) cudaFree(c->d_in[i]);
         if (c->d_out[i]) cudaFree(c->d_out[i]);
@@ -419,7 +463,8 @@ int afp_set_gains(afp_ctx* c, const double* gains, int32_t n_bands) {
 
 int32_t afp_out_frames(const afp_ctx* c, int32_t frames) {
     if (!c) return 0;
-    return c->cfg.chain == AFP_CHAIN_DAC ? frames * c->cfg.upsample : frames;
+    const long long n = (long long)frames * c->cfg.upsample;   // both chains compute at fs*U
+    return (int32_t)((n + c->decim - 1) / c->decim);
 }
 
 int32_t afp_out_elem_bytes(const afp_ctx* c) {
@@ -432,6 +477,7 @@ static int process_block_range(afp_ctx* c, const float* in, int64_t in_pitch, vo
                                int32_t frames, int s0, int ns, cudaStream_t st) {
     const int U = c->cfg.upsample;
     const bool ref = c->cfg.chain == AFP_CHAIN_REFERENCE;
+    const int mode = c->cfg.eq_mode;
     int rc;
     const float* cur = in; long long cur_pitch = in_pitch; int cur_len = frames;
     if (ref && U > 1) {   // interpolate to the processing rate (replaces soxr.resample, stream_process.py:66-77)
@@ -440,24 +486,71 @@ static int process_block_range(afp_ctx* c, const float* in, int64_t in_pitch, vo
         if (rc) return rc;
         cur = ta; cur_pitch = c->pitch_a; cur_len = frames * U;
     }
-    if (c->eq.active) {
-        float* tb = c->tmp_b + (long long)s0 * c->pitch_b;
+    const long long opitch = c->cfg.out_format == AFP_FMT_I24_PACKED ? out_pitch / 3 : out_pitch;
+    float* tb = c->tmp_b ? c->tmp_b + (long long)s0 * c->pitch_b : nullptr;
+
+    if (eq_is_buffer_same(c)) {
+        // stream_process_EQ.py:119-134.  Launch 1: eq[i] = sum_b g_b * same(buffer (*) h_b)[i] over the
+        // whole sliding buffer [last N-1 samples | block], zero-extended; the buffer rolls forward.
+        const int hm = c->xhist_len, lb = hm + cur_len;
+        StageIO io;
+        io.s0 = s0; io.ns = ns;
+        io.src0 = c->xhist[c->xhist_cur] + (long long)s0 * c->xhist_pitch; io.pitch0 = c->xhist_pitch; io.len0 = hm;
+        io.src1 = cur; io.pitch1 = cur_pitch; io.len1 = cur_len;
+        io.q_begin = c->eq_centre; io.n_q = lb;
+        io.out = tb; io.out_pitch = c->pitch_b;
+        io.hist_out = c->xhist[c->xhist_cur ^ 1] + (long long)s0 * c->xhist_pitch; io.hist_pitch = c->xhist_pitch;
+        io.hist_len = hm; io.hist_from = cur_len;
+        rc = launch_stage(c, c->eq, io, st);
+        if (rc) return rc;
+        // Launch 2: 'valid' main FIR over eq (:134), decimation and epilogue
+        StageIO m;
+        m.s0 = s0; m.ns = ns;
+        m.src1 = tb; m.pitch1 = c->pitch_b; m.len1 = lb;
+        m.q_begin = hm; m.n_q = cur_len;
+        m.out = out; m.out_pitch = opitch; m.fmt = c->cfg.out_format; m.dither = c->cfg.dither; m.decim = c->decim;
+        m.sample_base = c->out_samples;
+        return launch_stage(c, c->mainf, m, st);
+    }
+    if (mode == AFP_EQ_STATELESS_SAME) {
+        // stream_process_EQ_GUI.py:86-95: both filters 'same' over the block alone, nothing carried
+        if (c->eq.active) {
+            StageIO io;
+            io.s0 = s0; io.ns = ns;
+            io.src1 = cur; io.pitch1 = cur_pitch; io.len1 = cur_len;
+            io.q_begin = c->eq_centre; io.n_q = cur_len;
+            io.out = tb; io.out_pitch = c->pitch_b;
+            rc = launch_stage(c, c->eq, io, st);
+            if (rc) return rc;
+            cur = tb; cur_pitch = c->pitch_b;
+        }
+        StageIO m;
+        m.s0 = s0; m.ns = ns;
+        m.src1 = cur; m.pitch1 = cur_pitch; m.len1 = cur_len;
+        m.q_begin = (c->mainf.n_taps - 1) / 2; m.n_q = cur_len;
+        m.out = out; m.out_pitch = opitch; m.fmt = c->cfg.out_format; m.dither = c->cfg.dither; m.decim = c->decim;
+        m.sample_base = c->out_samples;
+        return launch_stage(c, c->mainf, m, st);
+    }
+    if (c->eq.active) {   // streaming EQ (fused or per band), state carried like any other FIR
         rc = run_streaming(c, c->eq, cur, cur_pitch, cur_len, tb, c->pitch_b, AFP_FMT_F32, AFP_DITHER_NONE, 1, 0, s0, ns, st);
         if (rc) return rc;
         cur = tb; cur_pitch = c->pitch_b;
     }
-    const int decim = ref ? U : 1;
-    const long long opitch = c->cfg.out_format == AFP_FMT_I24_PACKED ? out_pitch / 3 : out_pitch;
-    return run_streaming(c, c->mainf, cur, cur_pitch, cur_len, out, opitch, c->cfg.out_format, c->cfg.dither, decim,
+    return run_streaming(c, c->mainf, cur, cur_pitch, cur_len, out, opitch, c->cfg.out_format, c->cfg.dither, c->decim,
                          c->out_samples, s0, ns, st);
 }
 
 // the whole block has been launched: roll the ping-pong histories and the dither counter
 static void finish_block(afp_ctx* c, int32_t frames) {
     const bool ref = c->cfg.chain == AFP_CHAIN_REFERENCE;
+    const int mode = c->cfg.eq_mode;
     if (ref && c->cfg.upsample > 1) c->up.cur ^= 1;
-    if (c->eq.active) c->eq.cur ^= 1;
-    c->mainf.cur ^= 1;
+    if (eq_is_buffer_same(c)) c->xhist_cur ^= 1;
+    else if (mode != AFP_EQ_STATELESS_SAME) {
+        if (c->eq.active) c->eq.cur ^= 1;
+        c->mainf.cur ^= 1;
+    }
     c->out_samples += (unsigned long long)afp_out_frames(c, frames);
 }
 
@@ -466,9 +559,11 @@ static int check_ready(afp_ctx* c, int32_t frames) {
     if (!c->mainf.active) return fail(c, AFP_ERR_STATE, "afp_set_taps has not been called");
     if (c->cfg.chain == AFP_CHAIN_REFERENCE && c->cfg.upsample > 1 && !c->up.active)
         return fail(c, AFP_ERR_STATE, "afp_set_upsampler has not been called");
-    if (c->cfg.eq_mode != AFP_EQ_NONE && !c->eq.active) return fail(c, AFP_ERR_STATE, "afp_set_eq has not been called");
-    if (c->cfg.eq_mode == AFP_EQ_BUFFER_SAME || c->cfg.eq_mode == AFP_EQ_PER_BAND)
-        return fail(c, AFP_ERR_INVALID, "eq_mode not implemented yet in this build");
+    const int mode = c->cfg.eq_mode;
+    if (mode != AFP_EQ_NONE && mode != AFP_EQ_STATELESS_SAME && !c->eq.active)
+        return fail(c, AFP_ERR_STATE, "afp_set_eq has not been called");
+    if (((long long)frames * c->cfg.upsample) % c->decim != 0)
+        return fail(c, AFP_ERR_INVALID, "frames * upsample is not a multiple of the decimation factor");
     return AFP_OK;
 }
 
@@ -573,15 +668,28 @@ int afp_process_host(afp_ctx* c, const float* in, void* out, int32_t frames) {
     return afp_process_host_blocks(c, in, out, frames, 1);
 }
 
+// every device buffer that carries state between blocks: (current, other, bytes)
+struct StateBuf { float* cur; float* other; size_t bytes; };
+static std::vector<StateBuf> state_buffers(const afp_ctx* c) {
+    std::vector<StateBuf> v;
+    const Stage* st[3] = {&c->up, &c->eq, &c->mainf};
+    for (const Stage* s : st)
+        if (s->active && s->hist[0])
+            v.push_back({s->hist[s->cur], s->hist[s->cur ^ 1], (size_t)c->cfg.n_streams * s->hist_pitch * sizeof(float)});
+    if (c->xhist[0])
+        v.push_back({c->xhist[c->xhist_cur], c->xhist[c->xhist_cur ^ 1],
+                     (size_t)c->cfg.n_streams * c->xhist_pitch * sizeof(float)});
+    return v;
+}
+
 int afp_reset(afp_ctx* c) {
     if (!c) return AFP_ERR_INVALID;
     AFP_CUDA(c, cudaSetDevice(c->cfg.device));
     AFP_CUDA(c, cudaDeviceSynchronize());
-    Stage* st[3] = {&c->up, &c->eq, &c->mainf};
-    for (Stage* s : st)
-        if (s->active)
-            for (int i = 0; i < 2; ++i)
-                AFP_CUDA(c, cudaMemset(s->hist[i], 0, (size_t)c->cfg.n_streams * s->hist_pitch * sizeof(float)));
+    for (const StateBuf& b : state_buffers(c)) {
+        AFP_CUDA(c, cudaMemset(b.cur, 0, b.bytes));
+        AFP_CUDA(c, cudaMemset(b.other, 0, b.bytes));
+    }
     c->out_samples = 0;
     return AFP_OK;
 }
@@ -589,9 +697,7 @@ int afp_reset(afp_ctx* c) {
 int afp_state_size(const afp_ctx* c, size_t* bytes) {
     if (!c || !bytes) return AFP_ERR_INVALID;
     size_t n = 4 * sizeof(uint64_t);
-    const Stage* st[3] = {&c->up, &c->eq, &c->mainf};
-    for (const Stage* s : st)
-        if (s->active) n += (size_t)c->cfg.n_streams * s->hist_pitch * sizeof(float);
+    for (const StateBuf& b : state_buffers(c)) n += b.bytes;
     *bytes = n;
     return AFP_OK;
 }
@@ -605,13 +711,10 @@ int afp_get_state(afp_ctx* c, void* buf, size_t bytes) {
     uint64_t* hdr = static_cast<uint64_t*>(buf);
     hdr[0] = kStateMagic; hdr[1] = need; hdr[2] = c->out_samples; hdr[3] = 0;
     unsigned char* p = static_cast<unsigned char*>(buf) + 4 * sizeof(uint64_t);
-    Stage* st[3] = {&c->up, &c->eq, &c->mainf};
-    for (Stage* s : st)
-        if (s->active) {
-            const size_t n = (size_t)c->cfg.n_streams * s->hist_pitch * sizeof(float);
-            AFP_CUDA(c, cudaMemcpy(p, s->hist[s->cur], n, cudaMemcpyDeviceToHost));
-            p += n;
-        }
+    for (const StateBuf& b : state_buffers(c)) {
+        AFP_CUDA(c, cudaMemcpy(p, b.cur, b.bytes, cudaMemcpyDeviceToHost));
+        p += b.bytes;
+    }
     return AFP_OK;
 }
 
@@ -625,13 +728,10 @@ int afp_set_state(afp_ctx* c, const void* buf, size_t bytes) {
     AFP_CUDA(c, cudaDeviceSynchronize());
     c->out_samples = hdr[2];
     const unsigned char* p = static_cast<const unsigned char*>(buf) + 4 * sizeof(uint64_t);
-    Stage* st[3] = {&c->up, &c->eq, &c->mainf};
-    for (Stage* s : st)
-        if (s->active) {
-            const size_t n = (size_t)c->cfg.n_streams * s->hist_pitch * sizeof(float);
-            AFP_CUDA(c, cudaMemcpy(s->hist[s->cur], p, n, cudaMemcpyHostToDevice));
-            p += n;
-        }
+    for (const StateBuf& b : state_buffers(c)) {
+        AFP_CUDA(c, cudaMemcpy(b.cur, p, b.bytes, cudaMemcpyHostToDevice));
+        p += b.bytes;
+    }
     return AFP_OK;
 }
 

@@ -40,7 +40,7 @@
 
 namespace afp {
 
-constexpr int MAX_TAPS = 4096;   // floats in the per-launch tap table (all phases, zero padded)
+constexpr int MAX_TAPS = 6144;   // floats in the per-launch tap table (all phases / bands, zero padded)
 
 struct FirParams {
     const float* src0;           // [n_streams][pitch0]  first len0 logical samples
@@ -53,6 +53,8 @@ struct FirParams {
     int n_seg_total;             // n_streams * segs_per_stream
     int n_pairs;                 // work items: ceil(n_seg_total / 2)
     int n_chunks;                // padded taps per phase / T
+    int n_sub;                   // passes over the tap axis accumulated into one output (EQ bands), >= 1
+    int sub_stride;              // floats between the tables of consecutive passes
     void* out;                   // [n_streams][out_pitch] elements of the output format
     long long out_pitch;
     int decim;                   // keep output samples whose index % decim == 0
@@ -66,6 +68,7 @@ struct FirParams {
     int fast0, fast1, fast_hist, fast_out;   // 16-byte alignment guarantees, computed on the host
     int fast_all;                // every 4-sample group of every region is aligned and lies in one source
     float gain;                  // applied to the accumulators before the epilogue (1.0 = none)
+    float dither_lsb;            // float-output dither: value of one LSB (2^-(bits-1))
     alignas(16) float taps[MAX_TAPS];
 };
 
@@ -218,7 +221,7 @@ __device__ __forceinline__ void store_row(const FirParams& P, float (&y)[NOUT], 
         if (P.fmt == FMT_F32) {
             if (P.dither != DITHER_NONE) {
 #pragma unroll
-                for (int i = 0; i < NOUT; ++i) y[i] = dither_float(y[i], d[i]);
+                for (int i = 0; i < NOUT; ++i) y[i] = dither_float(y[i], d[i], P.dither_lsb);
             }
             float* o = reinterpret_cast<float*>(row) + o_base;
             if (full) {
@@ -299,7 +302,7 @@ __device__ __forceinline__ void store_row(const FirParams& P, float (&y)[NOUT], 
                 d = (P.dither == DITHER_TPDF) ? dither_lsb<DITHER_TPDF>(wa, wb) : dither_lsb<DITHER_RPDF>(wa, wb);
             }
             if (P.fmt == FMT_F32) {
-                reinterpret_cast<float*>(row)[od] = (P.dither != DITHER_NONE) ? dither_float(y[i], d) : y[i];
+                reinterpret_cast<float*>(row)[od] = (P.dither != DITHER_NONE) ? dither_float(y[i], d, P.dither_lsb) : y[i];
             } else if (P.fmt == FMT_I16) {
                 reinterpret_cast<short*>(row)[od] = (short)quantise<16>(y[i], d);
             } else {
@@ -455,17 +458,20 @@ fir_stream_kernel(const __grid_constant__ FirParams P) {
             for (int r = 0; r < T; ++r) acc[p][r] = make_float2(0.f, 0.f);
 
         float2 wa[T], wb[T];
-        load_block<T>(wb, region, b0);
-        int c = 0;
-        for (; c + 2 <= P.n_chunks; c += 2) {
-            load_block<T>(wa, region, b0 - c - 1);
-            chunk_fma<U, T>(acc, wa, wb, P.taps + c * (T * U));
-            load_block<T>(wb, region, b0 - c - 2);
-            chunk_fma<U, T>(acc, wb, wa, P.taps + (c + 1) * (T * U));
-        }
-        if (c < P.n_chunks) {
-            load_block<T>(wa, region, b0 - c - 1);
-            chunk_fma<U, T>(acc, wa, wb, P.taps + c * (T * U));
+        for (int sb = 0; sb < P.n_sub; ++sb) {      // one pass per EQ band (1 for a plain filter)
+            const float* tp = P.taps + sb * P.sub_stride;
+            load_block<T>(wb, region, b0);
+            int c = 0;
+            for (; c + 2 <= P.n_chunks; c += 2) {
+                load_block<T>(wa, region, b0 - c - 1);
+                chunk_fma<U, T>(acc, wa, wb, tp + c * (T * U));
+                load_block<T>(wb, region, b0 - c - 2);
+                chunk_fma<U, T>(acc, wb, wa, tp + (c + 1) * (T * U));
+            }
+            if (c < P.n_chunks) {
+                load_block<T>(wa, region, b0 - c - 1);
+                chunk_fma<U, T>(acc, wa, wb, tp + c * (T * U));
+            }
         }
         group_sync<NT>(tg, slot);      // the region may be overwritten by the next item's load
 

@@ -54,9 +54,10 @@ __device__ __forceinline__ int quantise(float y, float d) {
     return (y != y) ? 0 : q;
 }
 
-// Reference-style float dither at 24-bit scale: y + d * 2^-23, both steps rounded to float32.
-__device__ __forceinline__ float dither_float(float y, float d) {
-    return __fadd_rn(y, __fmul_rn(d, 1.1920928955078125e-07f));
+// Reference-style float dither (apply_dither(audio, bit_depth), stream_process.py:61-64): y + d * LSB with
+// LSB = 2^-(bit_depth-1), both steps rounded to float32.
+__device__ __forceinline__ float dither_float(float y, float d, float lsb) {
+    return __fadd_rn(y, __fmul_rn(d, lsb));
 }
 
 }  // namespace afp

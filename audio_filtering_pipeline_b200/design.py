@@ -221,11 +221,13 @@ def design_eq_bank(numtaps, samplerate, bands=None, min_phase=False):
 
 def combine_eq_taps(band_taps, gains):
     """Taps-domain EQ sum ``sum_b g_b * h_b`` (stream_process_EQ_GUI.py:86-90).  Bands of unequal
-    length are centre-aligned (zero-padded symmetrically) so that 'same'-style centring agrees."""
-    nmax = max(len(c) for c in band_taps)
-    acc = np.zeros(nmax)
+    length are aligned on their 'same' centres ``(N_b-1)//2`` - where scipy centres each band's output
+    in stream_process_EQ.py:128 - which is also how the engine lays out its EQ tables."""
+    cmax = max((len(c) - 1) // 2 for c in band_taps)
+    n = max(cmax - (len(c) - 1) // 2 + len(c) for c in band_taps)
+    acc = np.zeros(n)
     for c, g in zip(band_taps, gains):
         c = np.asarray(c, dtype=np.float64)
-        off = (nmax - len(c)) // 2
+        off = cmax - (len(c) - 1) // 2
         acc[off:off + len(c)] += float(g) * c
     return acc

@@ -35,12 +35,18 @@ class BatchFirEngine:
                        every U-th sample, the structure of stream_process.py:89-107.
     out_format         'f32' | 'i16' | 'i24' (int32 container) | 'i24_packed' (3-byte little endian)
     dither             'none' | 'tpdf' | 'rpdf'  (Philox4x32-10 keyed by seed/stream/sample index)
-    eq_mode            'none' | 'fused' (taps-domain sum, stream_process_EQ_GUI.py:86-90)
+    eq_mode            'none' | 'fused' (taps-domain sum, stream_process_EQ_GUI.py:86-90) | 'per_band'
+                       (every band convolved and accumulated, stream_process_EQ.py:127-129), both
+                       with carried state; parity modes 'buffer_same' / 'buffer_same_per_band'
+                       (the sliding-buffer 'same' + 'valid' arithmetic of stream_process_EQ.py:119-134)
+                       and 'stateless_same' (stream_process_EQ_GUI.py:86-95, nothing carried).
+    decimate           keep every n-th output sample (default: U for chain='reference', else 1)
+    dither_bits        bit depth of the float-output dither (apply_dither's ``bit_depth``; default 24)
     """
 
     def __init__(self, taps, n_streams=1, max_frames=1024, upsample=1, chain="dac", out_format="f32",
                  dither="none", seed=0, device=0, upsampler_taps=None, eq_bands=None, eq_gains=None,
-                 eq_mode="none", first_stream_id=0):
+                 eq_mode="none", first_stream_id=0, decimate=0, dither_bits=0):
         self._lib = _lib.load()
         self._ctx = C.c_void_p()
         if eq_bands is not None and eq_mode in ("none", None):
@@ -49,7 +55,8 @@ class BatchFirEngine:
                           upsample=int(upsample), chain=_lib.CHAIN[chain],
                           out_format=_lib.FMT[out_format], dither=_lib.DITHER[dither],
                           eq_mode=_lib.EQ_MODE[eq_mode], seed=int(seed) & (2 ** 64 - 1),
-                          first_stream_id=int(first_stream_id), reserved=0)
+                          first_stream_id=int(first_stream_id), decimate=int(decimate),
+                          dither_bits=int(dither_bits), reserved=0)
         _lib.check(self._lib.afp_create(C.byref(cfg), C.byref(self._ctx)))
         self.cfg = cfg
         self.n_streams, self.max_frames, self.upsample = int(n_streams), int(max_frames), int(upsample)

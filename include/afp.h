@@ -57,9 +57,12 @@ extern "C" {
 #define AFP_EQ_NONE 0
 #define AFP_EQ_FUSED 1         /* one FIR with taps sum_b g_b*h_b, state carried (stream_process_EQ_GUI.py:86-90) */
 #define AFP_EQ_PER_BAND 2      /* every band convolved separately and summed with its gain */
-#define AFP_EQ_BUFFER_SAME 3   /* parity mode: 'same' convolution over the [history|block] buffer,
-                                  zero-extended at both ends, recomputed every block
-                                  (stream_process_EQ.py:124-134) */
+#define AFP_EQ_BUFFER_SAME 3   /* parity mode: 'same' convolution over the [history|block] sliding buffer,
+                                  zero-extended at both ends, recomputed every block, then the 'valid'
+                                  main FIR (stream_process_EQ.py:119-134); taps-domain sum of the bands */
+#define AFP_EQ_BUFFER_SAME_PER_BAND 4  /* the same, each band accumulated separately (:127-129) */
+#define AFP_EQ_STATELESS_SAME 5 /* parity mode: no carried state; 'same' EQ then 'same' main filter over
+                                  the block alone (worker thread, stream_process_EQ_GUI.py:86-95) */
 
 typedef struct afp_ctx afp_ctx;
 
@@ -74,6 +77,9 @@ typedef struct afp_config {
     int32_t eq_mode;          /* AFP_EQ_* */
     uint64_t seed;            /* dither seed */
     int32_t first_stream_id;  /* global id of stream 0 (keeps dither identical under multi-GPU sharding) */
+    int32_t decimate;         /* keep every decimate-th output sample; 0 = default (U for AFP_CHAIN_REFERENCE,
+                                 1 for AFP_CHAIN_DAC); frames*rate must be a multiple of it */
+    int32_t dither_bits;      /* bit depth of the float-output dither (apply_dither's bit_depth); 0 = 24 */
     int32_t reserved;
 } afp_config;
 
