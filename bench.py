@@ -202,6 +202,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from audio_filtering_pipeline_b200.engine import BatchFirEngine, PinnedArray, measure_fma_peak
+    from audio_filtering_pipeline_b200.sharding import max_over_ranks
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -252,10 +253,7 @@ def run_ours(args):
     clocks = sampler.stop()
     launches = eng.kernel_launches - l0
     ms_total = e0.elapsed_time(e1)
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total_max = float(t.item())
+    ms_total_max = max_over_ranks(ms_total, dev)
     samples_rank = S * FRAMES * NB * K
     value = samples_rank * world / (ms_total_max * 1e-3) / 1e6
 
@@ -302,11 +300,8 @@ def run_ours(args):
     for _ in range(Ke):
         eng.process_host_blocks(hx.a, hy.a)
     torch.cuda.synchronize()
-    te = time.perf_counter() - t0
-    t = torch.tensor([te], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = S * FRAMES * NB * Ke * world / float(t.item()) / 1e6
+    te = max_over_ranks(time.perf_counter() - t0, dev)
+    e2e_value = S * FRAMES * NB * Ke * world / te / 1e6
     e2e = {"value": round(e2e_value, 2), "unit": "Msamples/s", "h2d_bytes_per_step": S * FRAMES * NB * 4,
            "d2h_bytes_per_step": S * FRAMES * NB * 4, "steps": Ke,
            "api": "BatchFirEngine.process_host_blocks (afp_process_host_blocks), pinned host memory"}
