@@ -50,17 +50,18 @@ struct Stage {
 
 typedef void (*kern_t)(const FirParams);
 
-template <int U, int T>
+template <int U, int T, bool MULTI>
 kern_t pick_nt(int nt) {
-    return nt == 256 ? (kern_t)afp::fir_stream_kernel<U, T, 256> : (kern_t)afp::fir_stream_kernel<U, T, 128>;
+    return nt == 256 ? (kern_t)afp::fir_stream_kernel<U, T, 256, MULTI> : (kern_t)afp::fir_stream_kernel<U, T, 128, MULTI>;
 }
 int tile_for(int U) { return U == 1 ? 16 : (U == 2 ? 8 : 4); }
-kern_t kernel_for(int U, int nt) {
+// multi = several tap tables accumulated into one output (per-band EQ); only U = 1 stages use it
+kern_t kernel_for(int U, int nt, bool multi = false) {
     switch (U) {
-        case 1: return pick_nt<1, 16>(nt);
-        case 2: return pick_nt<2, 8>(nt);
-        case 3: return pick_nt<3, 4>(nt);
-        case 4: return pick_nt<4, 4>(nt);
+        case 1: return multi ? pick_nt<1, 16, true>(nt) : pick_nt<1, 16, false>(nt);
+        case 2: return pick_nt<2, 8, false>(nt);
+        case 3: return pick_nt<3, 4, false>(nt);
+        case 4: return pick_nt<4, 4, false>(nt);
     }
     return nullptr;
 }
@@ -201,7 +202,7 @@ int launch_stage(afp_ctx* c, Stage& s, const StageIO& io, cudaStream_t stream) {
         if (g.nt == 0) return fail(c, AFP_ERR_INVALID, "filter/block combination does not fit in shared memory");
         // persistent grid: no more CTAs than fit on the device at once (items are dealt round-robin)
         int per_sm = 0;
-        AFP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kernel_for(s.U, g.nt), g.nt, g.smem));
+        AFP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kernel_for(s.U, g.nt, s.n_sub > 1), g.nt, g.smem));
         if (per_sm < 1) return fail(c, AFP_ERR_INVALID, "kernel does not fit on an SM with this geometry");
         // ... and never fewer than min(resident, items): items are dealt CTA-first, so a small launch
         // spreads over all SMs instead of filling every group of a few CTAs
@@ -241,7 +242,7 @@ int launch_stage(afp_ctx* c, Stage& s, const StageIO& io, cudaStream_t stream) {
     P.fast_out = (aligned16(io.out) && (io.out_pitch * eb) % 16 == 0) ? 1 : 0;
     std::memset(P.taps, 0, sizeof(P.taps));
     std::memcpy(P.taps, s.table.data(), s.table.size() * sizeof(float));
-    kern_t k = kernel_for(s.U, g.nt);
+    kern_t k = kernel_for(s.U, g.nt, s.n_sub > 1);
     k<<<g.grid, g.nt, g.smem, stream>>>(P);
     AFP_CUDA(c, cudaGetLastError());
     c->launches += 1;
@@ -382,10 +383,12 @@ int afp_create(const afp_config* cfg, afp_ctx** out_ctx) {
     if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
     if (prop.major != 10) return fail(nullptr, AFP_ERR_INVALID, "this library is built for sm_100a (B200) only");
     for (int U = 1; U <= 4; ++U)
-        for (int nt = 128; nt <= 256; nt <<= 1) {
-            e = cudaFuncSetAttribute((const void*)kernel_for(U, nt), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-            if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem)");
-        }
+        for (int nt = 128; nt <= 256; nt <<= 1)
+            for (int multi = 0; multi <= (U == 1 ? 1 : 0); ++multi) {
+                e = cudaFuncSetAttribute((const void*)kernel_for(U, nt, multi != 0),
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+                if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem)");
+            }
     afp_ctx* c = new (std::nothrow) afp_ctx();
     if (!c) return fail(nullptr, AFP_ERR_NOMEM, "out of host memory");
     c->cfg = *cfg;

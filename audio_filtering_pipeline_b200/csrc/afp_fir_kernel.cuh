@@ -348,7 +348,7 @@ __device__ __forceinline__ void group_sync(int tg, int slot) {
 // varying fastest, so a partly filled last round leaves every SM with the same number of busy
 // groups instead of leaving whole SMs idle (the 1024-CTA one-shot grid of the first version ran 3.46
 // waves in the time of 4).
-template <int U, int T, int NT>
+template <int U, int T, int NT, bool MULTI>
 __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 4))
 fir_stream_kernel(const __grid_constant__ FirParams P) {
     extern __shared__ float4 smem[];
@@ -458,8 +458,12 @@ fir_stream_kernel(const __grid_constant__ FirParams P) {
             for (int r = 0; r < T; ++r) acc[p][r] = make_float2(0.f, 0.f);
 
         float2 wa[T], wb[T];
-        for (int sb = 0; sb < P.n_sub; ++sb) {      // one pass per EQ band (1 for a plain filter)
-            const float* tp = P.taps + sb * P.sub_stride;
+        // MULTI: one pass per EQ band accumulated into the same outputs.  The single-pass instantiation
+        // keeps the tap address a pure function of the chunk counter, which is what lets ptxas hold the
+        // taps in uniform registers (LDCU + FFMA2 ..., UR.F32, ...).
+        const int n_sub = MULTI ? P.n_sub : 1;
+        for (int sb = 0; sb < n_sub; ++sb) {
+            const float* tp = MULTI ? P.taps + sb * P.sub_stride : P.taps;
             load_block<T>(wb, region, b0);
             int c = 0;
             for (; c + 2 <= P.n_chunks; c += 2) {
@@ -475,8 +479,9 @@ fir_stream_kernel(const __grid_constant__ FirParams P) {
         }
         group_sync<NT>(tg, slot);      // the region may be overwritten by the next item's load
 
-        // ---- epilogue: registers -> global, dither / quantise on the way
-#pragma unroll
+        // ---- epilogue: registers -> global, dither / quantise on the way (one copy of the code for
+        // both rows: the epilogue is large and runs once per item, keep it out of the i-cache's way)
+#pragma unroll 1
         for (int row = 0; row < 2; ++row) {
             const int seg = 2 * pair_idx + row;
             if (seg >= P.n_seg_total) continue;
