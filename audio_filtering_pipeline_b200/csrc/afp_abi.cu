@@ -50,21 +50,41 @@ struct Stage {
 
 typedef void (*kern_t)(const FirParams);
 
-template <int U, int T, bool MULTI>
-kern_t pick_nt(int nt) {
-    return nt == 256 ? (kern_t)afp::fir_stream_kernel<U, T, 256, MULTI> : (kern_t)afp::fir_stream_kernel<U, T, 128, MULTI>;
-}
 int tile_for(int U) { return U == 1 ? 16 : (U == 2 ? 8 : 4); }
-// multi = several tap tables accumulated into one output (per-band EQ); only U = 1 stages use it
-kern_t kernel_for(int U, int nt, bool multi = false) {
+
+// Kernel table.  Specialised epilogues (compile-time format/dither, decim == 1) exist for the hot
+// combinations; everything else runs the generic epilogue.  multi = several tap tables accumulated
+// into one output (per-band EQ, U = 1 only).  NT = 128 only when a 256-thread CTA does not fit.
+constexpr int kEpiF32 = afp::epi_code(AFP_FMT_F32, AFP_DITHER_NONE);
+constexpr int kEpiI24T = afp::epi_code(AFP_FMT_I24_IN_I32, AFP_DITHER_TPDF);
+constexpr int kEpiI16T = afp::epi_code(AFP_FMT_I16, AFP_DITHER_TPDF);
+constexpr int kEpiP24T = afp::epi_code(AFP_FMT_I24_PACKED, AFP_DITHER_TPDF);
+
+template <int U, int T>
+kern_t pick_kernel(int nt, bool multi, int epi) {
+    using namespace afp;
+    if (nt == 128) return (kern_t)fir_stream_kernel<U, T, 128, false, EPI_GENERIC>;
+    if (multi) return nullptr;
+    switch (epi) {
+        case kEpiF32: return (kern_t)fir_stream_kernel<U, T, 256, false, kEpiF32>;
+        case kEpiI24T: return (kern_t)fir_stream_kernel<U, T, 256, false, kEpiI24T>;
+        case kEpiI16T: return (kern_t)fir_stream_kernel<U, T, 256, false, kEpiI16T>;
+        case kEpiP24T: return (kern_t)fir_stream_kernel<U, T, 256, false, kEpiP24T>;
+        default: return (kern_t)fir_stream_kernel<U, T, 256, false, EPI_GENERIC>;
+    }
+}
+kern_t kernel_for(int U, int nt, bool multi, int epi) {
+    if (multi) return nt == 256 ? (kern_t)afp::fir_stream_kernel<1, 16, 256, true, afp::EPI_GENERIC>
+                                : (kern_t)afp::fir_stream_kernel<1, 16, 128, true, afp::EPI_GENERIC>;
     switch (U) {
-        case 1: return multi ? pick_nt<1, 16, true>(nt) : pick_nt<1, 16, false>(nt);
-        case 2: return pick_nt<2, 8, false>(nt);
-        case 3: return pick_nt<3, 4, false>(nt);
-        case 4: return pick_nt<4, 4, false>(nt);
+        case 1: return pick_kernel<1, 16>(nt, false, epi);
+        case 2: return pick_kernel<2, 8>(nt, false, epi);
+        case 3: return pick_kernel<3, 4>(nt, false, epi);
+        case 4: return pick_kernel<4, 4>(nt, false, epi);
     }
     return nullptr;
 }
+const int kAllEpi[] = {afp::EPI_GENERIC, kEpiF32, kEpiI24T, kEpiI16T, kEpiP24T};
 
 }  // namespace
 
@@ -150,13 +170,19 @@ int build_stage(afp_ctx* c, Stage& s, int kind, int U, const double* taps, int n
     return AFP_OK;
 }
 
-// CTA geometry for n_q base positions per stream with a halo of kq_pad
+// CTA geometry for n_q base positions per stream with a halo of kq_pad.
+// A thread group (tg threads) owns one segment of tg*T positions.  Small groups mean many independent
+// groups per SM (one group's load/epilogue hides behind the others' FMAs) but re-load the halo more
+// often; the halo is kept <= 1/4 of a segment unless the block itself is shorter.
 Geometry pick_geometry(int T, int kq_pad, int n_q, int n_streams) {
     Geometry best;
     double best_score = -1;
     for (int nt = 256; nt >= 128; nt >>= 1) {
-        int tg_log2 = 3;
-        while ((1 << tg_log2) * T < n_q && (1 << tg_log2) < nt) ++tg_log2;
+        int cover = 3;                                   // smallest group that covers the whole block
+        while ((1 << cover) * T < n_q && (1 << cover) < nt) ++cover;
+        int halo = 5;                                    // smallest warp-or-larger group with halo <= 25 %
+        while ((1 << halo) * T < 4 * kq_pad && (1 << halo) < nt) ++halo;
+        int tg_log2 = cover < halo ? cover : halo;
         for (;; ++tg_log2) {
             const int tg = 1 << tg_log2, slots = nt / tg;
             const int smem = slots * afp::region_granules(kq_pad + tg * T) * 16;
@@ -202,7 +228,8 @@ int launch_stage(afp_ctx* c, Stage& s, const StageIO& io, cudaStream_t stream) {
         if (g.nt == 0) return fail(c, AFP_ERR_INVALID, "filter/block combination does not fit in shared memory");
         // persistent grid: no more CTAs than fit on the device at once (items are dealt round-robin)
         int per_sm = 0;
-        AFP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kernel_for(s.U, g.nt, s.n_sub > 1), g.nt, g.smem));
+        AFP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &per_sm, (const void*)kernel_for(s.U, g.nt, s.n_sub > 1, afp::EPI_GENERIC), g.nt, g.smem));
         if (per_sm < 1) return fail(c, AFP_ERR_INVALID, "kernel does not fit on an SM with this geometry");
         // ... and never fewer than min(resident, items): items are dealt CTA-first, so a small launch
         // spreads over all SMs instead of filling every group of a few CTAs
@@ -220,6 +247,8 @@ int launch_stage(afp_ctx* c, Stage& s, const StageIO& io, cudaStream_t stream) {
     P.len0 = io.len0; P.len1 = io.len1;
     P.q_begin = io.q_begin; P.n_q = io.n_q;
     P.tg_log2 = g.tg_log2; P.segs_per_stream = g.segs_per_stream;
+    P.segs_shift = -1;
+    for (int b = 0; b < 30; ++b) if ((1 << b) == g.segs_per_stream) P.segs_shift = b;
     P.n_seg_total = S * g.segs_per_stream;
     P.n_pairs = (P.n_seg_total + 1) / 2;
     P.n_chunks = s.n_chunks; P.n_sub = s.n_sub; P.sub_stride = s.kq_pad * s.U;
@@ -242,7 +271,8 @@ int launch_stage(afp_ctx* c, Stage& s, const StageIO& io, cudaStream_t stream) {
     P.fast_out = (aligned16(io.out) && (io.out_pitch * eb) % 16 == 0) ? 1 : 0;
     std::memset(P.taps, 0, sizeof(P.taps));
     std::memcpy(P.taps, s.table.data(), s.table.size() * sizeof(float));
-    kern_t k = kernel_for(s.U, g.nt, s.n_sub > 1);
+    const int epi = io.decim == 1 ? afp::epi_code(io.fmt, io.dither) : afp::EPI_GENERIC;
+    kern_t k = kernel_for(s.U, g.nt, s.n_sub > 1, epi);
     k<<<g.grid, g.nt, g.smem, stream>>>(P);
     AFP_CUDA(c, cudaGetLastError());
     c->launches += 1;
@@ -384,11 +414,12 @@ int afp_create(const afp_config* cfg, afp_ctx** out_ctx) {
     if (prop.major != 10) return fail(nullptr, AFP_ERR_INVALID, "this library is built for sm_100a (B200) only");
     for (int U = 1; U <= 4; ++U)
         for (int nt = 128; nt <= 256; nt <<= 1)
-            for (int multi = 0; multi <= (U == 1 ? 1 : 0); ++multi) {
-                e = cudaFuncSetAttribute((const void*)kernel_for(U, nt, multi != 0),
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-                if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem)");
-            }
+            for (int multi = 0; multi <= (U == 1 ? 1 : 0); ++multi)
+                for (int epi : kAllEpi) {
+                    e = cudaFuncSetAttribute((const void*)kernel_for(U, nt, multi != 0, epi),
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+                    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem)");
+                }
     afp_ctx* c = new (std::nothrow) afp_ctx();
     if (!c) return fail(nullptr, AFP_ERR_NOMEM, "out of host memory");
     c->cfg = *cfg;

@@ -50,6 +50,7 @@ struct FirParams {
     int q_begin, n_q;            // base positions computed per stream
     int tg_log2;                 // log2(threads per segment); a segment is (1<<tg_log2)*T positions
     int segs_per_stream;
+    int segs_shift;              // log2(segs_per_stream) if it is a power of two, else -1
     int n_seg_total;             // n_streams * segs_per_stream
     int n_pairs;                 // work items: ceil(n_seg_total / 2)
     int n_chunks;                // padded taps per phase / T
@@ -158,9 +159,8 @@ __device__ __forceinline__ void hist_store4(const FirParams& P, float* hrow, int
 
 // ---- epilogue ---------------------------------------------------------------------------------
 template <int NOUT, int MODE>
-__device__ __forceinline__ void dither_values(float (&d)[NOUT], const FirParams& P, int stream, unsigned long long idx0) {
-    const uint32_t k0 = (uint32_t)P.seed, k1 = (uint32_t)(P.seed >> 32);
-    const uint32_t sid = (uint32_t)(P.stream_id0 + stream);
+__device__ __forceinline__ void dither_values(float (&d)[NOUT], unsigned long long seed, uint32_t sid, unsigned long long idx0) {
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     if ((idx0 & 1ull) == 0) {
 #pragma unroll
         for (int i = 0; i < NOUT; i += 2) {
@@ -199,10 +199,26 @@ __device__ __forceinline__ int elem_bytes(int fmt) {
     return fmt == FMT_I16 ? 2 : (fmt == FMT_I24_PACKED ? 3 : 4);
 }
 
+// EPI: epilogue specialisation.  EPI_GENERIC reads format / dither / decimation from the parameters;
+// EPI = fmt*4 + dither fixes them at compile time (decim == 1), which removes every branch and all
+// dead conversion code from the short-filter kernels, where the epilogue is a large share of the work.
+constexpr int EPI_GENERIC = -1;
+__host__ __device__ constexpr int epi_code(int fmt, int dither) { return fmt * 4 + dither; }
+
 // y[NOUT]: consecutive output samples o_base .. o_base+NOUT-1 (pre-decimation) of one stream row.
-template <int NOUT>
-__device__ __forceinline__ void store_row(const FirParams& P, float (&y)[NOUT], int stream, long long o_base, int n_valid) {
+template <int NOUT, int EPI>
+__device__ __forceinline__ void store_row(const FirParams& P_, float (&y)[NOUT], int stream, long long o_base, int n_valid) {
     if (n_valid <= 0) return;
+    struct View {   // same field names as FirParams, fmt / dither / decim possibly compile-time
+        const FirParams& p;
+        int fmt, dither, decim;
+        float gain, dither_lsb;
+        void* out; long long out_pitch;
+        unsigned long long seed, sample_base;
+        int stream_id0, fast_out;
+    };
+    const View P = {P_, EPI >= 0 ? (EPI >> 2) : P_.fmt, EPI >= 0 ? (EPI & 3) : P_.dither, EPI >= 0 ? 1 : P_.decim,
+                    P_.gain, P_.dither_lsb, P_.out, P_.out_pitch, P_.seed, P_.sample_base, P_.stream_id0, P_.fast_out};
     if (P.gain != 1.0f) {
 #pragma unroll
         for (int i = 0; i < NOUT; ++i) y[i] = __fmul_rn(y[i], P.gain);
@@ -211,8 +227,8 @@ __device__ __forceinline__ void store_row(const FirParams& P, float (&y)[NOUT], 
     if (P.decim == 1) {
         float d[NOUT];
         const unsigned long long idx0 = P.sample_base + (unsigned long long)o_base;
-        if (P.dither == DITHER_TPDF) dither_values<NOUT, DITHER_TPDF>(d, P, stream, idx0);
-        else if (P.dither == DITHER_RPDF) dither_values<NOUT, DITHER_RPDF>(d, P, stream, idx0);
+        if (P.dither == DITHER_TPDF) dither_values<NOUT, DITHER_TPDF>(d, P.seed, (uint32_t)(P.stream_id0 + stream), idx0);
+        else if (P.dither == DITHER_RPDF) dither_values<NOUT, DITHER_RPDF>(d, P.seed, (uint32_t)(P.stream_id0 + stream), idx0);
         else {
 #pragma unroll
             for (int i = 0; i < NOUT; ++i) d[i] = 0.f;
@@ -346,9 +362,17 @@ __device__ __forceinline__ void group_sync(int tg, int slot) {
 // Persistent over work items.  An item is one segment pair (row A, row B); it belongs to one thread
 // group (tg threads, one shared-memory region).  Items are dealt round-robin with the CTA index
 // varying fastest, so a partly filled last round leaves every SM with the same number of busy
-// groups instead of leaving whole SMs idle (the 1024-CTA one-shot grid of the first version ran 3.46
-// waves in the time of 4).
-template <int U, int T, int NT, bool MULTI>
+// groups instead of leaving whole SMs idle.
+struct RowItem {
+    const float* r0;     // src0 row
+    const float* r1;     // src1 row, pre-offset by -len0 so that logical sample n is r1[n]
+    float* h;            // history row, pre-offset so that logical sample n goes to h[n]
+    int start;           // logical index of pair 0 of the region
+    int stream, seg;     // stream index, segment index inside the stream
+    bool valid;
+};
+
+template <int U, int T, int NT, bool MULTI, int EPI>
 __global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 4))
 fir_stream_kernel(const __grid_constant__ FirParams P) {
     extern __shared__ float4 smem[];
@@ -365,87 +389,113 @@ fir_stream_kernel(const __grid_constant__ FirParams P) {
     const float4* region = region_w;
     const int b0 = P.n_chunks + lt;               // block holding this thread's own T positions
     const int stride = gridDim.x * slots;
+    const int n4 = region_pairs >> 2;
+    const int L = P.len0 + P.len1;
 
     for (int pair_idx = slot * gridDim.x + blockIdx.x; pair_idx < P.n_pairs; pair_idx += stride) {
+        // ---- which two rows
+        RowItem it[2];
+        {
+            const unsigned segA = 2u * (unsigned)pair_idx;
+            unsigned sA, gA;
+            if (P.segs_shift >= 0) { sA = segA >> P.segs_shift; gA = segA & ((1u << P.segs_shift) - 1u); }
+            else { sA = segA / (unsigned)P.segs_per_stream; gA = segA - sA * (unsigned)P.segs_per_stream; }
+            unsigned sB = sA, gB = gA + 1;
+            if (gB == (unsigned)P.segs_per_stream) { gB = 0; sB = sA + 1; }
+            it[0].stream = (int)sA; it[0].seg = (int)gA; it[0].valid = true;
+            it[1].stream = (int)sB; it[1].seg = (int)gB; it[1].valid = (int)(segA + 1) < P.n_seg_total;
+            if (!it[1].valid) { it[1].stream = (int)sA; it[1].seg = (int)gA; }   // keep addresses in range
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                it[r].start = P.q_begin + it[r].seg * lq - kq;
+                it[r].r0 = P.src0 + (long long)it[r].stream * P.pitch0;
+                it[r].r1 = P.src1 + (long long)it[r].stream * P.pitch1 - P.len0;
+                it[r].h = P.hist_out ? P.hist_out + (long long)it[r].stream * P.hist_pitch - P.hist_from : nullptr;
+            }
+        }
+
         // ---- load phase: global -> (row A, row B) interleaved pairs in shared memory, history out.
         // Every thread group loads and waits for its own region only, so groups drift apart and one
         // group's load / epilogue hides behind the others' FMA work.
-        {
-            const int segA = 2 * pair_idx, segB = segA + 1;
-            RowSrc ra, rb;
-            int sA = 0, sB = 0, gA = 0, gB = 0;
-            ra.valid = segA < P.n_seg_total;
-            rb.valid = segB < P.n_seg_total;
-            if (ra.valid) { sA = segA / P.segs_per_stream; gA = segA - sA * P.segs_per_stream; }
-            if (rb.valid) { sB = segB / P.segs_per_stream; gB = segB - sB * P.segs_per_stream; }
-            ra.r0 = P.src0 + (long long)sA * P.pitch0; ra.r1 = P.src1 + (long long)sA * P.pitch1;
-            rb.r0 = P.src0 + (long long)sB * P.pitch0; rb.r1 = P.src1 + (long long)sB * P.pitch1;
-            const int startA = P.q_begin + gA * lq - kq;      // logical index of pair 0 of the region
-            const int startB = P.q_begin + gB * lq - kq;
-            float* hA = (P.hist_out && ra.valid) ? P.hist_out + (long long)sA * P.hist_pitch : nullptr;
-            float* hB = (P.hist_out && rb.valid) ? P.hist_out + (long long)sB * P.hist_pitch : nullptr;
-            const int ownA = gA == 0 ? INT_MIN : startA + kq;
-            const int ownB = gB == 0 ? INT_MIN : startB + kq;
-            const int n4 = region_pairs >> 2;
-            if (P.fast_all) {
-                // Aligned case: every 4-sample group lies wholly in src0, in src1 or outside, so a group
-                // is one predicated LDG.128.  LOAD_B groups per row are requested before any is used:
-                // 2*LOAD_B independent 16-byte loads in flight per thread, one memory round trip per
-                // batch (the branchy generic loader below cost ~15 dependent round trips per item).
-                constexpr int LOAD_B = 6;
-                const int L = P.len0 + P.len1;
-                for (int base = lt; base < n4; base += tg * LOAD_B) {
-                    float4 a[LOAD_B], b[LOAD_B];
+        if (P.fast_all) {
+            // Aligned case: every 4-sample group lies wholly in src0, in src1 or outside, so a group
+            // is one predicated LDG.128.  LOAD_B groups per row are requested before any is used
+            // (2*LOAD_B independent 16-byte loads in flight per thread, one memory round trip per batch).
+            constexpr int LOAD_B = T == 16 ? 6 : (T == 8 ? 3 : 2);
+            // per row, in units of 4-sample groups: [ld0, ld1) is inside the sequence, < split reads src0,
+            // [hs0, hs1) goes to the next block's history
+            int ld0[2], ld1[2], split[2], hs0[2], hs1[2];
 #pragma unroll
-                    for (int k = 0; k < LOAD_B; ++k) {
-                        const int i4 = base + k * tg;
-                        const int nA = startA + 4 * i4, nB = startB + 4 * i4;
-                        a[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        b[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (i4 < n4 && ra.valid && nA >= 0 && nA < L)
-                            a[k] = __ldg(reinterpret_cast<const float4*>(nA < P.len0 ? ra.r0 + nA : ra.r1 + (nA - P.len0)));
-                        if (i4 < n4 && rb.valid && nB >= 0 && nB < L)
-                            b[k] = __ldg(reinterpret_cast<const float4*>(nB < P.len0 ? rb.r0 + nB : rb.r1 + (nB - P.len0)));
-                    }
+            for (int r = 0; r < 2; ++r) {
+                const int st = it[r].start;
+                ld0[r] = st < 0 ? (-st) >> 2 : 0;
+                ld1[r] = it[r].valid ? min(n4, (L - st) >> 2) : 0;
+                split[r] = (P.len0 - st) >> 2;
+                const int own = it[r].seg == 0 ? INT_MIN : st + kq;
+                const int hlo = max(P.hist_from, own), hhi = P.hist_from + P.hist_len;
+                hs0[r] = (it[r].h && it[r].valid) ? max((hlo - st) >> 2, 0) : 0;
+                hs1[r] = (it[r].h && it[r].valid) ? min((hhi - st) >> 2, n4) : 0;
+            }
+            for (int base = lt; base < n4; base += tg * LOAD_B) {
+                float4 v[2][LOAD_B];
 #pragma unroll
-                    for (int k = 0; k < LOAD_B; ++k) {
-                        const int i4 = base + k * tg;
-                        if (i4 < n4) {
-                            const int g = phys_granule(2 * i4);
-                            region_w[g] = make_float4(a[k].x, b[k].x, a[k].y, b[k].y);
-                            region_w[g + 1] = make_float4(a[k].z, b[k].z, a[k].w, b[k].w);
-                            const int nA = startA + 4 * i4, nB = startB + 4 * i4;
-                            const int hlo = P.hist_from, hhi = P.hist_from + P.hist_len;
-                            if (hA && nA >= max(hlo, ownA) && nA < hhi)
-                                *reinterpret_cast<float4*>(hA + (nA - hlo)) = a[k];
-                            if (hB && nB >= max(hlo, ownB) && nB < hhi)
-                                *reinterpret_cast<float4*>(hB + (nB - hlo)) = b[k];
+                for (int k = 0; k < LOAD_B; ++k) {
+                    const int i4 = base + k * tg;
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        v[r][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (i4 >= ld0[r] && i4 < ld1[r]) {
+                            const float* src = (i4 < split[r] ? it[r].r0 : it[r].r1) + it[r].start + 4 * i4;
+                            v[r][k] = __ldg(reinterpret_cast<const float4*>(src));
                         }
                     }
                 }
-            } else {
-#pragma unroll 2
-                for (int i4 = lt; i4 < n4; i4 += tg) {
-                    const float4 a = fetch4(P, ra, startA + 4 * i4);
-                    const float4 b = fetch4(P, rb, startB + 4 * i4);
-                    const int g = phys_granule(2 * i4);
-                    region_w[g] = make_float4(a.x, b.x, a.y, b.y);
-                    region_w[g + 1] = make_float4(a.z, b.z, a.w, b.w);
-                    if (hA) hist_store4(P, hA, startA + 4 * i4, a, ownA);
-                    if (hB) hist_store4(P, hB, startB + 4 * i4, b, ownB);
+#pragma unroll
+                for (int k = 0; k < LOAD_B; ++k) {
+                    const int i4 = base + k * tg;
+                    if (i4 < n4) {
+                        const int g = phys_granule(2 * i4);
+                        region_w[g] = make_float4(v[0][k].x, v[1][k].x, v[0][k].y, v[1][k].y);
+                        region_w[g + 1] = make_float4(v[0][k].z, v[1][k].z, v[0][k].w, v[1][k].w);
+#pragma unroll
+                        for (int r = 0; r < 2; ++r)
+                            if (i4 >= hs0[r] && i4 < hs1[r])
+                                *reinterpret_cast<float4*>(it[r].h + it[r].start + 4 * i4) = v[r][k];
+                    }
                 }
+            }
+        } else {
+            RowSrc rs[2];
+            float* hrow[2];
+            int own[2];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                rs[r].r0 = it[r].r0; rs[r].r1 = it[r].r1 + P.len0; rs[r].valid = it[r].valid;
+                hrow[r] = (it[r].h && it[r].valid) ? it[r].h + P.hist_from : nullptr;
+                own[r] = it[r].seg == 0 ? INT_MIN : it[r].start + kq;
+            }
+#pragma unroll 2
+            for (int i4 = lt; i4 < n4; i4 += tg) {
+                const float4 a = fetch4(P, rs[0], it[0].start + 4 * i4);
+                const float4 b = fetch4(P, rs[1], it[1].start + 4 * i4);
+                const int g = phys_granule(2 * i4);
+                region_w[g] = make_float4(a.x, b.x, a.y, b.y);
+                region_w[g + 1] = make_float4(a.z, b.z, a.w, b.w);
+                if (hrow[0]) hist_store4(P, hrow[0], it[0].start + 4 * i4, a, own[0]);
+                if (hrow[1]) hist_store4(P, hrow[1], it[1].start + 4 * i4, b, own[1]);
             }
         }
         group_sync<NT>(tg, slot);
 
-        // ---- L2 prefetch of the next item's rows (lanes 0..3 of the group: row A/B x src0/src1)
-        if (lt < 4 && pair_idx + stride < P.n_pairs) {
+        // ---- L2 prefetch of the next item's rows (lanes 0..3 of the group: row A/B x src0/src1).
+        // Only worth its instructions when a region is large (long filters: history >> block).
+        if (T == 16 && lt < 4 && pair_idx + stride < P.n_pairs) {
             const int seg = 2 * (pair_idx + stride) + (lt >> 1);
             if (seg < P.n_seg_total) {
                 const int s_ = seg / P.segs_per_stream, g_ = seg - s_ * P.segs_per_stream;
                 const int n0 = P.q_begin + g_ * lq - kq, n1 = n0 + region_pairs;   // logical range
                 if (lt & 1) prefetch_row_l2(P.src1 + (long long)s_ * P.pitch1, max(n0, P.len0) - P.len0,
-                                            min(n1, P.len0 + P.len1) - P.len0);
+                                            min(n1, L) - P.len0);
                 else        prefetch_row_l2(P.src0 + (long long)s_ * P.pitch0, max(n0, 0), min(n1, P.len0));
             }
         }
@@ -479,21 +529,22 @@ fir_stream_kernel(const __grid_constant__ FirParams P) {
         }
         group_sync<NT>(tg, slot);      // the region may be overwritten by the next item's load
 
-        // ---- epilogue: registers -> global, dither / quantise on the way (one copy of the code for
-        // both rows: the epilogue is large and runs once per item, keep it out of the i-cache's way)
-#pragma unroll 1
+        // ---- epilogue: registers -> global, dither / quantise on the way.  The generic epilogue is
+        // large: one copy for both rows keeps it out of the i-cache's way; specialised ones are unrolled.
+#pragma unroll (EPI >= 0 ? 2 : 1)
         for (int row = 0; row < 2; ++row) {
-            const int seg = 2 * pair_idx + row;
-            if (seg >= P.n_seg_total) continue;
-            const int s = seg / P.segs_per_stream, gi = seg - s * P.segs_per_stream;
-            const int q_local = gi * lq + lt * T;               // first base position (relative to q_begin)
+            const bool rvalid = row == 0 ? it[0].valid : it[1].valid;
+            const int rseg = row == 0 ? it[0].seg : it[1].seg;
+            const int rstream = row == 0 ? it[0].stream : it[1].stream;
+            if (!rvalid) continue;
+            const int q_local = rseg * lq + lt * T;               // first base position (relative to q_begin)
             const int nv = min(max(P.n_q - q_local, 0), T) * U;
             float y[U * T];
 #pragma unroll
             for (int r = 0; r < T; ++r)
 #pragma unroll
                 for (int p = 0; p < U; ++p) y[r * U + p] = row == 0 ? acc[p][r].x : acc[p][r].y;
-            store_row<U * T>(P, y, s, (long long)q_local * U, nv);
+            store_row<U * T, EPI>(P, y, rstream, (long long)q_local * U, nv);
         }
     }
 }
