@@ -185,7 +185,7 @@ Geometry pick_geometry(int T, int kq_pad, int n_q, int n_streams) {
         int tg_log2 = cover < halo ? cover : halo;
         for (;; ++tg_log2) {
             const int tg = 1 << tg_log2, slots = nt / tg;
-            const int smem = slots * afp::region_granules(kq_pad + tg * T) * 16;
+            const int smem = slots * afp::region_granules(kq_pad + tg * T, T) * 16;
             if (smem <= kMaxSmem) {
                 const int max_cta = nt == 256 ? 2 : 4;
                 int cta = kMaxSmem / (smem + 1024);

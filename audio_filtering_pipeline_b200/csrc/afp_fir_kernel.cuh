@@ -83,14 +83,18 @@ __device__ __forceinline__ void ffma2(float2& acc, const float2& x, float h) {
     acc = *reinterpret_cast<float2*>(&d);
 }
 
-// physical granule (16 B) index: one pad granule per 8
-__device__ __forceinline__ int phys_granule(int g) { return g + (g >> 3); }
-__host__ __device__ constexpr int region_granules(int pairs) { return (pairs / 2) + (pairs / 16) + 2; }
+// Shared-memory layout: 16-byte granules (2 pairs); a block of T pairs is T/2 granules followed by one
+// pad granule.  A thread reads whole blocks and consecutive lanes read consecutive blocks, so the lane
+// stride is T/2+1 granules - odd - and any 8 consecutive lanes of an LDS.128 hit 8 different 16-byte bank
+// groups whatever the chunk offset (one pad per 8 granules, the first layout, was only conflict free
+// for T = 16: ncu showed 44 % conflicting wavefronts for T = 4).
+template <int T>
+__device__ __forceinline__ int phys_granule(int g) { return g + g / (T / 2); }
+__host__ __device__ constexpr int region_granules(int pairs, int T) { return (pairs / T) * (T / 2 + 1) + 2; }
 
 template <int T>
 __device__ __forceinline__ void load_block(float2 (&w)[T], const float4* __restrict__ region, int block) {
-    const int g = block * (T / 2);
-    const float4* p = region + phys_granule(g);
+    const float4* p = region + block * (T / 2 + 1);
 #pragma unroll
     for (int m = 0; m < T / 2; ++m) {
         const float4 v = p[m];
@@ -372,8 +376,13 @@ struct RowItem {
     bool valid;
 };
 
+// resident CTAs per SM the register budget is compiled for: the T = 4 kernels hold few accumulators, so
+// a third CTA fits and covers more of the (latency-bound) load phase; T = 8 spills at 80 registers
+// (measured slower), T = 16 needs all 128
+__host__ __device__ constexpr int min_ctas(int T, int NT) { return NT == 256 ? (T == 4 ? 3 : 2) : (T == 4 ? 6 : 4); }
+
 template <int U, int T, int NT, bool MULTI, int EPI>
-__global__ void __launch_bounds__(NT, (NT == 256 ? 2 : 4))
+__global__ void __launch_bounds__(NT, min_ctas(T, NT))
 fir_stream_kernel(const __grid_constant__ FirParams P) {
     extern __shared__ float4 smem[];
     const int tid = threadIdx.x;
@@ -382,7 +391,7 @@ fir_stream_kernel(const __grid_constant__ FirParams P) {
     const int lq = tg * T;                         // base positions per segment
     const int kq = P.n_chunks * T;                 // padded taps per phase = halo
     const int region_pairs = kq + lq;
-    const int region_g = region_granules(region_pairs);
+    const int region_g = region_granules(region_pairs, T);
     const int slot = tid >> P.tg_log2;
     const int lt = tid & (tg - 1);
     float4* region_w = smem + slot * region_g;
@@ -454,7 +463,7 @@ fir_stream_kernel(const __grid_constant__ FirParams P) {
                 for (int k = 0; k < LOAD_B; ++k) {
                     const int i4 = base + k * tg;
                     if (i4 < n4) {
-                        const int g = phys_granule(2 * i4);
+                        const int g = phys_granule<T>(2 * i4);
                         region_w[g] = make_float4(v[0][k].x, v[1][k].x, v[0][k].y, v[1][k].y);
                         region_w[g + 1] = make_float4(v[0][k].z, v[1][k].z, v[0][k].w, v[1][k].w);
 #pragma unroll
@@ -478,7 +487,7 @@ fir_stream_kernel(const __grid_constant__ FirParams P) {
             for (int i4 = lt; i4 < n4; i4 += tg) {
                 const float4 a = fetch4(P, rs[0], it[0].start + 4 * i4);
                 const float4 b = fetch4(P, rs[1], it[1].start + 4 * i4);
-                const int g = phys_granule(2 * i4);
+                const int g = phys_granule<T>(2 * i4);
                 region_w[g] = make_float4(a.x, b.x, a.y, b.y);
                 region_w[g + 1] = make_float4(a.z, b.z, a.w, b.w);
                 if (hrow[0]) hist_store4(P, hrow[0], it[0].start + 4 * i4, a, own[0]);
