@@ -15,10 +15,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libafp_b200.so")
-SOURCES = ["afp_abi.cu"]
-DEPS = ["afp_abi.cu", "afp_fir_kernel.cuh", "afp_philox.cuh", os.path.join("..", "..", "include", "afp.h")]
+SOURCES = ["afp_abi.cu", "afp_kernels_u1.cu", "afp_kernels_u2.cu", "afp_kernels_u3.cu", "afp_kernels_u4.cu"]
+DEPS = SOURCES + ["afp_fir_kernel.cuh", "afp_kernel_table.cuh", "afp_philox.cuh",
+                  os.path.join("..", "..", "include", "afp.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
+              "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
 
 
 def _nvcc():
@@ -36,16 +37,33 @@ def is_stale():
 
 
 def build(force=False, verbose=False):
-    """Compile libafp_b200.so if missing or older than its sources.  Returns the library path."""
+    """Compile libafp_b200.so if missing or older than its sources.  Returns the library path.
+    The translation units (one per up-sampling factor + the ABI) are compiled in parallel."""
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    nvcc = _nvcc()
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+              ["-c", "-o", obj, os.path.join(CSRC, src)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
+        return obj, res.stdout + res.stderr
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    if verbose:
+        for _, log in results:
+            sys.stderr.write(log)
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + [o for o, _ in results]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     return LIB
 
 

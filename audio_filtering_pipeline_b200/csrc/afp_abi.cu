@@ -8,12 +8,13 @@
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "../../include/afp.h"
-#include "afp_fir_kernel.cuh"
+#include "afp_kernel_table.cuh"
 
 using afp::FirParams;
 
@@ -48,43 +49,38 @@ struct Stage {
     Geometry geo;
 };
 
-typedef void (*kern_t)(const FirParams);
+// Kernels live in one translation unit per up-sampling factor (afp_kernels_u{1..4}.cu, compiled in
+// parallel); each exports a lookup by (T, CTA size, multi-table, epilogue code) - afp_kernel_table.cuh.
+using afp::kern_t;
+using afp::kAllEpi;
 
-int tile_for(int U) { return U == 1 ? 16 : (U == 2 ? 8 : 4); }
-
-// Kernel table.  Specialised epilogues (compile-time format/dither, decim == 1) exist for the hot
-// combinations; everything else runs the generic epilogue.  multi = several tap tables accumulated
-// into one output (per-band EQ, U = 1 only).  NT = 128 only when a 256-thread CTA does not fit.
-constexpr int kEpiF32 = afp::epi_code(AFP_FMT_F32, AFP_DITHER_NONE);
-constexpr int kEpiI24T = afp::epi_code(AFP_FMT_I24_IN_I32, AFP_DITHER_TPDF);
-constexpr int kEpiI16T = afp::epi_code(AFP_FMT_I16, AFP_DITHER_TPDF);
-constexpr int kEpiP24T = afp::epi_code(AFP_FMT_I24_PACKED, AFP_DITHER_TPDF);
-
-template <int U, int T>
-kern_t pick_kernel(int nt, bool multi, int epi) {
-    using namespace afp;
-    if (nt == 128) return (kern_t)fir_stream_kernel<U, T, 128, false, EPI_GENERIC>;
-    if (multi) return nullptr;
-    switch (epi) {
-        case kEpiF32: return (kern_t)fir_stream_kernel<U, T, 256, false, kEpiF32>;
-        case kEpiI24T: return (kern_t)fir_stream_kernel<U, T, 256, false, kEpiI24T>;
-        case kEpiI16T: return (kern_t)fir_stream_kernel<U, T, 256, false, kEpiI16T>;
-        case kEpiP24T: return (kern_t)fir_stream_kernel<U, T, 256, false, kEpiP24T>;
-        default: return (kern_t)fir_stream_kernel<U, T, 256, false, EPI_GENERIC>;
-    }
-}
-kern_t kernel_for(int U, int nt, bool multi, int epi) {
-    if (multi) return nt == 256 ? (kern_t)afp::fir_stream_kernel<1, 16, 256, true, afp::EPI_GENERIC>
-                                : (kern_t)afp::fir_stream_kernel<1, 16, 128, true, afp::EPI_GENERIC>;
+kern_t kernel_for(int U, int T, int nt, bool multi, int epi) {
     switch (U) {
-        case 1: return pick_kernel<1, 16>(nt, false, epi);
-        case 2: return pick_kernel<2, 8>(nt, false, epi);
-        case 3: return pick_kernel<3, 4>(nt, false, epi);
-        case 4: return pick_kernel<4, 4>(nt, false, epi);
+        case 1: return afp_kernel_u1(T, nt, multi, epi);
+        case 2: return afp_kernel_u2(T, nt, multi, epi);
+        case 3: return afp_kernel_u3(T, nt, multi, epi);
+        case 4: return afp_kernel_u4(T, nt, multi, epi);
     }
     return nullptr;
 }
-const int kAllEpi[] = {afp::EPI_GENERIC, kEpiF32, kEpiI24T, kEpiI16T, kEpiP24T};
+
+// Tile (= chunk) sizes compiled for each U, largest first.
+const int kTiles[5][3] = {{0, 0, 0}, {16, 0, 0}, {8, 0, 0}, {4, 0, 0}, {8, 4, 0}};
+
+// Chunk size T for a filter of n taps at up-sampling U (measured, bench/sweep_tiles.sh on B200): the
+// largest tile wins for U = 1 (16) and U = 2 (8) at every length tried (51..501 taps); for U = 4 the
+// 8-tile wins from 63 taps per phase up (fewer shared-memory / constant-bank words per FMA) and the
+// 4-tile below (less zero padding of a 13..26-tap phase, 80 registers -> a third resident CTA).
+// AFP_FORCE_T overrides (tuning experiments).
+int tile_for(int U, int n_taps) {
+    const int kq = (n_taps + U - 1) / U;
+    if (const char* f = std::getenv("AFP_FORCE_T")) {
+        const int t = std::atoi(f);
+        for (int i = 0; i < 3; ++i) if (kTiles[U][i] && kTiles[U][i] == t) return t;
+    }
+    if (U == 4) return kq <= 32 ? 4 : 8;
+    return kTiles[U][0];
+}
 
 }  // namespace
 
@@ -144,7 +140,7 @@ int build_stage(afp_ctx* c, Stage& s, int kind, int U, const double* taps, int n
     if (n < 1) return fail(c, AFP_ERR_INVALID, "filter needs at least one tap");
     for (long long i = 0; i < (long long)n * n_sub; ++i)
         if (!std::isfinite(taps[i])) return fail(c, AFP_ERR_INVALID, "non-finite filter tap");
-    const int T = tile_for(U);
+    const int T = tile_for(U, n);
     const int kq = (n + U - 1) / U;
     const int n_chunks = (kq + T - 1) / T;
     if ((long long)n_chunks * T * U * n_sub > afp::MAX_TAPS)
@@ -229,7 +225,7 @@ int launch_stage(afp_ctx* c, Stage& s, const StageIO& io, cudaStream_t stream) {
         // persistent grid: no more CTAs than fit on the device at once (items are dealt round-robin)
         int per_sm = 0;
         AFP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-            &per_sm, (const void*)kernel_for(s.U, g.nt, s.n_sub > 1, afp::EPI_GENERIC), g.nt, g.smem));
+            &per_sm, (const void*)kernel_for(s.U, s.T, g.nt, s.n_sub > 1, afp::EPI_GENERIC), g.nt, g.smem));
         if (per_sm < 1) return fail(c, AFP_ERR_INVALID, "kernel does not fit on an SM with this geometry");
         // ... and never fewer than min(resident, items): items are dealt CTA-first, so a small launch
         // spreads over all SMs instead of filling every group of a few CTAs
@@ -272,7 +268,8 @@ int launch_stage(afp_ctx* c, Stage& s, const StageIO& io, cudaStream_t stream) {
     std::memset(P.taps, 0, sizeof(P.taps));
     std::memcpy(P.taps, s.table.data(), s.table.size() * sizeof(float));
     const int epi = io.decim == 1 ? afp::epi_code(io.fmt, io.dither) : afp::EPI_GENERIC;
-    kern_t k = kernel_for(s.U, g.nt, s.n_sub > 1, epi);
+    kern_t k = kernel_for(s.U, s.T, g.nt, s.n_sub > 1, epi);
+    if (!k) return fail(c, AFP_ERR_INVALID, "no kernel for this stage shape");
     k<<<g.grid, g.nt, g.smem, stream>>>(P);
     AFP_CUDA(c, cudaGetLastError());
     c->launches += 1;
@@ -413,13 +410,15 @@ int afp_create(const afp_config* cfg, afp_ctx** out_ctx) {
     if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
     if (prop.major != 10) return fail(nullptr, AFP_ERR_INVALID, "this library is built for sm_100a (B200) only");
     for (int U = 1; U <= 4; ++U)
-        for (int nt = 128; nt <= 256; nt <<= 1)
-            for (int multi = 0; multi <= (U == 1 ? 1 : 0); ++multi)
-                for (int epi : kAllEpi) {
-                    e = cudaFuncSetAttribute((const void*)kernel_for(U, nt, multi != 0, epi),
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-                    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem)");
-                }
+        for (int ti = 0; ti < 3 && kTiles[U][ti]; ++ti)
+            for (int nt = 128; nt <= 256; nt <<= 1)
+                for (int multi = 0; multi <= 1; ++multi)
+                    for (int epi : kAllEpi) {
+                        kern_t k = kernel_for(U, kTiles[U][ti], nt, multi != 0, epi);
+                        if (!k) continue;
+                        e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+                        if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem)");
+                    }
     afp_ctx* c = new (std::nothrow) afp_ctx();
     if (!c) return fail(nullptr, AFP_ERR_NOMEM, "out of host memory");
     c->cfg = *cfg;
