@@ -33,6 +33,8 @@ import time
 # the CPU legs run one process per core; keep BLAS/OpenMP pools from oversubscribing them
 for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
     os.environ.setdefault(_v, "1")
+# stdout carries exactly one JSON line: keep NCCL's version / debug banner on stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import numpy as np  # noqa: E402
 
