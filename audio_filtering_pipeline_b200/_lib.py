@@ -39,7 +39,7 @@ class Config(C.Structure):
         ("upsample", C.c_int32), ("chain", C.c_int32), ("out_format", C.c_int32),
         ("dither", C.c_int32), ("eq_mode", C.c_int32), ("seed", C.c_uint64),
         ("first_stream_id", C.c_int32), ("decimate", C.c_int32), ("dither_bits", C.c_int32),
-        ("reserved", C.c_int32),
+        ("same_buffer_len", C.c_int32),
     ]
 
 

@@ -329,7 +329,10 @@ int ensure_tmp(afp_ctx* c) {
     }
     const bool stateless = c->cfg.eq_mode == AFP_EQ_STATELESS_SAME;
     if (eq_is_buffer_same(c)) {
-        const int hm = c->mainf.n_taps - 1;
+        // carried samples: N_main-1, or (fixed buffer) everything but the newest full-size block
+        const int hm = c->cfg.same_buffer_len > 0 ? c->cfg.same_buffer_len - (int)rate_len : c->mainf.n_taps - 1;
+        if (hm < c->mainf.n_taps - 1)
+            return fail(c, AFP_ERR_INVALID, "same_buffer_len is shorter than max_frames*rate + N_main - 1");
         if (c->xhist_len != hm) {
             for (int i = 0; i < 2; ++i) { if (c->xhist[i]) cudaFree(c->xhist[i]); c->xhist[i] = nullptr; }
             c->xhist_pitch = (hm + 3) / 4 * 4 + 4;
@@ -540,7 +543,9 @@ static int process_block_range(afp_ctx* c, const float* in, int64_t in_pitch, vo
         StageIO m;
         m.s0 = s0; m.ns = ns;
         m.src1 = tb; m.pitch1 = c->pitch_b; m.len1 = lb;
-        m.q_begin = hm; m.n_q = cur_len;
+        // 'valid' outputs start N-1 samples into the buffer; with the default buffer that is also the
+        // start of the new block, with a longer fixed buffer these are the oldest outputs (:450-453)
+        m.q_begin = c->mainf.n_taps - 1; m.n_q = cur_len;
         m.out = out; m.out_pitch = opitch; m.fmt = c->cfg.out_format; m.dither = c->cfg.dither; m.decim = c->decim;
         m.sample_base = c->out_samples;
         return launch_stage(c, c->mainf, m, st);
@@ -595,6 +600,8 @@ static int check_ready(afp_ctx* c, int32_t frames) {
     const int mode = c->cfg.eq_mode;
     if (mode != AFP_EQ_NONE && mode != AFP_EQ_STATELESS_SAME && !c->eq.active)
         return fail(c, AFP_ERR_STATE, "afp_set_eq has not been called");
+    if (eq_is_buffer_same(c) && c->cfg.same_buffer_len > 0 && frames != c->cfg.max_frames)
+        return fail(c, AFP_ERR_INVALID, "a fixed same_buffer_len needs frames == max_frames on every call");
     if (((long long)frames * c->cfg.upsample) % c->decim != 0)
         return fail(c, AFP_ERR_INVALID, "frames * upsample is not a multiple of the decimation factor");
     return AFP_OK;

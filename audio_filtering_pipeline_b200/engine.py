@@ -42,11 +42,13 @@ class BatchFirEngine:
                        and 'stateless_same' (stream_process_EQ_GUI.py:86-95, nothing carried).
     decimate           keep every n-th output sample (default: U for chain='reference', else 1)
     dither_bits        bit depth of the float-output dither (apply_dither's ``bit_depth``; default 24)
+    same_buffer_len    'buffer_same*' only: fixed sliding-buffer length; 4*blocksize+512 gives the
+                       Waterfall GUI's callback (stream_process_GUI_Waterfall.py:132,431-458)
     """
 
     def __init__(self, taps, n_streams=1, max_frames=1024, upsample=1, chain="dac", out_format="f32",
                  dither="none", seed=0, device=0, upsampler_taps=None, eq_bands=None, eq_gains=None,
-                 eq_mode="none", first_stream_id=0, decimate=0, dither_bits=0):
+                 eq_mode="none", first_stream_id=0, decimate=0, dither_bits=0, same_buffer_len=0):
         self._lib = _lib.load()
         self._ctx = C.c_void_p()
         if eq_bands is not None and eq_mode in ("none", None):
@@ -56,7 +58,7 @@ class BatchFirEngine:
                           out_format=_lib.FMT[out_format], dither=_lib.DITHER[dither],
                           eq_mode=_lib.EQ_MODE[eq_mode], seed=int(seed) & (2 ** 64 - 1),
                           first_stream_id=int(first_stream_id), decimate=int(decimate),
-                          dither_bits=int(dither_bits), reserved=0)
+                          dither_bits=int(dither_bits), same_buffer_len=int(same_buffer_len))
         _lib.check(self._lib.afp_create(C.byref(cfg), C.byref(self._ctx)))
         self.cfg = cfg
         self.n_streams, self.max_frames, self.upsample = int(n_streams), int(max_frames), int(upsample)

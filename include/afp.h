@@ -80,7 +80,10 @@ typedef struct afp_config {
     int32_t decimate;         /* keep every decimate-th output sample; 0 = default (U for AFP_CHAIN_REFERENCE,
                                  1 for AFP_CHAIN_DAC); frames*rate must be a multiple of it */
     int32_t dither_bits;      /* bit depth of the float-output dither (apply_dither's bit_depth); 0 = 24 */
-    int32_t reserved;
+    int32_t same_buffer_len;  /* AFP_EQ_BUFFER_SAME*: total length of the sliding buffer in processing-rate
+                                 samples.  0 = N_main-1 + block (stream_process_EQ.py:44-45); the Waterfall GUI
+                                 uses a fixed 4*blocksize+512 and reads the OLDEST valid outputs
+                                 (stream_process_GUI_Waterfall.py:132,450-453) - a constant extra latency */
 } afp_config;
 
 typedef struct afp_stage_info {

@@ -58,6 +58,31 @@ def test_eq_buffer_same_batched_streams_and_state():
         np.testing.assert_array_equal(np.concatenate([y1, y2], axis=1), y)
 
 
+@pytest.mark.parametrize("mode", ["buffer_same_per_band", "buffer_same"])
+def test_waterfall_fixed_buffer_callback(mode):
+    """stream_process_GUI_Waterfall callback (golden): fixed 4*B+512 sliding buffer, per-band 'same',
+    'valid' main FIR, the OLDEST frames are read out (:132,431-458)."""
+    g = load_golden("cb_waterfall_9band")
+    N, B, U, fs = (int(v) for v in g["params"])
+    assert U == 1
+    nblk = g["pre_dither"].shape[0]
+    x = g["x"][: nblk * B].reshape(1, -1)
+    with BatchFirEngine(g["taps"], n_streams=1, max_frames=B, eq_bands=list(g["eq_taps"]),
+                        eq_gains=list(g["eq_gains"]), eq_mode=mode, same_buffer_len=4 * B + 512) as eng:
+        y = run_host(eng, x, B)
+    assert_parity(y[0], g["pre_dither"].reshape(-1).astype(np.float32), f"waterfall {mode}")
+    # cross-check with the oracle class on other data, 3 streams
+    rng = np.random.default_rng(11)
+    xs = (0.1 * rng.standard_normal((3, 5 * B))).astype(np.float32)
+    with BatchFirEngine(g["taps"], n_streams=3, max_frames=B, eq_bands=list(g["eq_taps"]),
+                        eq_gains=list(g["eq_gains"]), eq_mode=mode, same_buffer_len=4 * B + 512) as eng:
+        ys = run_host(eng, xs, B)
+    for s in range(3):
+        orc = rc.WaterfallBlockEq(g["taps"], g["eq_taps"], g["eq_gains"], B, 1)
+        ref = np.concatenate([orc.step(xs[s, i * B:(i + 1) * B], B) for i in range(5)])
+        assert_parity(ys[s], ref.astype(np.float32), f"waterfall oracle stream {s}")
+
+
 def test_stateless_same_matches_eq_gui_worker():
     """stream_process_EQ_GUI.process_audio (golden): fused EQ 'same' + main 'same', per block."""
     g = load_golden("eqgui_worker_stateless")
