@@ -46,7 +46,7 @@ class Config(C.Structure):
 class StageInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "kind", "upsample", "n_taps", "taps_per_phase_padded", "tile_taps", "threads",
-        "threads_per_segment", "smem_bytes", "grid", "history")]
+        "threads_per_segment", "smem_bytes", "grid", "history", "kernel")]
 
 
 _lib = None

@@ -210,18 +210,17 @@ constexpr int EPI_GENERIC = -1;
 __host__ __device__ constexpr int epi_code(int fmt, int dither) { return fmt * 4 + dither; }
 
 // y[NOUT]: consecutive output samples o_base .. o_base+NOUT-1 (pre-decimation) of one stream row.
-template <int NOUT, int EPI>
-__device__ __forceinline__ void store_row(const FirParams& P_, float (&y)[NOUT], int stream, long long o_base, int n_valid) {
+template <int NOUT, int EPI, class PT>
+__device__ __forceinline__ void store_row(const PT& P_, float (&y)[NOUT], int stream, long long o_base, int n_valid) {
     if (n_valid <= 0) return;
-    struct View {   // same field names as FirParams, fmt / dither / decim possibly compile-time
-        const FirParams& p;
+    struct View {   // the epilogue fields of FirParams / TcParams, fmt / dither / decim possibly compile-time
         int fmt, dither, decim;
         float gain, dither_lsb;
         void* out; long long out_pitch;
         unsigned long long seed, sample_base;
         int stream_id0, fast_out;
     };
-    const View P = {P_, EPI >= 0 ? (EPI >> 2) : P_.fmt, EPI >= 0 ? (EPI & 3) : P_.dither, EPI >= 0 ? 1 : P_.decim,
+    const View P = {EPI >= 0 ? (EPI >> 2) : P_.fmt, EPI >= 0 ? (EPI & 3) : P_.dither, EPI >= 0 ? 1 : P_.decim,
                     P_.gain, P_.dither_lsb, P_.out, P_.out_pitch, P_.seed, P_.sample_base, P_.stream_id0, P_.fast_out};
     if (P.gain != 1.0f) {
 #pragma unroll

@@ -97,6 +97,8 @@ typedef struct afp_stage_info {
     int32_t smem_bytes;
     int32_t grid;
     int32_t history;          /* carried samples per stream */
+    int32_t kernel;           /* kernel of the last launch: 0 = packed-FFMA2 direct form, 1 = tcgen05 / TMEM
+                                 Toeplitz 3xTF32 (long single-table U = 1 filters, 256/512/1024-frame blocks) */
 } afp_stage_info;
 
 const char* afp_version(void);

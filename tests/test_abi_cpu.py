@@ -28,7 +28,7 @@ def test_header_and_binding_agree(lib):
 def test_struct_layout_matches_header():
     assert C.sizeof(_lib.Config) == 56          # 8 x int32, uint64, 4 x int32 (the last: same_buffer_len)
     assert _lib.Config.seed.offset == 32
-    assert C.sizeof(_lib.StageInfo) == 40
+    assert C.sizeof(_lib.StageInfo) == 44
 
 
 def test_version_string(lib):
