@@ -50,8 +50,8 @@ struct Stage {
     Geometry geo;
     // tensor-core (tcgen05 / TMEM, 3xTF32) path for long single-table U = 1 filters: Toeplitz tap
     // tiles on the device; which kernel ran last (0 = FFMA2, 1 = tcgen05)
-    float* tc_w = nullptr;
-    int tc_chunks = 0;
+    float* tc_w[2] = {nullptr, nullptr};   // tap tiles for row length 32 and 64
+    int tc_chunks[2] = {0, 0};
     int last_kernel = 0;
 };
 
@@ -136,8 +136,7 @@ int rate_of(const afp_ctx* c) {   // processing rate / base rate
 
 void free_stage(Stage& s) {
     for (int i = 0; i < 2; ++i) { if (s.hist[i]) cudaFree(s.hist[i]); s.hist[i] = nullptr; }
-    if (s.tc_w) { cudaFree(s.tc_w); s.tc_w = nullptr; }
-    s.tc_chunks = 0;
+    for (int i = 0; i < 2; ++i) { if (s.tc_w[i]) cudaFree(s.tc_w[i]); s.tc_w[i] = nullptr; s.tc_chunks[i] = 0; }
     s.active = false;
 }
 
@@ -155,7 +154,7 @@ int build_stage(afp_ctx* c, Stage& s, int kind, int U, const double* taps, int n
     // kernel's row length), so a stage may switch kernel from one block to the next.
     const int tc_min = std::getenv("AFP_TC_MIN_TAPS") ? std::atoi(std::getenv("AFP_TC_MIN_TAPS")) : 640;
     const bool tc_ok = U == 1 && n_sub == 1 && n >= tc_min && !std::getenv("AFP_NO_TC");
-    const int n_chunks = tc_ok ? ((kq + 31) / 32) * (32 / T) : (kq + T - 1) / T;
+    const int n_chunks = tc_ok ? ((kq + 63) / 64) * (64 / T) : (kq + T - 1) / T;
     if ((long long)n_chunks * T * U * n_sub > afp::MAX_TAPS)
         return fail(c, AFP_ERR_INVALID, "filter (x bands) too long for the per-launch tap table (max 6144 padded taps)");
     const bool same_shape = s.active && s.kind == kind && s.U == U && s.n_chunks == n_chunks;
@@ -175,31 +174,34 @@ int build_stage(afp_ctx* c, Stage& s, int kind, int U, const double* taps, int n
     s.table.assign((size_t)s.kq_pad * U * n_sub, 0.f);
     for (int b = 0; b < n_sub; ++b)
         for (int i = 0; i < n; ++i) s.table[(size_t)b * s.kq_pad * U + i] = (float)taps[(size_t)b * n + i];
-    if (s.tc_w) { cudaFree(s.tc_w); s.tc_w = nullptr; }
-    s.tc_chunks = 0;
+    for (int i = 0; i < 2; ++i) { if (s.tc_w[i]) cudaFree(s.tc_w[i]); s.tc_w[i] = nullptr; s.tc_chunks[i] = 0; }
     if (tc_ok) {
-        // W slices: chunk d, k-step ks, column chunk cc, row (0..31: hi, j = row; 32..63: lo, j = row-32),
-        // 4 floats:  W[j][i] = h[32 d + j - i],  i = 8 ks + 4 cc + e;  hi = 13 low mantissa bits cleared
-        constexpr int R = afp::TC_ROW;
-        const int nc = (n + R - 2) / R + 1;
-        std::vector<float> w((size_t)nc * afp::TC_W_FLOATS, 0.f);
-        for (int d = 0; d < nc; ++d)
-            for (int ks = 0; ks < afp::TC_KSTEPS; ++ks)
-                for (int cc = 0; cc < 2; ++cc)
-                    for (int j = 0; j < R; ++j)
-                        for (int e = 0; e < 4; ++e) {
-                            const int k = R * d + j - (8 * ks + 4 * cc + e);
-                            if (k < 0 || k >= n) continue;
-                            const float hv = (float)taps[k];
-                            uint32_t u; std::memcpy(&u, &hv, 4); u &= 0xFFFFE000u;
-                            float hi; std::memcpy(&hi, &u, 4);
-                            const size_t base = (size_t)d * afp::TC_W_FLOATS + (size_t)ks * afp::TC_W_SLICE + (size_t)cc * (2 * R * 4);
-                            w[base + (size_t)j * 4 + e] = hi;
-                            w[base + (size_t)(R + j) * 4 + e] = hv - hi;
-                        }
-        AFP_CUDA(c, cudaMalloc(&s.tc_w, w.size() * sizeof(float)));
-        AFP_CUDA(c, cudaMemcpy(s.tc_w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
-        s.tc_chunks = nc;
+        // W slices for both row lengths R: chunk d, k-step ks, column chunk cc, row (0..R-1: hi, j = row;
+        // R..2R-1: lo, j = row-R), 4 floats:  W[j][i] = h[R d + j - i],  i = 8 ks + 4 cc + e;
+        // hi = the value with its 13 low mantissa bits cleared, lo = value - hi
+        for (int v = 0; v < 2; ++v) {
+            const int R = v == 0 ? 32 : 64;
+            const int ksteps = R / 8, w_slice = 2 * 2 * R * 4, w_floats = ksteps * w_slice;
+            const int nc = (n + R - 2) / R + 1;
+            std::vector<float> w((size_t)nc * w_floats, 0.f);
+            for (int d = 0; d < nc; ++d)
+                for (int ks = 0; ks < ksteps; ++ks)
+                    for (int cc = 0; cc < 2; ++cc)
+                        for (int j = 0; j < R; ++j)
+                            for (int e = 0; e < 4; ++e) {
+                                const int k = R * d + j - (8 * ks + 4 * cc + e);
+                                if (k < 0 || k >= n) continue;
+                                const float hv = (float)taps[k];
+                                uint32_t u; std::memcpy(&u, &hv, 4); u &= 0xFFFFE000u;
+                                float hi; std::memcpy(&hi, &u, 4);
+                                const size_t base = (size_t)d * w_floats + (size_t)ks * w_slice + (size_t)cc * (2 * R * 4);
+                                w[base + (size_t)j * 4 + e] = hi;
+                                w[base + (size_t)(R + j) * 4 + e] = hv - hi;
+                            }
+            AFP_CUDA(c, cudaMalloc(&s.tc_w[v], w.size() * sizeof(float)));
+            AFP_CUDA(c, cudaMemcpy(s.tc_w[v], w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+            s.tc_chunks[v] = nc;
+        }
     }
     s.active = true;
     return AFP_OK;
@@ -260,42 +262,48 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 // AFP_OK and sets *done when the block shape qualifies; otherwise leaves *done false.
 int launch_stage_tc(afp_ctx* c, Stage& s, const StageIO& io, cudaStream_t stream, bool* done) {
     *done = false;
-    constexpr int R = afp::TC_ROW;
-    if (!s.tc_w || io.decim != 1 || s.U != 1) return AFP_OK;
+    if (!s.tc_w[0] || io.decim != 1 || s.U != 1) return AFP_OK;
     const int frames = io.len1;
     if (io.len0 != s.kq_pad || io.q_begin != io.len0 || io.n_q != frames || !io.hist_out ||
         io.hist_len != s.kq_pad || io.hist_from != frames || io.pitch0 != s.kq_pad || io.hist_pitch != s.kq_pad) return AFP_OK;
-    if (frames % (8 * R) != 0) return AFP_OK;
-    const int nts = frames / (8 * R);
-    if (nts != 1 && nts != 2 && nts != 4) return AFP_OK;
     if (!aligned16(io.src0) || !aligned16(io.src1) || !aligned16(io.hist_out) || io.pitch1 % 4 != 0) return AFP_OK;
-    const int hist_rows = s.kq_pad / R, rows = hist_rows + frames / R;
-    const int data_bytes = 2 * afp::TC_STREAMS * rows * R * 4;
-    int slots = (kMaxSmem - data_bytes - 512) / (afp::TC_W_FLOATS * 4);
-    if (slots < 2) return AFP_OK;
-    if (slots > 8) slots = 8;
     const int epi = afp::epi_code(io.fmt, io.dither);
-    afp::tc_kern_t k = afp_kernel_tc(nts, epi);
-    if (!k) return AFP_OK;
-    afp::TcParams P{};
-    P.hist_in = io.src0; P.in = io.src1; P.in_pitch = io.pitch1; P.hist_out = io.hist_out;
-    P.out = io.out; P.out_pitch = io.out_pitch; P.w = s.tc_w;
-    P.n_streams = io.ns; P.frames = frames; P.hist_rows = hist_rows; P.n_chunks = s.tc_chunks;
-    P.n_items = (io.ns + afp::TC_STREAMS - 1) / afp::TC_STREAMS;
-    P.idesc_override = 0; P.w_slots = slots;
-    P.fmt = io.fmt; P.dither = io.dither; P.decim = 1;
-    const int eb = io.fmt == AFP_FMT_I16 ? 2 : (io.fmt == AFP_FMT_I24_PACKED ? 3 : 4);
-    P.fast_out = (aligned16(io.out) && (io.out_pitch * eb) % 16 == 0) ? 1 : 0;
-    P.seed = c->cfg.seed; P.sample_base = io.sample_base; P.stream_id0 = c->cfg.first_stream_id + io.s0;
-    P.gain = 1.0f; P.dither_lsb = std::ldexp(1.0f, -(c->dither_bits - 1));
-    const int smem = data_bytes + slots * afp::TC_W_FLOATS * 4 + 512;
-    const int grid = P.n_items < c->n_sm ? P.n_items : c->n_sm;
-    k<<<grid, afp::TC_THREADS, smem, stream>>>(P);
-    AFP_CUDA(c, cudaGetLastError());
-    c->launches += 1;
-    s.last_kernel = 1;
-    s.geo.nt = afp::TC_THREADS; s.geo.tg_log2 = 4; s.geo.smem = smem; s.geo.grid = grid; s.geo.key_nq = -1;
-    *done = true;
+    // row length 64 first (fewer, larger MMAs), then 32; each needs whole 8-row groups and room in
+    // shared memory for the 16-stream hi/lo tiles plus at least two 8 KB ring slots
+    for (int v = 1; v >= 0; --v) {
+        const int R = v == 0 ? 32 : 64;
+        if (std::getenv("AFP_TC_ROW") && std::atoi(std::getenv("AFP_TC_ROW")) != R) continue;   // tuning experiments
+        if (frames % (8 * R) != 0) continue;
+        const int nts = frames / (8 * R);
+        afp::tc_kern_t k = afp_kernel_tc(R, nts, epi);
+        if (!k) continue;
+        const int hist_rows = s.kq_pad / R, rows = hist_rows + frames / R;
+        const int data_bytes = 2 * afp::TC_STREAMS * rows * R * 4;
+        const int slot_bytes = 8192;
+        int slots = (kMaxSmem - data_bytes - 512) / slot_bytes;
+        if (slots < 2) continue;
+        if (slots > 8) slots = 8;
+        afp::TcParams P{};
+        P.hist_in = io.src0; P.in = io.src1; P.in_pitch = io.pitch1; P.hist_out = io.hist_out;
+        P.out = io.out; P.out_pitch = io.out_pitch; P.w = s.tc_w[v];
+        P.n_streams = io.ns; P.frames = frames; P.hist_rows = hist_rows; P.n_chunks = s.tc_chunks[v];
+        P.n_items = (io.ns + afp::TC_STREAMS - 1) / afp::TC_STREAMS;
+        P.idesc_override = 0; P.w_slots = slots;
+        P.fmt = io.fmt; P.dither = io.dither; P.decim = 1;
+        const int eb = io.fmt == AFP_FMT_I16 ? 2 : (io.fmt == AFP_FMT_I24_PACKED ? 3 : 4);
+        P.fast_out = (aligned16(io.out) && (io.out_pitch * eb) % 16 == 0) ? 1 : 0;
+        P.seed = c->cfg.seed; P.sample_base = io.sample_base; P.stream_id0 = c->cfg.first_stream_id + io.s0;
+        P.gain = 1.0f; P.dither_lsb = std::ldexp(1.0f, -(c->dither_bits - 1));
+        const int smem = data_bytes + slots * slot_bytes + 512;
+        const int grid = P.n_items < c->n_sm ? P.n_items : c->n_sm;
+        k<<<grid, afp::TC_THREADS, smem, stream>>>(P);
+        AFP_CUDA(c, cudaGetLastError());
+        c->launches += 1;
+        s.last_kernel = 1;
+        s.geo.nt = afp::TC_THREADS; s.geo.tg_log2 = 4; s.geo.smem = smem; s.geo.grid = grid; s.geo.key_nq = -1;
+        *done = true;
+        return AFP_OK;
+    }
     return AFP_OK;
 }
 
@@ -510,11 +518,14 @@ int afp_create(const afp_config* cfg, afp_ctx** out_ctx) {
                         e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
                         if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem)");
                     }
-    for (int nts : {1, 2, 4})
-        for (int epi : kAllEpi) {
-            e = cudaFuncSetAttribute((const void*)afp_kernel_tc(nts, epi), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-            if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, tensor path)");
-        }
+    for (int row : {32, 64})
+        for (int nts : {1, 2, 4})
+            for (int epi : kAllEpi) {
+                afp::tc_kern_t k = afp_kernel_tc(row, nts, epi);
+                if (!k) continue;
+                e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+                if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, tensor path)");
+            }
     afp_ctx* c = new (std::nothrow) afp_ctx();
     if (!c) return fail(nullptr, AFP_ERR_NOMEM, "out of host memory");
     c->cfg = *cfg;

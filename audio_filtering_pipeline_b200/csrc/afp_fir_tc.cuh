@@ -33,15 +33,24 @@
 
 namespace afp {
 
-#ifndef AFP_TC_ROW
-#define AFP_TC_ROW 32
-#endif
-constexpr int TC_ROW = AFP_TC_ROW;         // samples per row = outputs per accumulator row = K per chunk (32 or 64)
 constexpr int TC_STREAMS = 16;             // streams per work item (16 core groups of 8 rows = M 128)
 constexpr int TC_THREADS = 256;
-constexpr int TC_KSTEPS = TC_ROW / 8;      // K = 8 per tf32 MMA
-constexpr int TC_W_SLICE = 2 * 2 * TC_ROW * 4;     // floats per K-slice of taps: 2 column chunks x (64 hi + 64 lo rows) x 4
-constexpr int TC_W_FLOATS = TC_KSTEPS * TC_W_SLICE;   // one chunk d of taps = one ring slot (8 KB at R = 32)
+
+// Row length R (samples per row = outputs per accumulator row = K per chunk).  R = 64 halves the number
+// of MMAs (they are bound by operand fetch, ~64 B/clk measured, and by a per-instruction cost) but
+// needs blocks of 512 frames; R = 32 also takes 256-frame blocks.
+template <int R>
+struct TcCfg {
+    static constexpr int ROW = R;
+    static constexpr int KSTEPS = R / 8;                    // K = 8 per tf32 MMA
+    static constexpr int W_SLICE = 2 * 2 * R * 4;           // floats per K = 8 slice of taps: 2 column chunks x (R hi + R lo rows) x 4
+    static constexpr int W_FLOATS = KSTEPS * W_SLICE;       // one chunk d of taps (8 KB at R = 32, 32 KB at R = 64)
+    static constexpr int KPS = R == 32 ? 4 : 2;             // k-steps per ring slot (8 KB slots)
+    static constexpr int UPC = KSTEPS / KPS;                // ring units per chunk
+    static constexpr int SLOT_FLOATS = KPS * W_SLICE;
+    static constexpr int W_LBO = 2 * R * 16;                // W slice: 2R rows (R hi, R lo) per column chunk
+    static constexpr int W_SBO = 8 * 16;
+};
 
 struct TcParams {
     const float* hist_in;      // [n_streams][hist_rows*32]  carried samples (oldest first)
@@ -57,7 +66,7 @@ struct TcParams {
     int n_chunks;              // D + 1
     int n_items;               // ceil(n_streams / 16)
     unsigned idesc_override;   // timing experiments only (0 = the real instruction descriptor)
-    int w_slots;               // depth of the W ring in shared memory (2..8): hides the L2 latency of the tap tiles
+    int w_slots;               // depth of the W ring in shared memory (2, 4 or 8): hides the L2 latency of the tap tiles
     // epilogue (same meaning as FirParams)
     int fmt, dither, decim, fast_out;      // decim is always 1 here
     unsigned long long seed, sample_base;
@@ -128,12 +137,14 @@ __host__ __device__ constexpr uint32_t tc_idesc(int n) { return (1u << 4) | (2u 
 // byte offset of float (row r, column i) in a K-major core-matrix tile of `rows_padded` rows:
 // [column chunk i/4][row][4 floats]
 __host__ __device__ constexpr int tile_off(int r, int i, int rows_padded) { return (i >> 2) * rows_padded * 16 + r * 16 + ((i & 3) << 2); }
-constexpr int TC_W_LBO = 2 * TC_ROW * 16;  // W slice: 128 rows (64 hi, 64 lo) per column chunk
-constexpr int TC_W_SBO = 8 * 16;
 
-template <int EPI, int NTS>   // NTS = frames / (8 * TC_ROW): 8-row groups per stream and block
+template <int EPI, int NTS, int R>   // R = row length, NTS = frames / (8 R): 8-row groups per stream and block
 __global__ void __launch_bounds__(TC_THREADS, 1)
 fir_tc_kernel(const __grid_constant__ TcParams P) {
+    using Cfg = TcCfg<R>;
+    constexpr int TC_ROW = R, TC_KSTEPS = Cfg::KSTEPS, TC_W_SLICE = Cfg::W_SLICE, TC_W_FLOATS = Cfg::W_FLOATS;
+    constexpr int TC_KPS = Cfg::KPS, TC_UPC = Cfg::UPC, TC_SLOT_FLOATS = Cfg::SLOT_FLOATS, TC_W_LBO = Cfg::W_LBO, TC_W_SBO = Cfg::W_SBO;
+    (void)TC_KSTEPS; (void)TC_W_FLOATS;
     extern __shared__ __align__(128) unsigned char tc_smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int block_rows = P.frames / TC_ROW;                 // rows of the new block per stream
@@ -142,13 +153,14 @@ fir_tc_kernel(const __grid_constant__ TcParams P) {
     const int a_lbo = rows_p * 16;                            // bytes between column chunks of one stream
     const int pitch = (TC_ROW / 4) * a_lbo;                   // bytes per stream tile
     constexpr int n_t = NTS;                                  // 8-row groups per stream = accumulator sets
+    constexpr int N_ROLES = NTS == 1 ? 2 : 4;                 // MMA-issuing warps (warps 1..N_ROLES)
 
     // shared memory carve-up: data hi | data lo | W ring (2 x 8 KB) | barriers | tmem ptr
     unsigned char* data_hi = tc_smem;
     unsigned char* data_lo = data_hi + TC_STREAMS * pitch;
     unsigned char* wring = data_lo + TC_STREAMS * pitch;
     const int NS = P.w_slots;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(wring + NS * TC_W_FLOATS * 4);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wring + NS * TC_SLOT_FLOATS * 4);
     uint64_t* w_full = bars;          // [NS]
     uint64_t* w_empty = bars + 16;    // [NS]
     uint64_t* acc_full = bars + 32;   // [1]
@@ -161,8 +173,8 @@ fir_tc_kernel(const __grid_constant__ TcParams P) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 32) {
-        for (int i = 0; i < NS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-        mbar_init(acc_full, 1);
+        for (int i = 0; i < NS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], N_ROLES); }
+        mbar_init(acc_full, N_ROLES);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -226,57 +238,64 @@ fir_tc_kernel(const __grid_constant__ TcParams P) {
         // ---- phase 2: W producer (warp 0) and MMA issuer (warp 1); whole warps run the loops, one
         // elected lane issues, so every operand stays warp-uniform (uniform registers, no waterfall)
         if (warp_u == 0) {
-            for (int d = 0; d < P.n_chunks; ++d, ++w_prod) {
-                const int slot = w_prod % NS;
-                if (w_prod >= (uint32_t)NS) mbar_wait(&w_empty[slot], ((w_prod / NS) - 1) & 1);
+            uint32_t slot = w_prod % NS, round = w_prod / NS;   // (one division per item; NS need not be a power of two)
+            for (int u = 0; u < P.n_chunks * TC_UPC; ++u) {
+                if (round > 0) mbar_wait(&w_empty[slot], (round - 1) & 1);
                 if (elect_one()) {
-                    mbar_expect_tx(&w_full[slot], TC_W_FLOATS * 4);
-                    bulk_g2s(wring + slot * TC_W_FLOATS * 4, P.w + (size_t)d * TC_W_FLOATS, TC_W_FLOATS * 4, &w_full[slot]);
+                    mbar_expect_tx(&w_full[slot], TC_SLOT_FLOATS * 4);
+                    bulk_g2s(wring + slot * TC_SLOT_FLOATS * 4, P.w + (size_t)u * TC_SLOT_FLOATS, TC_SLOT_FLOATS * 4, &w_full[slot]);
                 }
                 __syncwarp();
+                if (++slot == (uint32_t)NS) { slot = 0; ++round; }
             }
-        } else if (warp_u == 1) {
+        } else if (warp_u >= 1 && warp_u <= N_ROLES) {
+            // MMA issuers.  The MMAs are small (128 x 64 x 8 and 128 x 32 x 8) and a single issuing warp
+            // spends ~90 clk per MMA on uniform-datapath bookkeeping (ncu: tensor pipe 2.5 % active with one
+            // issuer), so the accumulators are split over N_ROLES warps that issue independently: role =
+            // (row-group set, product family).  Each role commits its own MMAs to the slot's "empty"
+            // barrier and to acc_full (both initialised with N_ROLES arrivals).
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // The MMAs here are small (128 x 64 x 8), so the ISSUE path has to be as short as the tensor
-            // time: descriptors are affine in (chunk, set, k-step) - the start-address field counts
-            // 16-byte units and one row is one unit, so moving the A operand up a row is "low word - 1" -
-            // and everything but the per-chunk base is hoisted out of the loop.
+            const int role = warp_u - 1;
+            // Descriptors are affine in (chunk, set, k-step) - the start-address field counts 16-byte
+            // units and one row is one unit, so moving the A operand up a row is "low word - 1".
             const uint64_t a_hi_d = umma_desc(smem_u32(data_hi), a_lbo, pitch), a_lo_d = umma_desc(smem_u32(data_lo), a_lbo, pitch);
             const uint64_t w_d = umma_desc(smem_u32(wring), TC_W_LBO, TC_W_SBO);
             const uint32_t dhi_a = (uint32_t)(a_hi_d >> 32), dhi_w = (uint32_t)(w_d >> 32);   // same high word for hi / lo tiles
             const uint32_t a_k = (2u * a_lbo) >> 4;           // K = 8 = two column chunks
-            uint32_t a_off[NTS][TC_KSTEPS];                   // (set, k-step) offsets of the A start address
-#pragma unroll
-            for (int t = 0; t < NTS; ++t)
-#pragma unroll
-                for (int k = 0; k < TC_KSTEPS; ++k) a_off[t][k] = (uint32_t)(P.hist_rows + 8 * t) + k * a_k;
             const uint32_t id_wide = P.idesc_override ? P.idesc_override : tc_idesc(2 * TC_ROW), id_narrow = tc_idesc(TC_ROW);
-            for (int d = 0; d < P.n_chunks; ++d, ++w_cons) {
-                const int slot = w_cons % NS;
-                mbar_wait(&w_full[slot], (w_cons / NS) & 1);
+            // what this role issues per k-step: sets [t_lo, t_hi), wide and / or narrow product
+            const int t_lo = NTS == 1 ? 0 : (NTS == 2 ? role >> 1 : role), t_hi = t_lo + 1;
+            const bool do_wide = NTS == 4 ? true : (role & 1) == 0, do_narrow = NTS == 4 ? true : (role & 1) == 1;
+            uint32_t slot = w_cons % NS, phase = (w_cons / NS) & 1;
+            for (int u = 0; u < P.n_chunks * TC_UPC; ++u) {
+                const int d = u / TC_UPC, k0 = (u % TC_UPC) * TC_KPS;    // chunk and first k-step of this ring unit
+                mbar_wait(&w_full[slot], phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
-                    const uint32_t ah = (uint32_t)a_hi_d - (uint32_t)d, al = (uint32_t)a_lo_d - (uint32_t)d;
-                    const uint32_t wl = (uint32_t)w_d + (uint32_t)((slot * TC_W_FLOATS * 4) >> 4);
-                    const uint32_t fl = d == 0 ? 0u : 1u;      // first write of the accumulators
+                    const uint32_t ah = (uint32_t)a_hi_d + (uint32_t)P.hist_rows - (uint32_t)d + k0 * a_k;
+                    const uint32_t al = (uint32_t)a_lo_d + (uint32_t)P.hist_rows - (uint32_t)d + k0 * a_k;
+                    const uint32_t wl = (uint32_t)w_d + ((slot * (uint32_t)(TC_SLOT_FLOATS * 4)) >> 4);
+                    const uint32_t fl = u == 0 ? 0u : 1u;      // first write of the accumulators
+                    for (int t = t_lo; t < t_hi; ++t) {
+                        const uint32_t acc = tmem_base + (uint32_t)(t * 3 * TC_ROW);
 #pragma unroll
-                    for (int k = 0; k < TC_KSTEPS; ++k)
-#pragma unroll
-                        for (int t = 0; t < NTS; ++t) {
-                            const uint32_t acc = tmem_base + (uint32_t)(t * 3 * TC_ROW);
+                        for (int k = 0; k < TC_KPS; ++k) {
                             const uint32_t wk = wl + (uint32_t)((k * TC_W_SLICE * 4) >> 4);
+                            const uint32_t off = (uint32_t)(8 * t) + k * a_k;
                             const uint32_t f = k == 0 ? fl : 1u;
-                            umma_tf32(acc, ah + a_off[t][k], dhi_a, wk, dhi_w, id_wide, f);                  // x_hi * [W_hi | W_lo]
-                            umma_tf32(acc + 2 * TC_ROW, al + a_off[t][k], dhi_a, wk, dhi_w, id_narrow, f);   // x_lo * W_hi
+                            if (do_wide) umma_tf32(acc, ah + off, dhi_a, wk, dhi_w, id_wide, f);                    // x_hi * [W_hi | W_lo]
+                            if (do_narrow) umma_tf32(acc + 2 * TC_ROW, al + off, dhi_a, wk, dhi_w, id_narrow, f);   // x_lo * W_hi
                         }
-                    umma_commit(&w_empty[slot]);              // the MMAs that read this W slot are done -> slot free
+                    }
+                    umma_commit(&w_empty[slot]);              // this role's MMAs on the slot are done
                 }
                 __syncwarp();
+                if (++slot == (uint32_t)NS) { slot = 0; phase ^= 1; }
             }
-            if (elect_one()) umma_commit(acc_full);           // all MMAs of the item done -> accumulators readable
+            if (elect_one()) umma_commit(acc_full);           // this role's accumulators are final
             __syncwarp();
-        } else if (warp_u == 2) {
-            // the other warps idle through the MMA phase: pull the next item's rows into L2 meanwhile
+        } else if (warp_u == N_ROLES + 1) {
+            // a warp that idles through the MMA phase: pull the next item's rows into L2 meanwhile
             const int nitem = item + gridDim.x;
             if (nitem < P.n_items && lane < TC_STREAMS) {
                 const int s = nitem * TC_STREAMS + lane;
@@ -286,6 +305,8 @@ fir_tc_kernel(const __grid_constant__ TcParams P) {
                 }
             }
         }
+        w_cons += P.n_chunks * TC_UPC;                        // ring position after this item (same in every thread)
+        w_prod = w_cons;
         // ---- phase 3: accumulators -> registers -> dither / quantise -> HBM
         mbar_wait(acc_full, acc_phase & 1);
         acc_phase++;

@@ -35,7 +35,7 @@ kern_t pick_kernel(int nt, bool multi, int epi) {
 }  // namespace afp
 
 namespace afp { struct TcParams; typedef void (*tc_kern_t)(const TcParams); }
-afp::tc_kern_t afp_kernel_tc(int nts, int epi);   // tensor-core path, nts = frames / 256 in {1, 2, 4}
+afp::tc_kern_t afp_kernel_tc(int row, int nts, int epi);   // tensor-core path: row length 32 / 64, nts = frames / (8 row)
 afp::kern_t afp_kernel_u1(int T, int nt, bool multi, int epi);
 afp::kern_t afp_kernel_u2(int T, int nt, bool multi, int epi);
 afp::kern_t afp_kernel_u3(int T, int nt, bool multi, int epi);

@@ -271,6 +271,22 @@ def run_ours(args):
             traffic = json.load(open(prof)).get("c2_dram_bytes_per_launch")
         except Exception:
             traffic = None
+    info = eng.stage_info()[-1]
+    tensor = None
+    if info.get("kernel") == 1:
+        # tcgen05 path: MMA work actually issued per launch (3xTF32: x_hi*[W_hi|W_lo] as one N=128 MMA +
+        # x_lo*W_hi as one N=64 MMA per K=8 step, 64-sample Toeplitz chunks), against the nominal dense TF32 peak
+        R = 64
+        n_chunks = (N_TAPS + R - 2) // R + 1
+        items = (S + 15) // 16
+        mma_flops = 2.0 * items * n_chunks * (R // 8) * (FRAMES // (8 * R)) * (128 * 2 * R * 8 + 128 * R * 8)
+        tensor = {"kind": "tcgen05.mma kind::tf32, FP32 accumulators in TMEM, 3xTF32 split",
+                  "issued_tflops": round(mma_flops / (ms_launch * 1e-3) / 1e12, 1), "nominal_tf32_dense_peak_tflops": 1125.0,
+                  "note": "roofline.frac stays relative to the FP32-FMA roof of the north star (2N flop per sample); "
+                          "it can exceed 1 because the work runs on the tensor pipe"}
+        kernel_name = "afp::fir_tc_kernel<EPI_I24_TPDF, 1, 64> (tcgen05 / TMEM Toeplitz FIR)"
+    else:
+        kernel_name = "afp::fir_stream_kernel<1,16,256> (packed FFMA2)"
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -282,8 +298,9 @@ def run_ours(args):
         "unit": "TFLOP/s", "frac": round(achieved_tf / fma_peak_tflops, 4), "traffic": traffic,
         "peak_source": f"packed-FFMA2 issue loop measured in this run at {fma_mhz:.0f} MHz "
                        "(MEASURED_PEAKS.json has no FP32 entry; nominal 148 SM x 128 x 2 x 1.965 GHz = 74.4)",
-        "kernel": "afp::fir_stream_kernel<1,16,256>", "flop_per_sample": 2 * N_TAPS,
+        "kernel": kernel_name, "flop_per_sample": 2 * N_TAPS,
         "ms_per_launch": round(ms_launch, 5),
+        "tensor": tensor,
         "hbm": {"achieved_gbs": round(bytes_launch / (ms_launch * 1e-3) / 1e9, 1), "peak_gbs": hbm_peak,
                 "frac": round(bytes_launch / (ms_launch * 1e-3) / 1e9 / hbm_peak, 4),
                 "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},

@@ -7,6 +7,10 @@
 #include <cstdlib>
 #include <vector>
 #include "afp_fir_tc.cuh"
+#ifndef AFP_TC_ROW
+#define AFP_TC_ROW 64
+#endif
+using Cfg = afp::TcCfg<AFP_TC_ROW>;
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); return 1; } } while (0)
 
 static float trunc13(float v) { uint32_t u; memcpy(&u, &v, 4); u &= 0xFFFFE000u; float r; memcpy(&r, &u, 4); return r; }
@@ -16,7 +20,7 @@ int main(int argc, char** argv) {
     const int S = argc > 2 ? atoi(argv[2]) : 64;
     const int frames = argc > 3 ? atoi(argv[3]) : 512;
     const int iters = argc > 4 ? atoi(argv[4]) : 1;
-    const int R = afp::TC_ROW;
+    const int R = AFP_TC_ROW;
     const int n_chunks = (N + R - 2) / R + 1;          // d = 0 .. D, D = ceil((N-1+R-1)/R)
     const int maxd = getenv("MAXD") ? atoi(getenv("MAXD")) : 1000;   // debug: keep only chunks d <= MAXD
     const int mind = getenv("MIND") ? atoi(getenv("MIND")) : 0;
@@ -31,9 +35,9 @@ int main(int argc, char** argv) {
     for (auto& v : in) v = 0.2f * ((rand() / (float)RAND_MAX) - 0.5f);
     // W slices: chunk d, k-step ks, column chunk cc (2), row n (0..63 hi: j = n, 64..127 lo: j = n-64), 4 floats:
     // B[j][i] = h[R d + j - i] with i = 8 ks + 4 cc + e
-    std::vector<float> w((size_t)n_chunks * afp::TC_W_FLOATS, 0.f);
+    std::vector<float> w((size_t)n_chunks * Cfg::W_FLOATS, 0.f);
     for (int d = 0; d < n_chunks; ++d)
-        for (int ks = 0; ks < afp::TC_KSTEPS; ++ks)
+        for (int ks = 0; ks < Cfg::KSTEPS; ++ks)
             for (int cc = 0; cc < 2; ++cc)
                 for (int j = 0; j < R; ++j)
                     for (int e = 0; e < 4; ++e) {
@@ -41,7 +45,7 @@ int main(int argc, char** argv) {
                         const int k = R * d + j - i;
                         const float hv = (k >= 0 && k < N && d <= maxd && d >= mind) ? (float)h[k] : 0.f;
                         const float hi = trunc13(hv), lo = hv - hi;
-                        const size_t base = (size_t)d * afp::TC_W_FLOATS + (size_t)ks * afp::TC_W_SLICE + (size_t)cc * (2 * R * 4);
+                        const size_t base = (size_t)d * Cfg::W_FLOATS + (size_t)ks * Cfg::W_SLICE + (size_t)cc * (2 * R * 4);
                         w[base + (size_t)j * 4 + e] = hi;
                         w[base + (size_t)(R + j) * 4 + e] = lo;
                     }
@@ -59,7 +63,7 @@ int main(int argc, char** argv) {
     P.seed = 0; P.sample_base = 0; P.stream_id0 = 0; P.gain = 1.0f; P.dither_lsb = 0.f;
     const int rows = hist_rows + frames / R;
     const int data_bytes = 2 * 16 * rows * R * 4;
-    int slots = (232448 - data_bytes - 512) / (afp::TC_W_FLOATS * 4);
+    int slots = (232448 - data_bytes - 512) / (Cfg::SLOT_FLOATS * 4);
     if (slots > 8) slots = 8;
     if (getenv("SLOTS")) slots = atoi(getenv("SLOTS"));
     if (slots < 2) { printf("does not fit in shared memory\n"); return 1; }
@@ -69,9 +73,9 @@ int main(int argc, char** argv) {
         P.idesc_override = (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
         (void)m;
     }
-    const int smem = data_bytes + slots * afp::TC_W_FLOATS * 4 + 512;
+    const int smem = data_bytes + slots * Cfg::SLOT_FLOATS * 4 + 512;
     printf("W ring slots %d\n", slots);
-    auto kern = frames / (8 * R) == 1 ? afp::fir_tc_kernel<afp::EPI_GENERIC, 1> : (frames / (8 * R) == 2 ? afp::fir_tc_kernel<afp::EPI_GENERIC, 2> : afp::fir_tc_kernel<afp::EPI_GENERIC, 4>);
+    auto kern = frames / (8 * R) == 1 ? afp::fir_tc_kernel<afp::EPI_GENERIC, 1, AFP_TC_ROW> : (frames / (8 * R) == 2 ? afp::fir_tc_kernel<afp::EPI_GENERIC, 2, AFP_TC_ROW> : afp::fir_tc_kernel<afp::EPI_GENERIC, 4, AFP_TC_ROW>);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int grid = P.n_items < 148 ? P.n_items : 148;
     printf("smem %d bytes, grid %d\n", smem, grid);

@@ -49,8 +49,9 @@ def test_tensor_path_matches_lfilter(N, B, S):
         assert_parity(y[s], rc.streaming_fir(h, x[s]).astype(np.float32), f"N={N} B={B} s={s}")
 
 
-def test_1024_frame_blocks_four_row_groups():
-    """frames = 1024 -> four 8-row groups per stream (fits in shared memory up to ~600 taps)."""
+def test_1024_frame_blocks_several_row_groups():
+    """frames = 1024 -> two (64-sample rows) or four (32-sample rows) 8-row groups per stream; fits in
+    shared memory up to ~600 taps."""
     os.environ["AFP_TC_MIN_TAPS"] = "500"
     try:
         h = design.create_fir_filter(cutoff=9000, numtaps=577, window_type="kaiser", samplerate=96000)
