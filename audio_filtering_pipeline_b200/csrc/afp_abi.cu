@@ -15,6 +15,7 @@
 
 #include "../../include/afp.h"
 #include "afp_kernel_table.cuh"
+#include "afp_fir_row.cuh"
 #include "afp_fir_tc.cuh"
 
 using afp::FirParams;
@@ -52,7 +53,8 @@ struct Stage {
     // tiles on the device; which kernel ran last (0 = FFMA2, 1 = tcgen05)
     float* tc_w[2] = {nullptr, nullptr};   // tap tiles for row length 32 and 64
     int tc_chunks[2] = {0, 0};
-    int last_kernel = 0;
+    int last_kernel = 0;           // 0 = row-pair FFMA2, 1 = tcgen05, 2 = single-row FFMA2
+    int last_T = 0;                // tile of the last launch (the single-row kernel picks its own)
 };
 
 // Kernels live in one translation unit per up-sampling factor (afp_kernels_u{1..4}.cu, compiled in
@@ -69,6 +71,38 @@ kern_t kernel_for(int U, int T, int nt, bool multi, int epi) {
     }
     return nullptr;
 }
+
+kern_t row_kernel_for(int U, int T, int pad, int store, int epi) {
+    switch (U) {
+        case 1: return afp_kernel_row_u1(T, pad, store, epi);
+        case 2: return afp_kernel_row_u2(T, pad, store, epi);
+        case 4: return afp_kernel_row_u4(T, pad, store, epi);
+    }
+    return nullptr;
+}
+
+// Shape of the single-row kernel (afp_fir_row.cuh) for an up-sampling factor and phase length, from the
+// sweeps in bench/microbench/fir_row_test.cu on B200 (gpurun_out/row_probe*.txt):
+//   U = 1: 16-sample tiles; the FMA pipe is the bound, so the window loads must be conflict free: padded
+//          layout + cp.async; a thread's run is 64 B and transposing the stores does not pay.
+//   U = 2: <= 32 taps per phase: 8-sample tiles, direct stores, 64-thread groups (741 vs 700 Gsamples/s
+//          at 51 taps); longer: 16-sample tiles, transposed stores (514 vs 484 at 101 taps).
+//   U = 4: <= 16 taps per phase: 4-sample tiles, 128-thread groups (1168 vs 1045 at 51 taps); longer:
+//          8-sample tiles, one warp per group (925 vs 835 at 101 taps); transposed stores throughout.
+struct RowShape { int T = 0, pad = 0, store = 0, tg_log2 = 5; };
+RowShape pick_row_shape(int U, int kq) {
+    RowShape r;
+    if (U == 1) { r.T = 16; r.pad = 1; r.store = 0; r.tg_log2 = 5; }
+    else if (U == 2) {
+        if (kq <= 32) { r.T = 8; r.pad = 0; r.store = 0; r.tg_log2 = 6; }
+        else { r.T = 16; r.pad = 0; r.store = 2; r.tg_log2 = 5; }
+    } else if (U == 4) {
+        if (kq <= 16) { r.T = 4; r.pad = 0; r.store = 2; r.tg_log2 = 7; }
+        else { r.T = 8; r.pad = 0; r.store = 2; r.tg_log2 = 5; }
+    }
+    return r;
+}
+const RowShape kRowShapes[] = {{16, 1, 0, 5}, {8, 0, 0, 6}, {16, 0, 2, 5}, {4, 0, 2, 7}, {8, 0, 2, 5}};
 
 // Tile (= chunk) sizes compiled for each U, largest first.
 const int kTiles[5][3] = {{0, 0, 0}, {16, 0, 0}, {8, 0, 0}, {4, 0, 0}, {8, 4, 0}};
@@ -121,6 +155,12 @@ struct afp_ctx {
 
 namespace {
 
+// tuning / debugging switches from the environment: set and neither empty nor "0"
+bool env_flag(const char* name) {
+    const char* v = std::getenv(name);
+    return v && *v && std::strcmp(v, "0") != 0;
+}
+
 int fail(afp_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg; else g_create_error = msg;
     return code;
@@ -153,8 +193,11 @@ int build_stage(afp_ctx* c, Stage& s, int kind, int U, const double* taps, int n
     // then share one history format: the last kq_pad samples with kq_pad a multiple of 32 (the tensor
     // kernel's row length), so a stage may switch kernel from one block to the next.
     const int tc_min = std::getenv("AFP_TC_MIN_TAPS") ? std::atoi(std::getenv("AFP_TC_MIN_TAPS")) : 640;
-    const bool tc_ok = U == 1 && n_sub == 1 && n >= tc_min && !std::getenv("AFP_NO_TC");
-    const int n_chunks = tc_ok ? ((kq + 63) / 64) * (64 / T) : (kq + T - 1) / T;
+    const bool tc_ok = U == 1 && n_sub == 1 && n >= tc_min && !env_flag("AFP_NO_TC");
+    // History length = padded taps per phase.  A multiple of 16 (every tile size divides it, so the two
+    // FFMA2 kernels share one history format and a stage may switch kernel from block to block), with room
+    // for the extra tap slot the single-row kernel's U = 1 form needs (afp_fir_row.cuh).
+    const int n_chunks = tc_ok ? ((kq + 63) / 64) * (64 / T) : ((kq + (U == 1 ? 1 : 0) + 15) / 16) * (16 / T);
     if ((long long)n_chunks * T * U * n_sub > afp::MAX_TAPS)
         return fail(c, AFP_ERR_INVALID, "filter (x bands) too long for the per-launch tap table (max 6144 padded taps)");
     const bool same_shape = s.active && s.kind == kind && s.U == U && s.n_chunks == n_chunks;
@@ -307,12 +350,111 @@ int launch_stage_tc(afp_ctx* c, Stage& s, const StageIO& io, cudaStream_t stream
     return AFP_OK;
 }
 
+// 16-byte alignment facts of one launch (the loaders' fast paths)
+struct Align { int fast0, fast1, fast_hist, fast_all, fast_out; };
+Align alignment_of(const Stage& s, const StageIO& io) {
+    Align a;
+    const int eb = io.fmt == AFP_FMT_I16 ? 2 : (io.fmt == AFP_FMT_I24_PACKED ? 3 : 4);
+    const int start0 = io.q_begin - s.kq_pad;   // logical index of the first sample of segment 0's region
+    const bool n_al = start0 % 4 == 0;          // segment lengths are multiples of 4 in every geometry
+    a.fast0 = (io.len0 > 0 && n_al && aligned16(io.src0) && io.pitch0 % 4 == 0) ? 1 : 0;
+    a.fast1 = (io.len1 > 0 && n_al && aligned16(io.src1) && io.pitch1 % 4 == 0 && io.len0 % 4 == 0) ? 1 : 0;
+    a.fast_hist = (io.hist_out && n_al && aligned16(io.hist_out) && io.hist_pitch % 4 == 0 && io.hist_from % 4 == 0) ? 1 : 0;
+    // aligned fast loader: both sources vector-aligned, both lengths multiples of 4, history (if any) too
+    a.fast_all = (n_al && (io.len0 == 0 || a.fast0) && (io.len1 == 0 || (aligned16(io.src1) && io.pitch1 % 4 == 0))
+                  && io.len0 % 4 == 0 && io.len1 % 4 == 0
+                  && (!io.hist_out || (a.fast_hist && io.hist_len % 4 == 0))) ? 1 : 0;
+    a.fast_out = (aligned16(io.out) && (io.out_pitch * eb) % 16 == 0) ? 1 : 0;
+    return a;
+}
+
+void fill_common(afp_ctx* c, const Stage& s, const StageIO& io, const Align& a, FirParams& P) {
+    P.src0 = io.src0; P.src1 = io.src1;     // all pointers arrive offset to stream s0
+    P.pitch0 = io.pitch0; P.pitch1 = io.pitch1;
+    P.len0 = io.len0; P.len1 = io.len1;
+    P.q_begin = io.q_begin; P.n_q = io.n_q;
+    P.out = io.out; P.out_pitch = io.out_pitch;
+    P.decim = io.decim; P.fmt = io.fmt; P.dither = io.dither;
+    P.seed = c->cfg.seed; P.sample_base = io.sample_base; P.stream_id0 = c->cfg.first_stream_id + io.s0;
+    P.hist_out = io.hist_out; P.hist_pitch = io.hist_pitch; P.hist_len = io.hist_len; P.hist_from = io.hist_from;
+    P.gain = 1.0f;
+    P.dither_lsb = std::ldexp(1.0f, -(c->dither_bits - 1));
+    P.fast0 = a.fast0; P.fast1 = a.fast1; P.fast_hist = a.fast_hist; P.fast_all = a.fast_all; P.fast_out = a.fast_out;
+}
+
+FirParams& launch_params() {
+    static FirParams P;   // 25 KB: keep it off the stack; contexts are single-owner, launches serialised per process call
+    return P;
+}
+
+// Single-row kernel (afp_fir_row.cuh) for single-table stages with U in {1, 2, 4} whose buffers are all
+// 16-byte aligned.  Sets *done when it launched; otherwise the row-pair kernel takes the block.
+int launch_stage_row(afp_ctx* c, Stage& s, const StageIO& io, const Align& al, cudaStream_t stream, bool* done) {
+    *done = false;
+    if (env_flag("AFP_NO_ROW") || s.n_sub != 1 || !al.fast_all) return AFP_OK;
+    if (s.U != 1 && s.U != 2 && s.U != 4) return AFP_OK;
+    const int U = s.U, kq = (s.n_taps + U - 1) / U;
+    RowShape sh = pick_row_shape(U, kq);
+    const int T = sh.T;
+    const int step = afp::row_tail_step(U, T);
+    const int slots = (kq + (U == 1 ? 1 : 0) + step - 1) / step * step;     // tap slots per phase the FMA loop visits
+    if (slots > s.kq_pad || s.kq_pad % T != 0) return AFP_OK;
+    if (U == 1 && afp::row_tabb_offset(s.kq_pad) + s.kq_pad + 4 > afp::MAX_TAPS) return AFP_OK;
+    const int n_loop = (slots + T - 1) / T;
+    int tail = slots - (n_loop - 1) * T;
+    if (tail == T) tail = 0;
+    int tg_log2 = sh.tg_log2;
+    while (tg_log2 > 5 && (T << (tg_log2 - 1)) >= io.n_q) --tg_log2;      // short blocks: no idle warps
+    const int NT = 256;
+    int smem = afp::row_smem_bytes(U, T, NT, tg_log2, s.kq_pad, sh.store, sh.pad);
+    while (smem > kMaxSmem && tg_log2 > 5) { --tg_log2; smem = afp::row_smem_bytes(U, T, NT, tg_log2, s.kq_pad, sh.store, sh.pad); }
+    if (smem > kMaxSmem) return AFP_OK;
+    const int epi = io.decim == 1 ? afp::epi_code(io.fmt, io.dither) : afp::EPI_GENERIC;
+    kern_t k = row_kernel_for(U, T, sh.pad, sh.store, epi);
+    if (!k) return AFP_OK;
+    const int S = io.ns;
+    const int lq = T << tg_log2, slots_cta = NT >> tg_log2;
+    const int segs = (io.n_q + lq - 1) / lq;
+    const long long n_items = (long long)S * segs;
+    if (n_items <= 0 || n_items > INT_MAX) return AFP_OK;
+    int per_sm = 0;
+    AFP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, NT, smem));
+    if (per_sm < 1) return AFP_OK;
+    const long long want = (n_items + slots_cta - 1) / slots_cta, resident = (long long)per_sm * c->n_sm;
+    const int grid = (int)(want < resident ? want : resident);
+
+    FirParams& P = launch_params();
+    fill_common(c, s, io, al, P);
+    P.tg_log2 = tg_log2; P.segs_per_stream = segs; P.segs_shift = -1;
+    for (int b = 0; b < 30; ++b) if ((1 << b) == segs) P.segs_shift = b;
+    P.n_seg_total = (int)n_items; P.n_pairs = (int)((n_items + 1) / 2);
+    P.n_chunks = s.kq_pad / T; P.n_sub = tail; P.sub_stride = n_loop;
+    std::memset(P.taps, 0, sizeof(P.taps));
+    std::memcpy(P.taps, s.table.data(), (size_t)s.kq_pad * U * sizeof(float));
+    if (U == 1)   // pairs that start at an odd tap index: the table moved up by one sample
+        std::memcpy(P.taps + afp::row_tabb_offset(s.kq_pad) + 1, s.table.data(), (size_t)(s.kq_pad - 1) * sizeof(float));
+    k<<<grid, NT, smem, stream>>>(P);
+    AFP_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    s.last_kernel = 2; s.last_T = T;
+    s.geo.nt = NT; s.geo.tg_log2 = tg_log2; s.geo.smem = smem; s.geo.grid = grid; s.geo.segs_per_stream = segs;
+    s.geo.key_nq = -1;   // the row-pair kernel recomputes its own geometry if it runs next
+    *done = true;
+    return AFP_OK;
+}
+
 int launch_stage(afp_ctx* c, Stage& s, const StageIO& io, cudaStream_t stream) {
     {
         bool done = false;
         int rc = launch_stage_tc(c, s, io, stream, &done);
         if (rc || done) return rc;
-        s.last_kernel = 0;
+    }
+    const Align al = alignment_of(s, io);
+    {
+        bool done = false;
+        int rc = launch_stage_row(c, s, io, al, stream, &done);
+        if (rc || done) return rc;
+        s.last_kernel = 0; s.last_T = s.T;
     }
     const int S = io.ns;
     if (s.geo.key_nq != io.n_q || s.geo.key_ns != S) {
@@ -332,35 +474,14 @@ int launch_stage(afp_ctx* c, Stage& s, const StageIO& io, cudaStream_t stream) {
         s.geo = g;
     }
     const Geometry& g = s.geo;
-    static FirParams P;   // 16 KB: keep it off the stack; contexts are single-owner, launches serialised per process call
-    const int eb = io.fmt == AFP_FMT_I16 ? 2 : (io.fmt == AFP_FMT_I24_PACKED ? 3 : 4);
-    P.src0 = io.src0; P.src1 = io.src1;     // all pointers arrive offset to stream s0
-    P.pitch0 = io.pitch0; P.pitch1 = io.pitch1;
-    P.len0 = io.len0; P.len1 = io.len1;
-    P.q_begin = io.q_begin; P.n_q = io.n_q;
+    FirParams& P = launch_params();
+    fill_common(c, s, io, al, P);
     P.tg_log2 = g.tg_log2; P.segs_per_stream = g.segs_per_stream;
     P.segs_shift = -1;
     for (int b = 0; b < 30; ++b) if ((1 << b) == g.segs_per_stream) P.segs_shift = b;
     P.n_seg_total = S * g.segs_per_stream;
     P.n_pairs = (P.n_seg_total + 1) / 2;
     P.n_chunks = s.n_chunks; P.n_sub = s.n_sub; P.sub_stride = s.kq_pad * s.U;
-    P.out = io.out; P.out_pitch = io.out_pitch;
-    P.decim = io.decim; P.fmt = io.fmt; P.dither = io.dither;
-    P.seed = c->cfg.seed; P.sample_base = io.sample_base; P.stream_id0 = c->cfg.first_stream_id + io.s0;
-    P.hist_out = io.hist_out; P.hist_pitch = io.hist_pitch; P.hist_len = io.hist_len; P.hist_from = io.hist_from;
-    P.gain = 1.0f;
-    P.dither_lsb = std::ldexp(1.0f, -(c->dither_bits - 1));
-    const int start0 = io.q_begin - s.kq_pad;   // logical index of the first pair of segment 0's region
-    const int lq = (1 << g.tg_log2) * s.T;
-    const bool n_al = (start0 % 4 == 0) && (lq % 4 == 0);
-    P.fast0 = (io.len0 > 0 && n_al && aligned16(io.src0) && io.pitch0 % 4 == 0) ? 1 : 0;
-    P.fast1 = (io.len1 > 0 && n_al && aligned16(io.src1) && io.pitch1 % 4 == 0 && io.len0 % 4 == 0) ? 1 : 0;
-    P.fast_hist = (io.hist_out && n_al && aligned16(io.hist_out) && io.hist_pitch % 4 == 0 && io.hist_from % 4 == 0) ? 1 : 0;
-    // aligned fast loader: both sources vector-aligned, both lengths multiples of 4, history (if any) too
-    P.fast_all = (n_al && (io.len0 == 0 || P.fast0) && (io.len1 == 0 || (aligned16(io.src1) && io.pitch1 % 4 == 0))
-                  && io.len0 % 4 == 0 && io.len1 % 4 == 0
-                  && (!io.hist_out || (P.fast_hist && io.hist_len % 4 == 0))) ? 1 : 0;
-    P.fast_out = (aligned16(io.out) && (io.out_pitch * eb) % 16 == 0) ? 1 : 0;
     std::memset(P.taps, 0, sizeof(P.taps));
     std::memcpy(P.taps, s.table.data(), s.table.size() * sizeof(float));
     const int epi = io.decim == 1 ? afp::epi_code(io.fmt, io.dither) : afp::EPI_GENERIC;
@@ -518,6 +639,14 @@ int afp_create(const afp_config* cfg, afp_ctx** out_ctx) {
                         e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
                         if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem)");
                     }
+    for (int U : {1, 2, 4})
+        for (const RowShape& sh : kRowShapes)
+            for (int epi : kAllEpi) {
+                kern_t k = row_kernel_for(U, sh.T, sh.pad, sh.store, epi);
+                if (!k) continue;
+                e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+                if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, single-row kernel)");
+            }
     for (int row : {32, 64})
         for (int nts : {1, 2, 4})
             for (int epi : kAllEpi) {
@@ -887,7 +1016,7 @@ int afp_get_stage_info(const afp_ctx* c, int32_t stage, afp_stage_info* info) {
         if (!s->active) continue;
         if (k++ != stage) continue;
         info->kind = s->kind; info->upsample = s->U; info->n_taps = s->n_taps;
-        info->taps_per_phase_padded = s->kq_pad; info->tile_taps = s->T;
+        info->taps_per_phase_padded = s->kq_pad; info->tile_taps = s->last_T ? s->last_T : s->T;
         info->threads = s->geo.nt; info->threads_per_segment = s->geo.nt ? (1 << s->geo.tg_log2) : 0;
         info->smem_bytes = s->geo.smem; info->grid = s->geo.grid; info->history = s->kq_pad;
         info->kernel = s->last_kernel;

@@ -209,10 +209,19 @@ __device__ __forceinline__ int elem_bytes(int fmt) {
 constexpr int EPI_GENERIC = -1;
 __host__ __device__ constexpr int epi_code(int fmt, int dither) { return fmt * 4 + dither; }
 
+// Where a thread's finished, format-converted words go.  DirectSink: vector stores from registers.
+// (afp_fir_row.cuh adds a sink that stages them in shared memory and hands them to the bulk-copy engine.)
+struct DirectSink {
+    static constexpr bool kAllFull = false;   // true: the caller guarantees n_valid == NOUT and aligned output on every lane
+    template <int NB>
+    __device__ __forceinline__ void put(void* dst, const uint32_t (&w)[NB]) const { store_words<NB>(dst, w); }
+};
+
 // y[NOUT]: consecutive output samples o_base .. o_base+NOUT-1 (pre-decimation) of one stream row.
-template <int NOUT, int EPI, class PT>
-__device__ __forceinline__ void store_row(const PT& P_, float (&y)[NOUT], int stream, long long o_base, int n_valid) {
-    if (n_valid <= 0) return;
+template <int NOUT, int EPI, class PT, class SINK = DirectSink>
+__device__ __forceinline__ void store_row(const PT& P_, float (&y)[NOUT], int stream, long long o_base, int n_valid,
+                                          SINK sink = SINK()) {
+    if (!SINK::kAllFull && n_valid <= 0) return;
     struct View {   // the epilogue fields of FirParams / TcParams, fmt / dither / decim possibly compile-time
         int fmt, dither, decim;
         float gain, dither_lsb;
@@ -222,7 +231,7 @@ __device__ __forceinline__ void store_row(const PT& P_, float (&y)[NOUT], int st
     };
     const View P = {EPI >= 0 ? (EPI >> 2) : P_.fmt, EPI >= 0 ? (EPI & 3) : P_.dither, EPI >= 0 ? 1 : P_.decim,
                     P_.gain, P_.dither_lsb, P_.out, P_.out_pitch, P_.seed, P_.sample_base, P_.stream_id0, P_.fast_out};
-    if (P.gain != 1.0f) {
+    if (EPI < 0 && P.gain != 1.0f) {   // specialised epilogues are only selected with gain == 1
 #pragma unroll
         for (int i = 0; i < NOUT; ++i) y[i] = __fmul_rn(y[i], P.gain);
     }
@@ -236,7 +245,7 @@ __device__ __forceinline__ void store_row(const PT& P_, float (&y)[NOUT], int st
 #pragma unroll
             for (int i = 0; i < NOUT; ++i) d[i] = 0.f;
         }
-        const bool full = P.fast_out && n_valid == NOUT;
+        const bool full = SINK::kAllFull || (P.fast_out && n_valid == NOUT);
         if (P.fmt == FMT_F32) {
             if (P.dither != DITHER_NONE) {
 #pragma unroll
@@ -247,7 +256,7 @@ __device__ __forceinline__ void store_row(const PT& P_, float (&y)[NOUT], int st
                 uint32_t w[NOUT];
 #pragma unroll
                 for (int i = 0; i < NOUT; ++i) w[i] = __float_as_uint(y[i]);
-                store_words<NOUT>(o, w);
+                sink.template put<NOUT>(o, w);
             } else {
 #pragma unroll
                 for (int i = 0; i < NOUT; ++i) if (i < n_valid) o[i] = y[i];
@@ -261,7 +270,7 @@ __device__ __forceinline__ void store_row(const PT& P_, float (&y)[NOUT], int st
                 uint32_t w[NOUT / 2];
 #pragma unroll
                 for (int i = 0; i < NOUT / 2; ++i) w[i] = ((uint32_t)q[2 * i] & 0xFFFFu) | ((uint32_t)q[2 * i + 1] << 16);
-                store_words<NOUT / 2>(o, w);
+                sink.template put<NOUT / 2>(o, w);
             } else {
 #pragma unroll
                 for (int i = 0; i < NOUT; ++i) if (i < n_valid) o[i] = (short)q[i];
@@ -276,7 +285,7 @@ __device__ __forceinline__ void store_row(const PT& P_, float (&y)[NOUT], int st
                     uint32_t w[NOUT];
 #pragma unroll
                     for (int i = 0; i < NOUT; ++i) w[i] = (uint32_t)q[i];
-                    store_words<NOUT>(o, w);
+                    sink.template put<NOUT>(o, w);
                 } else {
 #pragma unroll
                     for (int i = 0; i < NOUT; ++i) if (i < n_valid) o[i] = q[i];
@@ -293,7 +302,7 @@ __device__ __forceinline__ void store_row(const PT& P_, float (&y)[NOUT], int st
                         w[3 * i + 1] = (b >> 8) | (c << 16);
                         w[3 * i + 2] = (c >> 16) | (e << 8);
                     }
-                    store_words<NOUT * 3 / 4>(o, w);
+                    sink.template put<NOUT * 3 / 4>(o, w);
                 } else {
 #pragma unroll
                     for (int i = 0; i < NOUT; ++i) if (i < n_valid) {

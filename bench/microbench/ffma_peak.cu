@@ -175,9 +175,9 @@ __global__ void __launch_bounds__(256) k_x2_rr(float* out, const float* in, int 
 // taps in shared memory at a warp-uniform address, FIR-like: 16 taps per chunk, chunk index runs
 __global__ void __launch_bounds__(256) k_smem_taps(float* out, const float* in, int iters, long long* cyc) {
     __shared__ float hs[1024];
-    __shared__ float xs[4096 + 64];
+    __shared__ float xs[256 * 20 + 64];
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) hs[i] = in[i];
-    for (int i = threadIdx.x; i < 4096 + 64; i += blockDim.x) xs[i] = in[i & 1023];
+    for (int i = threadIdx.x; i < 256 * 20 + 64; i += blockDim.x) xs[i] = in[i & 1023];
     __syncthreads();
     float acc[NACC], w[2 * NACC];
 #pragma unroll
@@ -234,6 +234,41 @@ __global__ void __launch_bounds__(256) k_x2_small(float* out, const float* in, i
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+// FFMA2 in the form  acc(y[r],y[r+1]) += x[n](scalar broadcast, ordinary register) * (h[k],h[k+1])
+// (tap PAIR in a 64-bit uniform register): SASS "FFMA2 R, R.F32, UR.F32x2.HI_LO, R.F32x2.HI_LO".
+// One row per thread, no row interleave: the inner loop of the single-row FIR kernel for U = 1, T = 16.
+__global__ void __launch_bounds__(256) k_x2_bc(float* out, const float* in, int iters, long long* cyc) {
+    unsigned long long acc[NACC / 2];
+    float w[2 * NACC];
+#pragma unroll
+    for (int i = 0; i < NACC / 2; ++i) acc[i] = 0ull;
+#pragma unroll
+    for (int i = 0; i < 2 * NACC; ++i) w[i] = in[threadIdx.x + i];
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        const float* ta = c_taps + (it & 15) * NTAP;          // even-start pairs
+        const float* tb = c_taps + 512 + (it & 15) * NTAP;    // odd-start pairs (table shifted by one)
+#pragma unroll
+        for (int m = 1; m < 2 * NACC; ++m) {
+#pragma unroll
+            for (int r = 0; r < NACC; r += 2) {
+                const int j = NACC + r - m;
+                if (j < 0 || j >= NACC) continue;
+                const float* tp = (m & 1) ? tb + (j - 1) : ta + j;
+                const unsigned long long h = *reinterpret_cast<const unsigned long long*>(tp);
+                const unsigned long long xx = ((unsigned long long)__float_as_uint(w[m]) << 32) | __float_as_uint(w[m]);
+                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[r / 2]) : "l"(xx), "l"(h));
+            }
+        }
+    }
+    long long t1 = clock64();
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < NACC / 2; ++i) s += __uint_as_float((unsigned)acc[i]) + __uint_as_float((unsigned)(acc[i] >> 32));
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
 typedef void (*kern_t)(float*, const float*, int, long long*);
 
 static void run(const char* name, kern_t k, int fma_per_iter_per_thread, int nsm, int ctas_per_sm, int threads) {
@@ -284,6 +319,7 @@ int main() {
         run("x2", k_x2, 2 * NACC * NTAP, nsm, c, 256);
         run("x2_small", k_x2_small, 2 * 4 * 8 * 8, nsm, c, 256);
         run("x2_rr", k_x2_rr, 2 * 4 * 8 * 8, nsm, c, 256);
+        run("x2_bc", k_x2_bc, NACC * NTAP, nsm, c, 256);
         run("smem_taps", k_smem_taps, NACC * NTAP, nsm, c, 256);
     }
     return 0;

@@ -79,14 +79,15 @@ def test_full_scale_signal_stays_in_tolerance():
 
 
 def test_kernels_interchange_block_by_block():
-    """512-frame blocks run on the tensor cores, odd-sized ones on the FFMA2 kernel; both read and write
-    the same carried history, so a stream may alternate freely."""
+    """512-frame blocks run on the tensor cores, other 16-byte-aligned sizes on the single-row FFMA2 kernel
+    (2), odd-sized ones on the row-pair FFMA2 kernel (0); all three read and write the same carried
+    history, so a stream may alternate freely."""
     h = remez1001()
     sizes = [512, 100, 256, 512, 37, 1024, 512]
     x = noise(4, sum(sizes))
     with BatchFirEngine(h, n_streams=4, max_frames=1024) as eng:
         y, kernels = run(eng, x, sizes)
-    assert kernels == [1, 0, 1, 1, 0, 0, 1]          # 1024 frames x 1001 taps does not fit in shared memory
+    assert kernels == [1, 2, 1, 1, 0, 2, 1]          # 1024 frames x 1001 taps does not fit the tensor kernel's shared memory
     for s in range(4):
         assert_parity(y[s], rc.streaming_fir(h, x[s]).astype(np.float32), f"stream {s}")
 
@@ -102,7 +103,7 @@ def test_tensor_and_ffma_paths_agree():
             y_ff, k_ff = run(eng, x, [512] * 3)
     finally:
         del os.environ["AFP_NO_TC"]
-    assert k_tc == [1, 1, 1] and k_ff == [0, 0, 0]
+    assert k_tc == [1, 1, 1] and k_ff == [2, 2, 2]      # without the tensor path: the single-row FFMA2 kernel
     assert np.abs(y_tc - y_ff).max() < 2e-6
 
 
