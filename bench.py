@@ -286,7 +286,8 @@ def run_ours(args):
                           "it can exceed 1 because the work runs on the tensor pipe"}
         kernel_name = "afp::fir_tc_kernel<EPI_I24_TPDF, 1, 64> (tcgen05 / TMEM Toeplitz FIR)"
     else:
-        kernel_name = "afp::fir_stream_kernel<1,16,256> (packed FFMA2)"
+        kernel_name = ("afp::fir_row_kernel<1,16,256> (packed FFMA2, single row)" if info.get("kernel") == 2
+                       else "afp::fir_stream_kernel<1,16,256> (packed FFMA2, row pair)")
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -328,6 +329,11 @@ def run_ours(args):
 
     line = None
     if rank == 0:
+        sweep = None
+        if world == 1 and not args.no_sweep:
+            del x, y
+            torch.cuda.empty_cache()
+            sweep = c5_sweep(local, hbm_peak, fma_peak_tflops)
         cpu_val, cores, sample = cpu_reference(taps, seconds_target=args.cpu_seconds)
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": "Msamples/s", "n_gpus": world,
@@ -339,6 +345,7 @@ def run_ours(args):
                              "sample": sample},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "stage": eng.stage_info(), "checksum": checksum,
+            "c5_sweep_kernel_only": sweep,
         }
         print(json.dumps(line))
     hx.free()
@@ -348,6 +355,47 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def c5_sweep(local, hbm_peak_gbs, fma_peak_tflops, iters=10):
+    """Kernel-only points of BASELINE.json configs[4] (batch sweep: {51,101,251} taps x {1,2,4}x up-sampling,
+    f32 out, 1024-frame blocks), device-resident I/O rotated over 3 buffer pairs (0.8-2 GB, far beyond L2),
+    CUDA events.  Work per output sample: 2*ceil(N/U) flop, 4/U + 4 bytes; the relevant roof
+    is the lower of the two."""
+    import torch
+    from audio_filtering_pipeline_b200.engine import BatchFirEngine
+    dev = torch.device("cuda", local)
+    out = []
+    for n_taps, up, streams in [(51, 1, 65536), (51, 2, 32768), (51, 4, 32768), (101, 1, 32768), (101, 2, 32768),
+                                (101, 4, 32768), (251, 1, 16384), (251, 2, 16384), (251, 4, 16384)]:
+        rng = np.random.default_rng(n_taps * 8 + up)
+        h = up * rng.standard_normal(n_taps) / n_taps
+        B = 1024
+        eng = BatchFirEngine(h, n_streams=streams, max_frames=B, upsample=up, device=local)
+        xs = [0.1 * torch.randn(streams, B, device=dev) for _ in range(3)]
+        ys = [torch.empty(streams, B * up, device=dev) for _ in range(3)]
+        for i in range(3):
+            eng.process(xs[i], ys[i])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            eng.process(xs[i % 3], ys[i % 3])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        n_out = streams * B * up
+        gs = n_out / ms / 1e6
+        flop, byts = 2.0 * -(-n_taps // up), 4.0 / up + 4.0
+        roof_fma, roof_hbm = fma_peak_tflops * 1e3 / flop, hbm_peak_gbs / byts     # Gsamples/s
+        bound = "hbm" if roof_hbm < roof_fma else "fp32_fma"
+        info = eng.stage_info()[-1]
+        out.append({"taps": n_taps, "upsample": up, "streams": streams, "frames": B, "gsamples_s": round(gs, 1),
+                    "tflops": round(gs * flop / 1e3, 1), "alg_gbs": round(gs * byts, 0), "bound": bound,
+                    "frac": round(gs / min(roof_fma, roof_hbm), 3), "kernel": info["kernel"], "tile": info["tile_taps"]})
+        eng.close()
+        del xs, ys
+    return out
 
 
 def main():
@@ -360,6 +408,7 @@ def main():
     ap.add_argument("--blocks", type=int, default=BLOCKS_PER_STEP, help="512-frame blocks per step")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-sweep", action="store_true", help="skip the short-filter kernel-only sweep (N = 1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
