@@ -128,6 +128,9 @@ struct afp_ctx {
     afp_config cfg{};
     std::string err;
     Stage up, eq, mainf;
+    // AFP_CHAIN_REFERENCE without EQ: interpolate -> FIR -> keep every U-th sample is ONE base-rate FIR with
+    // taps (h_up (*) h)[jU] (see rebuild_fused); when active it replaces the up / mainf launches
+    Stage fused;
     std::vector<std::vector<double>> bands;
     std::vector<double> gains;
     float* tmp_a = nullptr;          // interp output  [S][max_frames*U]
@@ -151,6 +154,7 @@ struct afp_ctx {
     cudaEvent_t ev_in[kSlots] = {}, ev_k[kSlots] = {}, ev_out[kSlots] = {};
     int slot_streams = 0;            // streams per staging slot
     cudaStream_t own_stream = nullptr, s_in = nullptr, s_out = nullptr;
+    FirParams params{};              // scratch for the kernel-parameter block of the launch being prepared
 };
 
 namespace {
@@ -213,6 +217,7 @@ int build_stage(afp_ctx* c, Stage& s, int kind, int U, const double* taps, int n
         s.geo = Geometry();
     }
     s.kind = kind; s.U = U; s.T = T; s.n_taps = n; s.n_sub = n_sub;
+    s.taps.assign(taps, taps + (size_t)n * n_sub);
     s.n_chunks = n_chunks; s.kq_pad = n_chunks * T;
     s.table.assign((size_t)s.kq_pad * U * n_sub, 0.f);
     for (int b = 0; b < n_sub; ++b)
@@ -382,10 +387,9 @@ void fill_common(afp_ctx* c, const Stage& s, const StageIO& io, const Align& a, 
     P.fast0 = a.fast0; P.fast1 = a.fast1; P.fast_hist = a.fast_hist; P.fast_all = a.fast_all; P.fast_out = a.fast_out;
 }
 
-FirParams& launch_params() {
-    static FirParams P;   // 25 KB: keep it off the stack; contexts are single-owner, launches serialised per process call
-    return P;
-}
+// 25 KB of launch parameters: kept in the context (off the stack; contexts are single-owner, so one
+// scratch copy per context is race free even with one host thread per GPU)
+FirParams& launch_params(afp_ctx* c) { return c->params; }
 
 // Single-row kernel (afp_fir_row.cuh) for single-table stages with U in {1, 2, 4} whose buffers are all
 // 16-byte aligned.  Sets *done when it launched; otherwise the row-pair kernel takes the block.
@@ -423,7 +427,7 @@ int launch_stage_row(afp_ctx* c, Stage& s, const StageIO& io, const Align& al, c
     const long long want = (n_items + slots_cta - 1) / slots_cta, resident = (long long)per_sm * c->n_sm;
     const int grid = (int)(want < resident ? want : resident);
 
-    FirParams& P = launch_params();
+    FirParams& P = launch_params(c);
     fill_common(c, s, io, al, P);
     P.tg_log2 = tg_log2; P.segs_per_stream = segs; P.segs_shift = -1;
     for (int b = 0; b < 30; ++b) if ((1 << b) == segs) P.segs_shift = b;
@@ -474,7 +478,7 @@ int launch_stage(afp_ctx* c, Stage& s, const StageIO& io, cudaStream_t stream) {
         s.geo = g;
     }
     const Geometry& g = s.geo;
-    FirParams& P = launch_params();
+    FirParams& P = launch_params(c);
     fill_common(c, s, io, al, P);
     P.tg_log2 = g.tg_log2; P.segs_per_stream = g.segs_per_stream;
     P.segs_shift = -1;
@@ -540,7 +544,7 @@ int ensure_tmp(afp_ctx* c) {
     const int S = c->cfg.n_streams, U = c->cfg.upsample;
     const bool ref = c->cfg.chain == AFP_CHAIN_REFERENCE;
     const long long rate_len = (long long)c->cfg.max_frames * (ref ? U : 1);   // EQ-rate samples per block
-    if (ref && U > 1 && !c->tmp_a) {
+    if (ref && U > 1 && !c->tmp_a && !c->fused.active) {   // the collapsed chain has no processing-rate intermediate
         c->pitch_a = (rate_len + 3) / 4 * 4;
         AFP_CUDA(c, cudaMalloc(&c->tmp_a, (size_t)S * c->pitch_a * sizeof(float)));
     }
@@ -670,7 +674,7 @@ int afp_create(const afp_config* cfg, afp_ctx** out_ctx) {
 int afp_destroy(afp_ctx* c) {
     if (!c) return AFP_OK;
     cudaSetDevice(c->cfg.device);
-    free_stage(c->up); free_stage(c->eq); free_stage(c->mainf);
+    free_stage(c->up); free_stage(c->eq); free_stage(c->mainf); free_stage(c->fused);
     if (c->tmp_a) cudaFree(c->tmp_a);
     if (c->tmp_b) cudaFree(c->tmp_b);
     for (int i = 0; i < 2; ++i) if (c->xhist[i]) cudaFree(c->xhist[i]);
@@ -688,11 +692,39 @@ int afp_destroy(afp_ctx* c) {
     return AFP_OK;
 }
 
+// The reference callback's chain (stream_process.py:96-107): up-sample by U -> FIR at fs*U -> processed[::U].
+// With zs = zero-stuffed input, y[nU] = sum_k h[k] sum_l h_up[l] zs[nU-k-l] = sum_m g[m] zs[nU-m], g = h_up (*) h,
+// and zs is non-zero only where m = jU:   y_dec[n] = sum_j g[jU] x[n-j].
+// So the whole chain is one base-rate FIR of ceil((N+L-1)/U) taps: one launch instead of two, no
+// processing-rate intermediate, ~U^2 fewer multiply-adds than computing every processing-rate sample and
+// dropping U-1 of U.  Exact in exact arithmetic; in float32 it skips the rounding of the up-sampled
+// intermediate (the staged form stays available: AFP_NO_COLLAPSE=1, and is what runs with an EQ stage or
+// a decimation factor other than U).
+static int rebuild_fused(afp_ctx* c) {
+    const int U = c->cfg.upsample;
+    const bool want = c->cfg.chain == AFP_CHAIN_REFERENCE && U > 1 && c->cfg.eq_mode == AFP_EQ_NONE && c->decim == U &&
+                      c->up.active && c->mainf.active && !env_flag("AFP_NO_COLLAPSE");
+    if (!want) { free_stage(c->fused); return AFP_OK; }
+    const std::vector<double>& a = c->up.taps;
+    const std::vector<double>& b = c->mainf.taps;
+    const size_t ng = a.size() + b.size() - 1, n0 = (ng + U - 1) / U;
+    std::vector<double> g0(n0, 0.0);
+    for (size_t j = 0; j < n0; ++j) {
+        const size_t m = j * U;                          // g[m] = sum_l a[l] * b[m-l]
+        const size_t l0 = m >= b.size() ? m - (b.size() - 1) : 0, l1 = std::min(m, a.size() - 1);
+        double acc = 0.0;
+        for (size_t l = l0; l <= l1; ++l) acc += a[l] * b[m - l];
+        g0[j] = acc;
+    }
+    return build_stage(c, c->fused, ST_MAIN, 1, g0.data(), (int)n0);
+}
+
 int afp_set_taps(afp_ctx* c, const double* taps, int32_t n) {
     if (!c || !taps) return fail(c, AFP_ERR_INVALID, "null argument");
     AFP_CUDA(c, cudaSetDevice(c->cfg.device));
     const int U = c->cfg.chain == AFP_CHAIN_DAC ? c->cfg.upsample : 1;
-    return build_stage(c, c->mainf, ST_MAIN, U, taps, n);
+    int rc = build_stage(c, c->mainf, ST_MAIN, U, taps, n);
+    return rc ? rc : rebuild_fused(c);
 }
 
 int afp_set_upsampler(afp_ctx* c, const double* taps, int32_t n) {
@@ -700,7 +732,8 @@ int afp_set_upsampler(afp_ctx* c, const double* taps, int32_t n) {
     if (c->cfg.chain != AFP_CHAIN_REFERENCE || c->cfg.upsample < 2)
         return fail(c, AFP_ERR_STATE, "an up-sampler prototype is only used by AFP_CHAIN_REFERENCE with upsample > 1");
     AFP_CUDA(c, cudaSetDevice(c->cfg.device));
-    return build_stage(c, c->up, ST_INTERP, c->cfg.upsample, taps, n);
+    int rc = build_stage(c, c->up, ST_INTERP, c->cfg.upsample, taps, n);
+    return rc ? rc : rebuild_fused(c);
 }
 
 int afp_set_eq(afp_ctx* c, const double* band_taps, const int32_t* band_len, int32_t n_bands, const double* gains) {
@@ -749,6 +782,10 @@ static int process_block_range(afp_ctx* c, const float* in, int64_t in_pitch, vo
     const int mode = c->cfg.eq_mode;
     int rc;
     const float* cur = in; long long cur_pitch = in_pitch; int cur_len = frames;
+    if (c->fused.active)  // interpolate -> FIR -> decimate collapsed into one base-rate FIR (rebuild_fused)
+        return run_streaming(c, c->fused, in, in_pitch, frames, out,
+                             c->cfg.out_format == AFP_FMT_I24_PACKED ? out_pitch / 3 : out_pitch,
+                             c->cfg.out_format, c->cfg.dither, 1, c->out_samples, s0, ns, st);
     if (ref && U > 1) {   // interpolate to the processing rate (replaces soxr.resample, stream_process.py:66-77)
         float* ta = c->tmp_a + (long long)s0 * c->pitch_a;
         rc = run_streaming(c, c->up, cur, cur_pitch, cur_len, ta, c->pitch_a, AFP_FMT_F32, AFP_DITHER_NONE, 1, 0, s0, ns, st);
@@ -816,6 +853,11 @@ static int process_block_range(afp_ctx* c, const float* in, int64_t in_pitch, vo
 static void finish_block(afp_ctx* c, int32_t frames) {
     const bool ref = c->cfg.chain == AFP_CHAIN_REFERENCE;
     const int mode = c->cfg.eq_mode;
+    if (c->fused.active) {
+        c->fused.cur ^= 1;
+        c->out_samples += (unsigned long long)afp_out_frames(c, frames);
+        return;
+    }
     if (ref && c->cfg.upsample > 1) c->up.cur ^= 1;
     if (eq_is_buffer_same(c)) c->xhist_cur ^= 1;
     else if (mode != AFP_EQ_STATELESS_SAME) {
@@ -941,12 +983,17 @@ int afp_process_host(afp_ctx* c, const float* in, void* out, int32_t frames) {
     return afp_process_host_blocks(c, in, out, frames, 1);
 }
 
+// the stages that actually run, in launch order
+static std::vector<const Stage*> live_stages(const afp_ctx* c) {
+    if (c->fused.active) return {&c->fused};
+    return {&c->up, &c->eq, &c->mainf};
+}
+
 // every device buffer that carries state between blocks: (current, other, bytes)
 struct StateBuf { float* cur; float* other; size_t bytes; };
 static std::vector<StateBuf> state_buffers(const afp_ctx* c) {
     std::vector<StateBuf> v;
-    const Stage* st[3] = {&c->up, &c->eq, &c->mainf};
-    for (const Stage* s : st)
+    for (const Stage* s : live_stages(c))
         if (s->active && s->hist[0])
             v.push_back({s->hist[s->cur], s->hist[s->cur ^ 1], (size_t)c->cfg.n_streams * s->hist_pitch * sizeof(float)});
     if (c->xhist[0])
@@ -1010,9 +1057,8 @@ int afp_set_state(afp_ctx* c, const void* buf, size_t bytes) {
 
 int afp_get_stage_info(const afp_ctx* c, int32_t stage, afp_stage_info* info) {
     if (!c || !info) return AFP_ERR_INVALID;
-    const Stage* st[3] = {&c->up, &c->eq, &c->mainf};
     int k = 0;
-    for (const Stage* s : st) {
+    for (const Stage* s : live_stages(c)) {
         if (!s->active) continue;
         if (k++ != stage) continue;
         info->kind = s->kind; info->upsample = s->U; info->n_taps = s->n_taps;

@@ -165,20 +165,22 @@ __device__ __forceinline__ void hist_store4(const FirParams& P, float* hrow, int
 template <int NOUT, int MODE>
 __device__ __forceinline__ void dither_values(float (&d)[NOUT], unsigned long long seed, uint32_t sid, unsigned long long idx0) {
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    if ((idx0 & 1ull) == 0) {
+    if (NOUT % 4 == 0 && (idx0 & 3ull) == 0) {     // the normal case: one Philox call per four samples
 #pragma unroll
-        for (int i = 0; i < NOUT; i += 2) {
-            const unsigned long long c = (idx0 + i) >> 1;
+        for (int i = 0; i < NOUT; i += 4) {
+            const unsigned long long c = (idx0 + i) >> 2;
             const Philox4 w = philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), sid, 0u, k0, k1);
-            d[i] = dither_lsb<MODE>(w.w[0], w.w[1]);
-            if (i + 1 < NOUT) d[i + 1] = dither_lsb<MODE>(w.w[2], w.w[3]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (i + j < NOUT) d[i + j] = dither_lsb<MODE>(w.w[j]);
         }
     } else {
 #pragma unroll
         for (int i = 0; i < NOUT; ++i) {
-            const unsigned long long idx = idx0 + i, c = idx >> 1;
+            const unsigned long long idx = idx0 + i, c = idx >> 2;
             const Philox4 w = philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), sid, 0u, k0, k1);
-            d[i] = (idx & 1ull) ? dither_lsb<MODE>(w.w[2], w.w[3]) : dither_lsb<MODE>(w.w[0], w.w[1]);
+            const uint32_t j = (uint32_t)idx & 3u;
+            d[i] = dither_lsb<MODE>(j == 0 ? w.w[0] : (j == 1 ? w.w[1] : (j == 2 ? w.w[2] : w.w[3])));
         }
     }
 }
@@ -324,10 +326,11 @@ __device__ __forceinline__ void store_row(const PT& P_, float (&y)[NOUT], int st
             const long long od = o / P.decim;
             float d = 0.f;
             if (P.dither != DITHER_NONE) {
-                const unsigned long long idx = P.sample_base + (unsigned long long)od, c = idx >> 1;
+                const unsigned long long idx = P.sample_base + (unsigned long long)od, c = idx >> 2;
                 const Philox4 w = philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), sid, 0u, k0, k1);
-                const uint32_t wa = (idx & 1ull) ? w.w[2] : w.w[0], wb = (idx & 1ull) ? w.w[3] : w.w[1];
-                d = (P.dither == DITHER_TPDF) ? dither_lsb<DITHER_TPDF>(wa, wb) : dither_lsb<DITHER_RPDF>(wa, wb);
+                const uint32_t j = (uint32_t)idx & 3u;
+                const uint32_t wj = j == 0 ? w.w[0] : (j == 1 ? w.w[1] : (j == 2 ? w.w[2] : w.w[3]));
+                d = (P.dither == DITHER_TPDF) ? dither_lsb<DITHER_TPDF>(wj) : dither_lsb<DITHER_RPDF>(wj);
             }
             if (P.fmt == FMT_F32) {
                 reinterpret_cast<float*>(row)[od] = (P.dither != DITHER_NONE) ? dither_float(y[i], d, P.dither_lsb) : y[i];

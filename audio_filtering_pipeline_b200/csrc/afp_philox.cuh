@@ -4,9 +4,10 @@
 // unseeded numpy RNG and never quantises, so this stage is build-defined.  The
 // arithmetic contract (bit for bit) is written down in oracle/dither_quant.py:
 //   key     = (seed lo, seed hi)
-//   counter = (c lo, c hi, stream_id, 0),  c = absolute_output_sample_index >> 1
-//   even samples use words (0,1) of the block, odd samples words (2,3); k = word >> 8
-//   TPDF d = float(k1 + k2 - (2^24-1)) * 2^-24      RPDF d = float(2*k1 + 1 - 2^24) * 2^-25
+//   counter = (c lo, c hi, stream_id, 0),  c = absolute_output_sample_index >> 2
+//   sample i uses output word i & 3 of its block (four samples per Philox call - SURVEY.md 8(d));
+//   a = word >> 16, b = word & 0xffff (two 16-bit uniforms)
+//   TPDF d = float(a + b - (2^16-1)) * 2^-16        RPDF d = float(2*a + 1 - 2^16) * 2^-17
 //   q = clip(rint(fl32(fl32(y*2^(bits-1)) + d)), -2^(bits-1), 2^(bits-1)-1)   (no fused multiply-add)
 #pragma once
 #include <cstdint>
@@ -36,22 +37,30 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
     return o;
 }
 
-// Dither value in LSB units from two 32-bit words.
+// Dither value in LSB units from one 32-bit word (two 16-bit uniforms).
+// The integer (a+b or 2a+1, < 2^18) becomes a float by planting it in the mantissa of 2^23 - one integer
+// add instead of an I2F conversion - and the offset and the power-of-two scale fold into one FMA whose
+// result is exactly representable, so the value is the one the definition above states.
 template <int MODE>
-__device__ __forceinline__ float dither_lsb(uint32_t wa, uint32_t wb) {
-    const int a = (int)(wa >> 8), b = (int)(wb >> 8);
-    if (MODE == DITHER_TPDF) return __fmul_rn((float)(a + b - ((1 << 24) - 1)), 5.9604644775390625e-08f);
-    return __fmul_rn((float)(2 * a + 1 - (1 << 24)), 2.98023223876953125e-08f);
+__device__ __forceinline__ float dither_lsb(uint32_t w) {
+    const uint32_t a = w >> 16, b = w & 0xFFFFu;
+    if (MODE == DITHER_TPDF) {
+        const float t = __uint_as_float(0x4B000000u + a + b);                    // 2^23 + a + b
+        return __fmaf_rn(t, 1.52587890625e-05f, -(8388608.0f + 65535.0f) * 1.52587890625e-05f);
+    }
+    const float t = __uint_as_float(0x4B000000u + 2u * a + 1u);                  // 2^23 + 2a + 1
+    return __fmaf_rn(t, 7.62939453125e-06f, -(8388608.0f + 65536.0f) * 7.62939453125e-06f);
 }
 
 // float sample -> integer code of a BITS-bit signed format, d in LSB units.
 template <int BITS>
 __device__ __forceinline__ int quantise(float y, float d) {
     constexpr float scale = (float)(1 << (BITS - 1));
-    float v = __fadd_rn(__fmul_rn(y, scale), d);
-    v = fminf(fmaxf(rintf(v), -scale), scale - 1.0f);   // fmaxf/fminf drop NaN -> -scale, fixed below
-    int q = __float2int_rn(v);
-    return (y != y) ? 0 : q;
+    constexpr int lim = 1 << (BITS - 1);
+    const float v = __fadd_rn(__fmul_rn(y, scale), d);
+    // round-half-even conversion (saturating; NaN -> 0), then the clip in the integer domain: the same
+    // codes as clip(rint(v)) with three instructions fewer
+    return min(max(__float2int_rn(v), -lim), lim - 1);
 }
 
 // Reference-style float dither (apply_dither(audio, bit_depth), stream_process.py:61-64): y + d * LSB with

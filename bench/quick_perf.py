@@ -26,11 +26,19 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--nbuf", type=int, default=4)
     ap.add_argument("--peak", action="store_true")
+    ap.add_argument("--chain", default="dac", choices=["dac", "reference"],
+                    help="reference: interpolate (129-tap Kaiser prototype) -> FIR -> keep every U-th sample")
     a = ap.parse_args()
     rng = np.random.default_rng(0)
     h = rng.standard_normal(a.taps) / a.taps
     S, B, U = a.streams, a.frames, a.up
-    eng = BatchFirEngine(h, n_streams=S, max_frames=B, upsample=U, out_format=a.fmt, dither=a.dither, seed=1)
+    kw = {}
+    if a.chain == "reference" and U > 1:
+        from audio_filtering_pipeline_b200 import design
+        kw = dict(chain="reference",
+                  upsampler_taps=U * design.create_fir_filter(cutoff=20000, numtaps=129, window_type="kaiser",
+                                                              samplerate=44100 * U))
+    eng = BatchFirEngine(h, n_streams=S, max_frames=B, upsample=U, out_format=a.fmt, dither=a.dither, seed=1, **kw)
     xs = [0.1 * torch.randn(S, B, device="cuda") for _ in range(a.nbuf)]
     out = eng.process(xs[0])
     for i in range(3):
@@ -43,7 +51,7 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.iters
-    n_out = S * B * U
+    n_out = S * B * (1 if a.chain == "reference" else U)
     eb = {"f32": 4, "i16": 2, "i24": 4, "i24_packed": 3}[a.fmt]
     res = {
         "taps": a.taps, "up": U, "frames": B, "streams": S, "fmt": a.fmt, "dither": a.dither,

@@ -7,11 +7,11 @@ SURVEY.md F6), so this stage is BUILD-DEFINED; the definition lives here and in
 
     counter-based RNG : Philox4x32-10 (Salmon et al., SC'11; Random123 constants)
         key     = (seed & 0xffffffff, seed >> 32)
-        counter = (c & 0xffffffff, c >> 32, stream_id, 0)   with c = absolute_sample_index >> 1
-        even samples use output words (0, 1), odd samples words (2, 3)
-    k1, k2  = word >> 8                          (24-bit integers)
-    TPDF    : d = float32(k1 + k2 - (2**24 - 1)) * 2**-24        in (-1, 1) LSB, triangular
-    RPDF    : d = float32(2*k1 + 1 - 2**24) * 2**-25             in (-0.5, 0.5) LSB, uniform
+        counter = (c & 0xffffffff, c >> 32, stream_id, 0)   with c = absolute_sample_index >> 2
+        sample i uses output word i & 3 (four samples per call)
+    a, b    = word >> 16, word & 0xffff          (two 16-bit integers)
+    TPDF    : d = float32(a + b - (2**16 - 1)) * 2**-16          in (-1, 1) LSB, triangular
+    RPDF    : d = float32(2*a + 1 - 2**16) * 2**-17              in (-0.5, 0.5) LSB, uniform
               (the reference's amplitude: (u-0.5)*2/2**bits == +-0.5 LSB at LSB = 2**-(bits-1))
     integer : q = clip(rint(fl32(fl32(y * 2**(bits-1)) + d)), -2**(bits-1), 2**(bits-1) - 1)
               rint = round-half-even, every operation rounded to float32 (no fused multiply-add)
@@ -64,18 +64,17 @@ def dither_lsb(mode, seed, stream_ids, sample_index):
     sample_index, stream_ids = np.broadcast_arrays(sample_index, stream_ids)
     if mode == DITHER_NONE:
         return np.zeros(sample_index.shape, dtype=np.float32)
-    ctr = sample_index >> np.uint64(1)
+    ctr = sample_index >> np.uint64(2)
     w = philox4x32_10(ctr & _MASK, ctr >> np.uint64(32), stream_ids, 0,
                       seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    odd = (sample_index & np.uint64(1)).astype(bool)
-    a = np.where(odd, w[2], w[0]).astype(np.int64) >> 8
-    b = np.where(odd, w[3], w[1]).astype(np.int64) >> 8
+    word = np.choose((sample_index & np.uint64(3)).astype(np.int64), list(w)).astype(np.int64)
+    a, b = word >> 16, word & 0xFFFF
     if mode == DITHER_TPDF:
-        t = a + b - ((1 << 24) - 1)
-        return (t.astype(np.float32) * np.float32(2.0 ** -24)).astype(np.float32)
+        t = a + b - ((1 << 16) - 1)
+        return (t.astype(np.float32) * np.float32(2.0 ** -16)).astype(np.float32)
     if mode == DITHER_RPDF:
-        t = 2 * a + 1 - (1 << 24)
-        return (t.astype(np.float32) * np.float32(2.0 ** -25)).astype(np.float32)
+        t = 2 * a + 1 - (1 << 16)
+        return (t.astype(np.float32) * np.float32(2.0 ** -17)).astype(np.float32)
     raise ValueError("unknown dither mode")
 
 

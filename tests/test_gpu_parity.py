@@ -73,10 +73,14 @@ def test_fir_stage_matches_reference_callback(tag):
     assert_parity(y[:, ::U], g["pre_dither"].astype(np.float32), f"{tag} FIR stage")
 
 
+@pytest.mark.parametrize("collapse", [True, False])
 @pytest.mark.parametrize("tag", ["c1", "default", "short"])
-def test_reference_chain_end_to_end(tag):
+def test_reference_chain_end_to_end(tag, collapse, monkeypatch):
     """interp -> FIR -> [::U] on device (chain='reference') against the reference callback's
-    pre-dither block (the golden run used the same streaming interpolator)."""
+    pre-dither block (the golden run used the same streaming interpolator): as ONE
+    base-rate FIR with taps (h_up (*) h)[::U] (the default) and as the staged two-kernel form."""
+    if not collapse:
+        monkeypatch.setenv("AFP_NO_COLLAPSE", "1")
     g = load_golden(f"cb_stream_process_{tag}")
     N, B, U, fs = (int(v) for v in g["params"])
     nblk = g["pre_dither"].shape[0]
@@ -84,7 +88,46 @@ def test_reference_chain_end_to_end(tag):
     with BatchFirEngine(g["taps"], n_streams=1, max_frames=B, upsample=U, chain="reference",
                         upsampler_taps=g["up_taps"]) as eng:
         y = run_blocks(eng, x, B)
+        stages = eng.stage_info()
+    assert len(stages) == (1 if collapse and U > 1 else (2 if U > 1 else 1))
     assert_parity(y[0], g["pre_dither"].reshape(-1).astype(np.float32), f"{tag} reference chain")
+
+
+def test_collapsed_reference_chain_batched_state_and_dither(monkeypatch):
+    """The collapsed chain on a batch: equals the staged chain within tolerance, the state blob restores
+    it, the dither counter advances per kept (base-rate) sample, ragged block sizes are fine."""
+    U, S, B = 4, 9, 1024
+    h = design.create_fir_filter(cutoff=[500, 8000], numtaps=251, window_type="kaiser", filter_type="bandpass",
+                                 samplerate=44100 * U)
+    h_up = U * design.create_fir_filter(cutoff=20000, numtaps=129, window_type="kaiser", samplerate=44100 * U)
+    sizes = [1024, 1000, 37, 512, 1024]
+    x = synth(S, sum(sizes), "noise")
+    xd = torch.from_numpy(x).cuda()
+
+    def go(**kw):
+        with BatchFirEngine(h, n_streams=S, max_frames=B, upsample=U, chain="reference", upsampler_taps=h_up, **kw) as e:
+            outs, pos = [], 0
+            for i, n in enumerate(sizes):
+                if i == 2:                                   # save / reset / restore in mid-stream
+                    blob = e.get_state()
+                    e.reset()
+                    e.set_state(blob)
+                outs.append(e.process(xd[:, pos:pos + n].contiguous()).cpu().numpy())
+                pos += n
+            return np.concatenate(outs, axis=1), len(e.stage_info())
+
+    y1, n1 = go()
+    monkeypatch.setenv("AFP_NO_COLLAPSE", "1")
+    y2, n2 = go()
+    monkeypatch.delenv("AFP_NO_COLLAPSE")
+    assert (n1, n2) == (1, 2) and y1.shape == (S, sum(sizes))
+    for s in range(S):
+        assert_parity(y1[s], y2[s], f"collapsed vs staged, stream {s}")
+        ref = rc.streaming_fir(h, rc.polyphase_upsample_whole(h_up, x[s], U).astype(np.float32))[::U]
+        assert_parity(y1[s], ref.astype(np.float32), f"collapsed vs oracle, stream {s}")
+    q1, _ = go(out_format="i24", dither="tpdf", seed=5)
+    ref_q = dq.epilogue(y1, dq.FMT_I24_IN_I32, dq.DITHER_TPDF, 5, np.arange(S), 0)
+    np.testing.assert_array_equal(q1, ref_q)
 
 
 @pytest.mark.parametrize("U,N,B", [(2, 251, 1024), (4, 251, 1024), (3, 129, 512), (4, 1001, 512),
