@@ -72,11 +72,11 @@ kern_t kernel_for(int U, int T, int nt, bool multi, int epi) {
     return nullptr;
 }
 
-kern_t row_kernel_for(int U, int T, int pad, int store, int epi) {
+kern_t row_kernel_for(int U, int T, int pad, int store, int epi, int spec_tgl) {
     switch (U) {
-        case 1: return afp_kernel_row_u1(T, pad, store, epi);
-        case 2: return afp_kernel_row_u2(T, pad, store, epi);
-        case 4: return afp_kernel_row_u4(T, pad, store, epi);
+        case 1: return afp_kernel_row_u1(T, pad, store, epi, spec_tgl);
+        case 2: return afp_kernel_row_u2(T, pad, store, epi, spec_tgl);
+        case 4: return afp_kernel_row_u4(T, pad, store, epi, spec_tgl);
     }
     return nullptr;
 }
@@ -414,7 +414,10 @@ int launch_stage_row(afp_ctx* c, Stage& s, const StageIO& io, const Align& al, c
     while (smem > kMaxSmem && tg_log2 > 5) { --tg_log2; smem = afp::row_smem_bytes(U, T, NT, tg_log2, s.kq_pad, sh.store, sh.pad); }
     if (smem > kMaxSmem) return AFP_OK;
     const int epi = io.decim == 1 ? afp::epi_code(io.fmt, io.dither) : afp::EPI_GENERIC;
-    kern_t k = row_kernel_for(U, T, sh.pad, sh.store, epi);
+    // streaming form (history | block, outputs for the block): the instantiation with the group size and the
+    // unclamped copy ranges compiled in, when the group size is the shape's own
+    const bool streaming = io.q_begin == s.kq_pad && io.len0 == s.kq_pad && io.len1 >= 4;
+    kern_t k = row_kernel_for(U, T, sh.pad, sh.store, epi, streaming ? tg_log2 : 0);
     if (!k) return AFP_OK;
     const int S = io.ns;
     const int lq = T << tg_log2, slots_cta = NT >> tg_log2;
@@ -646,10 +649,12 @@ int afp_create(const afp_config* cfg, afp_ctx** out_ctx) {
     for (int U : {1, 2, 4})
         for (const RowShape& sh : kRowShapes)
             for (int epi : kAllEpi) {
-                kern_t k = row_kernel_for(U, sh.T, sh.pad, sh.store, epi);
-                if (!k) continue;
-                e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-                if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, single-row kernel)");
+                for (int spec : {0, sh.tg_log2}) {
+                    kern_t k = row_kernel_for(U, sh.T, sh.pad, sh.store, epi, spec);
+                    if (!k) continue;
+                    e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+                    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, single-row kernel)");
+                }
             }
     for (int row : {32, 64})
         for (int nts : {1, 2, 4})

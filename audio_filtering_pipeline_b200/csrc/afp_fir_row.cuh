@@ -241,22 +241,26 @@ __host__ __device__ constexpr int row_tabb_offset(int kq) { return kq + 4; }
 // the number of tap slots in the last of them (0 = it is full).  Granularity of the specialised tails:
 __host__ __device__ constexpr int row_tail_step(int U, int T) { return U == 1 ? 4 : 2; }
 
-template <int U, int T, int NT, int EPI, int STORE, int PAD>
+// TGL: log2(threads per group) fixed at compile time (0 = read it from the parameters); STREAM: the launch is
+// the streaming form (q_begin == kq == len0, so no copy range needs clamping at the front and nothing lies
+// before the sequence) - both turn per-item uniform-datapath arithmetic into immediates.
+template <int U, int T, int NT, int EPI, int STORE, int PAD, int TGL = 0, bool STREAM = false>
 __global__ void __launch_bounds__(NT, row_min_ctas(U, T, NT))
 fir_row_kernel(const __grid_constant__ FirParams P) {
     static_assert(U == 1 || U % 2 == 0, "row kernel: U = 1 or even");
     using LY = RowLayout<T, PAD>;
     extern __shared__ float4 smem[];
     const int tid = threadIdx.x;
-    const int tg = 1 << P.tg_log2;                 // threads per segment (>= 32)
-    const int slots = NT >> P.tg_log2;             // thread groups per CTA
+    const int tgl = TGL ? TGL : P.tg_log2;
+    const int tg = 1 << tgl;                       // threads per segment (>= 32)
+    const int slots = NT >> tgl;                   // thread groups per CTA
     const int lq = tg * T;                         // base positions per segment
     const int kq = P.n_chunks * T;                 // padded taps per phase = halo
     const int region_s = kq + lq;
     const int region_g = LY::granules(region_s);
     // warp-uniform by construction (a group is one or more whole warps)
     const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    const int slot = warp_u >> (P.tg_log2 - 5);
+    const int slot = warp_u >> (tgl - 5);
     const bool lead_warp = ((warp_u << 5) & (tg - 1)) == 0;   // first warp of its group: issues the copies
     const int lt = tid & (tg - 1);
     // shared memory: [2 mbarriers per thread group | region buffers | store staging]
@@ -290,9 +294,9 @@ fir_row_kernel(const __grid_constant__ FirParams P) {
         const int start = P.q_begin + g * lq - kq;
         const float* r0 = P.src0 + ((long long)s * P.pitch0 + start);
         const float* r1 = P.src1 + ((long long)s * P.pitch1 - P.len0 + start);
-        const int i_lo = min(max((-start) >> 2, 0), n4);
-        const int i_hi = min(max((L - start) >> 2, i_lo), n4);
-        const int i_sp = min(max((P.len0 - start) >> 2, i_lo), i_hi);
+        const int i_lo = STREAM ? 0 : min(max((-start) >> 2, 0), n4);
+        const int i_hi = STREAM ? min((L - start) >> 2, n4) : min(max((L - start) >> 2, i_lo), n4);
+        const int i_sp = STREAM ? max((P.len0 - start) >> 2, 0) : min(max((P.len0 - start) >> 2, i_lo), i_hi);
         if (PAD == 0) {          // one elected lane: one bulk copy per source
             const unsigned n0 = AFP_ROW_DBG_LOADS(true) ? (unsigned)(i_sp - i_lo) * 16u : 0u;
             const unsigned n1 = AFP_ROW_DBG_LOADS(true) ? (unsigned)(i_hi - i_sp) * 16u : 0u;
@@ -368,7 +372,7 @@ fir_row_kernel(const __grid_constant__ FirParams P) {
                 }
             }
         }
-        if (start < 0 || start + region_s > L) {   // group-uniform; 'same'-mode launches only
+        if ((!STREAM && start < 0) || start + region_s > L) {   // group-uniform; 'same' modes, ragged last segment
             const int i_lo = min(max((-start) >> 2, 0), n4), i_hi = min(max((L - start) >> 2, i_lo), n4);
             for (int i4 = lt; i4 < n4; i4 += tg)
                 if (i4 < i_lo || i4 >= i_hi) region_w[LY::phys(i4)] = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -37,9 +37,11 @@ kern_t pick_kernel(int nt, bool multi, int epi) {
 namespace afp { struct TcParams; typedef void (*tc_kern_t)(const TcParams); }
 afp::tc_kern_t afp_kernel_tc(int row, int nts, int epi);   // tensor-core path: row length 32 / 64, nts = frames / (8 row)
 // single-row kernel (afp_fir_row.cuh): 256-thread CTAs, lookup by tile, layout (pad), store path, epilogue
-afp::kern_t afp_kernel_row_u1(int T, int pad, int store, int epi);
-afp::kern_t afp_kernel_row_u2(int T, int pad, int store, int epi);
-afp::kern_t afp_kernel_row_u4(int T, int pad, int store, int epi);
+// spec_tgl: log2(group size) when the launch is the streaming form (selects the instantiation with that
+// size compiled in, if there is one), else 0
+afp::kern_t afp_kernel_row_u1(int T, int pad, int store, int epi, int spec_tgl);
+afp::kern_t afp_kernel_row_u2(int T, int pad, int store, int epi, int spec_tgl);
+afp::kern_t afp_kernel_row_u4(int T, int pad, int store, int epi, int spec_tgl);
 afp::kern_t afp_kernel_u1(int T, int nt, bool multi, int epi);
 afp::kern_t afp_kernel_u2(int T, int nt, bool multi, int epi);
 afp::kern_t afp_kernel_u3(int T, int nt, bool multi, int epi);

@@ -30,6 +30,15 @@ template <int PAD> kern_t lookup_p(int U, int T, int store) {
     return nullptr;
 }
 static kern_t lookup(int U, int T, int store, int pad) { return pad ? lookup_p<1>(U, T, store) : lookup_p<0>(U, T, store); }
+// specialised instantiations (compile-time group size, streaming form) of the shapes the library uses
+static kern_t lookup_spec(int U, int T, int store, int pad, int tgl) {
+    if (U == 1 && T == 16 && store == 0 && pad == 1 && tgl == 5) return (kern_t)afp::fir_row_kernel<1, 16, 256, EPI, 0, 1, 5, true>;
+    if (U == 2 && T == 8 && store == 0 && pad == 0 && tgl == 6) return (kern_t)afp::fir_row_kernel<2, 8, 256, EPI, 0, 0, 6, true>;
+    if (U == 2 && T == 16 && store == 2 && pad == 0 && tgl == 5) return (kern_t)afp::fir_row_kernel<2, 16, 256, EPI, 2, 0, 5, true>;
+    if (U == 4 && T == 4 && store == 2 && pad == 0 && tgl == 7) return (kern_t)afp::fir_row_kernel<4, 4, 256, EPI, 2, 0, 7, true>;
+    if (U == 4 && T == 8 && store == 2 && pad == 0 && tgl == 5) return (kern_t)afp::fir_row_kernel<4, 8, 256, EPI, 2, 0, 5, true>;
+    return nullptr;
+}
 
 int main(int argc, char** argv) {
     const int N = argc > 1 ? atoi(argv[1]) : 51;
@@ -44,7 +53,8 @@ int main(int argc, char** argv) {
     const int dbg = argc > 10 ? atoi(argv[10]) : 0;   // needs -DAFP_ROW_DBG: 1 no FMA, 2 no stores, 4 no loads
     const int NT = 256, NBUF = 3;
     const int pad = argc > 11 ? atoi(argv[11]) : 0;   // 1: padded layout + cp.async loader, 0: linear + bulk copies
-    kern_t k = lookup(U, T, store, pad);
+    const int spec = argc > 12 ? atoi(argv[12]) : 0;   // 1: compile-time group size + streaming form
+    kern_t k = spec ? lookup_spec(U, T, store, pad, tg_log2) : lookup(U, T, store, pad);
     if (!k) { printf("no kernel for U=%d T=%d\n", U, T); return 1; }
     const int step = afp::row_tail_step(U, T);
     const int slots_needed = (((N + U - 1) / U + (U == 1 ? 1 : 0)) + step - 1) / step * step;   // tap slots per phase
@@ -142,7 +152,7 @@ int main(int argc, char** argv) {
     CK(cudaEventSynchronize(e1));
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= iters;
     const double gs = (double)n_out / ms / 1e6;
-    printf("  RESULT N=%d U=%d T=%d tg=%d store=%d pad=%d ctas=%d dbg=%d: %.4f ms  %.1f Gsamples/s  %.1f TFLOP/s (2N/U)  %.0f GB/s alg\n",
-           N, U, T, tg, store, pad, ctas, dbg, ms, gs, gs * 2.0 * ((N + U - 1) / U) / 1e3, gs * (4.0 / U + 4.0));
+    printf("  RESULT N=%d U=%d T=%d tg=%d store=%d pad=%d spec=%d ctas=%d dbg=%d: %.4f ms  %.1f Gsamples/s  %.1f TFLOP/s (2N/U)  %.0f GB/s alg\n",
+           N, U, T, tg, store, pad, spec, ctas, dbg, ms, gs, gs * 2.0 * ((N + U - 1) / U) / 1e3, gs * (4.0 / U + 4.0));
     return bad ? 2 : 0;
 }
