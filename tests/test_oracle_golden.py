@@ -133,3 +133,18 @@ def test_polyphase_upsampler_block_vs_whole():
         up = rc.PolyphaseUpsampler(h, U)
         blocks = np.concatenate([up.step(x[i:i + 512]) for i in range(0, 4096, 512)])
         assert np.abs(blocks - whole).max() < 1e-7
+
+
+def test_reference_chain_collapses_to_one_base_rate_fir():
+    """The identity behind afp_abi.cu::rebuild_fused, checked on the CPU with the oracle alone:
+    up-sample by U (zero-stuff + h_up) -> FIR h at fs*U -> [::U]  ==  base-rate FIR with taps (h_up (*) h)[::U]."""
+    from oracle import reference_chain as rc
+    rng = np.random.default_rng(3)
+    for U, L, N in [(4, 129, 251), (2, 33, 51), (3, 20, 7), (4, 5, 1001)]:
+        h_up = rng.standard_normal(L) / L
+        h = rng.standard_normal(N) / N
+        x = rng.standard_normal(600)
+        staged = rc.streaming_fir(h, rc.polyphase_upsample_whole(h_up, x, U))[::U]
+        g0 = np.convolve(h_up, h)[::U]
+        fused = rc.streaming_fir(g0, x)
+        np.testing.assert_allclose(fused[: len(staged)], staged, rtol=0, atol=1e-12)
