@@ -196,7 +196,9 @@ int build_stage(afp_ctx* c, Stage& s, int kind, int U, const double* taps, int n
     // Long single-table U = 1 filters can also run on the tensor cores (afp_fir_tc.cuh).  Both kernels
     // then share one history format: the last kq_pad samples with kq_pad a multiple of 32 (the tensor
     // kernel's row length), so a stage may switch kernel from one block to the next.
-    const int tc_min = std::getenv("AFP_TC_MIN_TAPS") ? std::atoi(std::getenv("AFP_TC_MIN_TAPS")) : 640;
+    // (crossover against the single-row FFMA2 kernel measured at 16384 streams: equal at 385 taps / 512-frame
+    // blocks, +13 % at 385 / 1024, +27 % at 501 / 1024 - gpurun_out call 20)
+    const int tc_min = std::getenv("AFP_TC_MIN_TAPS") ? std::atoi(std::getenv("AFP_TC_MIN_TAPS")) : 400;
     const bool tc_ok = U == 1 && n_sub == 1 && n >= tc_min && !env_flag("AFP_NO_TC");
     // History length = padded taps per phase.  A multiple of 16 (every tile size divides it, so the two
     // FFMA2 kernels share one history format and a stage may switch kernel from block to block), with room

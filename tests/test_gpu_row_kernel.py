@@ -50,7 +50,7 @@ def oracle(h, x, U):
 # tap counts chosen around every tile / tail boundary: U=1 tiles of 16 with 4-slot tails (N+1 slots),
 # U=2 tiles of 8 (<= 64 taps) / 16 with 2-slot tails, U=4 tiles of 4 (<= 64 taps) / 8
 @pytest.mark.parametrize("U,N", [(1, 1), (1, 2), (1, 3), (1, 7), (1, 15), (1, 16), (1, 47), (1, 51), (1, 52), (1, 63),
-                                 (1, 64), (1, 101), (1, 251), (1, 501),
+                                 (1, 64), (1, 101), (1, 251), (1, 385),
                                  (2, 2), (2, 9), (2, 27), (2, 51), (2, 64), (2, 65), (2, 101), (2, 129), (2, 251), (2, 501),
                                  (4, 3), (4, 33), (4, 51), (4, 64), (4, 65), (4, 99), (4, 101), (4, 103), (4, 251), (4, 1001)])
 def test_row_kernel_matches_oracle(U, N):

@@ -37,7 +37,8 @@ def run(eng, x, sizes):
     return np.concatenate(outs, axis=1), kernels
 
 
-@pytest.mark.parametrize("N,B,S", [(1001, 512, 37), (1001, 256, 16), (641, 512, 5), (900, 512, 1)])
+@pytest.mark.parametrize("N,B,S", [(1001, 512, 37), (1001, 256, 16), (641, 512, 5), (900, 512, 1), (449, 1024, 9),
+                                   (401, 512, 3)])
 def test_tensor_path_matches_lfilter(N, B, S):
     h = remez1001() if N == 1001 else design.create_fir_filter(cutoff=9000, numtaps=N, window_type="kaiser",
                                                              samplerate=96000)
