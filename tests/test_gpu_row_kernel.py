@@ -138,3 +138,32 @@ def test_row_kernel_large_batch_linearity():
     an = a[:64].cpu().numpy()
     for s in range(64):
         assert_parity(ya[s].cpu().numpy(), oracle(h, an[s], U), f"stream {s}")
+
+
+@pytest.mark.parametrize("U,N,fmt", [(4, 51, "f32"), (4, 101, "i16"), (2, 51, "i24"), (2, 129, "f32"), (1, 51, "i24_packed"),
+                                     (1, 251, "f32")])
+def test_row_kernel_writes_nothing_outside_its_rows(U, N, fmt):
+    """Guard bands: the caller's output rows are longer than the block needs (and the pitch is not a
+    multiple of a warp's store width); everything past the valid samples of every row must stay untouched,
+    for whole-warp blocks (transposed stores) and ragged ones (direct stores), and so must the samples of a
+    guard stream row below the batch."""
+    S = 7
+    h = taps(N, U)
+    dt = {"f32": torch.float32, "i16": torch.int16, "i24": torch.int32, "i24_packed": torch.uint8}[fmt]
+    k = 3 if fmt == "i24_packed" else 1
+    sentinel = 77
+    with BatchFirEngine(h, n_streams=S, max_frames=1024, upsample=U, out_format=fmt,
+                        dither="tpdf" if fmt != "f32" else "none", seed=9) as eng, \
+            BatchFirEngine(h, n_streams=S, max_frames=1024, upsample=U, out_format=fmt,
+                           dither="tpdf" if fmt != "f32" else "none", seed=9) as ref:
+        for frames in (1024, 1000, 516, 4):
+            x = torch.from_numpy(noise(S, frames, seed=frames)).cuda()
+            cols = frames * U * k
+            pad = 48 if fmt != "i24_packed" else 48 * 3                  # keeps rows 16-byte aligned
+            big = torch.full((S + 1, cols + pad), sentinel, dtype=dt, device="cuda")
+            eng.process(x, big[:S])
+            want = ref.process(x)
+            assert eng.stage_info()[-1]["kernel"] == ROW
+            assert torch.equal(big[:S, :cols], want), f"frames={frames}"
+            assert bool((big[:S, cols:] == sentinel).all()), f"frames={frames}: wrote past the end of a row"
+            assert bool((big[S] == sentinel).all()), f"frames={frames}: wrote below the batch"
