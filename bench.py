@@ -358,19 +358,20 @@ def run_ours(args):
 
 
 def c5_sweep(local, hbm_peak_gbs, fma_peak_tflops, iters=10):
-    """Kernel-only points of BASELINE.json configs[4] (batch sweep: {51,101,251} taps x {1,2,4}x up-sampling,
-    f32 out, 1024-frame blocks), device-resident I/O rotated over 3 buffer pairs (0.8-2 GB, far beyond L2),
+    """Kernel-only points of BASELINE.json configs[4] (batch sweep: {51,101,251,1001} taps x {1,2,4}x up-sampling,
+    f32 out, 1024-frame blocks - 512 for the 1001-tap U=1 case, the tensor kernel's block), device-resident I/O rotated over 3 buffer pairs (0.8-2 GB, far beyond L2),
     CUDA events.  Work per output sample: 2*ceil(N/U) flop, 4/U + 4 bytes; the relevant roof
     is the lower of the two."""
     import torch
     from audio_filtering_pipeline_b200.engine import BatchFirEngine
     dev = torch.device("cuda", local)
     out = []
-    for n_taps, up, streams in [(51, 1, 65536), (51, 2, 32768), (51, 4, 32768), (101, 1, 32768), (101, 2, 32768),
-                                (101, 4, 32768), (251, 1, 16384), (251, 2, 16384), (251, 4, 16384)]:
+    for n_taps, up, streams, B in [(51, 1, 65536, 1024), (51, 2, 32768, 1024), (51, 4, 32768, 1024),
+                                   (101, 1, 32768, 1024), (101, 2, 32768, 1024), (101, 4, 32768, 1024),
+                                   (251, 1, 16384, 1024), (251, 2, 16384, 1024), (251, 4, 16384, 1024),
+                                   (1001, 1, 16384, 512), (1001, 2, 8192, 1024), (1001, 4, 8192, 1024)]:
         rng = np.random.default_rng(n_taps * 8 + up)
         h = up * rng.standard_normal(n_taps) / n_taps
-        B = 1024
         eng = BatchFirEngine(h, n_streams=streams, max_frames=B, upsample=up, device=local)
         xs = [0.1 * torch.randn(streams, B, device=dev) for _ in range(3)]
         ys = [torch.empty(streams, B * up, device=dev) for _ in range(3)]
