@@ -46,6 +46,7 @@ struct Stage {
     std::vector<double> taps;       // as given (EQ: the centre-aligned taps-domain sum)
     std::vector<float> table;       // n_sub tables, natural order, each zero padded to U*kq_pad
     float* hist[2] = {nullptr, nullptr};
+    float* hist_scratch = nullptr;  // third history buffer: long blocks run on the tensor cores as a chain of sub-blocks
     long long hist_pitch = 0;
     int cur = 0;
     Geometry geo;
@@ -180,6 +181,7 @@ int rate_of(const afp_ctx* c) {   // processing rate / base rate
 
 void free_stage(Stage& s) {
     for (int i = 0; i < 2; ++i) { if (s.hist[i]) cudaFree(s.hist[i]); s.hist[i] = nullptr; }
+    if (s.hist_scratch) { cudaFree(s.hist_scratch); s.hist_scratch = nullptr; }
     for (int i = 0; i < 2; ++i) { if (s.tc_w[i]) cudaFree(s.tc_w[i]); s.tc_w[i] = nullptr; s.tc_chunks[i] = 0; }
     s.active = false;
 }
@@ -503,9 +505,51 @@ int launch_stage(afp_ctx* c, Stage& s, const StageIO& io, cudaStream_t stream) {
 }
 
 // streaming launch: history | new block, outputs for the new block, history rolled forward
+// Largest block (512 or 256 frames... up to 1024) one tensor-kernel launch of this stage can take: the
+// 16-stream hi/lo tiles of [history | block] plus two 8 KB tap-ring slots must fit in shared memory.
+int tc_max_block(const Stage& s) {
+    if (!s.tc_w[0] || s.U != 1) return 0;
+    for (int f : {1024, 512, 256}) {
+        const int R = f % 512 == 0 ? 64 : 32;
+        if (2 * afp::TC_STREAMS * (s.kq_pad + f) * 4 + 2 * 8192 + 512 <= kMaxSmem && afp_kernel_tc(R, f / (8 * R), afp::EPI_GENERIC)) return f;
+    }
+    return 0;
+}
+
 int run_streaming(afp_ctx* c, Stage& s, const float* in, long long in_pitch, int len,
                   void* out, long long out_pitch, int fmt, int dither, int decim,
                   unsigned long long sample_base, int s0, int ns, cudaStream_t stream) {
+    // A block too long for one tensor-kernel launch (the reference's default blocksize is 4096,
+    // stream_process.py:23) runs as a chain of sub-blocks, each a complete streaming launch: history A ->
+    // scratch -> A -> ... -> B, so the block still ends with its history in the "other" buffer like any
+    // single launch (+30 % over the FFMA2 kernel for >= 400-tap filters).
+    const int sub = (decim == 1 && !env_flag("AFP_NO_TC_CHAIN")) ? tc_max_block(s) : 0;
+    if (sub > 0 && len > sub && len % sub == 0 && aligned16(in) && in_pitch % 4 == 0) {
+        if (!s.hist_scratch) {
+            const size_t bytes = (size_t)c->cfg.n_streams * s.hist_pitch * sizeof(float);
+            AFP_CUDA(c, cudaMalloc(&s.hist_scratch, bytes));
+        }
+        const int k = len / sub;
+        const int eb = fmt == AFP_FMT_I16 ? 2 : (fmt == AFP_FMT_I24_PACKED ? 3 : 4);
+        float* const A = s.hist[s.cur];
+        float* const B = s.hist[s.cur ^ 1];
+        for (int j = 0; j < k; ++j) {
+            float* hin = j == 0 ? A : ((j & 1) ? s.hist_scratch : A);
+            float* hout = j == k - 1 ? B : (((j + 1) & 1) ? s.hist_scratch : A);
+            StageIO io;
+            io.s0 = s0; io.ns = ns;
+            io.src0 = hin + (long long)s0 * s.hist_pitch; io.pitch0 = s.hist_pitch; io.len0 = s.kq_pad;
+            io.src1 = in + (long long)j * sub; io.pitch1 = in_pitch; io.len1 = sub;
+            io.q_begin = s.kq_pad; io.n_q = sub;
+            io.out = static_cast<unsigned char*>(out) + (size_t)j * sub * eb; io.out_pitch = out_pitch;
+            io.fmt = fmt; io.dither = dither; io.decim = 1;
+            io.sample_base = sample_base + (unsigned long long)j * sub;
+            io.hist_out = hout + (long long)s0 * s.hist_pitch; io.hist_pitch = s.hist_pitch; io.hist_len = s.kq_pad; io.hist_from = sub;
+            int rc = launch_stage(c, s, io, stream);
+            if (rc) return rc;
+        }
+        return AFP_OK;
+    }
     StageIO io;
     io.s0 = s0; io.ns = ns;
     io.src0 = s.hist[s.cur] + (long long)s0 * s.hist_pitch; io.pitch0 = s.hist_pitch; io.len0 = s.kq_pad;

@@ -88,7 +88,7 @@ def test_kernels_interchange_block_by_block():
     x = noise(4, sum(sizes))
     with BatchFirEngine(h, n_streams=4, max_frames=1024) as eng:
         y, kernels = run(eng, x, sizes)
-    assert kernels == [1, 2, 1, 1, 0, 2, 1]          # 1024 frames x 1001 taps does not fit the tensor kernel's shared memory
+    assert kernels == [1, 2, 1, 1, 0, 1, 1]          # 1024 frames x 1001 taps: a chain of two 512-frame tensor launches
     for s in range(4):
         assert_parity(y[s], rc.streaming_fir(h, x[s]).astype(np.float32), f"stream {s}")
 
@@ -164,3 +164,24 @@ def test_long_fused_eq_runs_on_tensor_cores():
     for s in range(S):
         ref = lfilter(main, 1.0, lfilter(comb, 1.0, x[s].astype(np.float64)).astype(np.float32).astype(np.float64))
         assert_parity(y[s], ref.astype(np.float32), "fused EQ on tensor cores")
+
+
+@pytest.mark.parametrize("fmt,dither", [("f32", "none"), ("i24", "tpdf"), ("i24_packed", "tpdf")])
+def test_long_blocks_chain_through_the_tensor_kernel(fmt, dither):
+    """Blocks too long for one tensor-kernel launch (the reference's default blocksize is 4096) run as a chain
+    of 512-frame sub-blocks with the history handed through a scratch buffer: bit-identical to feeding the
+    512-frame blocks one by one (same kernel, same dither counters), state left where a single launch
+    leaves it, and within tolerance of the oracle."""
+    h = remez1001()
+    S, n = 21, 4096 + 2048 + 512 + 4096
+    x = noise(S, n, amp=0.2)
+    kw = dict(out_format=fmt, dither=dither, seed=11)
+    with BatchFirEngine(h, n_streams=S, max_frames=4096, **kw) as eng:
+        y_big, k_big = run(eng, x, [4096, 2048, 512, 4096])
+    with BatchFirEngine(h, n_streams=S, max_frames=512, **kw) as eng:
+        y_small, k_small = run(eng, x, [512] * (n // 512))
+    assert k_big == [1, 1, 1, 1] and set(k_small) == {1}
+    np.testing.assert_array_equal(y_big, y_small)
+    if fmt == "f32":
+        for s in range(0, S, 5):
+            assert_parity(y_big[s], rc.streaming_fir(h, x[s]).astype(np.float32), f"stream {s}")
