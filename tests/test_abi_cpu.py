@@ -71,3 +71,41 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+def _build_c_host(tmp_path):
+    """examples/c_host.c: a host in plain C99 against include/afp.h (what a cgo / JNI / FFI binding calls)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    _build.build()
+    libdir = os.path.join(ROOT, "audio_filtering_pipeline_b200")
+    exe = str(tmp_path / "c_host")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    "-o", exe, os.path.join(ROOT, "examples", "c_host.c"), "-L", libdir, "-lafp_b200", "-lm",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    return exe
+
+
+def test_plain_c_host_compiles_links_and_fails_loudly_without_a_gpu(tmp_path):
+    import subprocess
+    exe = _build_c_host(tmp_path)
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("GPU present: covered by the gpu-marked run")
+    except ImportError:
+        pass
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode != 0 and "afp_create" in res.stderr and "failed" in res.stderr
+
+
+@pytest.mark.gpu
+def test_plain_c_host_runs_on_the_gpu(tmp_path):
+    import subprocess
+    exe = _build_c_host(tmp_path)
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "-> ok" in res.stdout
