@@ -33,6 +33,8 @@ static kern_t lookup(int U, int T, int store, int pad) { return pad ? lookup_p<1
 // specialised instantiations (compile-time group size, streaming form) of the shapes the library uses
 static kern_t lookup_spec(int U, int T, int store, int pad, int tgl) {
     if (U == 1 && T == 16 && store == 0 && pad == 1 && tgl == 5) return (kern_t)afp::fir_row_kernel<1, 16, 256, EPI, 0, 1, 5, true>;
+    if (U == 1 && T == 16 && store == 0 && pad == 1 && tgl == -5) return (kern_t)afp::fir_row_kernel<1, 16, 128, EPI, 0, 1, 5, true>;   // 128-thread CTAs
+    if (U == 2 && T == 8 && store == 0 && pad == 0 && tgl == -6) return (kern_t)afp::fir_row_kernel<2, 8, 128, EPI, 0, 0, 6, true>;
     if (U == 2 && T == 8 && store == 0 && pad == 0 && tgl == 6) return (kern_t)afp::fir_row_kernel<2, 8, 256, EPI, 0, 0, 6, true>;
     if (U == 2 && T == 16 && store == 2 && pad == 0 && tgl == 5) return (kern_t)afp::fir_row_kernel<2, 16, 256, EPI, 2, 0, 5, true>;
     if (U == 4 && T == 4 && store == 2 && pad == 0 && tgl == 7) return (kern_t)afp::fir_row_kernel<4, 4, 256, EPI, 2, 0, 7, true>;
@@ -51,10 +53,10 @@ int main(int argc, char** argv) {
     const int store = argc > 8 ? atoi(argv[8]) : 0;
     int ctas = argc > 9 ? atoi(argv[9]) : 0;
     const int dbg = argc > 10 ? atoi(argv[10]) : 0;   // needs -DAFP_ROW_DBG: 1 no FMA, 2 no stores, 4 no loads
-    const int NT = 256, NBUF = 3;
+    const int NT = (argc > 13 && atoi(argv[13]) == 128) ? 128 : 256, NBUF = 3;   // argv[13]: CTA size
     const int pad = argc > 11 ? atoi(argv[11]) : 0;   // 1: padded layout + cp.async loader, 0: linear + bulk copies
     const int spec = argc > 12 ? atoi(argv[12]) : 0;   // 1: compile-time group size + streaming form
-    kern_t k = spec ? lookup_spec(U, T, store, pad, tg_log2) : lookup(U, T, store, pad);
+    kern_t k = spec ? lookup_spec(U, T, store, pad, NT == 128 ? -tg_log2 : tg_log2) : lookup(U, T, store, pad);
     if (!k) { printf("no kernel for U=%d T=%d\n", U, T); return 1; }
     const int step = afp::row_tail_step(U, T);
     const int slots_needed = (((N + U - 1) / U + (U == 1 ? 1 : 0)) + step - 1) / step * step;   // tap slots per phase
