@@ -614,7 +614,7 @@ int ensure_tmp(afp_ctx* c) {
             if (c->tmp_b) { cudaFree(c->tmp_b); c->tmp_b = nullptr; }
         }
     }
-    if ((c->eq.active || stateless) && !c->tmp_b) {
+    if ((c->eq.active || stateless) && !c->tmp_b && !c->fused.active) {
         const long long need = rate_len + (eq_is_buffer_same(c) ? c->xhist_len : 0);
         c->pitch_b = (need + 3) / 4 * 4;
         AFP_CUDA(c, cudaMalloc(&c->tmp_b, (size_t)S * c->pitch_b * sizeof(float)));
@@ -751,23 +751,40 @@ int afp_destroy(afp_ctx* c) {
 // dropping U-1 of U.  Exact in exact arithmetic; in float32 it skips the rounding of the up-sampled
 // intermediate (the staged form stays available: AFP_NO_COLLAPSE=1, and is what runs with an EQ stage or
 // a decimation factor other than U).
-static int rebuild_fused(afp_ctx* c) {
+// The same holds with the streaming fused EQ (one table sum_b g_b h_b, AFP_EQ_FUSED) in the chain: it is one
+// more LTI stage at the processing rate, so g = h_up (*) eq (*) h; and with U = 1 the EQ and the main FIR are
+// one filter eq (*) h (one launch, no intermediate, and >= 400 combined taps reach the tensor path).  Not
+// done for the DAC chain with U > 1: there the EQ runs at the base rate and folding it into the polyphase
+// filter would multiply its cost by U.  keep_state: a gain change keeps the carried history (it holds input
+// samples only, so it is valid for any taps); a new filter or EQ bank resets it like every other stage.
+static std::vector<double> convolve(const std::vector<double>& a, const std::vector<double>& b) {
+    std::vector<double> g(a.size() + b.size() - 1, 0.0);
+    for (size_t i = 0; i < a.size(); ++i)
+        for (size_t k = 0; k < b.size(); ++k) g[i + k] += a[i] * b[k];
+    return g;
+}
+
+static int rebuild_fused(afp_ctx* c, bool keep_state = false) {
     const int U = c->cfg.upsample;
-    const bool want = c->cfg.chain == AFP_CHAIN_REFERENCE && U > 1 && c->cfg.eq_mode == AFP_EQ_NONE && c->decim == U &&
-                      c->up.active && c->mainf.active && !env_flag("AFP_NO_COLLAPSE");
+    const bool ref_up = c->cfg.chain == AFP_CHAIN_REFERENCE && U > 1;
+    const bool eq_ok = c->cfg.eq_mode == AFP_EQ_NONE || (c->cfg.eq_mode == AFP_EQ_FUSED && c->eq.active);
+    const bool shape_ok = ref_up ? (c->decim == U && c->up.active) : (U == 1 && c->decim == 1 && c->cfg.eq_mode == AFP_EQ_FUSED);
+    const bool want = eq_ok && shape_ok && c->mainf.active && !env_flag("AFP_NO_COLLAPSE");
     if (!want) { free_stage(c->fused); return AFP_OK; }
-    const std::vector<double>& a = c->up.taps;
-    const std::vector<double>& b = c->mainf.taps;
-    const size_t ng = a.size() + b.size() - 1, n0 = (ng + U - 1) / U;
-    std::vector<double> g0(n0, 0.0);
-    for (size_t j = 0; j < n0; ++j) {
-        const size_t m = j * U;                          // g[m] = sum_l a[l] * b[m-l]
-        const size_t l0 = m >= b.size() ? m - (b.size() - 1) : 0, l1 = std::min(m, a.size() - 1);
-        double acc = 0.0;
-        for (size_t l = l0; l <= l1; ++l) acc += a[l] * b[m - l];
-        g0[j] = acc;
+    std::vector<double> g = c->mainf.taps;
+    if (c->cfg.eq_mode == AFP_EQ_FUSED) g = convolve(c->eq.taps, g);
+    if (ref_up) g = convolve(c->up.taps, g);
+    const int step = ref_up ? U : 1;
+    std::vector<double> g0((g.size() + step - 1) / step);
+    for (size_t j = 0; j < g0.size(); ++j) g0[j] = g[j * step];
+    if ((long long)g0.size() + 16 > afp::MAX_TAPS) { free_stage(c->fused); return AFP_OK; }   // too long for one table: stay staged
+    // two tensor-kernel stages beat one FFMA2 stage: do not merge EQ and main FIR into a filter that is too
+    // long for the tensor kernel's shared memory (16 streams x [history | 256 frames], hi + lo, + tap ring)
+    if (!ref_up) {
+        const long long kq64 = ((long long)g0.size() + 63) / 64 * 64;
+        if (2 * afp::TC_STREAMS * (kq64 + 256) * 4 + 2 * 8192 + 512 > kMaxSmem) { free_stage(c->fused); return AFP_OK; }
     }
-    return build_stage(c, c->fused, ST_MAIN, 1, g0.data(), (int)n0);
+    return build_stage(c, c->fused, ST_MAIN, 1, g0.data(), (int)g0.size(), 1, keep_state);
 }
 
 int afp_set_taps(afp_ctx* c, const double* taps, int32_t n) {
@@ -800,7 +817,8 @@ int afp_set_eq(afp_ctx* c, const double* band_taps, const int32_t* band_len, int
         p += band_len[b];
         c->gains.push_back(gains ? gains[b] : 1.0);
     }
-    return rebuild_eq(c, true);
+    int rc = rebuild_eq(c, true);
+    return rc ? rc : rebuild_fused(c, false);
 }
 
 int afp_set_gains(afp_ctx* c, const double* gains, int32_t n_bands) {
@@ -811,7 +829,8 @@ int afp_set_gains(afp_ctx* c, const double* gains, int32_t n_bands) {
         if (!std::isfinite(gains[b])) return fail(c, AFP_ERR_INVALID, "non-finite gain");
         c->gains[b] = gains[b];
     }
-    return rebuild_eq(c, false);
+    int rc = rebuild_eq(c, false);
+    return rc ? rc : rebuild_fused(c, true);
 }
 
 int32_t afp_out_frames(const afp_ctx* c, int32_t frames) {

@@ -231,9 +231,16 @@ def test_helper_shims():
     assert_parity(down, refd.astype(np.float32), "safe_downsample")
 
 
-def test_decimate_option_and_gain_update():
-    """decimate keeps every n-th output; set_gains swaps the EQ table without touching the state."""
+@pytest.mark.parametrize("collapse", [True, False])
+def test_decimate_option_and_gain_update(collapse, monkeypatch):
+    """decimate keeps every n-th output; set_gains swaps the EQ table without touching the state.  With the EQ
+    folded into the main FIR (the default for the streaming fused form at U = 1) the carried state is the INPUT,
+    so after a gain change the new gains also apply to the carried samples - what the reference's sliding
+    input_buffer does (stream_process_EQ.py:119-129); the staged form (AFP_NO_COLLAPSE=1) carries EQ outputs
+    computed with the old gains through the main filter's history."""
     from scipy.signal import lfilter
+    if not collapse:
+        monkeypatch.setenv("AFP_NO_COLLAPSE", "1")
     h = design.create_fir_filter(cutoff=5000, numtaps=151, samplerate=48000)
     x = (0.1 * np.random.default_rng(5).standard_normal((2, 4096))).astype(np.float32)
     with BatchFirEngine(h, n_streams=2, max_frames=1024, decimate=4) as e:
@@ -246,10 +253,14 @@ def test_decimate_option_and_gain_update():
         ya = run_host(e, x[:, :2048], 1024)
         e.set_gains(g2)
         yb = run_host(e, x[:, 2048:], 1024)
+        assert len(e.stage_info()) == (1 if collapse else 2)
     for s in range(2):
         xs = x[s].astype(np.float64)
         e1 = lfilter(design.combine_eq_taps(bank, g1), 1.0, xs)
         e2 = lfilter(design.combine_eq_taps(bank, g2), 1.0, xs)
-        eq = np.concatenate([e1[:2048], e2[2048:]]).astype(np.float32).astype(np.float64)
-        ref = lfilter(h, 1.0, eq)
+        if collapse:
+            ref = np.concatenate([lfilter(h, 1.0, e1)[:2048], lfilter(h, 1.0, e2)[2048:]])
+        else:
+            eq = np.concatenate([e1[:2048], e2[2048:]]).astype(np.float32).astype(np.float64)
+            ref = lfilter(h, 1.0, eq)
         assert_parity(np.concatenate([ya[s], yb[s]]), ref.astype(np.float32), "gain swap")

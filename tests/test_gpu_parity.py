@@ -130,6 +130,30 @@ def test_collapsed_reference_chain_batched_state_and_dither(monkeypatch):
     np.testing.assert_array_equal(q1, ref_q)
 
 
+def test_reference_chain_with_fused_eq_collapses_too(monkeypatch):
+    """up-sample -> fused EQ -> FIR -> [::U]: one base-rate filter (h_up (*) eq (*) h)[::U]; equals the staged
+    three-launch chain within tolerance."""
+    U, S, B = 4, 5, 1024
+    fs = 44100 * U
+    h = design.create_fir_filter(cutoff=16000, numtaps=201, samplerate=fs)
+    h_up = U * design.create_fir_filter(cutoff=20000, numtaps=129, window_type="kaiser", samplerate=fs)
+    bank = design.design_eq_bank(129, fs)
+    gains = [1.2, 1.0, 0.8, 1.0, 1.5, 1.0, 0.5, 1.0, 1.3]
+    x = synth(S, B * 4, "noise")
+
+    def go():
+        with BatchFirEngine(h, n_streams=S, max_frames=B, upsample=U, chain="reference", upsampler_taps=h_up,
+                            eq_bands=bank, eq_gains=gains, eq_mode="fused") as e:
+            return run_blocks(e, x, B), len(e.stage_info())
+
+    y1, n1 = go()
+    monkeypatch.setenv("AFP_NO_COLLAPSE", "1")
+    y2, n2 = go()
+    assert (n1, n2) == (1, 3) and y1.shape == (S, B * 4)
+    for s in range(S):
+        assert_parity(y1[s], y2[s], f"collapsed vs staged with EQ, stream {s}")
+
+
 @pytest.mark.parametrize("U,N,B", [(2, 251, 1024), (4, 251, 1024), (3, 129, 512), (4, 1001, 512),
                                    (2, 51, 256), (4, 51, 100), (2, 501, 4096)])
 def test_dac_chain_polyphase(U, N, B):
@@ -159,9 +183,13 @@ def test_min_phase_variant_c4():
         assert_parity(y[s], rc.polyphase_upsample_whole(2 * hm, x[s], 2).astype(np.float32), "min-phase")
 
 
-def test_eq_fused_streaming():
-    """Kernel (3), fused form: (sum_b g_b h_b) * x followed by the main FIR, state carried."""
+@pytest.mark.parametrize("collapse", [True, False])
+def test_eq_fused_streaming(collapse, monkeypatch):
+    """Kernel (3), fused form: (sum_b g_b h_b) * x followed by the main FIR, state carried - as one filter
+    eq (*) main (default at U = 1) and as two launches."""
     from scipy.signal import lfilter
+    if not collapse:
+        monkeypatch.setenv("AFP_NO_COLLAPSE", "1")
     fs = 48000
     bank = design.design_eq_bank(129, fs, design.EQ_BANDS_10)
     gains = [1.2, 1.0, 0.8, 1.0, 1.5, 1.0, 0.5, 1.0, 1.3, 0.9]
@@ -170,6 +198,7 @@ def test_eq_fused_streaming():
     x = synth(S, B * 5, "noise")
     with BatchFirEngine(main, n_streams=S, max_frames=B, eq_bands=bank, eq_gains=gains, eq_mode="fused") as eng:
         y = run_blocks(eng, x, B)
+        assert len(eng.stage_info()) == (1 if collapse else 2)
     comb = design.combine_eq_taps(bank, gains)
     for s in range(S):
         ref = lfilter(main, 1.0, lfilter(comb, 1.0, x[s].astype(np.float64)).astype(np.float32).astype(np.float64))
