@@ -77,6 +77,7 @@ kern_t row_kernel_for(int U, int T, int pad, int store, int epi, int spec_tgl) {
     switch (U) {
         case 1: return afp_kernel_row_u1(T, pad, store, epi, spec_tgl);
         case 2: return afp_kernel_row_u2(T, pad, store, epi, spec_tgl);
+        case 3: return afp_kernel_row_u3(T, pad, store, epi, spec_tgl);
         case 4: return afp_kernel_row_u4(T, pad, store, epi, spec_tgl);
     }
     return nullptr;
@@ -97,7 +98,8 @@ RowShape pick_row_shape(int U, int kq) {
     else if (U == 2) {
         if (kq <= 32) { r.T = 8; r.pad = 0; r.store = 0; r.tg_log2 = 6; }
         else { r.T = 16; r.pad = 0; r.store = 2; r.tg_log2 = 5; }
-    } else if (U == 4) {
+    } else if (U == 3) { r.T = 8; r.pad = 0; r.store = 2; r.tg_log2 = 5; }   // phase-major form, not swept
+    else if (U == 4) {
         if (kq <= 16) { r.T = 4; r.pad = 0; r.store = 2; r.tg_log2 = 7; }
         else { r.T = 8; r.pad = 0; r.store = 2; r.tg_log2 = 5; }
     }
@@ -205,7 +207,7 @@ int build_stage(afp_ctx* c, Stage& s, int kind, int U, const double* taps, int n
     // History length = padded taps per phase.  A multiple of 16 (every tile size divides it, so the two
     // FFMA2 kernels share one history format and a stage may switch kernel from block to block), with room
     // for the extra tap slot the single-row kernel's U = 1 form needs (afp_fir_row.cuh).
-    const int n_chunks = tc_ok ? ((kq + 63) / 64) * (64 / T) : ((kq + (U == 1 ? 1 : 0) + 15) / 16) * (16 / T);
+    const int n_chunks = tc_ok ? ((kq + 63) / 64) * (64 / T) : ((kq + (U % 2 == 1 ? 1 : 0) + 15) / 16) * (16 / T);
     if ((long long)n_chunks * T * U * n_sub > afp::MAX_TAPS)
         return fail(c, AFP_ERR_INVALID, "filter (x bands) too long for the per-launch tap table (max 6144 padded taps)");
     const bool same_shape = s.active && s.kind == kind && s.U == U && s.n_chunks == n_chunks;
@@ -400,14 +402,14 @@ FirParams& launch_params(afp_ctx* c) { return c->params; }
 int launch_stage_row(afp_ctx* c, Stage& s, const StageIO& io, const Align& al, cudaStream_t stream, bool* done) {
     *done = false;
     if (env_flag("AFP_NO_ROW") || s.n_sub != 1 || !al.fast_all) return AFP_OK;
-    if (s.U != 1 && s.U != 2 && s.U != 4) return AFP_OK;
+    if (s.U < 1 || s.U > 4) return AFP_OK;
     const int U = s.U, kq = (s.n_taps + U - 1) / U;
     RowShape sh = pick_row_shape(U, kq);
     const int T = sh.T;
     const int step = afp::row_tail_step(U, T);
-    const int slots = (kq + (U == 1 ? 1 : 0) + step - 1) / step * step;     // tap slots per phase the FMA loop visits
+    const int slots = (kq + (U % 2 == 1 ? 1 : 0) + step - 1) / step * step;     // tap slots per phase the FMA loop visits
     if (slots > s.kq_pad || s.kq_pad % T != 0) return AFP_OK;
-    if (U == 1 && afp::row_tabb_offset(s.kq_pad) + s.kq_pad + 4 > afp::MAX_TAPS) return AFP_OK;
+    if (U % 2 == 1 && U * afp::row_phase_stride(s.kq_pad) > afp::MAX_TAPS) return AFP_OK;
     const int n_loop = (slots + T - 1) / T;
     int tail = slots - (n_loop - 1) * T;
     if (tail == T) tail = 0;
@@ -441,9 +443,19 @@ int launch_stage_row(afp_ctx* c, Stage& s, const StageIO& io, const Align& al, c
     P.n_seg_total = (int)n_items; P.n_pairs = (int)((n_items + 1) / 2);
     P.n_chunks = s.kq_pad / T; P.n_sub = tail; P.sub_stride = n_loop;
     std::memset(P.taps, 0, sizeof(P.taps));
-    std::memcpy(P.taps, s.table.data(), (size_t)s.kq_pad * U * sizeof(float));
-    if (U == 1)   // pairs that start at an odd tap index: the table moved up by one sample
-        std::memcpy(P.taps + afp::row_tabb_offset(s.kq_pad) + 1, s.table.data(), (size_t)(s.kq_pad - 1) * sizeof(float));
+    if (U % 2 == 0) {
+        std::memcpy(P.taps, s.table.data(), (size_t)s.kq_pad * U * sizeof(float));
+    } else {
+        // odd U: per phase p the sub-filter h_p[j] = h[jU+p] in natural order, then the same table moved up by
+        // one sample (pairs that start at an odd tap index)
+        const int ps = afp::row_phase_stride(s.kq_pad), ob = afp::row_tabb_offset(s.kq_pad);
+        for (int p = 0; p < U; ++p)
+            for (int j = 0; j < s.kq_pad; ++j) {
+                const float v = s.table[(size_t)j * U + p];
+                P.taps[p * ps + j] = v;
+                if (j + 1 < s.kq_pad + 4) P.taps[p * ps + ob + 1 + j] = v;
+            }
+    }
     k<<<grid, NT, smem, stream>>>(P);
     AFP_CUDA(c, cudaGetLastError());
     c->launches += 1;
@@ -692,7 +704,7 @@ int afp_create(const afp_config* cfg, afp_ctx** out_ctx) {
                         e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
                         if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem)");
                     }
-    for (int U : {1, 2, 4})
+    for (int U : {1, 2, 3, 4})
         for (const RowShape& sh : kRowShapes)
             for (int epi : kAllEpi) {
                 for (int spec : {0, sh.tg_log2}) {

@@ -10,7 +10,9 @@
 //   * U even: lanes = phases (p, p+1) of one base position, taps (h[jU+p], h[jU+p+1]) - an aligned pair
 //     of the natural tap table;
 //   * U = 1:  lanes = positions (r, r+1), taps (h[k], h[k+1]); k takes both parities, so the launch
-//     carries a second copy of the table shifted by one sample (pairs starting at odd k).
+//     carries a second copy of the table shifted by one sample (pairs starting at odd k);
+//   * U odd > 1 (U = 3): every phase p is a U = 1 problem with the sub-filter h_p[j] = h[jU+p]: lanes =
+//     positions (r, r+1) of one phase, one table pair per phase; the epilogue interleaves the phases.
 // Consequences, compared with the row-pair kernel:
 //   * no row interleave: shared memory holds the plain, contiguous samples of ONE row segment, so the
 //     loader is one or two bulk copies (cp.async.bulk global -> shared, completion on an mbarrier) issued
@@ -93,6 +95,8 @@ __device__ __forceinline__ void load_wblock(float (&w)[T], const float4* __restr
 template <int U, int T, int J>
 __device__ __forceinline__ void chunk_fma_even(u64 (&acc)[U * T / 2], const float (&lo)[T], const float (&hi)[T],
                                                const float* __restrict__ tp) {
+#pragma unroll
+    if (U % 2 != 0) return;   // (odd-U kernels instantiate this in dead code)
 #pragma unroll
     for (int j = 0; j < J; ++j) {
 #pragma unroll
@@ -230,7 +234,7 @@ __host__ __device__ constexpr int row_smem_bytes(int U, int T, int NT, int tg_lo
 
 // resident CTAs per SM the register budget is compiled for
 __host__ __device__ constexpr int row_min_ctas(int U, int T, int NT) {
-    return (NT == 256 ? 1 : 2) * (U * T >= 32 ? 3 : 4);
+    return (NT == 256 ? 1 : 2) * (U * T >= 24 ? 3 : 4);
 }
 
 // Tap-table layout in FirParams::taps for this kernel: natural table (U * kq floats), then - U = 1 only -
@@ -239,7 +243,9 @@ __host__ __device__ constexpr int row_tabb_offset(int kq) { return kq + 4; }
 // FirParams::n_sub and sub_stride are free in this kernel's launches (single table only): sub_stride
 // carries the number of chunks that hold taps (the history / halo, n_chunks * T, may be longer) and n_sub
 // the number of tap slots in the last of them (0 = it is full).  Granularity of the specialised tails:
-__host__ __device__ constexpr int row_tail_step(int U, int T) { return U == 1 ? 4 : 2; }
+__host__ __device__ constexpr int row_tail_step(int U, int T) { return U % 2 == 1 ? 4 : 2; }
+// odd U: phase p's natural table sits at p * row_phase_stride(kq), its shifted copy row_tabb_offset(kq) further
+__host__ __device__ constexpr int row_phase_stride(int kq) { return 2 * (kq + 4); }
 
 // TGL: log2(threads per group) fixed at compile time (0 = read it from the parameters); STREAM: the launch is
 // the streaming form (q_begin == kq == len0, so no copy range needs clamping at the front and nothing lies
@@ -247,7 +253,7 @@ __host__ __device__ constexpr int row_tail_step(int U, int T) { return U == 1 ? 
 template <int U, int T, int NT, int EPI, int STORE, int PAD, int TGL = 0, bool STREAM = false>
 __global__ void __launch_bounds__(NT, row_min_ctas(U, T, NT))
 fir_row_kernel(const __grid_constant__ FirParams P) {
-    static_assert(U == 1 || U % 2 == 0, "row kernel: U = 1 or even");
+    static_assert(U >= 1 && U <= 4, "row kernel: U in 1..4");
     using LY = RowLayout<T, PAD>;
     extern __shared__ float4 smem[];
     const int tid = threadIdx.x;
@@ -386,19 +392,24 @@ fir_row_kernel(const __grid_constant__ FirParams P) {
         float wa[T], wb[T];
         load_wblock<T, PAD>(wb, region, b0);
         int c = 0;
-        if (U == 1) {
-            u64(&a1)[T / 2] = reinterpret_cast<u64(&)[T / 2]>(acc);
+        if (U % 2 == 1) {
+            // phase-major accumulators: acc[p*(T/2) + r/2] = (y_p[r], y_p[r+1])
+            u64(&ap)[U][T / 2] = reinterpret_cast<u64(&)[U][T / 2]>(acc);
             const float* ta = P.taps;
             const float* tb = P.taps + row_tabb_offset(kq);
+            const int ps = row_phase_stride(kq);
             for (; c + 2 <= n_full; c += 2) {
                 load_wblock<T, PAD>(wa, region, b0 - c - 1);
-                chunk_fma_u1<T, T>(a1, wa, wb, ta + c * T, tb + c * T);
+#pragma unroll
+                for (int p = 0; p < U; ++p) chunk_fma_u1<T, T>(ap[p], wa, wb, ta + p * ps + c * T, tb + p * ps + c * T);
                 load_wblock<T, PAD>(wb, region, b0 - c - 2);
-                chunk_fma_u1<T, T>(a1, wb, wa, ta + (c + 1) * T, tb + (c + 1) * T);
+#pragma unroll
+                for (int p = 0; p < U; ++p) chunk_fma_u1<T, T>(ap[p], wb, wa, ta + p * ps + (c + 1) * T, tb + p * ps + (c + 1) * T);
             }
             if (c < n_full) {
                 load_wblock<T, PAD>(wa, region, b0 - c - 1);
-                chunk_fma_u1<T, T>(a1, wa, wb, ta + c * T, tb + c * T);
+#pragma unroll
+                for (int p = 0; p < U; ++p) chunk_fma_u1<T, T>(ap[p], wa, wb, ta + p * ps + c * T, tb + p * ps + c * T);
 #pragma unroll
                 for (int i = 0; i < T; ++i) wb[i] = wa[i];
                 ++c;
@@ -406,10 +417,13 @@ fir_row_kernel(const __grid_constant__ FirParams P) {
             if (tail) {
                 load_wblock<T, PAD>(wa, region, b0 - c - 1);
                 ta += c * T; tb += c * T;
-                if (T >= 8 && tail == 4) chunk_fma_u1<T, 4>(a1, wa, wb, ta, tb);
-                else if (T >= 16 && tail == 8) chunk_fma_u1<T, (T >= 16 ? 8 : T)>(a1, wa, wb, ta, tb);
-                else if (T >= 16 && tail == 12) chunk_fma_u1<T, (T >= 16 ? 12 : T)>(a1, wa, wb, ta, tb);
-                else chunk_fma_u1<T, T>(a1, wa, wb, ta, tb);
+#pragma unroll
+                for (int p = 0; p < U; ++p) {
+                    if (T >= 8 && tail == 4) chunk_fma_u1<T, 4>(ap[p], wa, wb, ta + p * ps, tb + p * ps);
+                    else if (T >= 16 && tail == 8) chunk_fma_u1<T, (T >= 16 ? 8 : T)>(ap[p], wa, wb, ta + p * ps, tb + p * ps);
+                    else if (T >= 16 && tail == 12) chunk_fma_u1<T, (T >= 16 ? 12 : T)>(ap[p], wa, wb, ta + p * ps, tb + p * ps);
+                    else chunk_fma_u1<T, T>(ap[p], wa, wb, ta + p * ps, tb + p * ps);
+                }
             }
         } else {
             const float* tp = P.taps;
@@ -441,10 +455,21 @@ fir_row_kernel(const __grid_constant__ FirParams P) {
         const int q_local = seg * lq + lt * T;
         const int nv = min(max(P.n_q - q_local, 0), T) * U;
         float y[U * T];
+        if (U % 2 == 1 && U > 1) {     // phase-major pairs -> output order y[r*U + p]
 #pragma unroll
-        for (int i = 0; i < U * T / 2; ++i) {
-            y[2 * i] = __uint_as_float((unsigned)acc[i]);
-            y[2 * i + 1] = __uint_as_float((unsigned)(acc[i] >> 32));
+            for (int p = 0; p < U; ++p)
+#pragma unroll
+                for (int r = 0; r < T; r += 2) {
+                    const u64 a = acc[p * (T / 2) + r / 2];
+                    y[r * U + p] = __uint_as_float((unsigned)a);
+                    y[(r + 1) * U + p] = __uint_as_float((unsigned)(a >> 32));
+                }
+        } else {
+#pragma unroll
+            for (int i = 0; i < U * T / 2; ++i) {
+                y[2 * i] = __uint_as_float((unsigned)acc[i]);
+                y[2 * i + 1] = __uint_as_float((unsigned)(acc[i] >> 32));
+            }
         }
         const long long o_base = (long long)q_local * U;
         if (STORE == 2) {

@@ -41,6 +41,7 @@ afp::tc_kern_t afp_kernel_tc(int row, int nts, int epi);   // tensor-core path: 
 // size compiled in, if there is one), else 0
 afp::kern_t afp_kernel_row_u1(int T, int pad, int store, int epi, int spec_tgl);
 afp::kern_t afp_kernel_row_u2(int T, int pad, int store, int epi, int spec_tgl);
+afp::kern_t afp_kernel_row_u3(int T, int pad, int store, int epi, int spec_tgl);
 afp::kern_t afp_kernel_row_u4(int T, int pad, int store, int epi, int spec_tgl);
 afp::kern_t afp_kernel_u1(int T, int nt, bool multi, int epi);
 afp::kern_t afp_kernel_u2(int T, int nt, bool multi, int epi);

@@ -99,7 +99,7 @@ typedef struct afp_stage_info {
     int32_t history;          /* carried samples per stream */
     int32_t kernel;           /* kernel of the last launch: 0 = packed-FFMA2 row-pair form, 1 = tcgen05 / TMEM
                                  Toeplitz 3xTF32 (long single-table U = 1 filters, 256/512/1024-frame blocks),
-                                 2 = packed-FFMA2 single-row form (single-table stages, U in {1, 2, 4}, aligned buffers) */
+                                 2 = packed-FFMA2 single-row form (single-table stages, aligned buffers) */
 } afp_stage_info;
 
 const char* afp_version(void);

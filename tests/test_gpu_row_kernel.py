@@ -48,10 +48,11 @@ def oracle(h, x, U):
 
 
 # tap counts chosen around every tile / tail boundary: U=1 tiles of 16 with 4-slot tails (N+1 slots),
-# U=2 tiles of 8 (<= 64 taps) / 16 with 2-slot tails, U=4 tiles of 4 (<= 64 taps) / 8
+# U=2 tiles of 8 (<= 64 taps) / 16 with 2-slot tails, U=3 tiles of 8 (phase-major form), U=4 tiles of 4 (<= 64 taps) / 8
 @pytest.mark.parametrize("U,N", [(1, 1), (1, 2), (1, 3), (1, 7), (1, 15), (1, 16), (1, 47), (1, 51), (1, 52), (1, 63),
                                  (1, 64), (1, 101), (1, 251), (1, 385),
                                  (2, 2), (2, 9), (2, 27), (2, 51), (2, 64), (2, 65), (2, 101), (2, 129), (2, 251), (2, 501),
+                                 (3, 2), (3, 5), (3, 33), (3, 129), (3, 251), (3, 1001),
                                  (4, 3), (4, 33), (4, 51), (4, 64), (4, 65), (4, 99), (4, 101), (4, 103), (4, 251), (4, 1001)])
 def test_row_kernel_matches_oracle(U, N):
     h = taps(N, U)
@@ -64,7 +65,8 @@ def test_row_kernel_matches_oracle(U, N):
         assert_parity(y[s], oracle(h, x[s], U), f"U={U} N={N} s={s}")
 
 
-@pytest.mark.parametrize("U,N,B", [(1, 51, 1024), (2, 51, 1024), (4, 51, 1024), (4, 101, 512), (2, 101, 2048), (1, 251, 4096)])
+@pytest.mark.parametrize("U,N,B", [(1, 51, 1024), (2, 51, 1024), (4, 51, 1024), (4, 101, 512), (2, 101, 2048), (1, 251, 4096),
+                                   (3, 129, 1024), (3, 34, 512)])
 def test_row_and_pair_kernels_agree_bit_for_bit(U, N, B):
     """Both kernels accumulate the taps of an output in the same order with fused multiply-adds, so the
     float results must be identical, not merely within tolerance."""
@@ -96,7 +98,7 @@ def test_kernels_interchange_on_one_history():
         assert_parity(y[s], oracle(h, x[s], 1), f"s={s}")
 
 
-@pytest.mark.parametrize("U", [1, 2, 4])
+@pytest.mark.parametrize("U", [1, 2, 3, 4])
 @pytest.mark.parametrize("fmt,mode", [("i24", "tpdf"), ("i16", "tpdf"), ("i24_packed", "tpdf"), ("i24", "rpdf"),
                                       ("f32", "tpdf"), ("i16", "none")])
 def test_row_kernel_epilogues_bit_exact(U, fmt, mode):
@@ -141,7 +143,7 @@ def test_row_kernel_large_batch_linearity():
 
 
 @pytest.mark.parametrize("U,N,fmt", [(4, 51, "f32"), (4, 101, "i16"), (2, 51, "i24"), (2, 129, "f32"), (1, 51, "i24_packed"),
-                                     (1, 251, "f32")])
+                                     (1, 251, "f32"), (3, 51, "f32"), (3, 129, "i24_packed"), (3, 20, "i16")])
 def test_row_kernel_writes_nothing_outside_its_rows(U, N, fmt):
     """Guard bands: the caller's output rows are longer than the block needs (and the pitch is not a
     multiple of a warp's store width); everything past the valid samples of every row must stay untouched,
