@@ -199,6 +199,27 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's host threads to the CPUs NVML reports as local to GPU `index`, so that the pinned
+    staging buffers it allocates next are first-touched on that GPU's NUMA node (multi-GPU e2e runs are bound
+    by host memory / PCIe root traffic).  Returns (previous affinity, description) - the caller restores the
+    affinity before the CPU-baseline leg."""
+    prev = os.sched_getaffinity(0)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (max(prev) + 64) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1} & prev
+        if cpus and cpus != prev:
+            os.sched_setaffinity(0, cpus)
+            return prev, f"{len(cpus)} of {len(prev)} cpus local to gpu {index}"
+        return prev, "gpu-local cpu set == process cpu set"
+    except Exception as exc:          # noqa: BLE001 - best effort only
+        return prev, f"unavailable ({type(exc).__name__})"
+
+
 # --------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -211,6 +232,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    prev_affinity, numa_note = bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -328,6 +350,8 @@ def run_ours(args):
     checksum = int(np.bitwise_xor.reduce(hy.a.ravel()[:: 4099]))
 
     line = None
+    os.sched_setaffinity(0, prev_affinity)      # the CPU legs use every core the process was given
+    e2e["host_affinity"] = numa_note
     if rank == 0:
         sweep = None
         if world == 1 and not args.no_sweep:
