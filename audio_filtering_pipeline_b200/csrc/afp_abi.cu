@@ -56,6 +56,10 @@ struct Stage {
     int tc_chunks[2] = {0, 0};
     int last_kernel = 0;           // 0 = row-pair FFMA2, 1 = tcgen05, 2 = single-row FFMA2
     int last_T = 0;                // tile of the last launch (the single-row kernel picks its own)
+    // per-launch host work of the single-row kernel that only depends on the stage: its tap-table image
+    // and the occupancy of the kernel it last used
+    std::vector<float> row_taps; int row_taps_T = 0;
+    const void* occ_kernel = nullptr; int occ_smem = 0, occ_per_sm = 0;
 };
 
 // Kernels live in one translation unit per up-sampling factor (afp_kernels_u{1..4}.cu, compiled in
@@ -224,6 +228,7 @@ int build_stage(afp_ctx* c, Stage& s, int kind, int U, const double* taps, int n
     }
     s.kind = kind; s.U = U; s.T = T; s.n_taps = n; s.n_sub = n_sub;
     s.taps.assign(taps, taps + (size_t)n * n_sub);
+    s.row_taps.clear(); s.row_taps_T = 0;
     s.n_chunks = n_chunks; s.kq_pad = n_chunks * T;
     s.table.assign((size_t)s.kq_pad * U * n_sub, 0.f);
     for (int b = 0; b < n_sub; ++b)
@@ -397,7 +402,7 @@ void fill_common(afp_ctx* c, const Stage& s, const StageIO& io, const Align& a, 
 // scratch copy per context is race free even with one host thread per GPU)
 FirParams& launch_params(afp_ctx* c) { return c->params; }
 
-// Single-row kernel (afp_fir_row.cuh) for single-table stages with U in {1, 2, 4} whose buffers are all
+// Single-row kernel (afp_fir_row.cuh) for single-table stages (U = 1..4) whose buffers are all
 // 16-byte aligned.  Sets *done when it launched; otherwise the row-pair kernel takes the block.
 int launch_stage_row(afp_ctx* c, Stage& s, const StageIO& io, const Align& al, cudaStream_t stream, bool* done) {
     *done = false;
@@ -430,8 +435,12 @@ int launch_stage_row(afp_ctx* c, Stage& s, const StageIO& io, const Align& al, c
     const int segs = (io.n_q + lq - 1) / lq;
     const long long n_items = (long long)S * segs;
     if (n_items <= 0 || n_items > INT_MAX) return AFP_OK;
-    int per_sm = 0;
-    AFP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, NT, smem));
+    if (s.occ_kernel != (const void*)k || s.occ_smem != smem) {
+        int per_sm_q = 0;
+        AFP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_q, (const void*)k, NT, smem));
+        s.occ_kernel = (const void*)k; s.occ_smem = smem; s.occ_per_sm = per_sm_q;
+    }
+    const int per_sm = s.occ_per_sm;
     if (per_sm < 1) return AFP_OK;
     const long long want = (n_items + slots_cta - 1) / slots_cta, resident = (long long)per_sm * c->n_sm;
     const int grid = (int)(want < resident ? want : resident);
@@ -442,20 +451,24 @@ int launch_stage_row(afp_ctx* c, Stage& s, const StageIO& io, const Align& al, c
     for (int b = 0; b < 30; ++b) if ((1 << b) == segs) P.segs_shift = b;
     P.n_seg_total = (int)n_items; P.n_pairs = (int)((n_items + 1) / 2);
     P.n_chunks = s.kq_pad / T; P.n_sub = tail; P.sub_stride = n_loop;
-    std::memset(P.taps, 0, sizeof(P.taps));
-    if (U % 2 == 0) {
-        std::memcpy(P.taps, s.table.data(), (size_t)s.kq_pad * U * sizeof(float));
-    } else {
-        // odd U: per phase p the sub-filter h_p[j] = h[jU+p] in natural order, then the same table moved up by
-        // one sample (pairs that start at an odd tap index)
-        const int ps = afp::row_phase_stride(s.kq_pad), ob = afp::row_tabb_offset(s.kq_pad);
-        for (int p = 0; p < U; ++p)
-            for (int j = 0; j < s.kq_pad; ++j) {
-                const float v = s.table[(size_t)j * U + p];
-                P.taps[p * ps + j] = v;
-                if (j + 1 < s.kq_pad + 4) P.taps[p * ps + ob + 1 + j] = v;
-            }
+    if (s.row_taps_T != T || s.row_taps.size() != (size_t)afp::MAX_TAPS) {
+        s.row_taps.assign(afp::MAX_TAPS, 0.f);
+        if (U % 2 == 0) {
+            std::memcpy(s.row_taps.data(), s.table.data(), (size_t)s.kq_pad * U * sizeof(float));
+        } else {
+            // odd U: per phase p the sub-filter h_p[j] = h[jU+p] in natural order, then the same table moved up
+            // by one sample (pairs that start at an odd tap index)
+            const int ps = afp::row_phase_stride(s.kq_pad), ob = afp::row_tabb_offset(s.kq_pad);
+            for (int p = 0; p < U; ++p)
+                for (int j = 0; j < s.kq_pad; ++j) {
+                    const float v = s.table[(size_t)j * U + p];
+                    s.row_taps[p * ps + j] = v;
+                    s.row_taps[p * ps + ob + 1 + j] = v;
+                }
+        }
+        s.row_taps_T = T;
     }
+    std::memcpy(P.taps, s.row_taps.data(), sizeof(P.taps));
     k<<<grid, NT, smem, stream>>>(P);
     AFP_CUDA(c, cudaGetLastError());
     c->launches += 1;
