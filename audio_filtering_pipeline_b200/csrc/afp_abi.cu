@@ -88,7 +88,7 @@ kern_t row_kernel_for(int U, int T, int pad, int store, int epi, int spec_tgl) {
 }
 
 // Shape of the single-row kernel (afp_fir_row.cuh) for an up-sampling factor and phase length, from the
-// sweeps in bench/microbench/fir_row_test.cu on B200 (gpurun_out/row_probe*.txt):
+// sweeps in bench/microbench/fir_row_test.cu on B200 (profiles/r01_experiments/row_probe*.txt):
 //   U = 1: 16-sample tiles; the FMA pipe is the bound, so the window loads must be conflict free: padded
 //          layout + cp.async; a thread's run is 64 B and transposing the stores does not pay.
 //   U = 2: <= 32 taps per phase: 8-sample tiles, direct stores, 64-thread groups (741 vs 700 Gsamples/s
@@ -205,7 +205,7 @@ int build_stage(afp_ctx* c, Stage& s, int kind, int U, const double* taps, int n
     // then share one history format: the last kq_pad samples with kq_pad a multiple of 32 (the tensor
     // kernel's row length), so a stage may switch kernel from one block to the next.
     // (crossover against the single-row FFMA2 kernel measured at 16384 streams: equal at 385 taps / 512-frame
-    // blocks, +13 % at 385 / 1024, +27 % at 501 / 1024 - gpurun_out call 20)
+    // blocks, +13 % at 385 / 1024, +27 % at 501 / 1024 - measured with bench/quick_perf.py, AFP_TC_MIN_TAPS=300 vs 5000)
     const int tc_min = std::getenv("AFP_TC_MIN_TAPS") ? std::atoi(std::getenv("AFP_TC_MIN_TAPS")) : 400;
     const bool tc_ok = U == 1 && n_sub == 1 && n >= tc_min && !env_flag("AFP_NO_TC");
     // History length = padded taps per phase.  A multiple of 16 (every tile size divides it, so the two

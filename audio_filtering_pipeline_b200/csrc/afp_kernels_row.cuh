@@ -7,7 +7,7 @@
 namespace afp {
 
 // TGL = 0: general form (any group size, any launch geometry).  TGL > 0: the streaming form with that
-// group size compiled in (-6.5 % executed instructions, +1-5 % throughput: gpurun_out/row_probe7.txt).
+// group size compiled in (-6.5 % executed instructions, +1-5 % throughput: profiles/r01_experiments/row_probe7.txt).
 template <int U, int T, int PAD, int STORE, int TGL>
 kern_t pick_row_kernel_1(int epi) {
     constexpr bool ST = TGL != 0;
