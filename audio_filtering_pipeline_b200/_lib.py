@@ -23,7 +23,7 @@ SYMBOLS = [
     "afp_set_eq", "afp_set_gains", "afp_process", "afp_process_host", "afp_process_host_blocks", "afp_out_frames",
     "afp_out_elem_bytes", "afp_reset", "afp_state_size", "afp_get_state", "afp_set_state",
     "afp_get_stage_info", "afp_kernel_launches", "afp_host_alloc", "afp_host_free",
-    "afp_measure_fma_peak",
+    "afp_measure_fma_peak", "afp_set_agc", "afp_agc_block",
 ]
 
 
@@ -47,6 +47,18 @@ class StageInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "kind", "upsample", "n_taps", "taps_per_phase_padded", "tile_taps", "threads",
         "threads_per_segment", "smem_bytes", "grid", "history", "kernel")]
+
+
+class AgcParams(C.Structure):
+    """afp_agc_params; the defaults are apply_agc's (stream_process_AGC.py:43) and its call site's clip (:143)."""
+    _fields_ = [("target_level", C.c_double), ("max_gain", C.c_double), ("attack", C.c_double),
+                ("release", C.c_double), ("clip", C.c_double), ("window_size", C.c_int32),
+                ("reserved", C.c_int32)]
+
+    @classmethod
+    def make(cls, target_level=0.1, window_size=512, max_gain=10.0, attack=0.01, release=0.1, clip=0.99):
+        return cls(float(target_level), float(max_gain), float(attack), float(release), float(clip),
+                   int(window_size), 0)
 
 
 _lib = None
@@ -91,6 +103,8 @@ def load():
     lib.afp_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     lib.afp_host_free.argtypes = [vp]
     lib.afp_measure_fma_peak.argtypes = [i32, dp, dp]
+    lib.afp_set_agc.argtypes = [vp, C.POINTER(AgcParams)]
+    lib.afp_agc_block.argtypes = [vp, C.POINTER(AgcParams), vp, i64, vp, i64, i32, i32, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int:   # default: status code

@@ -10,6 +10,7 @@ stream_process.py keeps its structure and only swaps its imports (see INTEGRATIO
     apply_dither             <- stream_process.py:61-64
     safe_upsample            <- stream_process.py:66-77, stream_process_EQ_GUI.py:420-427
     safe_downsample          <- stream_process_EQ_GUI.py:429-436
+    apply_agc                <- stream_process_AGC.py:43-89
 
 All arithmetic runs on the GPU through BatchFirEngine; there is no numpy fallback - if the CUDA
 library or the device is missing, constructing any of these raises.  What the callback does on a
@@ -26,7 +27,7 @@ from . import design
 from .engine import BatchFirEngine
 
 __all__ = ["make_audio_callback", "OverlapAddFilter", "process_audio_block", "apply_dither",
-           "safe_upsample", "safe_downsample", "StreamChain"]
+           "safe_upsample", "safe_downsample", "apply_agc", "StreamChain"]
 
 
 class StreamChain:
@@ -39,7 +40,7 @@ class StreamChain:
                  window_type="hamming", filter_type="lowpass", method="window", channels=1,
                  eq_bands=None, eq_gains=None, eq_numtaps=None, eq_mode="buffer_same_per_band",
                  min_phase=False, dither=True, bit_depth=24, seed=0, device=0, upsampler_taps=None,
-                 fir_coeff=None):
+                 fir_coeff=None, agc=None):
         self.samplerate, self.upsample_factor, self.blocksize = int(samplerate), int(upsample_factor), int(blocksize)
         self.channels = int(channels)
         up_rate = self.samplerate * self.upsample_factor                     # stream_process.py:20
@@ -65,7 +66,7 @@ class StreamChain:
             upsample=self.upsample_factor, chain="reference", out_format="f32",
             dither="rpdf" if dither else "none", dither_bits=bit_depth, seed=seed, device=device,
             upsampler_taps=upsampler_taps, eq_bands=bands, eq_gains=eq_gains,
-            eq_mode=eq_mode if bands is not None else "none")
+            eq_mode=eq_mode if bands is not None else "none", agc=agc)
         self.audio_buffer = deque(maxlen=4)                                   # stream_process.py:50
         self.silence_block = np.zeros((self.blocksize, self.channels), dtype=np.float32)
         self._planar = np.zeros((self.channels, self.blocksize), dtype=np.float32)
@@ -195,6 +196,27 @@ def apply_dither(audio, bit_depth=24):
     eng = _cached(("dither", flat.shape[1], int(bit_depth)), lambda: BatchFirEngine(
         [1.0], n_streams=1, max_frames=flat.shape[1], dither="rpdf", dither_bits=int(bit_depth), seed=0x5EED))
     return eng.process_host(flat).reshape(a.shape)
+
+
+def apply_agc(signal, target_level=0.1, window_size=512, alpha=0.01, max_gain=10.0, attack=0.01, release=0.1):
+    """Moving-RMS automatic gain control of one block (stream_process_AGC.py:43-89): same positional
+    arguments (``alpha`` is accepted and unused, as there), same [n, 1] result shape; float32 instead of
+    the reference's float64.  The clip to +-0.99 belongs to the caller (:143) and is not applied here.
+    Where the reference's loop raises (a zero-sample attack / release constant, a window longer than
+    the block) and returns the block unchanged, so does this."""
+    import torch
+    sig = np.asarray(signal, dtype=np.float32)
+    sig = np.atleast_2d(sig).T if sig.ndim == 1 else sig                       # :52-53
+    try:
+        x = np.ascontiguousarray(sig[:, 0])[None, :]
+        eng = _cached(("agc",), lambda: BatchFirEngine([1.0], n_streams=1, max_frames=1))
+        xd = torch.from_numpy(x).cuda(eng.device)
+        y = eng.agc_block(xd, target_level=target_level, window_size=window_size, max_gain=max_gain,
+                          attack=attack, release=release, clip=0.0)
+        return y.cpu().numpy()[0][:, None]
+    except Exception as exc:                                                   # noqa: BLE001 (:87-89)
+        print(f"AGC error: {exc}, shape={sig.shape}")
+        return sig
 
 
 def safe_upsample(data, sr=44100, upsr=176400):

@@ -17,6 +17,9 @@
 #include "afp_kernel_table.cuh"
 #include "afp_fir_row.cuh"
 #include "afp_fir_tc.cuh"
+#include "afp_agc.cuh"
+
+afp::agc_kern_t afp_kernel_agc(bool checked, int scan_blocks);   // afp_kernels_agc.cu: scan_blocks in {1, 2, 4, 8}
 
 using afp::FirParams;
 
@@ -140,6 +143,11 @@ struct afp_ctx {
     Stage fused;
     std::vector<std::vector<double>> bands;
     std::vector<double> gains;
+    // AGC ahead of the chain (afp_set_agc; stream_process_AGC.py:131-143): parameters and its output block
+    bool agc_on = false;
+    afp_agc_params agc{};
+    float* tmp_agc = nullptr;        // [S][pitch_agc]
+    long long pitch_agc = 0;
     float* tmp_a = nullptr;          // interp output  [S][max_frames*U]
     float* tmp_b = nullptr;          // EQ output      [S][pitch_b]
     long long pitch_a = 0, pitch_b = 0;
@@ -302,6 +310,66 @@ Geometry pick_geometry(int T, int kq_pad, int n_q, int n_streams) {
         }
     }
     return best;
+}
+
+// ---- AGC (afp_agc.cuh).  Shared memory per CTA: one float row per stream of the work item (odd pitch)
+// + one float64 prefix-sum row per warp + a flag per stream.  Two CTAs per SM when at least 8 streams
+// fit in half an SM's shared memory (one CTA's serial recurrence phase overlaps the other's memory
+// phases), else one CTA with as many streams as fit.
+struct AgcPlan { int warps = 0, group = 0, pitch = 0, ctas_per_sm = 0; size_t smem = 0; };
+bool plan_agc(int frames, int n_streams, int n_sm, AgcPlan& pl) {
+    const int pitch = frames | 1;
+    const size_t row = (size_t)pitch * sizeof(float) + sizeof(int);
+    struct Try { size_t budget; int warps, min_group, ctas; };
+    const Try tries[] = {{112 * 1024, 4, 8, 2}, {224 * 1024, 4, 4, 1}, {224 * 1024, 2, 1, 1}, {224 * 1024, 1, 1, 1}};
+    for (const Try& t : tries) {
+        const size_t fixed = (size_t)t.warps * (frames + 1) * sizeof(double) + 16;
+        if (fixed + row * t.min_group > t.budget) continue;
+        long long g = (long long)((t.budget - fixed) / row);
+        if (g > 32 * t.warps) g = 32 * t.warps;
+        // small batches: spread the streams over all SMs rather than filling a few CTAs
+        const long long spread = ((long long)n_streams + (long long)n_sm * t.ctas - 1) / ((long long)n_sm * t.ctas);
+        if (g > spread) g = spread < 1 ? 1 : spread;
+        pl.warps = t.warps; pl.group = (int)g; pl.pitch = pitch; pl.ctas_per_sm = t.ctas;
+        pl.smem = ((((size_t)g * pitch * sizeof(float)) + 7) & ~(size_t)7) + (size_t)t.warps * (frames + 1) * sizeof(double) +
+                  (size_t)g * sizeof(int);
+        return true;
+    }
+    return false;
+}
+
+int launch_agc(afp_ctx* c, const afp_agc_params& a, const float* in, long long in_pitch, float* out, long long out_pitch,
+               int ns, int frames, cudaStream_t stream) {
+    if (ns < 1 || frames < 1) return AFP_OK;
+    AgcPlan pl;
+    if (!plan_agc(frames, ns, c->n_sm, pl))
+        return fail(c, AFP_ERR_INVALID, "AGC: the block is too long for one SM's shared memory (about 19000 frames)");
+    afp::AgcParams P{};
+    P.in = in; P.in_pitch = in_pitch; P.out = out; P.out_pitch = out_pitch;
+    P.n_streams = ns; P.frames = frames;
+    const int W = a.window_size;
+    // window < 1: np.ones(0)/0 -> np.convolve raises; window > frames: the gains cannot be applied
+    // (shape mismatch) - both end in the reference's except branch, block returned unchanged (:87-89)
+    P.passthrough = (W < 1 || W > frames) ? 1 : 0;
+    P.window = W < 1 ? 1 : W; P.left = P.window / 2; P.right = (P.window - 1) / 2;   // np.convolve 'same' centring
+    P.inv_window = (float)(1.0 / P.window);
+    P.group = pl.group; P.pitch = pl.pitch; P.n_items = (ns + pl.group - 1) / pl.group;
+    P.target = (float)a.target_level; P.max_gain = (float)a.max_gain; P.min_gain = 0.1f;   // :83
+    P.clip = (float)a.clip;
+    const int att_n = (int)(a.attack * (double)W), rel_n = (int)(a.release * (double)W);   // :56-57
+    P.att_ok = att_n != 0; P.rel_ok = rel_n != 0;
+    const double aa = P.att_ok ? 1.0 - std::exp(-1.0 / att_n) : 0.0, ar = P.rel_ok ? 1.0 - std::exp(-1.0 / rel_n) : 0.0;   // :73-78
+    P.a_att = (float)aa; P.c_att = (float)(1.0 - aa); P.a_rel = (float)ar; P.c_rel = (float)(1.0 - ar);
+    const bool checked = !(P.att_ok && P.rel_ok);
+    int sb = 1;
+    while (sb < 8 && 128 * sb < frames) sb *= 2;   // loads of up to 1024 samples of a stream issued at once
+    afp::agc_kern_t k = afp_kernel_agc(checked, sb);
+    int grid = c->n_sm * pl.ctas_per_sm;
+    if (grid > P.n_items) grid = P.n_items;
+    k<<<grid, 32 * pl.warps, pl.smem, stream>>>(P);
+    AFP_CUDA(c, cudaGetLastError());
+    c->launches++;
+    return AFP_OK;
 }
 
 struct StageIO {
@@ -618,6 +686,10 @@ int ensure_tmp(afp_ctx* c) {
     const int S = c->cfg.n_streams, U = c->cfg.upsample;
     const bool ref = c->cfg.chain == AFP_CHAIN_REFERENCE;
     const long long rate_len = (long long)c->cfg.max_frames * (ref ? U : 1);   // EQ-rate samples per block
+    if (c->agc_on && !c->tmp_agc) {
+        c->pitch_agc = ((long long)c->cfg.max_frames + 3) / 4 * 4;
+        AFP_CUDA(c, cudaMalloc(&c->tmp_agc, (size_t)S * c->pitch_agc * sizeof(float)));
+    }
     if (ref && U > 1 && !c->tmp_a && !c->fused.active) {   // the collapsed chain has no processing-rate intermediate
         c->pitch_a = (rate_len + 3) / 4 * 4;
         AFP_CUDA(c, cudaMalloc(&c->tmp_a, (size_t)S * c->pitch_a * sizeof(float)));
@@ -735,6 +807,11 @@ int afp_create(const afp_config* cfg, afp_ctx** out_ctx) {
                 e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
                 if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, tensor path)");
             }
+    for (bool checked : {false, true})
+        for (int sb : {1, 2, 4, 8}) {
+            e = cudaFuncSetAttribute((const void*)afp_kernel_agc(checked, sb), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+            if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, AGC)");
+        }
     afp_ctx* c = new (std::nothrow) afp_ctx();
     if (!c) return fail(nullptr, AFP_ERR_NOMEM, "out of host memory");
     c->cfg = *cfg;
@@ -751,6 +828,7 @@ int afp_destroy(afp_ctx* c) {
     if (!c) return AFP_OK;
     cudaSetDevice(c->cfg.device);
     free_stage(c->up); free_stage(c->eq); free_stage(c->mainf); free_stage(c->fused);
+    if (c->tmp_agc) cudaFree(c->tmp_agc);
     if (c->tmp_a) cudaFree(c->tmp_a);
     if (c->tmp_b) cudaFree(c->tmp_b);
     for (int i = 0; i < 2; ++i) if (c->xhist[i]) cudaFree(c->xhist[i]);
@@ -858,6 +936,26 @@ int afp_set_gains(afp_ctx* c, const double* gains, int32_t n_bands) {
     return rc ? rc : rebuild_fused(c, true);
 }
 
+int afp_set_agc(afp_ctx* c, const afp_agc_params* p) {
+    if (!c) return AFP_ERR_INVALID;
+    if (!p) { c->agc_on = false; return AFP_OK; }
+    if (!(p->max_gain == p->max_gain) || !(p->target_level == p->target_level))
+        return fail(c, AFP_ERR_INVALID, "AGC: NaN parameter");
+    c->agc = *p;
+    c->agc_on = true;
+    return AFP_OK;
+}
+
+int afp_agc_block(afp_ctx* c, const afp_agc_params* p, const float* in, int64_t in_pitch, float* out, int64_t out_pitch,
+                  int32_t n_streams, int32_t frames, void* cuda_stream) {
+    if (!c) return AFP_ERR_INVALID;
+    if (!p || !in || !out) return fail(c, AFP_ERR_INVALID, "null argument");
+    if (n_streams < 0 || frames < 0) return fail(c, AFP_ERR_INVALID, "negative size");
+    if (in_pitch < frames || out_pitch < frames) return fail(c, AFP_ERR_INVALID, "pitch smaller than frames");
+    AFP_CUDA(c, cudaSetDevice(c->cfg.device));
+    return launch_agc(c, *p, in, in_pitch, out, out_pitch, n_streams, frames, (cudaStream_t)cuda_stream);
+}
+
 int32_t afp_out_frames(const afp_ctx* c, int32_t frames) {
     if (!c) return 0;
     const long long n = (long long)frames * c->cfg.upsample;   // both chains compute at fs*U
@@ -876,6 +974,12 @@ static int process_block_range(afp_ctx* c, const float* in, int64_t in_pitch, vo
     const bool ref = c->cfg.chain == AFP_CHAIN_REFERENCE;
     const int mode = c->cfg.eq_mode;
     int rc;
+    if (c->agc_on) {   // gain-controlled block replaces the input of everything below (stream_process_AGC.py:131-146)
+        float* tg = c->tmp_agc + (long long)s0 * c->pitch_agc;
+        rc = launch_agc(c, c->agc, in, in_pitch, tg, c->pitch_agc, ns, frames, st);
+        if (rc) return rc;
+        in = tg; in_pitch = c->pitch_agc;
+    }
     const float* cur = in; long long cur_pitch = in_pitch; int cur_len = frames;
     if (c->fused.active)  // interpolate -> FIR -> decimate collapsed into one base-rate FIR (rebuild_fused)
         return run_streaming(c, c->fused, in, in_pitch, frames, out,

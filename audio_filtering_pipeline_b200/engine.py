@@ -44,11 +44,14 @@ class BatchFirEngine:
     dither_bits        bit depth of the float-output dither (apply_dither's ``bit_depth``; default 24)
     same_buffer_len    'buffer_same*' only: fixed sliding-buffer length; 4*blocksize+512 gives the
                        Waterfall GUI's callback (stream_process_GUI_Waterfall.py:132,431-458)
+    agc                None | dict(target_level=0.1, window_size=512, max_gain=10.0, attack=0.01,
+                       release=0.1, clip=0.99): automatic gain control of every input block ahead of the
+                       chain, per block and stateless (stream_process_AGC.py:43-89,131-143)
     """
 
     def __init__(self, taps, n_streams=1, max_frames=1024, upsample=1, chain="dac", out_format="f32",
                  dither="none", seed=0, device=0, upsampler_taps=None, eq_bands=None, eq_gains=None,
-                 eq_mode="none", first_stream_id=0, decimate=0, dither_bits=0, same_buffer_len=0):
+                 eq_mode="none", first_stream_id=0, decimate=0, dither_bits=0, same_buffer_len=0, agc=None):
         self._lib = _lib.load()
         self._ctx = C.c_void_p()
         if eq_bands is not None and eq_mode in ("none", None):
@@ -71,6 +74,8 @@ class BatchFirEngine:
                 self.set_upsampler(upsampler_taps)
             if eq_bands is not None:
                 self.set_eq(eq_bands, eq_gains)
+            if agc is not None:
+                self.set_agc(**agc)
         except Exception:
             self.close()
             raise
@@ -97,6 +102,33 @@ class BatchFirEngine:
     def set_gains(self, gains):
         g, gp = _dbl(gains)
         _lib.check(self._lib.afp_set_gains(self._ctx, gp, len(g)), self._ctx)
+
+    def set_agc(self, enabled=True, **params):
+        """Switch the input AGC on (keyword arguments of ``apply_agc`` plus ``clip``) or off
+        (``set_agc(False)``).  Takes effect at the next block."""
+        if not enabled:
+            _lib.check(self._lib.afp_set_agc(self._ctx, None), self._ctx)
+            return
+        p = _lib.AgcParams.make(**params)
+        _lib.check(self._lib.afp_set_agc(self._ctx, C.byref(p)), self._ctx)
+
+    def agc_block(self, x, out=None, **params):
+        """The AGC kernel alone on a float32 CUDA tensor [rows, frames] (any row count)."""
+        import torch
+        if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2:
+            raise ValueError("x must be a float32 CUDA tensor of shape [rows, frames]")
+        if x.stride(1) != 1:
+            x = x.contiguous()
+        if out is None:
+            out = torch.empty_like(x, memory_format=torch.contiguous_format)
+        p = _lib.AgcParams.make(**params)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        rows, frames = x.shape
+        # (the stride of a one-row tensor is arbitrary)
+        xp, op = (x.stride(0), out.stride(0)) if rows > 1 else (max(x.stride(0), frames), max(out.stride(0), frames))
+        _lib.check(self._lib.afp_agc_block(self._ctx, C.byref(p), x.data_ptr(), xp, out.data_ptr(), op,
+                                           rows, frames, stream), self._ctx)
+        return out
 
     # -- processing --------------------------------------------------------------------------
     def out_frames(self, frames):

@@ -17,6 +17,8 @@
  *   chain = AFP_CHAIN_REFERENCE       processed[::UPSAMPLE_FACTOR]       stream_process.py:106
  *   afp_process_host                  the body of audio_callback(indata, outdata, frames, ...)
  *                                     stream_process.py:79-120 (host buffers in, host buffers out)
+ *   afp_set_agc / afp_agc_block       apply_agc + np.clip(+-0.99) ahead of the up-sampler
+ *                                     stream_process_AGC.py:43-89,131-143
  *
  * Data layout: planar, stream-major.  in[s*in_pitch + i] is frame i of stream s (float32 at the
  * base rate); out[s*out_pitch + j] is output sample j of stream s in `out_format`.  A "stream" is
@@ -102,6 +104,21 @@ typedef struct afp_stage_info {
                                  2 = packed-FFMA2 single-row form (single-table stages, aligned buffers) */
 } afp_stage_info;
 
+/* Automatic gain control of the input block (stream_process_AGC.py:43-89), per block and stateless like
+ * the reference.  Defaults of apply_agc / of its call site in comments. */
+typedef struct afp_agc_params {
+    double target_level;      /* 0.1   target RMS */
+    double max_gain;          /* 10.0 */
+    double attack;            /* 0.01  fraction of window_size: int(attack*window_size) samples, evaluated in
+                                       double exactly as Python does */
+    double release;           /* 0.1   likewise.  A constant of 0 samples makes the reference's loop divide by
+                                       zero when that branch is first taken; it then returns the block
+                                       unchanged (:87-89), and so does the affected stream here */
+    double clip;              /* 0.99  np.clip of the result at the call site (:143); <= 0 = none */
+    int32_t window_size;      /* 512   moving-RMS window in samples; the call site passes min(512, blocksize/2) */
+    int32_t reserved;         /* 0 */
+} afp_agc_params;
+
 const char* afp_version(void);
 
 int afp_create(const afp_config* cfg, afp_ctx** out_ctx);
@@ -130,6 +147,14 @@ int afp_process_host(afp_ctx* ctx, const float* in_host, void* out_host, int32_t
  * device->host copies of successive blocks / stream chunks overlap on three CUDA streams. */
 int afp_process_host_blocks(afp_ctx* ctx, const float* in_host, void* out_host, int32_t frames,
                             int32_t n_blocks);
+
+/* AGC as the first stage of every following afp_process* call (ahead of the interpolator, as in
+ * stream_process_AGC.py:131-146); params == NULL switches it off.  Carries no state. */
+int afp_set_agc(afp_ctx* ctx, const afp_agc_params* params);
+/* The AGC alone: out[s][i] = clip(in[s][i] * gain[s][i]) for n_streams rows of `frames` samples (device
+ * pointers, pitches in elements, asynchronous on cuda_stream; in and out must not overlap). */
+int afp_agc_block(afp_ctx* ctx, const afp_agc_params* params, const float* in_dev, int64_t in_pitch,
+                  float* out_dev, int64_t out_pitch, int32_t n_streams, int32_t frames, void* cuda_stream);
 
 int32_t afp_out_frames(const afp_ctx* ctx, int32_t frames);
 int32_t afp_out_elem_bytes(const afp_ctx* ctx);

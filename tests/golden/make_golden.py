@@ -12,6 +12,7 @@ What is executed, unmodified, from /root/reference:
   * stream_process_GUI_Presets.OverlapAddFilter / process_audio_block  -> ola_*.npz
   * stream_process_GUI_Waterfall.make_audio_callback                   -> cb_waterfall_*.npz
   * stream_process_EQ_GUI.process_audio (worker thread) + min-phase call sites -> eqgui_*.npz
+  * stream_process_AGC.apply_agc (+ the clip of its call site)         -> agc_blocks.npz
 
 What is stubbed (absent from the container and outside the hot path): sounddevice, tkinter,
 matplotlib, plot_filter, samplerate, and the import-time side effects (sudo cpufreq-set,
@@ -403,6 +404,52 @@ def gen_eq_gui_worker():
          eq_gains=np.array(gains), y=np.stack(ys), params=np.array([N, B, U, fs]))
 
 
+def gen_agc():
+    """stream_process_AGC.apply_agc (:43-89) on single blocks, called the way the worker loop calls it
+    (:131-143: [n, 1] float32 block, window min(512, bs // 2), then np.clip +-0.99), plus direct calls
+    with other windows - among them windows short enough that int(attack * window) == 0, where the
+    reference divides by zero inside its loop, catches the exception and returns the block unchanged."""
+    import contextlib
+    import io
+    import stream_process_AGC as ag
+    rng = np.random.default_rng(11)
+    cases = []
+
+    def level_steps(n, levels):
+        seg = n // len(levels)
+        env = np.repeat(np.asarray(levels, dtype=np.float64), seg)
+        env = np.pad(env, (0, n - len(env)), mode="edge")
+        return (env * rng.standard_normal(n)).astype(np.float32)
+
+    blocks = {
+        "noise_1024": (0.3 * rng.standard_normal(1024)).astype(np.float32),
+        "steps_1024": level_steps(1024, [0.5, 0.002, 0.2, 0.02]),
+        "quiet_1024": (1e-4 * rng.standard_normal(1024)).astype(np.float32),
+        "sweep_2048": sweep_and_noise(2048, 44100, seed=2),
+        "steps_4096": level_steps(4096, [0.01, 0.9, 0.05, 0.4, 0.001, 0.3]),
+        "odd_777": level_steps(777, [0.2, 0.01, 0.6]),
+        "silence_512": np.zeros(512, dtype=np.float32),
+        "loud_1024": np.clip(2.5 * rng.standard_normal(1024), -4, 4).astype(np.float32),
+    }
+    arrays, meta = {}, []
+    for name, x in blocks.items():
+        n = len(x)
+        variants = [dict(target_level=0.1, window_size=min(512, n // 2), max_gain=10.0, attack=0.01, release=0.1),
+                    dict(target_level=0.05, window_size=256, max_gain=4.0, attack=0.02, release=0.3),
+                    dict(target_level=0.2, window_size=101, max_gain=20.0, attack=0.1, release=0.01),   # odd window, attack slower than release
+                    dict(target_level=0.1, window_size=64, max_gain=10.0, attack=0.01, release=0.1),    # int(0.64) == 0 -> error path
+                    dict(target_level=0.1, window_size=n, max_gain=10.0, attack=0.01, release=0.1)]     # window == block
+        for kw in variants:
+            with contextlib.redirect_stdout(io.StringIO()) as log:
+                y = ag.apply_agc(x.reshape(-1, 1).copy(), **kw)
+            key = f"{name}_{len(meta)}"
+            arrays["x_" + name] = x
+            arrays["y_" + key] = np.asarray(y)[:, 0]
+            meta.append(dict(kw, key=key, block=name, errored=bool(log.getvalue().startswith("AGC error"))))
+    arrays["meta"] = np.array(json.dumps(meta))
+    save("agc_blocks", **arrays)
+
+
 def main():
     soxr = install_stubs()
     print("design ...");            gen_design()
@@ -412,6 +459,7 @@ def main():
     print("overlap-add ...");       gen_overlap_add()
     print("waterfall ...");         gen_waterfall(soxr)
     print("EQ_GUI worker ...");     gen_eq_gui_worker()
+    print("AGC ...");               gen_agc()
     manifest = {
         "generated_by": "tests/golden/make_golden.py",
         "reference": REF,

@@ -148,3 +148,38 @@ def test_reference_chain_collapses_to_one_base_rate_fir():
         g0 = np.convolve(h_up, h)[::U]
         fused = rc.streaming_fir(g0, x)
         np.testing.assert_allclose(fused[: len(staged)], staged, rtol=0, atol=1e-12)
+
+
+def _agc_cases():
+    import json
+    g = load_golden("agc_blocks")
+    return g, json.loads(str(g["meta"]))
+
+
+def test_agc_oracle_matches_apply_agc():
+    """oracle/agc.py against the reference's own apply_agc (stream_process_AGC.py:43-89) on every
+    golden block, the error path (block returned unchanged) included."""
+    from oracle import agc
+    g, meta = _agc_cases()
+    assert sum(m["errored"] for m in meta) >= 4 and sum(not m["errored"] for m in meta) >= 20
+    for m in meta:
+        x, y_ref = g["x_" + m["block"]], g["y_" + m["key"]]
+        y = agc.apply_agc(x, target_level=m["target_level"], window_size=m["window_size"],
+                          max_gain=m["max_gain"], attack=m["attack"], release=m["release"])
+        if m["errored"]:
+            assert y.dtype == np.float32 and np.array_equal(y, x) and np.array_equal(y_ref, x), m["key"]
+        else:
+            assert y.dtype == np.float64
+            np.testing.assert_allclose(y, y_ref, rtol=1e-13, atol=0, err_msg=m["key"])
+
+
+def test_agc_stage_is_call_site_window_and_clip():
+    from oracle import agc
+    g, meta = _agc_cases()
+    for m in meta:
+        x = g["x_" + m["block"]]
+        if m["window_size"] != min(512, len(x) // 2) or m["target_level"] != 0.1:
+            continue
+        y = agc.agc_stage(x)
+        np.testing.assert_allclose(y, np.clip(g["y_" + m["key"]], -0.99, 0.99), rtol=1e-13, atol=0)
+        assert np.abs(y).max() <= 0.99
