@@ -19,7 +19,7 @@
 #include "afp_fir_tc.cuh"
 #include "afp_agc.cuh"
 
-afp::agc_kern_t afp_kernel_agc(bool checked, int scan_blocks);   // afp_kernels_agc.cu: scan_blocks in {1, 2, 4, 8}
+afp::agc_kern_t afp_kernel_agc(int variant, int scan_blocks);   // afp_kernels_agc.cu: variant AGC_*, scan_blocks 1 / 2
 
 using afp::FirParams;
 
@@ -316,14 +316,15 @@ Geometry pick_geometry(int T, int kq_pad, int n_q, int n_streams) {
 // + one float64 prefix-sum row per warp + a flag per stream.  Two CTAs per SM when at least 8 streams
 // fit in half an SM's shared memory (one CTA's serial recurrence phase overlaps the other's memory
 // phases), else one CTA with as many streams as fit.
-struct AgcPlan { int warps = 0, group = 0, pitch = 0, ctas_per_sm = 0; size_t smem = 0; };
+struct AgcPlan { int warps = 0, group = 0, pitch = 0, ctas_per_sm = 0, scratch = 0; size_t smem = 0; };
 bool plan_agc(int frames, int n_streams, int n_sm, AgcPlan& pl) {
     const int pitch = frames | 1;
     const size_t row = (size_t)pitch * sizeof(float) + sizeof(int);
     struct Try { size_t budget; int warps, min_group, ctas; };
     const Try tries[] = {{112 * 1024, 4, 8, 2}, {224 * 1024, 4, 4, 1}, {224 * 1024, 2, 1, 1}, {224 * 1024, 1, 1, 1}};
     for (const Try& t : tries) {
-        const size_t fixed = (size_t)t.warps * (frames + 1) * sizeof(double) + 16;
+        const int scratch = afp::agc_phys(frames) + 2;   // prefix sums 0..frames, one pad double per 16
+        const size_t fixed = (size_t)t.warps * scratch * sizeof(double) + 16;
         if (fixed + row * t.min_group > t.budget) continue;
         long long g = (long long)((t.budget - fixed) / row);
         if (g > 32 * t.warps) g = 32 * t.warps;
@@ -331,7 +332,8 @@ bool plan_agc(int frames, int n_streams, int n_sm, AgcPlan& pl) {
         const long long spread = ((long long)n_streams + (long long)n_sm * t.ctas - 1) / ((long long)n_sm * t.ctas);
         if (g > spread) g = spread < 1 ? 1 : spread;
         pl.warps = t.warps; pl.group = (int)g; pl.pitch = pitch; pl.ctas_per_sm = t.ctas;
-        pl.smem = ((((size_t)g * pitch * sizeof(float)) + 7) & ~(size_t)7) + (size_t)t.warps * (frames + 1) * sizeof(double) +
+        pl.scratch = scratch;
+        pl.smem = ((((size_t)g * pitch * sizeof(float)) + 7) & ~(size_t)7) + (size_t)t.warps * scratch * sizeof(double) +
                   (size_t)g * sizeof(int);
         return true;
     }
@@ -360,10 +362,14 @@ int launch_agc(afp_ctx* c, const afp_agc_params& a, const float* in, long long i
     P.att_ok = att_n != 0; P.rel_ok = rel_n != 0;
     const double aa = P.att_ok ? 1.0 - std::exp(-1.0 / att_n) : 0.0, ar = P.rel_ok ? 1.0 - std::exp(-1.0 / rel_n) : 0.0;   // :73-78
     P.a_att = (float)aa; P.c_att = (float)(1.0 - aa); P.a_rel = (float)ar; P.c_rel = (float)(1.0 - ar);
-    const bool checked = !(P.att_ok && P.rel_ok);
-    int sb = 1;
-    while (sb < 8 && 128 * sb < frames) sb *= 2;   // loads of up to 1024 samples of a stream issued at once
-    afp::agc_kern_t k = afp_kernel_agc(checked, sb);
+    P.scratch = pl.scratch;
+    // The reference divides by (rms + 1e-10).  Wherever the gain is not clamped to max_gain, rms exceeds
+    // target/max_gain; if that is >= 1e-4 the epsilon moves the gain by < 1e-6 relative and the kernel may
+    // use target*rsqrt(mean) (a zero window then gives +inf -> max_gain, as the reference's 1e9 clip does).
+    const bool fast = a.target_level > 0 && a.max_gain > 0 && a.target_level / a.max_gain >= 1e-4;
+    P.fast_scale = (float)(a.target_level * std::sqrt((double)P.window));
+    const int variant = !(P.att_ok && P.rel_ok) ? afp::AGC_CHECKED : (fast ? afp::AGC_FAST : afp::AGC_EXACT);
+    afp::agc_kern_t k = afp_kernel_agc(variant, frames > 512 ? 2 : 1);
     int grid = c->n_sm * pl.ctas_per_sm;
     if (grid > P.n_items) grid = P.n_items;
     k<<<grid, 32 * pl.warps, pl.smem, stream>>>(P);
@@ -807,9 +813,9 @@ int afp_create(const afp_config* cfg, afp_ctx** out_ctx) {
                 e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
                 if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, tensor path)");
             }
-    for (bool checked : {false, true})
-        for (int sb : {1, 2, 4, 8}) {
-            e = cudaFuncSetAttribute((const void*)afp_kernel_agc(checked, sb), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    for (int variant : {afp::AGC_FAST, afp::AGC_EXACT, afp::AGC_CHECKED})
+        for (int sb : {1, 2}) {
+            e = cudaFuncSetAttribute((const void*)afp_kernel_agc(variant, sb), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
             if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, AGC)");
         }
     afp_ctx* c = new (std::nothrow) afp_ctx();

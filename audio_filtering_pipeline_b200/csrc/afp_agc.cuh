@@ -14,13 +14,17 @@
 //
 // One work item = `group` streams x one block.  Shared memory holds one float row per stream (odd
 // pitch: lane = stream accesses are conflict-free) plus one float64 prefix-sum row per warp.
-//   phase 1  warp per stream: x (coalesced 16-byte loads) -> x^2 in float32 as numpy does -> float64
-//            inclusive prefix sums (warp shuffles; 4 independent 128-sample scans in flight) -> window
-//            sum as a difference of two prefix sums (float64: a quiet window after a loud passage keeps
-//            its digits) -> desired gain, float32, into the stream's row
-//   phase 2  lane per stream: the recurrence, in place
-//   phase 3  warp per stream: x again (an L2 hit, the item was read a few microseconds ago) times the
-//            limited gain, clip, coalesced store
+//   phase 1  warp per stream: a lane takes 16 consecutive samples (four 16-byte loads) -> x^2 in float32
+//            as numpy does -> float64 running sums in registers -> one warp scan of the lane totals per
+//            512 samples -> exclusive prefix sums in the warp's scratch row (one pad double per 16, so the
+//            lane stride is 17 doubles: conflict-free) -> window sum as a difference of two prefix sums
+//            (float64: a quiet window after a loud passage keeps its digits) -> desired gain, float32,
+//            into the stream's row.  FAST instantiation: target*rsqrt(mean) - the reference's "+ 1e-10"
+//            under the division only matters where the gain is clamped to max_gain anyway (host check).
+//   phase 2  lane per stream: the recurrence, in place; both branches in one packed FFMA2
+//            (s * (1-a_att, 1-a_rel) + d * (a_att, a_rel)), then FMNMX
+//   phase 3  all threads over (stream, 4-sample chunk), 8 loads in flight each: x again (an L2 hit, the
+//            item was read a few microseconds ago) times the limited gain, clip, coalesced 16-byte stores
 // Two CTAs per SM when the rows fit (host plan in afp_abi.cu), so one CTA's serial phase 2 overlaps the
 // other's memory phases.  HBM-bound by design: 8 bytes per sample, no intermediate leaves the SM.
 //
@@ -38,14 +42,16 @@ namespace afp {
 struct AgcParams {
     const float* in;           // [n_streams][in_pitch]
     long long in_pitch;
-    float* out;                // [n_streams][out_pitch]   (may alias `in`)
+    float* out;                // [n_streams][out_pitch]   (must not overlap `in`)
     long long out_pitch;
     int n_streams, frames;
     int window, left, right;   // window length; samples before / after the centre: left + 1 + right = window
     int group;                 // streams per work item
     int pitch;                 // floats per stream row in shared memory (odd)
     int n_items;
+    int scratch;               // doubles per warp in the prefix-sum scratch
     float inv_window;
+    float fast_scale;          // target * sqrt(window): desired = min(fast_scale * rsqrt(window sum), max_gain)
     float target, max_gain, min_gain, clip;   // clip <= 0: no output clip
     float a_att, c_att, a_rel, c_rel;          // alpha and 1 - alpha of the two branches
     int att_ok, rel_ok;        // 0: that branch raises in the reference
@@ -53,6 +59,11 @@ struct AgcParams {
 };
 
 typedef void (*agc_kern_t)(const AgcParams);
+
+// kernel variants
+constexpr int AGC_FAST = 0;      // both constants valid, epsilon-free gain
+constexpr int AGC_EXACT = 1;     // both constants valid, target / (rms + 1e-10)
+constexpr int AGC_CHECKED = 2;   // a zero-sample constant: explicit comparison, failing streams pass through
 
 __device__ __forceinline__ double shfl_up_f64(double v, int delta) {
     int lo = __double2loint(v), hi = __double2hiint(v);
@@ -66,26 +77,57 @@ __device__ __forceinline__ double shfl_f64(double v, int src) {
     hi = __shfl_sync(0xffffffffu, hi, src);
     return __hiloint2double(hi, lo);
 }
-
-// approximate sqrt / divide (MUFU + one multiply, ~2 ulp): the gain only has to hold 1e-5
+// approximate sqrt / reciprocal sqrt (MUFU, ~2 ulp): the gain only has to hold 1e-5
 __device__ __forceinline__ float sqrt_approx(float v) {
     float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float rsqrt_approx(float v) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ unsigned long long agc_pack(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
     return r;
 }
 
-// SB = independent 128-sample scans in flight per warp: every load of a block of up to 128*SB samples is
-// issued before the first use (one exposed memory latency per stream when frames <= 1024)
-template <bool CHECKED, int SB>
+// smoothed[i] = max|min(c_att*s + a_att*d, c_rel*s + a_rel*d): FMUL2, FFMA2 (s is the scalar-broadcast
+// operand), FMNMX; the dependent chain per step is FFMA2 -> FMNMX
+template <bool TAKE_MAX>
+__device__ __forceinline__ float agc_recur(float* row, int n, float s, unsigned long long cc, unsigned long long aa) {
+#pragma unroll 16
+    for (int i = 1; i < n; ++i) {
+        const float d = row[i];
+        unsigned long long t;
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(agc_pack(d, d)), "l"(aa));
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(t) : "l"(agc_pack(s, s)), "l"(cc));
+        const float2 br = *reinterpret_cast<float2*>(&t);
+        s = TAKE_MAX ? fmaxf(br.x, br.y) : fminf(br.x, br.y);
+        row[i] = s;
+    }
+    return s;
+}
+
+constexpr int AGC_LANE_RUN = 16;                   // consecutive samples per lane in the prefix scan
+constexpr int AGC_SCAN = 32 * AGC_LANE_RUN;        // samples per warp scan
+// index of prefix sum k in the scratch row: one pad double per 16
+__host__ __device__ constexpr int agc_phys(int k) { return k + (k >> 4); }
+
+// SB = 512-sample scans in flight per warp: every load of up to 512*SB samples of a stream is issued
+// before the first use
+template <int VARIANT, int SB>
 __global__ void agc_kernel(const __grid_constant__ AgcParams P) {
-    constexpr int AGC_SCAN_BLOCKS = SB;
+    constexpr bool CHECKED = VARIANT == AGC_CHECKED;
     extern __shared__ __align__(16) unsigned char agc_smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, n_warps = blockDim.x >> 5;
     const int n = P.frames, G = P.group;
     float* rows = reinterpret_cast<float*>(agc_smem);
     const size_t rows_bytes = (((size_t)G * P.pitch * sizeof(float)) + 7) & ~(size_t)7;
-    double* pfx = reinterpret_cast<double*>(agc_smem + rows_bytes) + (size_t)warp * (n + 1);
-    int* failed = reinterpret_cast<int*>(agc_smem + rows_bytes + (size_t)n_warps * (n + 1) * sizeof(double));
+    double* pfx = reinterpret_cast<double*>(agc_smem + rows_bytes) + (size_t)warp * P.scratch;
+    int* failed = reinterpret_cast<int*>(agc_smem + rows_bytes + (size_t)n_warps * P.scratch * sizeof(double));
 
     for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
         const int s0 = item * G;
@@ -98,52 +140,61 @@ __global__ void agc_kernel(const __grid_constant__ AgcParams P) {
                 const bool al = (reinterpret_cast<uintptr_t>(x) & 15u) == 0;
                 if (lane == 0) { pfx[0] = 0.0; if (CHECKED) failed[sl] = 0; }
                 double carry = 0.0;
-                for (int base = 0; base < n; base += 128 * AGC_SCAN_BLOCKS) {
-                    double p[AGC_SCAN_BLOCKS][4], tot[AGC_SCAN_BLOCKS];
+                for (int base = 0; base < n; base += AGC_SCAN * SB) {
+                    float v[SB][AGC_LANE_RUN];
 #pragma unroll
-                    for (int b = 0; b < AGC_SCAN_BLOCKS; ++b) {
-                        const int i = base + 128 * b + 4 * lane;
-                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (al && i + 3 < n) v = __ldg(reinterpret_cast<const float4*>(x + i));
-                        else {
-                            if (i < n) v.x = __ldg(x + i);
-                            if (i + 1 < n) v.y = __ldg(x + i + 1);
-                            if (i + 2 < n) v.z = __ldg(x + i + 2);
-                            if (i + 3 < n) v.w = __ldg(x + i + 3);
+                    for (int b = 0; b < SB; ++b) {
+                        const int i = base + AGC_SCAN * b + AGC_LANE_RUN * lane;
+                        if (al && i + AGC_LANE_RUN <= n) {
+#pragma unroll
+                            for (int q = 0; q < AGC_LANE_RUN / 4; ++q) {
+                                const float4 t = __ldg(reinterpret_cast<const float4*>(x + i) + q);
+                                v[b][4 * q] = t.x; v[b][4 * q + 1] = t.y; v[b][4 * q + 2] = t.z; v[b][4 * q + 3] = t.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < AGC_LANE_RUN; ++j) v[b][j] = i + j < n ? __ldg(x + i + j) : 0.f;
                         }
-                        // np.square of a float32 array stays float32 (:60); the sums are float64 (:62)
-                        p[b][0] = (double)__fmul_rn(v.x, v.x);
-                        p[b][1] = p[b][0] + (double)__fmul_rn(v.y, v.y);
-                        p[b][2] = p[b][1] + (double)__fmul_rn(v.z, v.z);
-                        p[b][3] = p[b][2] + (double)__fmul_rn(v.w, v.w);
-                        tot[b] = p[b][3];
                     }
 #pragma unroll
-                    for (int off = 1; off < 32; off <<= 1)
+                    for (int b = 0; b < SB; ++b) {
+                        // np.square of a float32 array stays float32 (:60); the sums are float64 (:62)
+                        double run[AGC_LANE_RUN];
+                        run[0] = (double)__fmul_rn(v[b][0], v[b][0]);
 #pragma unroll
-                        for (int b = 0; b < AGC_SCAN_BLOCKS; ++b) {
-                            const double t = shfl_up_f64(tot[b], off);
-                            if (lane >= off) tot[b] += t;
+                        for (int j = 1; j < AGC_LANE_RUN; ++j) run[j] = run[j - 1] + (double)__fmul_rn(v[b][j], v[b][j]);
+                        double tot = run[AGC_LANE_RUN - 1];
+#pragma unroll
+                        for (int off = 1; off < 32; off <<= 1) {
+                            const double t = shfl_up_f64(tot, off);
+                            if (lane >= off) tot += t;
                         }
-#pragma unroll
-                    for (int b = 0; b < AGC_SCAN_BLOCKS; ++b) {
-                        double excl = shfl_up_f64(tot[b], 1);
+                        double excl = shfl_up_f64(tot, 1);
                         excl = (lane == 0 ? 0.0 : excl) + carry;
-                        const int i = base + 128 * b + 4 * lane;
+                        const int i = base + AGC_SCAN * b + AGC_LANE_RUN * lane;
+                        if (i + AGC_LANE_RUN <= n) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (i + j < n) pfx[i + j + 1] = excl + p[b][j];
-                        carry += shfl_f64(tot[b], 31);
+                            for (int j = 0; j < AGC_LANE_RUN; ++j) pfx[agc_phys(i + j + 1)] = excl + run[j];
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < AGC_LANE_RUN; ++j)
+                                if (i + j < n) pfx[agc_phys(i + j + 1)] = excl + run[j];
+                        }
+                        carry += shfl_f64(tot, 31);
                     }
                 }
                 __syncwarp();
                 float* row = rows + (size_t)sl * P.pitch;
 #pragma unroll 4
                 for (int i = lane; i < n; i += 32) {
-                    const int hi = min(i + P.right, n - 1), lo = max(i - P.left, 0);
-                    const double sum = pfx[hi + 1] - pfx[lo];
-                    const float rms = sqrt_approx((float)sum * P.inv_window);
-                    row[i] = fminf(fmaxf(__fdividef(P.target, rms + 1e-10f), 0.f), P.max_gain);
+                    const int hi = min(i + P.right, n - 1) + 1, lo = max(i - P.left, 0);
+                    const float sum = (float)(pfx[agc_phys(hi)] - pfx[agc_phys(lo)]);
+                    if (VARIANT == AGC_FAST) {
+                        row[i] = fminf(P.fast_scale * rsqrt_approx(sum), P.max_gain);
+                    } else {
+                        const float rms = sqrt_approx(sum * P.inv_window);
+                        row[i] = fminf(fmaxf(__fdividef(P.target, rms + 1e-10f), 0.f), P.max_gain);
+                    }
                 }
                 __syncwarp();
             }
@@ -153,22 +204,9 @@ __global__ void agc_kernel(const __grid_constant__ AgcParams P) {
                 float* row = rows + (size_t)tid * P.pitch;
                 float s = row[0];
                 if (!CHECKED) {
-                    const float aA = P.a_att, cA = P.c_att, aR = P.a_rel, cR = P.c_rel;
-                    if (aA >= aR) {
-#pragma unroll 8
-                        for (int i = 1; i < n; ++i) {
-                            const float d = row[i];
-                            s = fmaxf(fmaf(cA, s, aA * d), fmaf(cR, s, aR * d));
-                            row[i] = s;
-                        }
-                    } else {
-#pragma unroll 8
-                        for (int i = 1; i < n; ++i) {
-                            const float d = row[i];
-                            s = fminf(fmaf(cA, s, aA * d), fmaf(cR, s, aR * d));
-                            row[i] = s;
-                        }
-                    }
+                    const unsigned long long cc = agc_pack(P.c_att, P.c_rel), aa = agc_pack(P.a_att, P.a_rel);
+                    if (P.a_att >= P.a_rel) s = agc_recur<true>(row, n, s, cc, aa);
+                    else                    s = agc_recur<false>(row, n, s, cc, aa);
                 } else {
                     bool bad = false;
 #pragma unroll 4

@@ -1,20 +1,18 @@
-// agc_kernel instantiations (afp_agc.cuh): the fast max/min form and the checked form that mirrors
-// the reference's divide-by-zero path, each with 1 / 2 / 4 / 8 scans of 128 samples in flight per warp.
+// agc_kernel instantiations (afp_agc.cuh): variant (fast / exact gain / checked recurrence) x one or two
+// 512-sample scans in flight per warp.
 #include "afp_agc.cuh"
 
 namespace {
-template <bool CHECKED>
+template <int VARIANT>
 afp::agc_kern_t pick(int scan_blocks) {
-    switch (scan_blocks) {
-        case 1: return (afp::agc_kern_t)afp::agc_kernel<CHECKED, 1>;
-        case 2: return (afp::agc_kern_t)afp::agc_kernel<CHECKED, 2>;
-        case 4: return (afp::agc_kern_t)afp::agc_kernel<CHECKED, 4>;
-        case 8: return (afp::agc_kern_t)afp::agc_kernel<CHECKED, 8>;
-        default: return nullptr;
-    }
+    return scan_blocks == 1 ? (afp::agc_kern_t)afp::agc_kernel<VARIANT, 1> : (afp::agc_kern_t)afp::agc_kernel<VARIANT, 2>;
 }
 }  // namespace
 
-afp::agc_kern_t afp_kernel_agc(bool checked, int scan_blocks) {
-    return checked ? pick<true>(scan_blocks) : pick<false>(scan_blocks);
+afp::agc_kern_t afp_kernel_agc(int variant, int scan_blocks) {
+    switch (variant) {
+        case afp::AGC_FAST: return pick<afp::AGC_FAST>(scan_blocks);
+        case afp::AGC_EXACT: return pick<afp::AGC_EXACT>(scan_blocks);
+        default: return pick<afp::AGC_CHECKED>(scan_blocks);
+    }
 }
