@@ -23,7 +23,7 @@ SYMBOLS = [
     "afp_set_eq", "afp_set_gains", "afp_process", "afp_process_host", "afp_process_host_blocks", "afp_out_frames",
     "afp_out_elem_bytes", "afp_reset", "afp_state_size", "afp_get_state", "afp_set_state",
     "afp_get_stage_info", "afp_kernel_launches", "afp_host_alloc", "afp_host_free",
-    "afp_measure_fma_peak", "afp_set_agc", "afp_agc_block",
+    "afp_measure_fma_peak", "afp_set_agc", "afp_agc_block", "afp_process_host_interleaved",
 ]
 
 
@@ -89,6 +89,7 @@ def load():
     lib.afp_process.argtypes = [vp, vp, i64, vp, i64, i32, vp]
     lib.afp_process_host.argtypes = [vp, vp, vp, i32]
     lib.afp_process_host_blocks.argtypes = [vp, vp, vp, i32, i32]
+    lib.afp_process_host_interleaved.argtypes = [vp, vp, vp, i32, i32]
     lib.afp_out_frames.argtypes = [vp, i32]
     lib.afp_out_frames.restype = i32
     lib.afp_out_elem_bytes.argtypes = [vp]

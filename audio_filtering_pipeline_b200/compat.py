@@ -77,9 +77,8 @@ class StreamChain:
         if x.ndim == 1:
             x = x[:, None]
         frames = x.shape[0]
-        planar = np.ascontiguousarray(x[:, :self.channels].T)
-        y = self.engine.process_host(planar)
-        return np.ascontiguousarray(y.T[:frames])
+        # [frames, channels] goes to the device as it is; the (de)interleave runs there
+        return self.engine.process_host_interleaved(x[:, :self.channels])[:frames]
 
     def close(self):
         self.engine.close()

@@ -168,6 +168,9 @@ struct afp_ctx {
     unsigned char* d_out[kSlots] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_in[kSlots] = {}, ev_k[kSlots] = {}, ev_out[kSlots] = {};
     int slot_streams = 0;            // streams per staging slot
+    // afp_process_host_interleaved: frame-major device copies of one block in / out
+    float* d_il_in = nullptr;
+    unsigned char* d_il_out = nullptr;
     cudaStream_t own_stream = nullptr, s_in = nullptr, s_out = nullptr;
     FirParams params{};              // scratch for the kernel-parameter block of the launch being prepared
 };
@@ -313,24 +316,31 @@ Geometry pick_geometry(int T, int kq_pad, int n_q, int n_streams) {
 }
 
 // ---- AGC (afp_agc.cuh).  Shared memory per CTA: one float row per stream of the work item (odd pitch)
-// + one float64 prefix-sum row per warp + a flag per stream.  Two CTAs per SM when at least 8 streams
-// fit in half an SM's shared memory (one CTA's serial recurrence phase overlaps the other's memory
-// phases), else one CTA with as many streams as fit.
+// + one float64 prefix-sum row per warp + a flag per stream.  Two (short blocks: three) CTAs per SM when at
+// least 8 streams fit in that share of an SM's shared memory (one CTA's serial recurrence phase overlaps
+// the others' memory phases), else one CTA with as many streams as fit.
 struct AgcPlan { int warps = 0, group = 0, pitch = 0, ctas_per_sm = 0, scratch = 0; size_t smem = 0; };
 bool plan_agc(int frames, int n_streams, int n_sm, AgcPlan& pl) {
-    const int pitch = frames | 1;
+    const int pitch = 4 * (((frames + 3) / 4) | 1);   // an odd number of 16-byte units
     const size_t row = (size_t)pitch * sizeof(float) + sizeof(int);
     struct Try { size_t budget; int warps, min_group, ctas; };
-    const Try tries[] = {{112 * 1024, 4, 8, 2}, {224 * 1024, 4, 4, 1}, {224 * 1024, 2, 1, 1}, {224 * 1024, 1, 1, 1}};
-    for (const Try& t : tries) {
+    const Try tries[] = {{74 * 1024, 4, 8, 3}, {112 * 1024, 4, 8, 2}, {224 * 1024, 4, 4, 1}, {224 * 1024, 2, 1, 1}, {224 * 1024, 1, 1, 1}};
+    // three smaller CTAs per SM pay for short blocks (measured, 16384 streams: 512 frames 192 vs 160
+    // Gsamples/s, 256 frames 140 vs 113; 1024 frames 165 vs 169)
+    const int plan_from = frames <= 512 ? 0 : 1;
+    for (int ti = plan_from; ti < 5; ++ti) {
+        const Try& t = tries[ti];
         const int scratch = afp::agc_phys(frames) + 2;   // prefix sums 0..frames, one pad double per 16
         const size_t fixed = (size_t)t.warps * scratch * sizeof(double) + 16;
         if (fixed + row * t.min_group > t.budget) continue;
         long long g = (long long)((t.budget - fixed) / row);
         if (g > 32 * t.warps) g = 32 * t.warps;
-        // small batches: spread the streams over all SMs rather than filling a few CTAs
-        const long long spread = ((long long)n_streams + (long long)n_sm * t.ctas - 1) / ((long long)n_sm * t.ctas);
-        if (g > spread) g = spread < 1 ? 1 : spread;
+        // equal work per CTA: with `rounds` items per CTA the group that covers the batch exactly (also spreads
+        // a small batch over all SMs instead of filling a few CTAs)
+        const long long grid = (long long)n_sm * t.ctas;
+        const long long items = (n_streams + g - 1) / g, rounds = (items + grid - 1) / grid;
+        const long long even = (n_streams + rounds * grid - 1) / (rounds * grid);
+        if (g > even) g = even < 1 ? 1 : even;
         pl.warps = t.warps; pl.group = (int)g; pl.pitch = pitch; pl.ctas_per_sm = t.ctas;
         pl.scratch = scratch;
         pl.smem = ((((size_t)g * pitch * sizeof(float)) + 7) & ~(size_t)7) + (size_t)t.warps * scratch * sizeof(double) +
@@ -725,6 +735,34 @@ int ensure_tmp(afp_ctx* c) {
     return AFP_OK;
 }
 
+// ---- wire format of a sounddevice stream (stream_process.py:128-136: [frames, channels] float32 buffers)
+// <-> the planar stream-major layout of the kernels.  in[(session*frames + f)*C + ch] <-> row session*C + ch.
+__global__ void __launch_bounds__(256) deinterleave_kernel(const float* __restrict__ in, float* __restrict__ out, int sessions,
+                                                           int frames, int C, long long out_pitch) {
+    const long long total = (long long)sessions * frames;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int se = (int)(t / frames), f = (int)(t - (long long)se * frames);
+        const float* src = in + t * C;
+        for (int ch = 0; ch < C; ++ch) out[((long long)se * C + ch) * out_pitch + f] = src[ch];
+    }
+}
+// planar rows of EB-byte samples -> frame-major [session][sample][channel]
+template <int EB>
+__global__ void __launch_bounds__(256) interleave_kernel(const unsigned char* __restrict__ in, unsigned char* __restrict__ out,
+                                                         int sessions, int n, int C, long long in_pitch_bytes) {
+    const long long total = (long long)sessions * n;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int se = (int)(t / n), j = (int)(t - (long long)se * n);
+        unsigned char* dst = out + t * C * EB;
+        for (int ch = 0; ch < C; ++ch) {
+            const unsigned char* src = in + ((long long)se * C + ch) * in_pitch_bytes + (long long)j * EB;
+            if (EB == 4) *reinterpret_cast<uint32_t*>(dst + ch * 4) = *reinterpret_cast<const uint32_t*>(src);
+            else if (EB == 2) *reinterpret_cast<uint16_t*>(dst + ch * 2) = *reinterpret_cast<const uint16_t*>(src);
+            else { dst[ch * 3] = src[0]; dst[ch * 3 + 1] = src[1]; dst[ch * 3 + 2] = src[2]; }
+        }
+    }
+}
+
 template <int N>
 __global__ void __launch_bounds__(256) fma_peak_kernel(float* out, const float* in, int iters, long long* cyc) {
     float2 acc[N], w[2 * N];
@@ -835,6 +873,8 @@ int afp_destroy(afp_ctx* c) {
     cudaSetDevice(c->cfg.device);
     free_stage(c->up); free_stage(c->eq); free_stage(c->mainf); free_stage(c->fused);
     if (c->tmp_agc) cudaFree(c->tmp_agc);
+    if (c->d_il_in) cudaFree(c->d_il_in);
+    if (c->d_il_out) cudaFree(c->d_il_out);
     if (c->tmp_a) cudaFree(c->tmp_a);
     if (c->tmp_b) cudaFree(c->tmp_b);
     for (int i = 0; i < 2; ++i) if (c->xhist[i]) cudaFree(c->xhist[i]);
@@ -1186,6 +1226,46 @@ int afp_process_host_blocks(afp_ctx* c, const float* in, void* out, int32_t fram
 
 int afp_process_host(afp_ctx* c, const float* in, void* out, int32_t frames) {
     return afp_process_host_blocks(c, in, out, frames, 1);
+}
+
+int afp_process_host_interleaved(afp_ctx* c, const float* in, void* out, int32_t frames, int32_t channels) {
+    if (!c) return AFP_ERR_INVALID;
+    if (!in || !out) return fail(c, AFP_ERR_INVALID, "null buffer");
+    const int S = c->cfg.n_streams;
+    if (channels < 1 || S % channels != 0) return fail(c, AFP_ERR_INVALID, "n_streams is not a multiple of channels");
+    if (channels == 1) return afp_process_host_blocks(c, in, out, frames, 1);   // mono: the two layouts coincide
+    int rc = check_ready(c, frames);
+    if (rc) return rc;
+    if (frames == 0) return AFP_OK;
+    AFP_CUDA(c, cudaSetDevice(c->cfg.device));
+    rc = ensure_tmp(c);
+    if (rc) return rc;
+    rc = ensure_host_staging(c);
+    if (rc) return rc;
+    const int eb = afp_out_elem_bytes(c), out_n = afp_out_frames(c, frames), sessions = S / channels;
+    if (!c->d_il_in) {
+        AFP_CUDA(c, cudaMalloc(&c->d_il_in, (size_t)S * c->cfg.max_frames * sizeof(float)));
+        AFP_CUDA(c, cudaMalloc(&c->d_il_out, (size_t)S * afp_out_frames(c, c->cfg.max_frames) * eb));
+    }
+    cudaStream_t st = c->own_stream;
+    const size_t in_bytes = (size_t)S * frames * sizeof(float), out_bytes = (size_t)S * out_n * eb;
+    AFP_CUDA(c, cudaMemcpyAsync(c->d_il_in, in, in_bytes, cudaMemcpyHostToDevice, st));
+    auto grid_for = [&](long long total) { long long g = (total + 255) / 256; return (int)(g < 1 ? 1 : (g > 8LL * c->n_sm ? 8LL * c->n_sm : g)); };
+    deinterleave_kernel<<<grid_for((long long)sessions * frames), 256, 0, st>>>(c->d_il_in, c->d_in[0], sessions, frames, channels, frames);
+    AFP_CUDA(c, cudaGetLastError());
+    rc = process_block_range(c, c->d_in[0], frames, c->d_out[0], (int64_t)out_n * (eb == 3 ? 3 : 1), frames, 0, S, st);
+    if (rc) return rc;
+    const long long pitch_bytes = (long long)out_n * eb;
+    const int g = grid_for((long long)sessions * out_n);
+    if (eb == 4) interleave_kernel<4><<<g, 256, 0, st>>>(c->d_out[0], c->d_il_out, sessions, out_n, channels, pitch_bytes);
+    else if (eb == 2) interleave_kernel<2><<<g, 256, 0, st>>>(c->d_out[0], c->d_il_out, sessions, out_n, channels, pitch_bytes);
+    else interleave_kernel<3><<<g, 256, 0, st>>>(c->d_out[0], c->d_il_out, sessions, out_n, channels, pitch_bytes);
+    AFP_CUDA(c, cudaGetLastError());
+    c->launches += 2;
+    AFP_CUDA(c, cudaMemcpyAsync(out, c->d_il_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    AFP_CUDA(c, cudaStreamSynchronize(st));
+    finish_block(c, frames);
+    return AFP_OK;
 }
 
 // the stages that actually run, in launch order

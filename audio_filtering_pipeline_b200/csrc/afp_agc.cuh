@@ -12,8 +12,9 @@
 // there is no fixed-size associative scan - every stream is one sequential chain of `frames` steps of
 // FFMA -> FMNMX (8 clk).  Parallelism comes from the batch: one LANE per stream in that phase.
 //
-// One work item = `group` streams x one block.  Shared memory holds one float row per stream (odd
-// pitch: lane = stream accesses are conflict-free) plus one float64 prefix-sum row per warp.
+// One work item = `group` streams x one block.  Shared memory holds one float row per stream (pitch = an
+// odd number of 16-byte units: lane = stream 128-bit accesses are conflict-free) plus one float64
+// prefix-sum row per warp.
 //   phase 1  warp per stream: a lane takes 16 consecutive samples (four 16-byte loads) -> x^2 in float32
 //            as numpy does -> float64 running sums in registers -> one warp scan of the lane totals per
 //            512 samples -> exclusive prefix sums in the warp's scratch row (one pad double per 16, so the
@@ -21,10 +22,10 @@
 //            (float64: a quiet window after a loud passage keeps its digits) -> desired gain, float32,
 //            into the stream's row.  FAST instantiation: target*rsqrt(mean) - the reference's "+ 1e-10"
 //            under the division only matters where the gain is clamped to max_gain anyway (host check).
-//   phase 2  lane per stream: the recurrence, in place; both branches in one packed FFMA2
-//            (s * (1-a_att, 1-a_rel) + d * (a_att, a_rel)), then FMNMX
-//   phase 3  all threads over (stream, 4-sample chunk), 8 loads in flight each: x again (an L2 hit, the
-//            item was read a few microseconds ago) times the limited gain, clip, coalesced 16-byte stores
+//   phase 2  lane per stream: the recurrence, in place; both branches in packed FFMA2s
+//            (s * (1-a_att, 1-a_rel) + d * (a_att, a_rel)), then FMNMX; four steps per LDS.128 / STS.128
+//   phase 3  warp per stream, 4-sample chunks, 8 loads in flight per lane: x again (an L2 hit, the item
+//            was read a few microseconds ago) times the limited gain, clip, coalesced 16-byte stores
 // Two CTAs per SM when the rows fit (host plan in afp_abi.cu), so one CTA's serial phase 2 overlaps the
 // other's memory phases.  HBM-bound by design: 8 bytes per sample, no intermediate leaves the SM.
 //
@@ -47,7 +48,7 @@ struct AgcParams {
     int n_streams, frames;
     int window, left, right;   // window length; samples before / after the centre: left + 1 + right = window
     int group;                 // streams per work item
-    int pitch;                 // floats per stream row in shared memory (odd)
+    int pitch;                 // floats per stream row in shared memory: 4 x an odd number
     int n_items;
     int scratch;               // doubles per warp in the prefix-sum scratch
     float inv_window;
@@ -94,27 +95,95 @@ __device__ __forceinline__ unsigned long long agc_pack(float a, float b) {
     return r;
 }
 
-// smoothed[i] = max|min(c_att*s + a_att*d, c_rel*s + a_rel*d): FMUL2, FFMA2 (s is the scalar-broadcast
-// operand), FMNMX; the dependent chain per step is FFMA2 -> FMNMX
+// smoothed[i] = max|min(c_att*s + a_att*d, c_rel*s + a_rel*d): two FFMA2 (d and s are the scalar-broadcast
+// operands, the coefficient pairs sit in uniform registers) and FMNMX; the dependent chain per step is
+// FFMA2 -> FMNMX.  Rows are read and written four steps at a time (LDS.128 / STS.128: the row pitch is an
+// odd number of 16-byte units, so lane = stream accesses are conflict-free): 3.5 instructions per step -
+// this phase runs on one warp per CTA and is bound by that warp's issue rate.
+__device__ __forceinline__ unsigned long long agc_scaled(float d, unsigned long long aa) {   // (a_att*d, a_rel*d)
+    unsigned long long t;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(t) : "l"(agc_pack(d, d)), "l"(aa), "l"(0ULL));
+    return t;
+}
 template <bool TAKE_MAX>
-__device__ __forceinline__ float agc_recur(float* row, int n, float s, unsigned long long cc, unsigned long long aa) {
-#pragma unroll 16
-    for (int i = 1; i < n; ++i) {
-        const float d = row[i];
-        unsigned long long t;
-        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(agc_pack(d, d)), "l"(aa));
-        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(t) : "l"(agc_pack(s, s)), "l"(cc));
-        const float2 br = *reinterpret_cast<float2*>(&t);
-        s = TAKE_MAX ? fmaxf(br.x, br.y) : fminf(br.x, br.y);
-        row[i] = s;
+__device__ __forceinline__ float agc_step(float s, unsigned long long t, unsigned long long cc) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(t) : "l"(agc_pack(s, s)), "l"(cc));
+    const float2 br = *reinterpret_cast<float2*>(&t);
+    return TAKE_MAX ? fmaxf(br.x, br.y) : fminf(br.x, br.y);
+}
+template <bool TAKE_MAX>
+__device__ __forceinline__ void agc_recur(float* row, int n, unsigned long long cc, unsigned long long aa) {
+    float4* r4 = reinterpret_cast<float4*>(row);
+    float4 v = r4[0];
+    float s = v.x;                                   // smoothed[0] = desired[0]   (:69)
+    v.y = s = agc_step<TAKE_MAX>(s, agc_scaled(v.y, aa), cc);
+    v.z = s = agc_step<TAKE_MAX>(s, agc_scaled(v.z, aa), cc);
+    v.w = s = agc_step<TAKE_MAX>(s, agc_scaled(v.w, aa), cc);
+    r4[0] = v;
+    const int n4 = (n + 3) >> 2;                     // (the slots past n in the last group are never read back)
+#pragma unroll 4
+    for (int q = 1; q < n4; ++q) {
+        v = r4[q];
+        // the four products first: they do not depend on s and stay off the chain
+        const unsigned long long t0 = agc_scaled(v.x, aa), t1 = agc_scaled(v.y, aa), t2 = agc_scaled(v.z, aa),
+                                 t3 = agc_scaled(v.w, aa);
+        v.x = s = agc_step<TAKE_MAX>(s, t0, cc);
+        v.y = s = agc_step<TAKE_MAX>(s, t1, cc);
+        v.z = s = agc_step<TAKE_MAX>(s, t2, cc);
+        v.w = s = agc_step<TAKE_MAX>(s, t3, cc);
+        r4[q] = v;
     }
-    return s;
 }
 
-constexpr int AGC_LANE_RUN = 16;                   // consecutive samples per lane in the prefix scan
+constexpr int AGC_LANE_RUN = 16;                   // consecutive samples per lane in the prefix scan (agc_load_run)
 constexpr int AGC_SCAN = 32 * AGC_LANE_RUN;        // samples per warp scan
 // index of prefix sum k in the scratch row: one pad double per 16
 __host__ __device__ constexpr int agc_phys(int k) { return k + (k >> 4); }
+
+// desired gain over samples [i0, i1) of one stream (a warp; lanes stride 32).  LO0: the window starts
+// before the block (lower prefix sum is 0); HIN: it ends past the block (upper prefix sum is the total).
+// A step of 32 samples is a step of exactly 34 doubles in the padded scratch row, so the addresses are
+// affine in the iteration count.
+template <int VARIANT, bool LO0, bool HIN>
+__device__ __forceinline__ void agc_gain_span(const AgcParams& P, const double* pfx, float* row, int i0, int i1, int lane,
+                                              double total) {
+    int i = i0 + lane;
+    if (i >= i1) return;
+    const double* ph = pfx + agc_phys(HIN ? 0 : i + P.right + 1);
+    const double* pl = pfx + agc_phys(LO0 ? 0 : i - P.left);
+    float* r = row + i;
+#pragma unroll 4
+    for (; i < i1; i += 32, ph += 34, pl += 34, r += 32) {
+        const double hi = HIN ? total : *ph, lo = LO0 ? 0.0 : *pl;
+        const float sum = (float)(hi - lo);
+        if (VARIANT == AGC_FAST) {
+            *r = fminf(P.fast_scale * rsqrt_approx(sum), P.max_gain);
+        } else {
+            const float rms = sqrt_approx(sum * P.inv_window);
+            *r = fminf(fmaxf(__fdividef(P.target, rms + 1e-10f), 0.f), P.max_gain);
+        }
+    }
+}
+
+// 16 consecutive samples per lane and 512-sample scan block, zero past the end of the row
+template <int SB>
+__device__ __forceinline__ void agc_load_run(float (&v)[SB][16], const float* x, int base, int n, int lane) {
+    const bool al = (reinterpret_cast<uintptr_t>(x) & 15u) == 0;
+#pragma unroll
+    for (int b = 0; b < SB; ++b) {
+        const int i = base + 512 * b + 16 * lane;
+        if (al && i + 16 <= n) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(x + i) + q);
+                v[b][4 * q] = t.x; v[b][4 * q + 1] = t.y; v[b][4 * q + 2] = t.z; v[b][4 * q + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[b][j] = i + j < n ? __ldg(x + i + j) : 0.f;
+        }
+    }
+}
 
 // SB = 512-sample scans in flight per warp: every load of up to 512*SB samples of a stream is issued
 // before the first use
@@ -137,25 +206,11 @@ __global__ void agc_kernel(const __grid_constant__ AgcParams P) {
                 const int s = s0 + sl;
                 if (s >= P.n_streams) break;
                 const float* x = P.in + (long long)s * P.in_pitch;
-                const bool al = (reinterpret_cast<uintptr_t>(x) & 15u) == 0;
                 if (lane == 0) { pfx[0] = 0.0; if (CHECKED) failed[sl] = 0; }
                 double carry = 0.0;
                 for (int base = 0; base < n; base += AGC_SCAN * SB) {
                     float v[SB][AGC_LANE_RUN];
-#pragma unroll
-                    for (int b = 0; b < SB; ++b) {
-                        const int i = base + AGC_SCAN * b + AGC_LANE_RUN * lane;
-                        if (al && i + AGC_LANE_RUN <= n) {
-#pragma unroll
-                            for (int q = 0; q < AGC_LANE_RUN / 4; ++q) {
-                                const float4 t = __ldg(reinterpret_cast<const float4*>(x + i) + q);
-                                v[b][4 * q] = t.x; v[b][4 * q + 1] = t.y; v[b][4 * q + 2] = t.z; v[b][4 * q + 3] = t.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < AGC_LANE_RUN; ++j) v[b][j] = i + j < n ? __ldg(x + i + j) : 0.f;
-                        }
-                    }
+                    agc_load_run<SB>(v, x, base, n, lane);
 #pragma unroll
                     for (int b = 0; b < SB; ++b) {
                         // np.square of a float32 array stays float32 (:60); the sums are float64 (:62)
@@ -185,16 +240,17 @@ __global__ void agc_kernel(const __grid_constant__ AgcParams P) {
                 }
                 __syncwarp();
                 float* row = rows + (size_t)sl * P.pitch;
-#pragma unroll 4
-                for (int i = lane; i < n; i += 32) {
-                    const int hi = min(i + P.right, n - 1) + 1, lo = max(i - P.left, 0);
-                    const float sum = (float)(pfx[agc_phys(hi)] - pfx[agc_phys(lo)]);
-                    if (VARIANT == AGC_FAST) {
-                        row[i] = fminf(P.fast_scale * rsqrt_approx(sum), P.max_gain);
-                    } else {
-                        const float rms = sqrt_approx(sum * P.inv_window);
-                        row[i] = fminf(fmaxf(__fdividef(P.target, rms + 1e-10f), 0.f), P.max_gain);
-                    }
+                // three index ranges, so that the loops carry no clamps: [0, m1) / [m1, m2) / [m2, n) with
+                // m1, m2 = the first sample whose window no longer starts before the block (left) and the
+                // first one whose window ends past it (n - 1 - right), in order
+                {
+                    const int hc = max(n - 1 - P.right, 0), lc = min(P.left, n);
+                    const int m1 = min(lc, hc), m2 = max(lc, hc);
+                    const double total = pfx[agc_phys(n)];
+                    agc_gain_span<VARIANT, true, false>(P, pfx, row, 0, m1, lane, total);
+                    if (lc <= hc) agc_gain_span<VARIANT, false, false>(P, pfx, row, m1, m2, lane, total);
+                    else          agc_gain_span<VARIANT, true, true>(P, pfx, row, m1, m2, lane, total);   // window covers the block
+                    agc_gain_span<VARIANT, false, true>(P, pfx, row, m2, n, lane, total);
                 }
                 __syncwarp();
             }
@@ -202,13 +258,13 @@ __global__ void agc_kernel(const __grid_constant__ AgcParams P) {
             // ---- phase 2: the attack / release recurrence, one lane per stream
             if (tid < G && s0 + tid < P.n_streams) {
                 float* row = rows + (size_t)tid * P.pitch;
-                float s = row[0];
                 if (!CHECKED) {
                     const unsigned long long cc = agc_pack(P.c_att, P.c_rel), aa = agc_pack(P.a_att, P.a_rel);
-                    if (P.a_att >= P.a_rel) s = agc_recur<true>(row, n, s, cc, aa);
-                    else                    s = agc_recur<false>(row, n, s, cc, aa);
+                    if (P.a_att >= P.a_rel) agc_recur<true>(row, n, cc, aa);
+                    else                    agc_recur<false>(row, n, cc, aa);
                 } else {
                     bool bad = false;
+                    float s = row[0];
 #pragma unroll 4
                     for (int i = 1; i < n; ++i) {
                         const float d = row[i];
@@ -222,37 +278,39 @@ __global__ void agc_kernel(const __grid_constant__ AgcParams P) {
             }
             __syncthreads();
         }
-        // ---- phase 3: apply.  All threads over (stream, 4-sample chunk) with 8 loads in flight each: the
-        // x rows come back from L2, the only latency left to hide in this phase
+        // ---- phase 3: apply.  Warp per stream, 4-sample chunks, 8 loads in flight per lane: the x rows come
+        // back from L2, the only latency left to hide in this phase
         const float cl = P.clip > 0.f ? P.clip : 3.0e38f;
         const bool vec = (n & 3) == 0 && ((P.in_pitch | P.out_pitch) & 3) == 0 &&
                          ((reinterpret_cast<uintptr_t>(P.in) | reinterpret_cast<uintptr_t>(P.out)) & 15u) == 0;
         if (vec) {
-            const int n4 = n >> 2, g_here = min(G, P.n_streams - s0), total = g_here * n4;
+            const int n4 = n >> 2;
             constexpr int LB = 8;
-            for (int base = tid; base < total; base += blockDim.x * LB) {
-                float4 v[LB];
+            for (int sl = warp; sl < G; sl += n_warps) {
+                const int s = s0 + sl;
+                if (s >= P.n_streams) break;
+                const float4* x4 = reinterpret_cast<const float4*>(P.in + (long long)s * P.in_pitch);
+                float4* y4 = reinterpret_cast<float4*>(P.out + (long long)s * P.out_pitch);
+                const float* row = rows + (size_t)sl * P.pitch;
+                const bool unity = P.passthrough || (CHECKED && failed[sl] != 0);
+                const float g_lo = unity ? 1.f : P.min_gain, g_hi = unity ? 1.f : P.max_gain;   // gain pinned to 1
+                for (int c0 = lane; c0 < n4; c0 += 32 * LB) {
+                    float4 v[LB];
 #pragma unroll
-                for (int u = 0; u < LB; ++u) {
-                    const int idx = base + u * blockDim.x;
-                    if (idx < total) {
-                        const int sl = idx / n4, c4 = idx - sl * n4;
-                        v[u] = __ldg(reinterpret_cast<const float4*>(P.in + (long long)(s0 + sl) * P.in_pitch) + c4);
-                    }
-                }
+                    for (int u = 0; u < LB; ++u)
+                        if (c0 + 32 * u < n4) v[u] = __ldg(x4 + c0 + 32 * u);
 #pragma unroll
-                for (int u = 0; u < LB; ++u) {
-                    const int idx = base + u * blockDim.x;
-                    if (idx < total) {
-                        const int sl = idx / n4, c4 = idx - sl * n4;
-                        const float* row = rows + (size_t)sl * P.pitch + 4 * c4;
-                        const bool unity = P.passthrough || (CHECKED && failed[sl] != 0);
-                        float4 y;
-                        y.x = fminf(fmaxf(__fmul_rn(v[u].x, unity ? 1.f : fminf(fmaxf(row[0], P.min_gain), P.max_gain)), -cl), cl);
-                        y.y = fminf(fmaxf(__fmul_rn(v[u].y, unity ? 1.f : fminf(fmaxf(row[1], P.min_gain), P.max_gain)), -cl), cl);
-                        y.z = fminf(fmaxf(__fmul_rn(v[u].z, unity ? 1.f : fminf(fmaxf(row[2], P.min_gain), P.max_gain)), -cl), cl);
-                        y.w = fminf(fmaxf(__fmul_rn(v[u].w, unity ? 1.f : fminf(fmaxf(row[3], P.min_gain), P.max_gain)), -cl), cl);
-                        reinterpret_cast<float4*>(P.out + (long long)(s0 + sl) * P.out_pitch)[c4] = y;
+                    for (int u = 0; u < LB; ++u) {
+                        const int c4 = c0 + 32 * u;
+                        if (c4 < n4) {
+                            const float4 g = *reinterpret_cast<const float4*>(row + 4 * c4);
+                            float4 y;
+                            y.x = fminf(fmaxf(__fmul_rn(v[u].x, fminf(fmaxf(g.x, g_lo), g_hi)), -cl), cl);
+                            y.y = fminf(fmaxf(__fmul_rn(v[u].y, fminf(fmaxf(g.y, g_lo), g_hi)), -cl), cl);
+                            y.z = fminf(fmaxf(__fmul_rn(v[u].z, fminf(fmaxf(g.z, g_lo), g_hi)), -cl), cl);
+                            y.w = fminf(fmaxf(__fmul_rn(v[u].w, fminf(fmaxf(g.w, g_lo), g_hi)), -cl), cl);
+                            y4[c4] = y;
+                        }
                     }
                 }
             }

@@ -168,6 +168,26 @@ class BatchFirEngine:
         _lib.check(self._lib.afp_process_host(self._ctx, x.ctypes.data, out.ctypes.data, frames), self._ctx)
         return out
 
+    def process_host_interleaved(self, x, out=None):
+        """One block in the sounddevice wire format: x float32 [frames, channels] (one session) or
+        [sessions, frames, channels] -> the same shape with ``out_frames`` frames, in ``out_format``
+        ('i24_packed': a trailing axis of 3 bytes).  Stream s = session*channels + channel."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        single = x.ndim == 2
+        if single:
+            x = x[None]
+        if x.ndim != 3 or x.shape[0] * x.shape[2] != self.n_streams:
+            raise ValueError("x must have shape [sessions, frames, channels] with sessions*channels == n_streams")
+        se, frames, ch = x.shape
+        shape = (se, self.out_frames(frames), ch) + ((3,) if self.fmt == 3 else ())
+        if out is None:
+            out = np.empty(shape, dtype=_NP_DTYPE[self.fmt])
+        elif out.size != int(np.prod(shape)) or not out.flags.c_contiguous or out.dtype != _NP_DTYPE[self.fmt]:
+            raise ValueError("out has the wrong shape / dtype")
+        _lib.check(self._lib.afp_process_host_interleaved(self._ctx, x.ctypes.data, out.ctypes.data, frames, ch),
+                   self._ctx)
+        return out.reshape(shape[1:]) if single and out.ndim == len(shape) else out
+
     def process_host_blocks(self, x, out=None):
         """``n`` consecutive blocks with host arrays, block-major: x float32 [n, S, frames] ->
         [n, S, out_cols].  Copies and kernels of successive blocks overlap (three CUDA streams);

@@ -156,6 +156,12 @@ int afp_set_agc(afp_ctx* ctx, const afp_agc_params* params);
 int afp_agc_block(afp_ctx* ctx, const afp_agc_params* params, const float* in_dev, int64_t in_pitch,
                   float* out_dev, int64_t out_pitch, int32_t n_streams, int32_t frames, void* cuda_stream);
 
+/* One block in the wire format of a sounddevice / PortAudio stream (stream_process.py:128-136): frame-major
+ * host buffers in[session][frames][channels] float32 -> out[session][afp_out_frames][channels] in
+ * `out_format` (float32, or int16 / int24 PCM).  Stream s = session*channels + channel; n_streams must be a
+ * multiple of `channels`.  The (de)interleave runs on the device; synchronous like afp_process_host. */
+int afp_process_host_interleaved(afp_ctx* ctx, const float* in_host, void* out_host, int32_t frames, int32_t channels);
+
 int32_t afp_out_frames(const afp_ctx* ctx, int32_t frames);
 int32_t afp_out_elem_bytes(const afp_ctx* ctx);
 
