@@ -23,7 +23,7 @@ SYMBOLS = [
     "afp_set_eq", "afp_set_gains", "afp_process", "afp_process_host", "afp_process_host_blocks", "afp_out_frames",
     "afp_out_elem_bytes", "afp_reset", "afp_state_size", "afp_get_state", "afp_set_state",
     "afp_get_stage_info", "afp_kernel_launches", "afp_host_alloc", "afp_host_free",
-    "afp_measure_fma_peak", "afp_set_agc", "afp_agc_block", "afp_process_host_interleaved",
+    "afp_measure_fma_peak", "afp_set_agc", "afp_agc_block", "afp_process_host_interleaved", "afp_swap_taps",
 ]
 
 
@@ -84,6 +84,7 @@ def load():
     lib.afp_last_error.argtypes = [vp]
     lib.afp_set_taps.argtypes = [vp, dp, i32]
     lib.afp_set_upsampler.argtypes = [vp, dp, i32]
+    lib.afp_swap_taps.argtypes = [vp, dp, i32]
     lib.afp_set_eq.argtypes = [vp, dp, C.POINTER(i32), i32, dp]
     lib.afp_set_gains.argtypes = [vp, dp, i32]
     lib.afp_process.argtypes = [vp, vp, i64, vp, i64, i32, vp]

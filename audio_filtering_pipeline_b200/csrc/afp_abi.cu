@@ -227,15 +227,32 @@ int build_stage(afp_ctx* c, Stage& s, int kind, int U, const double* taps, int n
         return fail(c, AFP_ERR_INVALID, "filter (x bands) too long for the per-launch tap table (max 6144 padded taps)");
     const bool same_shape = s.active && s.kind == kind && s.U == U && s.n_chunks == n_chunks;
     if (!(keep_state && same_shape)) {
+        // keep_state with a different padded length: the carried samples move over right-aligned (a history
+        // row is the last hist_pitch input samples, oldest first); what the old row did not hold is zero
+        float* old_hist = nullptr;
+        long long old_pitch = 0;
+        if (keep_state && s.active && s.kind == kind && s.U == U && s.hist[s.cur]) {
+            old_hist = s.hist[s.cur]; old_pitch = s.hist_pitch;
+            s.hist[s.cur] = nullptr;                      // survives free_stage
+        }
         free_stage(s);
         s.hist_pitch = (long long)n_chunks * T;
         const size_t bytes = (size_t)c->cfg.n_streams * s.hist_pitch * sizeof(float);
         for (int i = 0; i < 2; ++i) {
-            AFP_CUDA(c, cudaMalloc(&s.hist[i], bytes));
-            AFP_CUDA(c, cudaMemset(s.hist[i], 0, bytes));
+            cudaError_t e = cudaMalloc(&s.hist[i], bytes);
+            if (e == cudaSuccess) e = cudaMemset(s.hist[i], 0, bytes);
+            if (e != cudaSuccess) { if (old_hist) cudaFree(old_hist); return cuda_fail(c, e, "history allocation"); }
         }
         s.cur = 0;
         s.geo = Geometry();
+        if (old_hist) {
+            const long long k = old_pitch < s.hist_pitch ? old_pitch : s.hist_pitch;
+            cudaError_t e = cudaMemcpy2D(s.hist[0] + (s.hist_pitch - k), (size_t)s.hist_pitch * sizeof(float),
+                                         old_hist + (old_pitch - k), (size_t)old_pitch * sizeof(float),
+                                         (size_t)k * sizeof(float), (size_t)c->cfg.n_streams, cudaMemcpyDeviceToDevice);
+            cudaFree(old_hist);
+            if (e != cudaSuccess) return cuda_fail(c, e, "history migration");
+        }
     }
     s.kind = kind; s.U = U; s.T = T; s.n_taps = n; s.n_sub = n_sub;
     s.taps.assign(taps, taps + (size_t)n * n_sub);
@@ -942,6 +959,16 @@ int afp_set_taps(afp_ctx* c, const double* taps, int32_t n) {
     const int U = c->cfg.chain == AFP_CHAIN_DAC ? c->cfg.upsample : 1;
     int rc = build_stage(c, c->mainf, ST_MAIN, U, taps, n);
     return rc ? rc : rebuild_fused(c);
+}
+
+int afp_swap_taps(afp_ctx* c, const double* taps, int32_t n) {
+    if (!c || !taps) return fail(c, AFP_ERR_INVALID, "null argument");
+    if (!c->mainf.active) return fail(c, AFP_ERR_STATE, "afp_set_taps has not been called");
+    AFP_CUDA(c, cudaSetDevice(c->cfg.device));
+    AFP_CUDA(c, cudaDeviceSynchronize());   // blocks in flight still read the current history rows
+    const int U = c->cfg.chain == AFP_CHAIN_DAC ? c->cfg.upsample : 1;
+    int rc = build_stage(c, c->mainf, ST_MAIN, U, taps, n, 1, true);
+    return rc ? rc : rebuild_fused(c, true);
 }
 
 int afp_set_upsampler(afp_ctx* c, const double* taps, int32_t n) {

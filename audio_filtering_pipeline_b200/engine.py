@@ -86,6 +86,13 @@ class BatchFirEngine:
         _lib.check(self._lib.afp_set_taps(self._ctx, p, len(a)), self._ctx)
         self.taps = a
 
+    def swap_taps(self, taps):
+        """New main filter from the next block on, carried samples kept (the reference's live filter
+        swap, stream_process_EQ_GUI.py:380-385): no restart transient."""
+        a, p = _dbl(taps)
+        _lib.check(self._lib.afp_swap_taps(self._ctx, p, len(a)), self._ctx)
+        self.taps = a
+
     def set_upsampler(self, taps):
         a, p = _dbl(taps)
         _lib.check(self._lib.afp_set_upsampler(self._ctx, p, len(a)), self._ctx)

@@ -129,6 +129,11 @@ const char* afp_last_error(const afp_ctx* ctx);   /* ctx may be NULL: error of t
  * carried state of the stage it changes, like OverlapAddFilter.set_coefficients
  * (stream_process_GUI_Presets.py:44-67); afp_set_gains does not. */
 int afp_set_taps(afp_ctx* ctx, const double* taps, int32_t n_taps);
+/* Replace the main filter between two blocks WITHOUT touching the carried samples - the reference's swap
+ * of active_filter_params under filter_lock (stream_process_EQ_GUI.py:380-385; deferred form
+ * stream_process_AGC.py:27-29,102-108), which leaves input_buffer alone: the next block is the new filter
+ * over the true past input, no restart transient.  A longer filter sees zeros beyond what was carried. */
+int afp_swap_taps(afp_ctx* ctx, const double* taps, int32_t n_taps);
 int afp_set_upsampler(afp_ctx* ctx, const double* taps, int32_t n_taps);
 int afp_set_eq(afp_ctx* ctx, const double* band_taps, const int32_t* band_len, int32_t n_bands,
                const double* gains);
