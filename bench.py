@@ -353,11 +353,12 @@ def run_ours(args):
     os.sched_setaffinity(0, prev_affinity)      # the CPU legs use every core the process was given
     e2e["host_affinity"] = numa_note
     if rank == 0:
-        sweep = None
+        sweep = agc = None
         if world == 1 and not args.no_sweep:
             del x, y
             torch.cuda.empty_cache()
             sweep = c5_sweep(local, hbm_peak, fma_peak_tflops)
+            agc = agc_points(local, hbm_peak)
         cpu_val, cores, sample = cpu_reference(taps, seconds_target=args.cpu_seconds)
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": "Msamples/s", "n_gpus": world,
@@ -369,7 +370,7 @@ def run_ours(args):
                              "sample": sample},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "stage": eng.stage_info(), "checksum": checksum,
-            "c5_sweep_kernel_only": sweep,
+            "c5_sweep_kernel_only": sweep, "agc_kernel_only": agc,
         }
         print(json.dumps(line))
     hx.free()
@@ -420,6 +421,34 @@ def c5_sweep(local, hbm_peak_gbs, fma_peak_tflops, iters=10):
                     "frac": round(gs / min(roof_fma, roof_hbm), 3), "kernel": info["kernel"], "tile": info["tile_taps"]})
         eng.close()
         del xs, ys
+    return out
+
+
+def agc_points(local, hbm_peak_gbs, iters=10):
+    """Kernel-only points of the AGC kernel (csrc/afp_agc.cuh): HBM-bound by design,
+    4 bytes in + 4 bytes out per sample; 3 rotating input buffers (0.2-0.8 GB, beyond L2), CUDA events."""
+    import torch
+    from audio_filtering_pipeline_b200.engine import BatchFirEngine
+    dev = torch.device("cuda", local)
+    out = []
+    with BatchFirEngine([1.0], n_streams=1, max_frames=1, device=local) as eng:
+        for streams, frames, window in [(16384, 1024, 512), (65536, 1024, 512), (16384, 512, 256)]:
+            xs = [0.05 * torch.randn(streams, frames, device=dev) for _ in range(3)]
+            y = torch.empty_like(xs[0])
+            for i in range(3):
+                eng.agc_block(xs[i], out=y, window_size=window)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(iters):
+                eng.agc_block(xs[i % 3], out=y, window_size=window)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            gs = streams * frames / ms / 1e6
+            out.append({"streams": streams, "frames": frames, "window": window, "gsamples_s": round(gs, 1),
+                        "alg_gbs": round(gs * 8, 0), "bound": "hbm", "frac": round(gs * 8 / hbm_peak_gbs, 3)})
+            del xs, y
     return out
 
 

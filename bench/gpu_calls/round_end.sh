@@ -8,11 +8,13 @@ ncu --set full --import-source on --clock-control none -k regex:fir_tc -s 2 -c 1
 ncu --set full --import-source on --clock-control none -k regex:fir_row -s 3 -c 1 -o gpurun_out/r01_row_n51u4 python bench/quick_perf.py --taps 51 --up 4 --frames 1024 --streams 32768 --iters 2 > gpurun_out/ncu_f1.log 2>&1
 ncu --set full --import-source on --clock-control none -k regex:fir_row -s 3 -c 1 -o gpurun_out/r01_row_n51u1 python bench/quick_perf.py --taps 51 --up 1 --frames 1024 --streams 65536 --iters 2 > gpurun_out/ncu_f2.log 2>&1
 ncu --set full --import-source on --clock-control none -k regex:fir_row -s 3 -c 1 -o gpurun_out/r01_row_n101u2 python bench/quick_perf.py --taps 101 --up 2 --frames 1024 --streams 32768 --iters 2 > gpurun_out/ncu_f3.log 2>&1
+ncu --set full --import-source on --clock-control none -k regex:agc_kernel -s 3 -c 1 -o gpurun_out/r01_agc_16384x1024 python bench/agc_perf.py --streams 16384 --frames 1024 --window 512 --iters 4 > gpurun_out/ncu_f4.log 2>&1
 python - <<'PY'
 import json
 d=json.loads(open('gpurun_out/bench_final.json').read().strip().splitlines()[-1])
 print('value',d['value'],'e2e',d['e2e']['value'],'frac',d['roofline']['frac'],'cpu',d['cpu_baseline']['value'],'launches',d['gpu_launches'],d['clocks'])
 for r in d['c5_sweep_kernel_only']: print(r['taps'],r['upsample'],r['gsamples_s'],r['bound'],r['frac'])
+for r in d['agc_kernel_only']: print('agc', r)
 print(open('gpurun_out/bench_final_ref.json').read()[:300])
 PY
 ls -la gpurun_out/r01_*.ncu-rep
