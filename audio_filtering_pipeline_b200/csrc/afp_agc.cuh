@@ -112,25 +112,50 @@ __device__ __forceinline__ float agc_step(float s, unsigned long long t, unsigne
     return TAKE_MAX ? fmaxf(br.x, br.y) : fminf(br.x, br.y);
 }
 template <bool TAKE_MAX>
+__device__ __forceinline__ float agc_group(float4& v, float s, unsigned long long cc, unsigned long long aa) {
+    // the four products first: they do not depend on s and stay off the chain
+    const unsigned long long t0 = agc_scaled(v.x, aa), t1 = agc_scaled(v.y, aa), t2 = agc_scaled(v.z, aa),
+                             t3 = agc_scaled(v.w, aa);
+    v.x = s = agc_step<TAKE_MAX>(s, t0, cc);
+    v.y = s = agc_step<TAKE_MAX>(s, t1, cc);
+    v.z = s = agc_step<TAKE_MAX>(s, t2, cc);
+    v.w = s = agc_step<TAKE_MAX>(s, t3, cc);
+    return s;
+}
+// The chain costs 13.5 clk per step on this part (bench/microbench/agc_chain.cu: packed and scalar forms
+// alike); a shared-memory load issued one group ahead is not back in time (29 clk + the store queue in
+// front of it), which made the first version 25 clk per step.  So: 16 steps per iteration, the NEXT 16
+// loaded before the current ones are computed.
+template <bool TAKE_MAX>
 __device__ __forceinline__ void agc_recur(float* row, int n, unsigned long long cc, unsigned long long aa) {
     float4* r4 = reinterpret_cast<float4*>(row);
+    const int n4 = (n + 3) >> 2;                     // (the slots past n in the last group are never read back)
     float4 v = r4[0];
     float s = v.x;                                   // smoothed[0] = desired[0]   (:69)
     v.y = s = agc_step<TAKE_MAX>(s, agc_scaled(v.y, aa), cc);
     v.z = s = agc_step<TAKE_MAX>(s, agc_scaled(v.z, aa), cc);
     v.w = s = agc_step<TAKE_MAX>(s, agc_scaled(v.w, aa), cc);
     r4[0] = v;
-    const int n4 = (n + 3) >> 2;                     // (the slots past n in the last group are never read back)
-#pragma unroll 4
-    for (int q = 1; q < n4; ++q) {
+    int q = 1;
+    if (q + 4 <= n4) {
+        float4 c0 = r4[q], c1 = r4[q + 1], c2 = r4[q + 2], c3 = r4[q + 3];
+        for (; q + 8 <= n4; q += 4) {
+            const float4 d0 = r4[q + 4], d1 = r4[q + 5], d2 = r4[q + 6], d3 = r4[q + 7];
+            s = agc_group<TAKE_MAX>(c0, s, cc, aa); r4[q] = c0;
+            s = agc_group<TAKE_MAX>(c1, s, cc, aa); r4[q + 1] = c1;
+            s = agc_group<TAKE_MAX>(c2, s, cc, aa); r4[q + 2] = c2;
+            s = agc_group<TAKE_MAX>(c3, s, cc, aa); r4[q + 3] = c3;
+            c0 = d0; c1 = d1; c2 = d2; c3 = d3;
+        }
+        s = agc_group<TAKE_MAX>(c0, s, cc, aa); r4[q] = c0;
+        s = agc_group<TAKE_MAX>(c1, s, cc, aa); r4[q + 1] = c1;
+        s = agc_group<TAKE_MAX>(c2, s, cc, aa); r4[q + 2] = c2;
+        s = agc_group<TAKE_MAX>(c3, s, cc, aa); r4[q + 3] = c3;
+        q += 4;
+    }
+    for (; q < n4; ++q) {
         v = r4[q];
-        // the four products first: they do not depend on s and stay off the chain
-        const unsigned long long t0 = agc_scaled(v.x, aa), t1 = agc_scaled(v.y, aa), t2 = agc_scaled(v.z, aa),
-                                 t3 = agc_scaled(v.w, aa);
-        v.x = s = agc_step<TAKE_MAX>(s, t0, cc);
-        v.y = s = agc_step<TAKE_MAX>(s, t1, cc);
-        v.z = s = agc_step<TAKE_MAX>(s, t2, cc);
-        v.w = s = agc_step<TAKE_MAX>(s, t3, cc);
+        s = agc_group<TAKE_MAX>(v, s, cc, aa);
         r4[q] = v;
     }
 }
