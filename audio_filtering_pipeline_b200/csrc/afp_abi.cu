@@ -19,7 +19,7 @@
 #include "afp_fir_tc.cuh"
 #include "afp_agc.cuh"
 
-afp::agc_kern_t afp_kernel_agc(int variant, int scan_blocks);   // afp_kernels_agc.cu: variant AGC_*, scan_blocks 1 / 2
+afp::agc_kern_t afp_kernel_agc(int variant, int scan_blocks, int team);   // afp_kernels_agc.cu: variant AGC_*, scan_blocks 1 / 2, team 1 / 2
 
 using afp::FirParams;
 
@@ -336,7 +336,7 @@ Geometry pick_geometry(int T, int kq_pad, int n_q, int n_streams) {
 // + one float64 prefix-sum row per warp + a flag per stream.  Two (short blocks: three) CTAs per SM when at
 // least 8 streams fit in that share of an SM's shared memory (one CTA's serial recurrence phase overlaps
 // the others' memory phases), else one CTA with as many streams as fit.
-struct AgcPlan { int warps = 0, group = 0, pitch = 0, ctas_per_sm = 0, scratch = 0; size_t smem = 0; };
+struct AgcPlan { int warps = 0, team = 1, group = 0, pitch = 0, ctas_per_sm = 0, scratch = 0; size_t smem = 0; };   // warps = prefix rows (teams)
 bool plan_agc(int frames, int n_streams, int n_sm, AgcPlan& pl) {
     const int pitch = 4 * (((frames + 3) / 4) | 1);   // an odd number of 16-byte units
     const size_t row = (size_t)pitch * sizeof(float) + sizeof(int);
@@ -348,7 +348,7 @@ bool plan_agc(int frames, int n_streams, int n_sm, AgcPlan& pl) {
     for (int ti = plan_from; ti < 5; ++ti) {
         const Try& t = tries[ti];
         const int scratch = afp::agc_phys(frames) + 2;   // prefix sums 0..frames, one pad double per 16
-        const size_t fixed = (size_t)t.warps * scratch * sizeof(double) + 16;
+        const size_t fixed = (size_t)t.warps * (scratch + 1) * sizeof(double) + 16;
         if (fixed + row * t.min_group > t.budget) continue;
         long long g = (long long)((t.budget - fixed) / row);
         if (g > 32 * t.warps) g = 32 * t.warps;
@@ -360,8 +360,13 @@ bool plan_agc(int frames, int n_streams, int n_sm, AgcPlan& pl) {
         if (g > even) g = even < 1 ? 1 : even;
         pl.warps = t.warps; pl.group = (int)g; pl.pitch = pitch; pl.ctas_per_sm = t.ctas;
         pl.scratch = scratch;
-        pl.smem = ((((size_t)g * pitch * sizeof(float)) + 7) & ~(size_t)7) + (size_t)t.warps * scratch * sizeof(double) +
+        pl.smem = ((((size_t)g * pitch * sizeof(float)) + 7) & ~(size_t)7) + (size_t)t.warps * (scratch + 1) * sizeof(double) +
                   (size_t)g * sizeof(int);
+        // two warps per prefix row above 512 frames (measured, 16384 streams: 1024 frames 211 vs 175 Gsamples/s,
+        // 2048: 136 vs 103, 4096: 58 vs 47; 512 frames 115 vs 199 - three 4-warp CTAs per SM win there);
+        // AFP_AGC_TEAM=1|2 overrides for A/B runs
+        pl.team = frames > 512 ? 2 : 1;
+        if (const char* v = std::getenv("AFP_AGC_TEAM")) pl.team = std::atoi(v) == 2 ? 2 : 1;
         return true;
     }
     return false;
@@ -396,10 +401,11 @@ int launch_agc(afp_ctx* c, const afp_agc_params& a, const float* in, long long i
     const bool fast = a.target_level > 0 && a.max_gain > 0 && a.target_level / a.max_gain >= 1e-4;
     P.fast_scale = (float)(a.target_level * std::sqrt((double)P.window));
     const int variant = !(P.att_ok && P.rel_ok) ? afp::AGC_CHECKED : (fast ? afp::AGC_FAST : afp::AGC_EXACT);
-    afp::agc_kern_t k = afp_kernel_agc(variant, frames > 512 ? 2 : 1);
+    const int part = pl.team == 2 ? (((frames + 1) / 2 + 15) & ~15) : frames;   // samples per warp in the gain phase
+    afp::agc_kern_t k = afp_kernel_agc(variant, part > 512 ? 2 : 1, pl.team);
     int grid = c->n_sm * pl.ctas_per_sm;
     if (grid > P.n_items) grid = P.n_items;
-    k<<<grid, 32 * pl.warps, pl.smem, stream>>>(P);
+    k<<<grid, 32 * pl.warps * pl.team, pl.smem, stream>>>(P);
     AFP_CUDA(c, cudaGetLastError());
     c->launches++;
     return AFP_OK;
@@ -869,10 +875,11 @@ int afp_create(const afp_config* cfg, afp_ctx** out_ctx) {
                 if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, tensor path)");
             }
     for (int variant : {afp::AGC_FAST, afp::AGC_EXACT, afp::AGC_CHECKED})
-        for (int sb : {1, 2}) {
-            e = cudaFuncSetAttribute((const void*)afp_kernel_agc(variant, sb), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-            if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, AGC)");
-        }
+        for (int sb : {1, 2})
+            for (int team : {1, 2}) {
+                e = cudaFuncSetAttribute((const void*)afp_kernel_agc(variant, sb, team), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+                if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, AGC)");
+            }
     afp_ctx* c = new (std::nothrow) afp_ctx();
     if (!c) return fail(nullptr, AFP_ERR_NOMEM, "out of host memory");
     c->cfg = *cfg;

@@ -211,31 +211,48 @@ __device__ __forceinline__ void agc_load_run(float (&v)[SB][16], const float* x,
 }
 
 // SB = 512-sample scans in flight per warp: every load of up to 512*SB samples of a stream is issued
-// before the first use
-template <int VARIANT, int SB>
-__global__ void agc_kernel(const __grid_constant__ AgcParams P) {
+// before the first use.
+// TEAM = warps per stream in phase 1 (1 or 2).  The float64 scratch row is what limits the resident warps
+// (8.7 KB per 1024-frame stream in flight); with TEAM = 2 two warps share one row and take half a stream
+// each - the second adds the first one's total as its carry - so the SM holds twice the warps in the same
+// shared memory.  The members meet at a named barrier (id 1 + team, 64 threads) three times per stream:
+// carry published, prefix row complete, prefix row free again.
+template <int TEAM>
+__device__ __forceinline__ void agc_team_sync(int team) {
+    if (TEAM == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(32 * TEAM) : "memory");
+}
+
+template <int VARIANT, int SB, int TEAM>
+__global__ void __launch_bounds__(TEAM == 2 ? 256 : 128, TEAM == 2 ? 2 : 3) agc_kernel(const __grid_constant__ AgcParams P) {
     constexpr bool CHECKED = VARIANT == AGC_CHECKED;
     extern __shared__ __align__(16) unsigned char agc_smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, n_warps = blockDim.x >> 5;
+    const int team = warp / TEAM, member = warp % TEAM, n_teams = n_warps / TEAM;
     const int n = P.frames, G = P.group;
     float* rows = reinterpret_cast<float*>(agc_smem);
     const size_t rows_bytes = (((size_t)G * P.pitch * sizeof(float)) + 7) & ~(size_t)7;
-    double* pfx = reinterpret_cast<double*>(agc_smem + rows_bytes) + (size_t)warp * P.scratch;
-    int* failed = reinterpret_cast<int*>(agc_smem + rows_bytes + (size_t)n_warps * P.scratch * sizeof(double));
+    double* pfx = reinterpret_cast<double*>(agc_smem + rows_bytes) + (size_t)team * P.scratch;
+    double* team_tot = reinterpret_cast<double*>(agc_smem + rows_bytes) + (size_t)n_teams * P.scratch + team;
+    int* failed = reinterpret_cast<int*>(agc_smem + rows_bytes + ((size_t)n_teams * P.scratch + n_teams) * sizeof(double));
+    // this warp's part of a stream in phase 1: [h0, h1), a multiple of 16 samples from the start
+    const int nh = TEAM == 1 ? n : ((((n + 1) >> 1) + 15) & ~15);
+    const int h0 = min(member * nh, n), h1 = min(h0 + nh, n);
 
     for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
         const int s0 = item * G;
         if (!P.passthrough) {
             // ---- phase 1: desired gain of every sample
-            for (int sl = warp; sl < G; sl += n_warps) {
+            for (int sl = team; sl < G; sl += n_teams) {
                 const int s = s0 + sl;
                 if (s >= P.n_streams) break;
                 const float* x = P.in + (long long)s * P.in_pitch;
-                if (lane == 0) { pfx[0] = 0.0; if (CHECKED) failed[sl] = 0; }
+                if (member == 0 && lane == 0) { pfx[0] = 0.0; if (CHECKED) failed[sl] = 0; }
                 double carry = 0.0;
-                for (int base = 0; base < n; base += AGC_SCAN * SB) {
+                bool have_carry = member == 0;
+                for (int base = h0; base < h1; base += AGC_SCAN * SB) {
                     float v[SB][AGC_LANE_RUN];
-                    agc_load_run<SB>(v, x, base, n, lane);
+                    agc_load_run<SB>(v, x, base, h1, lane);
 #pragma unroll
                     for (int b = 0; b < SB; ++b) {
                         // np.square of a float32 array stays float32 (:60); the sums are float64 (:62)
@@ -250,34 +267,43 @@ __global__ void agc_kernel(const __grid_constant__ AgcParams P) {
                             if (lane >= off) tot += t;
                         }
                         double excl = shfl_up_f64(tot, 1);
+                        if (TEAM == 2 && !have_carry) {      // second member: the first half's total, once
+                            agc_team_sync<TEAM>(team);
+                            carry = *team_tot;
+                            have_carry = true;
+                        }
                         excl = (lane == 0 ? 0.0 : excl) + carry;
                         const int i = base + AGC_SCAN * b + AGC_LANE_RUN * lane;
-                        if (i + AGC_LANE_RUN <= n) {
+                        if (i + AGC_LANE_RUN <= h1) {
 #pragma unroll
                             for (int j = 0; j < AGC_LANE_RUN; ++j) pfx[agc_phys(i + j + 1)] = excl + run[j];
                         } else {
 #pragma unroll
                             for (int j = 0; j < AGC_LANE_RUN; ++j)
-                                if (i + j < n) pfx[agc_phys(i + j + 1)] = excl + run[j];
+                                if (i + j < h1) pfx[agc_phys(i + j + 1)] = excl + run[j];
                         }
                         carry += shfl_f64(tot, 31);
                     }
                 }
-                __syncwarp();
+                if (TEAM == 2) {
+                    if (member == 0) { if (lane == 0) *team_tot = carry; agc_team_sync<TEAM>(team); }
+                    else if (!have_carry) agc_team_sync<TEAM>(team);      // (empty second half)
+                }
+                agc_team_sync<TEAM>(team);                                // prefix row complete
                 float* row = rows + (size_t)sl * P.pitch;
                 // three index ranges, so that the loops carry no clamps: [0, m1) / [m1, m2) / [m2, n) with
                 // m1, m2 = the first sample whose window no longer starts before the block (left) and the
-                // first one whose window ends past it (n - 1 - right), in order
+                // first one whose window ends past it (n - 1 - right), in order; each member its own part
                 {
                     const int hc = max(n - 1 - P.right, 0), lc = min(P.left, n);
                     const int m1 = min(lc, hc), m2 = max(lc, hc);
                     const double total = pfx[agc_phys(n)];
-                    agc_gain_span<VARIANT, true, false>(P, pfx, row, 0, m1, lane, total);
-                    if (lc <= hc) agc_gain_span<VARIANT, false, false>(P, pfx, row, m1, m2, lane, total);
-                    else          agc_gain_span<VARIANT, true, true>(P, pfx, row, m1, m2, lane, total);   // window covers the block
-                    agc_gain_span<VARIANT, false, true>(P, pfx, row, m2, n, lane, total);
+                    agc_gain_span<VARIANT, true, false>(P, pfx, row, max(0, h0), min(m1, h1), lane, total);
+                    if (lc <= hc) agc_gain_span<VARIANT, false, false>(P, pfx, row, max(m1, h0), min(m2, h1), lane, total);
+                    else          agc_gain_span<VARIANT, true, true>(P, pfx, row, max(m1, h0), min(m2, h1), lane, total);   // window covers the block
+                    agc_gain_span<VARIANT, false, true>(P, pfx, row, max(m2, h0), min(n, h1), lane, total);
                 }
-                __syncwarp();
+                agc_team_sync<TEAM>(team);                                // prefix row free for the next stream
             }
             __syncthreads();
             // ---- phase 2: the attack / release recurrence, one lane per stream
