@@ -22,10 +22,12 @@
 // ~38 clk + bytes/128 per MMA), so every A tile should be read as few times as possible.  The three
 // accumulators are added in the epilogue.
 //
-// One CTA per SM, 256 threads, one work item = 16 streams x one block of `frames` (multiple of 512)
-// samples:  phase 1 all threads load [history | block] -> hi/lo tiles (+ next history to HBM);
-// phase 2 warp 1 issues the MMAs while warp 0 feeds W slices (one K = 8 slice = 4 KB per ring slot);
-// phase 3 eight warps read the accumulators (tcgen05.ld), dither / quantise and store.
+// One CTA per SM, 512 threads, one work item = 16 streams x one block of `frames` (multiple of 512)
+// samples:  load: [history | block] -> hi/lo tiles (+ next history to HBM);  MMA: warps 1.. issue while
+// warp 0 feeds W slices (one K = 8 slice = 4 KB per ring slot);  epilogue: warps 0-7 read the accumulators
+// (tcgen05.ld), dither / quantise and store.  The sample tiles fill shared memory, so the next item cannot
+// be loaded under the MMAs - but it can be loaded under the EPILOGUE: once the accumulators are final the
+// tiles are free, and warps 8-15 fill them with the next item while warps 0-7 drain TMEM.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -34,7 +36,8 @@
 namespace afp {
 
 constexpr int TC_STREAMS = 16;             // streams per work item (16 core groups of 8 rows = M 128)
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 512;            // warps 0-7: tap ring, MMA issue, epilogue; warps 8-15: loaders of the NEXT item
+constexpr int TC_MAIN_THREADS = 256;
 
 // Row length R (samples per row = outputs per accumulator row = K per chunk).  R = 64 halves the number
 // of MMAs (they are bound by operand fetch, ~64 B/clk measured, and by a per-instruction cost) but
@@ -190,18 +193,19 @@ fir_tc_kernel(const __grid_constant__ TcParams P) {
     const int total = hist_len + P.frames;                    // samples per stream tile
     const int n4 = total >> 2;
 
-    for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
-        const int s0 = item * TC_STREAMS;
-        // ---- phase 1: [history | block] -> hi / lo swizzled tiles; next block's history -> HBM
+    // ---- load of one item by `lthreads` threads (ltid = index among them)
+    auto load_item = [&](int item_l, int ltid, int lthreads) {
+        const int s0 = item_l * TC_STREAMS;
+        // ---- load: [history | block] -> hi / lo swizzled tiles; next block's history -> HBM
         // consecutive threads take consecutive ROWS of one column chunk: their 16-byte shared-memory
         // stores are contiguous (no bank conflicts in the core-matrix layout); the global loads are 16 B
         // per 128-byte row, the other chunks of the row follow from L1/L2
         constexpr int LB = 8;                                 // loads in flight per thread
-        for (int base = tid; base < TC_STREAMS * n4; base += TC_THREADS * LB) {
+        for (int base = ltid; base < TC_STREAMS * n4; base += lthreads * LB) {
             float4 v[LB];
 #pragma unroll
             for (int u = 0; u < LB; ++u) {
-                const int idx = base + u * TC_THREADS;
+                const int idx = base + u * lthreads;
                 v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (idx < TC_STREAMS * n4) {
                     const int sl = idx / n4, g = idx - sl * n4;   // local stream, (chunk, row) index in its tile
@@ -214,7 +218,7 @@ fir_tc_kernel(const __grid_constant__ TcParams P) {
             }
 #pragma unroll
             for (int u = 0; u < LB; ++u) {
-                const int idx = base + u * TC_THREADS;
+                const int idx = base + u * lthreads;
                 if (idx < TC_STREAMS * n4) {
                     const int sl = idx / n4, g = idx - sl * n4;
                     const int c = g / rows, r = g - c * rows;
@@ -233,8 +237,12 @@ fir_tc_kernel(const __grid_constant__ TcParams P) {
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA unit
-        __syncthreads();
+    };
+    if (blockIdx.x < P.n_items) load_item(blockIdx.x, tid, TC_THREADS);   // first item: everybody loads
+    __syncthreads();
 
+    for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+        const int s0 = item * TC_STREAMS;
         // ---- phase 2: W producer (warp 0) and MMA issuer (warp 1); whole warps run the loops, one
         // elected lane issues, so every operand stays warp-uniform (uniform registers, no waterfall)
         if (warp_u == 0) {
@@ -315,6 +323,12 @@ fir_tc_kernel(const __grid_constant__ TcParams P) {
         // warp w reads TMEM lanes 32*(w%4)..+31 (accumulator rows); warps 0-3 take the low 32 outputs of
         // each 64-output row, warps 4-7 the high 32
         constexpr int H = TC_ROW / 32;                        // 32-output pieces per accumulator row
+        if (warp_u >= TC_MAIN_THREADS / 32) {
+            // the accumulators are final, so the MMAs have read the sample tiles for the last time: warps 8-15
+            // refill them with the next item while warps 0-7 drain TMEM
+            const int nitem = item + gridDim.x;
+            if (nitem < P.n_items) load_item(nitem, tid - TC_MAIN_THREADS, TC_THREADS - TC_MAIN_THREADS);
+        } else
         for (int u = warp >> 2; u < n_t * H; u += 2) {        // warps 0-3 and 4-7 alternate over (set, piece)
             const int t = u / H, half = u % H;
             const int m = 32 * (warp & 3) + lane;             // accumulator row = TMEM lane
