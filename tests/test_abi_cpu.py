@@ -109,3 +109,22 @@ def test_plain_c_host_runs_on_the_gpu(tmp_path):
     res = subprocess.run([exe], capture_output=True, text=True)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "-> ok" in res.stdout
+
+
+def test_agc_struct_layout_and_signature():
+    """afp_agc_params: five doubles, window_size, reserved (include/afp.h); compat.apply_agc keeps the
+    reference's positional arguments and defaults (stream_process_AGC.py:43)."""
+    import inspect
+    assert C.sizeof(_lib.AgcParams) == 48 and _lib.AgcParams.window_size.offset == 40
+    p = _lib.AgcParams.make()
+    assert (p.target_level, p.window_size, p.max_gain, p.attack, p.release, p.clip) == (0.1, 512, 10.0, 0.01, 0.1, 0.99)
+    src = open(os.path.join(ROOT, "audio_filtering_pipeline_b200", "compat.py")).read()
+    assert ("def apply_agc(signal, target_level=0.1, window_size=512, alpha=0.01, max_gain=10.0, attack=0.01, "
+            "release=0.1):") in src
+
+
+def test_new_entry_points_reject_null_without_a_gpu(lib):
+    assert lib.afp_set_agc(None, None) == _lib.ERR_INVALID
+    assert lib.afp_swap_taps(None, None, 0) == _lib.ERR_INVALID
+    assert lib.afp_agc_block(None, None, None, 0, None, 0, 0, 0, None) == _lib.ERR_INVALID
+    assert lib.afp_process_host_interleaved(None, None, None, 0, 1) == _lib.ERR_INVALID
