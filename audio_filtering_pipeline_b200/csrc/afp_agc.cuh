@@ -212,6 +212,13 @@ __device__ __forceinline__ void agc_load_run(float (&v)[SB][16], const float* x,
 
 // SB = 512-sample scans in flight per warp: every load of up to 512*SB samples of a stream is issued
 // before the first use.
+// pull a row into L2 (16-byte aligned interior of [r, r + n))
+__device__ __forceinline__ void agc_prefetch_l2(const float* r, int n) {
+    const unsigned long long lo = (reinterpret_cast<unsigned long long>(r) + 15ull) & ~15ull;
+    const unsigned long long hi = reinterpret_cast<unsigned long long>(r + n) & ~15ull;
+    if (hi > lo) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"((unsigned)(hi - lo)) : "memory");
+}
+
 // TEAM = warps per stream in phase 1 (1 or 2).  The float64 scratch row is what limits the resident warps
 // (8.7 KB per 1024-frame stream in flight); with TEAM = 2 two warps share one row and take half a stream
 // each - the second adds the first one's total as its carry - so the SM holds twice the warps in the same
@@ -306,7 +313,17 @@ __global__ void __launch_bounds__(TEAM == 2 ? 256 : 128, TEAM == 2 ? 2 : 3) agc_
                 agc_team_sync<TEAM>(team);                                // prefix row free for the next stream
             }
             __syncthreads();
-            // ---- phase 2: the attack / release recurrence, one lane per stream
+            // ---- phase 2: the attack / release recurrence, one lane per stream.  Meanwhile the last warp (it
+            // has no stream of its own here) pulls the next item's rows into L2, so that phase 1 of the next
+            // item starts from L2 instead of HBM latency.
+            if (warp == n_warps - 1) {
+                const int nitem = item + gridDim.x;
+                if (nitem < P.n_items)
+                    for (int sl = lane; sl < G; sl += 32) {
+                        const int sn = nitem * G + sl;
+                        if (sn < P.n_streams) agc_prefetch_l2(P.in + (long long)sn * P.in_pitch, n);
+                    }
+            }
             if (tid < G && s0 + tid < P.n_streams) {
                 float* row = rows + (size_t)tid * P.pitch;
                 if (!CHECKED) {
