@@ -23,7 +23,7 @@ SYMBOLS = [
     "afp_set_eq", "afp_set_gains", "afp_process", "afp_process_host", "afp_process_host_blocks", "afp_out_frames",
     "afp_out_elem_bytes", "afp_reset", "afp_state_size", "afp_get_state", "afp_set_state",
     "afp_get_stage_info", "afp_kernel_launches", "afp_host_alloc", "afp_host_free",
-    "afp_measure_fma_peak", "afp_set_agc", "afp_agc_block", "afp_process_host_interleaved", "afp_swap_taps",
+    "afp_measure_fma_peak", "afp_set_agc", "afp_agc_block", "afp_process_host_interleaved", "afp_swap_taps", "afp_spectrum_db",
 ]
 
 
@@ -105,6 +105,7 @@ def load():
     lib.afp_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     lib.afp_host_free.argtypes = [vp]
     lib.afp_measure_fma_peak.argtypes = [i32, dp, dp]
+    lib.afp_spectrum_db.argtypes = [vp, vp, i64, vp, i64, i32, i32, vp]
     lib.afp_set_agc.argtypes = [vp, C.POINTER(AgcParams)]
     lib.afp_agc_block.argtypes = [vp, C.POINTER(AgcParams), vp, i64, vp, i64, i32, i32, vp]
     for name in SYMBOLS:

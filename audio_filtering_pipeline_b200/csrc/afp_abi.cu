@@ -18,6 +18,8 @@
 #include "afp_fir_row.cuh"
 #include "afp_fir_tc.cuh"
 #include "afp_agc.cuh"
+#include "afp_spectrum.cuh"
+#include <map>
 
 afp::agc_kern_t afp_kernel_agc(int variant, int scan_blocks, int team);   // afp_kernels_agc.cu: variant AGC_*, scan_blocks 1 / 2, team 1 / 2
 
@@ -168,6 +170,8 @@ struct afp_ctx {
     unsigned char* d_out[kSlots] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_in[kSlots] = {}, ev_k[kSlots] = {}, ev_out[kSlots] = {};
     int slot_streams = 0;            // streams per staging slot
+    // afp_spectrum_db: per block length n, device tables [window n floats | twiddles n/2 float2]
+    std::map<int, float*> spec_tables;
     // afp_process_host_interleaved: frame-major device copies of one block in / out
     float* d_il_in = nullptr;
     unsigned char* d_il_out = nullptr;
@@ -897,6 +901,7 @@ int afp_destroy(afp_ctx* c) {
     cudaSetDevice(c->cfg.device);
     free_stage(c->up); free_stage(c->eq); free_stage(c->mainf); free_stage(c->fused);
     if (c->tmp_agc) cudaFree(c->tmp_agc);
+    for (auto& kv : c->spec_tables) cudaFree(kv.second);
     if (c->d_il_in) cudaFree(c->d_il_in);
     if (c->d_il_out) cudaFree(c->d_il_out);
     if (c->tmp_a) cudaFree(c->tmp_a);
@@ -1034,6 +1039,45 @@ int afp_agc_block(afp_ctx* c, const afp_agc_params* p, const float* in, int64_t 
     if (in_pitch < frames || out_pitch < frames) return fail(c, AFP_ERR_INVALID, "pitch smaller than frames");
     AFP_CUDA(c, cudaSetDevice(c->cfg.device));
     return launch_agc(c, *p, in, in_pitch, out, out_pitch, n_streams, frames, (cudaStream_t)cuda_stream);
+}
+
+int afp_spectrum_db(afp_ctx* c, const float* in, int64_t in_pitch, float* out, int64_t out_pitch, int32_t n_streams,
+                    int32_t frames, void* cuda_stream) {
+    if (!c) return AFP_ERR_INVALID;
+    if (!in || !out) return fail(c, AFP_ERR_INVALID, "null buffer");
+    if (n_streams < 0) return fail(c, AFP_ERR_INVALID, "negative size");
+    int log2n = 0;
+    while ((1 << log2n) < frames) ++log2n;
+    if (frames < 64 || frames > 4096 || (1 << log2n) != frames)
+        return fail(c, AFP_ERR_INVALID, "spectrum: frames must be a power of two in 64..4096");
+    if (in_pitch < frames || out_pitch < frames / 2 + 1) return fail(c, AFP_ERR_INVALID, "pitch smaller than the row");
+    if (n_streams == 0) return AFP_OK;
+    AFP_CUDA(c, cudaSetDevice(c->cfg.device));
+    float*& tab = c->spec_tables[frames];
+    if (!tab) {
+        // np.hanning(n) = 0.5 - 0.5 cos(2 pi k / (n - 1)); twiddles exp(-2 pi i k / n): float64 on the host
+        std::vector<float> h((size_t)2 * frames);
+        const double pi = 3.14159265358979323846;
+        for (int k = 0; k < frames; ++k) h[k] = (float)(0.5 - 0.5 * std::cos(2.0 * pi * k / (frames - 1)));
+        for (int k = 0; k < frames / 2; ++k) {
+            h[frames + 2 * k] = (float)std::cos(-2.0 * pi * k / frames);
+            h[frames + 2 * k + 1] = (float)std::sin(-2.0 * pi * k / frames);
+        }
+        AFP_CUDA(c, cudaMalloc(&tab, h.size() * sizeof(float)));
+        AFP_CUDA(c, cudaMemcpy(tab, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    afp::SpectrumParams P{};
+    P.in = in; P.in_pitch = in_pitch; P.out = out; P.out_pitch = out_pitch;
+    P.window = tab; P.twiddle = reinterpret_cast<const float2*>(tab + frames);
+    P.n_streams = n_streams; P.n = frames; P.log2n = log2n;
+    const size_t smem = (size_t)frames * sizeof(float2);
+    const int per_sm = frames <= 1024 ? 6 : (frames <= 2048 ? 4 : 2);
+    int grid = c->n_sm * per_sm;
+    if (grid > n_streams) grid = n_streams;
+    afp::spectrum_db_kernel<<<grid, afp::SPEC_THREADS, smem, (cudaStream_t)cuda_stream>>>(P);
+    AFP_CUDA(c, cudaGetLastError());
+    c->launches++;
+    return AFP_OK;
 }
 
 int32_t afp_out_frames(const afp_ctx* c, int32_t frames) {

@@ -137,6 +137,23 @@ class BatchFirEngine:
                                            rows, frames, stream), self._ctx)
         return out
 
+    def spectrum_db(self, x, out=None):
+        """Waterfall rows (stream_process_GUI_Waterfall.py:471-476) of a float32 CUDA tensor [rows, frames]:
+        ``20*log10(|rfft(x*hanning)| + 1e-12)`` -> [rows, frames//2 + 1].  frames: power of two, 64..4096."""
+        import torch
+        if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2:
+            raise ValueError("x must be a float32 CUDA tensor of shape [rows, frames]")
+        if x.stride(1) != 1:
+            x = x.contiguous()
+        rows, frames = x.shape
+        if out is None:
+            out = torch.empty((rows, frames // 2 + 1), dtype=torch.float32, device=x.device)
+        xp, op = (x.stride(0), out.stride(0)) if rows > 1 else (max(x.stride(0), frames), max(out.stride(0), frames // 2 + 1))
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(self._lib.afp_spectrum_db(self._ctx, x.data_ptr(), xp, out.data_ptr(), op, rows, frames, stream),
+                   self._ctx)
+        return out
+
     # -- processing --------------------------------------------------------------------------
     def out_frames(self, frames):
         return int(self._lib.afp_out_frames(self._ctx, int(frames)))

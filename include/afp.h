@@ -19,6 +19,7 @@
  *                                     stream_process.py:79-120 (host buffers in, host buffers out)
  *   afp_set_agc / afp_agc_block       apply_agc + np.clip(+-0.99) ahead of the up-sampler
  *                                     stream_process_AGC.py:43-89,131-143
+ *   afp_spectrum_db                   waterfall row: hanning, rfft, dB   stream_process_GUI_Waterfall.py:471-476
  *
  * Data layout: planar, stream-major.  in[s*in_pitch + i] is frame i of stream s (float32 at the
  * base rate); out[s*out_pitch + j] is output sample j of stream s in `out_format`.  A "stream" is
@@ -166,6 +167,13 @@ int afp_agc_block(afp_ctx* ctx, const afp_agc_params* params, const float* in_de
  * `out_format` (float32, or int16 / int24 PCM).  Stream s = session*channels + channel; n_streams must be a
  * multiple of `channels`.  The (de)interleave runs on the device; synchronous like afp_process_host. */
 int afp_process_host_interleaved(afp_ctx* ctx, const float* in_host, void* out_host, int32_t frames, int32_t channels);
+
+/* The waterfall row the reference computes from every output block while its display is on
+ * (stream_process_GUI_Waterfall.py:471-476): out[s][k] = 20*log10(|rfft(in[s][0:frames] * hanning(frames))[k]|
+ * + 1e-12), k = 0..frames/2, for n_streams rows (device pointers, pitches in elements, asynchronous on
+ * cuda_stream).  frames: a power of two, 64..4096 (the GUI's block sizes); anything else is AFP_ERR_INVALID. */
+int afp_spectrum_db(afp_ctx* ctx, const float* in_dev, int64_t in_pitch, float* out_dev, int64_t out_pitch,
+                    int32_t n_streams, int32_t frames, void* cuda_stream);
 
 int32_t afp_out_frames(const afp_ctx* ctx, int32_t frames);
 int32_t afp_out_elem_bytes(const afp_ctx* ctx);

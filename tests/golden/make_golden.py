@@ -13,6 +13,7 @@ What is executed, unmodified, from /root/reference:
   * stream_process_GUI_Waterfall.make_audio_callback                   -> cb_waterfall_*.npz
   * stream_process_EQ_GUI.process_audio (worker thread) + min-phase call sites -> eqgui_*.npz
   * stream_process_AGC.apply_agc (+ the clip of its call site)         -> agc_blocks.npz
+  * stream_process_GUI_Waterfall's waterfall row (show_waterfall on)   -> waterfall_spectrum.npz
 
 What is stubbed (absent from the container and outside the hot path): sounddevice, tkinter,
 matplotlib, plot_filter, samplerate, and the import-time side effects (sudo cpufreq-set,
@@ -374,6 +375,38 @@ def gen_waterfall(soxr):
          pre_dither=np.stack(pre), outdata=outs, params=np.array([N, B, U, fs]))
 
 
+def gen_waterfall_spectrum(soxr):
+    """The waterfall row of the same callback (stream_process_GUI_Waterfall.py:471-476): Hann-windowed
+    rfft of the block just written to outdata, 20*log10(|X| + 1e-12).  show_waterfall = True."""
+    import stream_process_GUI_Waterfall as wf
+    from fir_filter import create_fir_filter
+    N, B, U, fs, nblk = 129, 1024, 1, 44100, 4
+    bands = [(20, 60), (60, 120), (120, 250), (250, 500), (500, 1000), (1000, 2000),
+             (2000, 4000), (4000, 8000), (8000, 16000)]
+    gains = [1.0] * 9
+    eq_taps = [create_fir_filter(method="window", cutoff=b, numtaps=N, window_type="hamming",
+                                 filter_type="bandpass", samplerate=fs * U) for b in bands]
+    main = create_fir_filter(method="window", cutoff=14000, numtaps=N, window_type="hamming",
+                             filter_type="lowpass", samplerate=fs * U)
+    buf = np.zeros(B * 4 + 512, dtype=np.float32)
+    gui = types.SimpleNamespace(
+        eq_filters=eq_taps, eq_gains=[_Anything(value=g) for g in gains], fir_coeff=main,
+        input_buffer=buf, eq_output=np.zeros_like(buf), audio_buffer=[],
+        silence_block=np.zeros(B, dtype=np.float32), last_output=np.zeros(B, dtype=np.float32),
+        show_waterfall=_Anything(value=True), waterfall_data=[],
+        get_gains=lambda: gains, get_dsp_config=lambda: (fs, U, B))
+    cb = wf.make_audio_callback(gui)
+    x = sweep_and_noise(nblk * B, fs, seed=4)
+    outs = np.zeros((nblk, B), dtype=np.float32)
+    for i in range(nblk):
+        indata = x[i * B:(i + 1) * B].reshape(B, 1).copy()
+        outdata = np.zeros((B, 1), dtype=np.float32)
+        np.random.seed(400 + i)
+        cb(indata, outdata, B, None, None)
+        outs[i] = outdata[:, 0]
+    save("waterfall_spectrum", outdata=outs, spectrum_db=np.stack(gui.waterfall_data), params=np.array([B, fs]))
+
+
 def gen_eq_gui_worker():
     """stream_process_EQ_GUI.process_audio is an endless worker loop fed by two queues (:65-113);
     run it on a daemon thread for a handful of blocks at U=1 (resamplers bypassed, :422-423)."""
@@ -460,6 +493,7 @@ def main():
     print("waterfall ...");         gen_waterfall(soxr)
     print("EQ_GUI worker ...");     gen_eq_gui_worker()
     print("AGC ...");               gen_agc()
+    print("waterfall spectrum ..."); gen_waterfall_spectrum(soxr)
     manifest = {
         "generated_by": "tests/golden/make_golden.py",
         "reference": REF,

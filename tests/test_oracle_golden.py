@@ -183,3 +183,10 @@ def test_agc_stage_is_call_site_window_and_clip():
         y = agc.agc_stage(x)
         np.testing.assert_allclose(y, np.clip(g["y_" + m["key"]], -0.99, 0.99), rtol=1e-13, atol=0)
         assert np.abs(y).max() <= 0.99
+
+
+def test_spectrum_oracle_matches_waterfall_rows():
+    from oracle import spectrum
+    g = load_golden("waterfall_spectrum")
+    for blk, row in zip(g["outdata"], g["spectrum_db"]):
+        np.testing.assert_allclose(spectrum.spectrum_db(blk), row, rtol=0, atol=1e-9)
