@@ -1,8 +1,8 @@
 // Waterfall row of one block per stream: out[k] = 20*log10(|rfft(x * hanning(n))[k]| + 1e-12), k = 0..n/2
 // (stream_process_GUI_Waterfall.py:471-476).  One CTA per stream at a time (persistent over streams): the
 // windowed block goes to shared memory in bit-reversed order as complex numbers, log2(n) radix-2 stages in
-// place (twiddles and window from host-built float64 -> float32 tables), then magnitude and dB of the first
-// n/2 + 1 bins.  n is a power of two, 64..4096 (16 KB of shared memory at 2048, 32 KB at 4096).
+// place, two per pass (twiddles and window from host-built float64 -> float32 tables), then magnitude and dB
+// of the first n/2 + 1 bins.  n is a power of two, 64..4096 (12 KB of shared memory at 1024, 48 KB at 4096).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -21,24 +21,52 @@ struct SpectrumParams {
 
 constexpr int SPEC_THREADS = 256;
 
+__device__ __forceinline__ float2 spec_mul(float2 b, float2 w) {
+    return make_float2(fmaf(b.x, w.x, -b.y * w.y), fmaf(b.x, w.y, b.y * w.x));
+}
+
+// Two radix-2 stages per pass: a thread takes the four elements {i, i+h, i+2h, i+3h} (h = 2^st, i with
+// bits st and st+1 clear), does the stage-st butterflies on (i, i+h), (i+2h, i+3h) and the stage-(st+1)
+// butterflies on (i, i+2h), (i+h, i+3h) in registers: half the barriers and shared-memory round trips.
+// Twiddles come from a shared-memory copy of the table.
 __global__ void __launch_bounds__(SPEC_THREADS) spectrum_db_kernel(const __grid_constant__ SpectrumParams P) {
-    extern __shared__ float2 spec_x[];
+    extern __shared__ float2 spec_smem[];
     const int n = P.n, tid = threadIdx.x;
+    float2* spec_x = spec_smem;                    // [n]
+    float2* tw = spec_smem + n;                    // [n/2]
+    for (int k = tid; k < (n >> 1); k += SPEC_THREADS) tw[k] = __ldg(P.twiddle + k);
     for (int s = blockIdx.x; s < P.n_streams; s += gridDim.x) {
         const float* x = P.in + (long long)s * P.in_pitch;
         for (int i = tid; i < n; i += SPEC_THREADS)
             spec_x[__brev((unsigned)i) >> (32 - P.log2n)] = make_float2(__ldg(x + i) * __ldg(P.window + i), 0.f);
         __syncthreads();
-        for (int st = 0; st < P.log2n; ++st) {
-            const int half = 1 << st;
+        int st = 0;
+        if (P.log2n & 1) {                         // odd number of stages: one plain radix-2 stage first (all twiddles 1)
             for (int j = tid; j < (n >> 1); j += SPEC_THREADS) {
-                const int k = j & (half - 1);
-                const int i0 = ((j >> st) << (st + 1)) + k, i1 = i0 + half;
-                const float2 w = __ldg(P.twiddle + (size_t)k * (n >> (st + 1)));
-                const float2 a = spec_x[i0], b = spec_x[i1];
-                const float2 t = make_float2(fmaf(b.x, w.x, -b.y * w.y), fmaf(b.x, w.y, b.y * w.x));
-                spec_x[i0] = make_float2(a.x + t.x, a.y + t.y);
-                spec_x[i1] = make_float2(a.x - t.x, a.y - t.y);
+                const float2 a = spec_x[2 * j], b = spec_x[2 * j + 1];
+                spec_x[2 * j] = make_float2(a.x + b.x, a.y + b.y);
+                spec_x[2 * j + 1] = make_float2(a.x - b.x, a.y - b.y);
+            }
+            __syncthreads();
+            st = 1;
+        }
+        for (; st < P.log2n; st += 2) {
+            const int h = 1 << st;
+            for (int j = tid; j < (n >> 2); j += SPEC_THREADS) {
+                const int k = j & (h - 1);
+                const int i0 = ((j >> st) << (st + 2)) + k;
+                const float2 w1 = tw[(size_t)k * (n >> (st + 1))];            // stage st:     W_{2h}^k
+                const float2 w2a = tw[(size_t)k * (n >> (st + 2))];           // stage st + 1: W_{4h}^k
+                const float2 w2b = tw[(size_t)(k + h) * (n >> (st + 2))];     //               W_{4h}^{k+h}
+                float2 a = spec_x[i0], b = spec_x[i0 + h], c = spec_x[i0 + 2 * h], d = spec_x[i0 + 3 * h];
+                const float2 tb = spec_mul(b, w1), td = spec_mul(d, w1);
+                const float2 a1 = make_float2(a.x + tb.x, a.y + tb.y), b1 = make_float2(a.x - tb.x, a.y - tb.y);
+                const float2 c1 = make_float2(c.x + td.x, c.y + td.y), d1 = make_float2(c.x - td.x, c.y - td.y);
+                const float2 tc = spec_mul(c1, w2a), te = spec_mul(d1, w2b);
+                spec_x[i0] = make_float2(a1.x + tc.x, a1.y + tc.y);
+                spec_x[i0 + 2 * h] = make_float2(a1.x - tc.x, a1.y - tc.y);
+                spec_x[i0 + h] = make_float2(b1.x + te.x, b1.y + te.y);
+                spec_x[i0 + 3 * h] = make_float2(b1.x - te.x, b1.y - te.y);
             }
             __syncthreads();
         }
