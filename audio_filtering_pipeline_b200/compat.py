@@ -40,7 +40,7 @@ class StreamChain:
                  window_type="hamming", filter_type="lowpass", method="window", channels=1,
                  eq_bands=None, eq_gains=None, eq_numtaps=None, eq_mode="buffer_same_per_band",
                  min_phase=False, dither=True, bit_depth=24, seed=0, device=0, upsampler_taps=None,
-                 fir_coeff=None, agc=None):
+                 fir_coeff=None, agc=None, show_waterfall=False):
         self.samplerate, self.upsample_factor, self.blocksize = int(samplerate), int(upsample_factor), int(blocksize)
         self.channels = int(channels)
         up_rate = self.samplerate * self.upsample_factor                     # stream_process.py:20
@@ -67,6 +67,8 @@ class StreamChain:
             dither="rpdf" if dither else "none", dither_bits=bit_depth, seed=seed, device=device,
             upsampler_taps=upsampler_taps, eq_bands=bands, eq_gains=eq_gains,
             eq_mode=eq_mode if bands is not None else "none", agc=agc)
+        self.show_waterfall = bool(show_waterfall)                            # stream_process_GUI_Waterfall.py:471
+        self.waterfall_data = deque(maxlen=50)                                # :112
         self.audio_buffer = deque(maxlen=4)                                   # stream_process.py:50
         self.silence_block = np.zeros((self.blocksize, self.channels), dtype=np.float32)
         self._planar = np.zeros((self.channels, self.blocksize), dtype=np.float32)
@@ -79,6 +81,13 @@ class StreamChain:
         frames = x.shape[0]
         # [frames, channels] goes to the device as it is; the (de)interleave runs there
         return self.engine.process_host_interleaved(x[:, :self.channels])[:frames]
+
+    def waterfall_row(self, column):
+        """``20*log10(|rfft(column * hanning)| + 1e-12)`` of one output column on the GPU
+        (stream_process_GUI_Waterfall.py:473-475); float32 [len(column)//2 + 1]."""
+        import torch
+        x = torch.from_numpy(np.ascontiguousarray(column, dtype=np.float32)[None, :]).cuda(self.engine.device)
+        return self.engine.spectrum_db(x)[0].cpu().numpy()
 
     def close(self):
         self.engine.close()
@@ -99,6 +108,12 @@ def make_audio_callback(chain, verbose=True):
                 y = np.resize(y, (frames, y.shape[1]))                         # :106-107
             chain.audio_buffer.append(y.copy())                                # :110
             outdata[:, :y.shape[1]] = y
+            if chain.show_waterfall:                                           # stream_process_GUI_Waterfall.py:471-478
+                try:
+                    chain.waterfall_data.append(chain.waterfall_row(outdata[:, 0]))
+                except Exception as exc:                                       # noqa: BLE001
+                    if verbose:
+                        print(f"Waterfall error: {exc}")
         except Exception as exc:                                               # noqa: BLE001 (:115-120)
             if verbose:
                 print(f"Processing error: {exc}")

@@ -66,3 +66,20 @@ def test_rejects_other_lengths(eng):
     for n in (1000, 32, 8192):
         with pytest.raises(Exception):
             eng.spectrum_db(torch.zeros((1, n), device="cuda"))
+
+
+def test_callback_collects_waterfall_rows():
+    """make_audio_callback with show_waterfall on appends one row per block to chain.waterfall_data
+    (stream_process_GUI_Waterfall.py:471-476): the row is the spectrum of what was written to outdata."""
+    from audio_filtering_pipeline_b200 import compat
+    B = 1024
+    chain = compat.StreamChain(samplerate=44100, upsample_factor=1, blocksize=B, numtaps=129, cutoff=9000, dither=False,
+                               show_waterfall=True)
+    cb = compat.make_audio_callback(chain, verbose=False)
+    x = (0.2 * np.random.default_rng(2).standard_normal((3 * B, 1))).astype(np.float32)
+    for i in range(3):
+        out = np.zeros((B, 1), dtype=np.float32)
+        cb(x[i * B:(i + 1) * B], out, B, None, None)
+        assert len(chain.waterfall_data) == i + 1
+        check(chain.waterfall_data[-1], ospec.spectrum_db(out[:, 0]))
+    chain.close()
