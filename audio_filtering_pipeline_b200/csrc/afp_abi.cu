@@ -1070,12 +1070,10 @@ int afp_spectrum_db(afp_ctx* c, const float* in, int64_t in_pitch, float* out, i
     P.in = in; P.in_pitch = in_pitch; P.out = out; P.out_pitch = out_pitch;
     P.window = tab; P.twiddle = reinterpret_cast<const float2*>(tab + frames);
     P.n_streams = n_streams; P.n = frames; P.log2n = log2n;
-    const size_t smem = (size_t)(afp::spec_pad(frames) + frames / 2) * sizeof(float2);   // padded samples + twiddle copy
+    const size_t smem = (size_t)(afp::spec_pad(frames / 2) + frames / 4) * sizeof(float2);   // padded packed samples + twiddle copy
     const int per_sm = frames <= 1024 ? 8 : (frames <= 2048 ? 4 : 2);
     int grid = c->n_sm * per_sm;
     if (grid > n_streams) grid = n_streams;
-    if (smem > 48 * 1024)   // 4096 frames: just over the default dynamic shared-memory limit
-        AFP_CUDA(c, cudaFuncSetAttribute((const void*)afp::spectrum_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     afp::spectrum_db_kernel<<<grid, afp::SPEC_THREADS, smem, (cudaStream_t)cuda_stream>>>(P);
     AFP_CUDA(c, cudaGetLastError());
     c->launches++;
