@@ -221,9 +221,10 @@ def apply_agc(signal, target_level=0.1, window_size=512, alpha=0.01, max_gain=10
     import torch
     sig = np.asarray(signal, dtype=np.float32)
     sig = np.atleast_2d(sig).T if sig.ndim == 1 else sig                       # :52-53
+    # (outside the try: a missing library or device must raise, not look like the reference's pass-through)
+    eng = _cached(("agc",), lambda: BatchFirEngine([1.0], n_streams=1, max_frames=1))
     try:
         x = np.ascontiguousarray(sig[:, 0])[None, :]
-        eng = _cached(("agc",), lambda: BatchFirEngine([1.0], n_streams=1, max_frames=1))
         xd = torch.from_numpy(x).cuda(eng.device)
         y = eng.agc_block(xd, target_level=target_level, window_size=window_size, max_gain=max_gain,
                           attack=attack, release=release, clip=0.0)
@@ -236,16 +237,17 @@ def apply_agc(signal, target_level=0.1, window_size=512, alpha=0.01, max_gain=10
 def safe_upsample(data, sr=44100, upsr=176400):
     """Interpolation by ``upsr/sr`` (1..4).  Streaming polyphase FIR with carried state in place of the
     reference's one-shot ``soxr.resample`` per block; zeros on failure like :75-77."""
+    x = np.asarray(data, dtype=np.float32)
+    x = x[:, 0] if x.ndim > 1 else x                                           # :70
+    if upsr == sr:
+        return x.astype(np.float32)                                            # stream_process_EQ_GUI.py:422-423
+    if upsr < sr:
+        return safe_downsample(x, sr, upsr, int(round(len(x) * upsr / sr)))
+    factor = int(round(upsr / sr))
+    # (outside the try: a missing library or device must raise, not turn into the reference's block of zeros)
+    eng = _cached(("up", factor, len(x), int(sr)), lambda: BatchFirEngine(
+        design.design_upsampler(factor, sr), n_streams=1, max_frames=len(x), upsample=factor, chain="dac"))
     try:
-        x = np.asarray(data, dtype=np.float32)
-        x = x[:, 0] if x.ndim > 1 else x                                       # :70
-        if upsr == sr:
-            return x.astype(np.float32)                                        # stream_process_EQ_GUI.py:422-423
-        if upsr < sr:
-            return safe_downsample(x, sr, upsr, int(round(len(x) * upsr / sr)))
-        factor = int(round(upsr / sr))
-        eng = _cached(("up", factor, len(x), int(sr)), lambda: BatchFirEngine(
-            design.design_upsampler(factor, sr), n_streams=1, max_frames=len(x), upsample=factor, chain="dac"))
         return eng.process_host(x[None, :])[0]
     except Exception as exc:                                                   # noqa: BLE001
         print(f"Upsample error: {exc}")
@@ -254,14 +256,14 @@ def safe_upsample(data, sr=44100, upsr=176400):
 
 def safe_downsample(data, upsr, sr, expected_len):
     """Anti-alias FIR + keep every ``upsr/sr``-th sample (stream_process_EQ_GUI.py:429-436)."""
+    x = np.asarray(data, dtype=np.float32).ravel()
+    if upsr == sr:
+        return x
+    factor = int(round(upsr / sr))
+    eng = _cached(("down", factor, len(x), int(sr)), lambda: BatchFirEngine(
+        design.design_upsampler(factor, sr) / factor, n_streams=1, max_frames=len(x), upsample=1,
+        chain="dac", decimate=factor))                                         # (raises without library / device)
     try:
-        x = np.asarray(data, dtype=np.float32).ravel()
-        if upsr == sr:
-            return x
-        factor = int(round(upsr / sr))
-        eng = _cached(("down", factor, len(x), int(sr)), lambda: BatchFirEngine(
-            design.design_upsampler(factor, sr) / factor, n_streams=1, max_frames=len(x), upsample=1,
-            chain="dac", decimate=factor))
         y = eng.process_host(x[None, :])[0]
         return np.resize(y, expected_len) if len(y) != expected_len else y
     except Exception as exc:                                                   # noqa: BLE001

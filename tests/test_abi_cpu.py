@@ -51,6 +51,15 @@ def test_no_cpu_fallback(lib):
     from audio_filtering_pipeline_b200.engine import BatchFirEngine
     with pytest.raises(_lib.AfpError):
         BatchFirEngine([1.0])
+    # the reference-shaped helpers keep the reference's "zeros / unchanged block on a processing error"
+    # convention, but a missing device is not a processing error: it raises
+    import numpy as np
+    from audio_filtering_pipeline_b200 import compat
+    blk = np.zeros(64, dtype=np.float32)
+    for call in (lambda: compat.apply_agc(blk), lambda: compat.safe_upsample(blk, 44100, 88200),
+                 lambda: compat.safe_downsample(blk, 88200, 44100, 32), lambda: compat.apply_dither(blk)):
+        with pytest.raises(_lib.AfpError):
+            call()
 
 
 def test_argument_validation_needs_no_gpu(lib):
