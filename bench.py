@@ -118,7 +118,9 @@ def run_reference(args):
     taps = c2_taps()
     cores = len(os.sched_getaffinity(0))
     pool = mp.get_context("fork").Pool(cores)
-    n_streams, n_blocks = 8, 16           # per core per step: a bounded sample of the workload
+    # per core per step: a bounded sample of the workload, long enough (~0.2 s) that the pool dispatch and the
+    # per-call set-up inside the worker stay a few per cent of the step - the reference is not undersold
+    n_streams, n_blocks = 8, 256
     job = [(taps, n_streams, n_blocks, i) for i in range(cores)]
     for _ in range(args.warmup):
         pool.map(_cpu_worker, job)
