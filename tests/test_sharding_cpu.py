@@ -57,3 +57,28 @@ def test_gloo_world_size_2():
     assert [r[1:3] for r in res] == [(0, 500), (500, 500)]
     assert all(r[3] == 2.0 for r in res)             # max over ranks
     assert all(r[4] == 1000.0 for r in res)          # sum over ranks
+
+
+def test_reference_arm_prints_one_line_on_rank_0_only():
+    """bench.py --impl reference under torchrun: rank 0 alone runs the CPU arm and prints the JSON line with
+    the contract's keys; every other rank exits 0 without work or output."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+           "--warmup", "0"]
+    env1 = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r1 = subprocess.run(cmd, env=env1, capture_output=True, text=True, timeout=120)
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
+    env0 = dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    r0 = subprocess.run(cmd, env=env0, capture_output=True, text=True, timeout=300)
+    assert r0.returncode == 0, r0.stderr[-500:]
+    lines = [l for l in r0.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["unit"] == "Msamples/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and "workload" in d["config"]
