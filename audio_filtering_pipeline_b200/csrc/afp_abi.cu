@@ -336,8 +336,8 @@ Geometry pick_geometry(int T, int kq_pad, int n_q, int n_streams) {
     return best;
 }
 
-// ---- AGC (afp_agc.cuh).  Shared memory per CTA: one float row per stream of the work item (odd pitch)
-// + one float64 prefix-sum row per warp + a flag per stream.  Two (short blocks: three) CTAs per SM when at
+// ---- AGC (afp_agc.cuh).  Shared memory per CTA: one float row per stream of the work item (pitch 4 x odd)
+// + one float64 prefix-sum row per warp or warp pair + a flag per stream.  Two (short blocks: three) CTAs per SM when at
 // least 8 streams fit in that share of an SM's shared memory (one CTA's serial recurrence phase overlaps
 // the others' memory phases), else one CTA with as many streams as fit.
 struct AgcPlan { int warps = 0, team = 1, group = 0, pitch = 0, ctas_per_sm = 0, scratch = 0; size_t smem = 0; };   // warps = prefix rows (teams)
