@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libafp_b200.so")
 
-OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOMEM = 0, 1, 2, 3, 4
+OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOMEM, ERR_RANGE = 0, 1, 2, 3, 4, 5
 CHAIN = {"dac": 0, "reference": 1}
 FMT = {"f32": 0, "i16": 1, "i24": 2, "i24_in_i32": 2, "i24_packed": 3}
 DITHER = {"none": 0, None: 0, False: 0, "tpdf": 1, True: 1, "rpdf": 2}
@@ -24,6 +24,7 @@ SYMBOLS = [
     "afp_out_elem_bytes", "afp_reset", "afp_state_size", "afp_get_state", "afp_set_state",
     "afp_get_stage_info", "afp_kernel_launches", "afp_host_alloc", "afp_host_free",
     "afp_measure_fma_peak", "afp_set_agc", "afp_agc_block", "afp_process_host_interleaved", "afp_swap_taps", "afp_spectrum_db",
+    "afp_process_blocks", "afp_range_status",
 ]
 
 
@@ -88,6 +89,8 @@ def load():
     lib.afp_set_eq.argtypes = [vp, dp, C.POINTER(i32), i32, dp]
     lib.afp_set_gains.argtypes = [vp, dp, i32]
     lib.afp_process.argtypes = [vp, vp, i64, vp, i64, i32, vp]
+    lib.afp_process_blocks.argtypes = [vp, vp, i64, i64, vp, i64, i64, i32, i32, vp]
+    lib.afp_range_status.argtypes = [vp, C.POINTER(i32)]
     lib.afp_process_host.argtypes = [vp, vp, vp, i32]
     lib.afp_process_host_blocks.argtypes = [vp, vp, vp, i32, i32]
     lib.afp_process_host_interleaved.argtypes = [vp, vp, vp, i32, i32]

@@ -17,10 +17,12 @@
 #include "afp_kernel_table.cuh"
 #include "afp_fir_row.cuh"
 #include "afp_fir_tc.cuh"
+#include "afp_fir_tc2.cuh"
 #include "afp_agc.cuh"
 #include "afp_spectrum.cuh"
 #include <map>
 
+afp::tc2_kern_t afp_kernel_tc2(int epi);                                    // afp_kernels_tc2.cu
 afp::agc_kern_t afp_kernel_agc(int variant, int scan_blocks, int team);   // afp_kernels_agc.cu: variant AGC_*, scan_blocks 1 / 2, team 1 / 2
 
 using afp::FirParams;
@@ -59,7 +61,10 @@ struct Stage {
     // tiles on the device; which kernel ran last (0 = FFMA2, 1 = tcgen05)
     float* tc_w[2] = {nullptr, nullptr};   // tap tiles for row length 32 and 64
     int tc_chunks[2] = {0, 0};
-    int last_kernel = 0;           // 0 = row-pair FFMA2, 1 = tcgen05, 2 = single-row FFMA2
+    // split-FP16 tensor kernel (afp_fir_tc2.cuh): Hankel tap cores [2][n_cores][8][8] halves, chunk count D + 1
+    void* tc2_w = nullptr;
+    int tc2_cores = 0, tc2_chunks = 0;
+    int last_kernel = 0;           // 0 = row-pair FFMA2, 1 = tcgen05 (3xTF32), 2 = single-row FFMA2, 3 = tcgen05 (split FP16)
     int last_T = 0;                // tile of the last launch (the single-row kernel picks its own)
     // per-launch host work of the single-row kernel that only depends on the stage: its tap-table image
     // and the occupancy of the kernel it last used
@@ -177,6 +182,7 @@ struct afp_ctx {
     unsigned char* d_il_out = nullptr;
     cudaStream_t own_stream = nullptr, s_in = nullptr, s_out = nullptr;
     FirParams params{};              // scratch for the kernel-parameter block of the launch being prepared
+    unsigned int* range_flag = nullptr;   // device word: set by the split-FP16 tensor kernel when a sample exceeds FP16's range
 };
 
 namespace {
@@ -204,6 +210,7 @@ void free_stage(Stage& s) {
     for (int i = 0; i < 2; ++i) { if (s.hist[i]) cudaFree(s.hist[i]); s.hist[i] = nullptr; }
     if (s.hist_scratch) { cudaFree(s.hist_scratch); s.hist_scratch = nullptr; }
     for (int i = 0; i < 2; ++i) { if (s.tc_w[i]) cudaFree(s.tc_w[i]); s.tc_w[i] = nullptr; s.tc_chunks[i] = 0; }
+    if (s.tc2_w) { cudaFree(s.tc2_w); s.tc2_w = nullptr; s.tc2_cores = s.tc2_chunks = 0; }
     s.active = false;
 }
 
@@ -293,7 +300,31 @@ int build_stage(afp_ctx* c, Stage& s, int kind, int U, const double* taps, int n
             AFP_CUDA(c, cudaMemcpy(s.tc_w[v], w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
             s.tc_chunks[v] = nc;
         }
+        // split-FP16 kernel (afp_fir_tc2.cuh): Hankel cores C_q[jj][e] = hp[8 q + jj + e], hp[t] = h[t - 63];
+        // h = hi + lo * 2^-11, hi = fp16(h), lo = fp16((h - hi) * 2^11): first all hi cores, then all lo cores
+        if (s.tc2_w) { cudaFree(s.tc2_w); s.tc2_w = nullptr; }
+        const int D = (n + afp::TC2_R - 2) / afp::TC2_R;
+        if (D + 1 <= 17 && !env_flag("AFP_NO_TC2")) {
+            const int Q = afp::tc2_n_cores(D + 1);
+            std::vector<__half> w((size_t)2 * Q * 64);
+            for (int q = 0; q < Q; ++q)
+                for (int jj = 0; jj < 8; ++jj)
+                    for (int e = 0; e < 8; ++e) {
+                        const int k = 8 * q + jj + e - (afp::TC2_R - 1);
+                        const float hv = (k >= 0 && k < n) ? (float)taps[k] : 0.f;
+                        const __half hi = __float2half_rn(hv);
+                        const __half lo = __float2half_rn((hv - __half2float(hi)) * 2048.0f);
+                        w[(size_t)q * 64 + jj * 8 + e] = hi;
+                        w[(size_t)(Q + q) * 64 + jj * 8 + e] = lo;
+                    }
+            AFP_CUDA(c, cudaMalloc(&s.tc2_w, w.size() * sizeof(__half)));
+            AFP_CUDA(c, cudaMemcpy(s.tc2_w, w.data(), w.size() * sizeof(__half), cudaMemcpyHostToDevice));
+            s.tc2_cores = Q; s.tc2_chunks = D + 1;
+        }
     }
+    // the memsets / copies above ran on the legacy stream; the kernels run on non-blocking streams that do
+    // not order themselves after it
+    AFP_CUDA(c, cudaDeviceSynchronize());
     s.active = true;
     return AFP_OK;
 }
@@ -474,6 +505,45 @@ int launch_stage_tc(afp_ctx* c, Stage& s, const StageIO& io, cudaStream_t stream
         *done = true;
         return AFP_OK;
     }
+    return AFP_OK;
+}
+
+// Split-FP16 tensor kernel (afp_fir_tc2.cuh): n_blocks consecutive blocks of a streaming stage in ONE launch,
+// history read from s.hist[cur] and written to s.hist[cur ^ 1] (the caller flips cur once).  *done stays
+// false when the stage / shape does not qualify.
+int launch_stage_tc2(afp_ctx* c, Stage& s, const float* in, long long in_pitch, long long in_bstride, void* out,
+                     long long out_pitch, long long out_bstride, int frames, int n_blocks, int fmt, int dither,
+                     unsigned long long sample_base, int s0, int ns, cudaStream_t stream, bool* done) {
+    *done = false;
+    if (!s.tc2_w || s.U != 1 || env_flag("AFP_NO_TC2")) return AFP_OK;
+    if (frames < afp::TC2_STEP || frames % afp::TC2_STEP != 0 || n_blocks < 1) return AFP_OK;
+    if ((long long)frames * n_blocks > (1 << 30)) return AFP_OK;
+    const int eb = fmt == AFP_FMT_I16 ? 2 : (fmt == AFP_FMT_I24_PACKED ? 3 : 4);
+    if (!aligned16(in) || in_pitch % 4 != 0 || in_bstride % 4 != 0 || s.hist_pitch % 4 != 0 || s.kq_pad % 8 != 0) return AFP_OK;
+    const int D = s.tc2_chunks - 1, H = D <= 8 ? 8 : 16;
+    if ((H + 8) * afp::TC2_R < s.kq_pad) return AFP_OK;
+    afp::Tc2Params P{};
+    P.hist_in = s.hist[s.cur] + (long long)s0 * s.hist_pitch; P.hist_out = s.hist[s.cur ^ 1] + (long long)s0 * s.hist_pitch;
+    P.hist_pitch = s.hist_pitch; P.hist_len = s.kq_pad;
+    P.in = in; P.in_pitch = in_pitch; P.in_block_stride = in_bstride;
+    P.out = out; P.out_pitch = out_pitch; P.out_block_stride = out_bstride;
+    P.w = static_cast<const __half*>(s.tc2_w); P.n_cores = s.tc2_cores;
+    P.n_streams = ns; P.frames = frames; P.n_blocks = n_blocks; P.n_chunks = s.tc2_chunks; P.hist_rows = H;
+    P.n_groups = (ns + afp::TC2_STREAMS - 1) / afp::TC2_STREAMS;
+    P.range_flag = c->range_flag;
+    P.fmt = fmt; P.dither = dither; P.decim = 1;
+    P.fast_out = (aligned16(out) && (out_pitch * eb) % 16 == 0 && (out_bstride * eb) % 16 == 0) ? 1 : 0;
+    P.seed = c->cfg.seed; P.sample_base = sample_base; P.stream_id0 = c->cfg.first_stream_id + s0;
+    P.gain = 1.0f; P.dither_lsb = std::ldexp(1.0f, -(c->dither_bits - 1));
+    const int smem = afp::tc2_smem_bytes(s.tc2_chunks);
+    if (smem > kMaxSmem) return AFP_OK;
+    const int grid = P.n_groups < c->n_sm ? P.n_groups : c->n_sm;
+    afp_kernel_tc2(afp::epi_code(fmt, dither))<<<grid, afp::TC2_THREADS, smem, stream>>>(P);
+    AFP_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    s.last_kernel = 3;
+    s.geo.nt = afp::TC2_THREADS; s.geo.tg_log2 = 4; s.geo.smem = smem; s.geo.grid = grid; s.geo.key_nq = -1;
+    *done = true;
     return AFP_OK;
 }
 
@@ -659,6 +729,11 @@ int run_streaming(afp_ctx* c, Stage& s, const float* in, long long in_pitch, int
     // stream_process.py:23) runs as a chain of sub-blocks, each a complete streaming launch: history A ->
     // scratch -> A -> ... -> B, so the block still ends with its history in the "other" buffer like any
     // single launch (+30 % over the FFMA2 kernel for >= 400-tap filters).
+    if (decim == 1) {
+        bool done = false;
+        int rc = launch_stage_tc2(c, s, in, in_pitch, 0, out, out_pitch, 0, len, 1, fmt, dither, sample_base, s0, ns, stream, &done);
+        if (rc || done) return rc;
+    }
     const int sub = (decim == 1 && !env_flag("AFP_NO_TC_CHAIN")) ? tc_max_block(s) : 0;
     if (sub > 0 && len > sub && len % sub == 0 && aligned16(in) && in_pitch % 4 == 0) {
         if (!s.hist_scratch) {
@@ -750,6 +825,7 @@ int ensure_tmp(afp_ctx* c) {
                 AFP_CUDA(c, cudaMalloc(&c->xhist[i], (size_t)S * c->xhist_pitch * sizeof(float)));
                 AFP_CUDA(c, cudaMemset(c->xhist[i], 0, (size_t)S * c->xhist_pitch * sizeof(float)));
             }
+            AFP_CUDA(c, cudaDeviceSynchronize());   // (legacy-stream memsets vs. the non-blocking streams of the kernels)
             c->xhist_len = hm; c->xhist_cur = 0;
             if (c->tmp_b) { cudaFree(c->tmp_b); c->tmp_b = nullptr; }
         }
@@ -878,6 +954,10 @@ int afp_create(const afp_config* cfg, afp_ctx** out_ctx) {
                 e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
                 if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, tensor path)");
             }
+    for (int epi : kAllEpi) {
+        e = cudaFuncSetAttribute((const void*)afp_kernel_tc2(epi), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+        if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, split-FP16 tensor path)");
+    }
     for (int variant : {afp::AGC_FAST, afp::AGC_EXACT, afp::AGC_CHECKED})
         for (int sb : {1, 2})
             for (int team : {1, 2}) {
@@ -892,6 +972,10 @@ int afp_create(const afp_config* cfg, afp_ctx** out_ctx) {
     c->dither_bits = cfg->dither_bits > 0 ? cfg->dither_bits : 24;
     e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete c; return cuda_fail(nullptr, e, "cudaStreamCreate"); }
+    e = cudaMalloc(&c->range_flag, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(c->range_flag, 0, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaStreamDestroy(c->own_stream); delete c; return cuda_fail(nullptr, e, "range flag allocation"); }
     *out_ctx = c;
     return AFP_OK;
 }
@@ -901,6 +985,7 @@ int afp_destroy(afp_ctx* c) {
     cudaSetDevice(c->cfg.device);
     free_stage(c->up); free_stage(c->eq); free_stage(c->mainf); free_stage(c->fused);
     if (c->tmp_agc) cudaFree(c->tmp_agc);
+    if (c->range_flag) cudaFree(c->range_flag);
     for (auto& kv : c->spec_tables) cudaFree(kv.second);
     if (c->d_il_in) cudaFree(c->d_il_in);
     if (c->d_il_out) cudaFree(c->d_il_out);
@@ -1224,6 +1309,79 @@ int afp_process(afp_ctx* c, const float* in, int64_t in_pitch, void* out, int64_
     return AFP_OK;
 }
 
+// the one streaming stage of a chain that is a single filter (the collapsed reference chain, or a plain FIR
+// with no interpolator / EQ / AGC ahead of it); nullptr for every other chain
+static Stage* single_stage(afp_ctx* c) {
+    if (c->agc_on) return nullptr;
+    if (c->fused.active) return &c->fused;
+    if (c->cfg.chain == AFP_CHAIN_REFERENCE && c->cfg.upsample > 1) return nullptr;
+    if (c->eq.active || c->cfg.eq_mode != AFP_EQ_NONE) return nullptr;
+    return c->mainf.active ? &c->mainf : nullptr;
+}
+
+// the split-FP16 tensor kernel saw a sample beyond FP16's range since the last check: report and clear
+static int check_range(afp_ctx* c) {
+    unsigned int flag = 0;
+    AFP_CUDA(c, cudaMemcpy(&flag, c->range_flag, sizeof(flag), cudaMemcpyDeviceToHost));
+    if (!flag) return AFP_OK;
+    AFP_CUDA(c, cudaMemset(c->range_flag, 0, sizeof(flag)));
+    AFP_CUDA(c, cudaDeviceSynchronize());
+    return fail(c, AFP_ERR_RANGE, "an input sample exceeds +-65504 (the split-FP16 tensor path's range; audio is +-1): "
+                                  "the affected outputs are not valid; AFP_NO_TC2=1 selects the 3xTF32 / FFMA2 kernels");
+}
+
+int afp_range_status(afp_ctx* c, int32_t* exceeded) {
+    if (!c || !exceeded) return AFP_ERR_INVALID;
+    AFP_CUDA(c, cudaSetDevice(c->cfg.device));
+    const int rc = check_range(c);
+    *exceeded = rc == AFP_ERR_RANGE ? 1 : 0;
+    return rc == AFP_ERR_RANGE ? AFP_OK : rc;
+}
+
+int afp_process_blocks(afp_ctx* c, const float* in, int64_t in_pitch, int64_t in_block_stride, void* out, int64_t out_pitch,
+                       int64_t out_block_stride, int32_t frames, int32_t n_blocks, void* cuda_stream) {
+    if (!c) return AFP_ERR_INVALID;
+    if (!in || !out) return fail(c, AFP_ERR_INVALID, "null buffer");
+    if (n_blocks < 0) return fail(c, AFP_ERR_INVALID, "negative block count");
+    int rc = check_ready(c, frames);
+    if (rc) return rc;
+    if (frames == 0 || n_blocks == 0) return AFP_OK;
+    if (in_pitch < frames) return fail(c, AFP_ERR_INVALID, "in_pitch smaller than frames");
+    const int out_n = afp_out_frames(c, frames);
+    const int64_t unit = c->cfg.out_format == AFP_FMT_I24_PACKED ? 3 : 1;
+    if (out_pitch < (int64_t)out_n * unit) return fail(c, AFP_ERR_INVALID, "out_pitch smaller than the output row");
+    if (n_blocks > 1 && (in_block_stride < frames || out_block_stride < (int64_t)out_n * unit))
+        return fail(c, AFP_ERR_INVALID, "block stride smaller than a row");
+    AFP_CUDA(c, cudaSetDevice(c->cfg.device));
+    rc = ensure_tmp(c);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int S = c->cfg.n_streams;
+    if (Stage* s = single_stage(c)) {
+        // one launch for all the blocks: the CTA that owns a stream group walks its blocks with the window in
+        // shared memory; the carried history is read once and written once
+        bool done = false;
+        if (s->U == 1 && c->decim == 1) {
+            rc = launch_stage_tc2(c, *s, in, in_pitch, in_block_stride, out, out_pitch / unit, out_block_stride / unit, frames, n_blocks,
+                                  c->cfg.out_format, c->cfg.dither, c->out_samples, 0, S, st, &done);
+            if (rc) return rc;
+        }
+        if (done) {
+            s->cur ^= 1;
+            c->out_samples += (unsigned long long)out_n * (unsigned long long)n_blocks;
+            return AFP_OK;
+        }
+    }
+    const int eb = afp_out_elem_bytes(c);
+    for (int b = 0; b < n_blocks; ++b) {
+        rc = process_block_range(c, in + (int64_t)b * in_block_stride, in_pitch,
+                                 static_cast<unsigned char*>(out) + (int64_t)b * out_block_stride * (eb == 3 ? 1 : eb), out_pitch, frames, 0, S, st);
+        if (rc) return rc;
+        finish_block(c, frames);
+    }
+    return AFP_OK;
+}
+
 static int ensure_host_staging(afp_ctx* c) {
     if (c->d_in[0]) return AFP_OK;
     const int S = c->cfg.n_streams;
@@ -1299,7 +1457,7 @@ int afp_process_host_blocks(afp_ctx* c, const float* in, void* out, int32_t fram
     }
     AFP_CUDA(c, cudaStreamSynchronize(c->s_out));
     AFP_CUDA(c, cudaStreamSynchronize(c->own_stream));
-    return AFP_OK;
+    return check_range(c);
 }
 
 int afp_process_host(afp_ctx* c, const float* in, void* out, int32_t frames) {
@@ -1343,7 +1501,7 @@ int afp_process_host_interleaved(afp_ctx* c, const float* in, void* out, int32_t
     AFP_CUDA(c, cudaMemcpyAsync(out, c->d_il_out, out_bytes, cudaMemcpyDeviceToHost, st));
     AFP_CUDA(c, cudaStreamSynchronize(st));
     finish_block(c, frames);
-    return AFP_OK;
+    return check_range(c);
 }
 
 // the stages that actually run, in launch order
@@ -1373,6 +1531,8 @@ int afp_reset(afp_ctx* c) {
         AFP_CUDA(c, cudaMemset(b.cur, 0, b.bytes));
         AFP_CUDA(c, cudaMemset(b.other, 0, b.bytes));
     }
+    if (c->range_flag) AFP_CUDA(c, cudaMemset(c->range_flag, 0, sizeof(unsigned int)));
+    AFP_CUDA(c, cudaDeviceSynchronize());   // the memsets run on the legacy stream, the kernels on non-blocking ones
     c->out_samples = 0;
     return AFP_OK;
 }
@@ -1415,6 +1575,7 @@ int afp_set_state(afp_ctx* c, const void* buf, size_t bytes) {
         AFP_CUDA(c, cudaMemcpy(b.cur, p, b.bytes, cudaMemcpyHostToDevice));
         p += b.bytes;
     }
+    AFP_CUDA(c, cudaDeviceSynchronize());   // (pageable-memory copies may still be in flight on the legacy stream)
     return AFP_OK;
 }
 

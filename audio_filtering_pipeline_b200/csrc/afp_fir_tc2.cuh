@@ -1,0 +1,368 @@
+// Tensor-core FIR, second form: split-FP16 operands, Hankel tap cores resident in shared memory, consecutive
+// blocks of a stream group processed by one CTA (afp_process_blocks).  Long U = 1 filters (400..1025 taps).
+//
+// Same Toeplitz blocking as afp_fir_tc.cuh - rows of R = 64 samples, y[R m + j] = sum_d sum_i X[m-d][i] W_d[i][j],
+// the A operand of chunk d being the one sample tile moved up d rows through the descriptor start address -
+// with three changes, each from a measurement (bench/microbench/umma_peak.cu, profiles/r02/umma_peak.txt):
+//
+//  1. No tap traffic.  The first kernel streams the Toeplitz blocks W_d (R x R floats per chunk, 557 KB for
+//     1001 taps) from L2 for every work item: at the tensor pipe's own pace that is ~43 B/clk/SM, the whole
+//     chip's L2 bandwidth.  Here the samples of a row are stored in REVERSED order, X'[m][i] = x[R m + R-1-i],
+//     which turns the tap block into a Hankel matrix,  W'_d[i][j] = hp[R d + i + j],  hp[t] = h[t - (R-1)].
+//     In the K-major core-matrix layout a core (8 rows j x 16 bytes of i) of a Hankel matrix depends on
+//     (i0 + j0) only, so ONE array of cores  C_q[jj][e] = hp[8 q + jj + e]  serves every chunk, k-step and
+//     column group: the B descriptor of (chunk d, k-step ks) starts at core 8 d + 2 ks with leading and
+//     stride byte offsets both 128.  1001 taps -> 143 cores x 128 B = 18 KB (+ the same for the low parts),
+//     loaded once per CTA.
+//  2. FP16 split instead of TF32 split.  x = hi + lo * 2^-11 with hi = fp16(x), lo = fp16((x - hi) * 2^11),
+//     the same for the taps: 11 + 11 significant bits per operand, exactly what the 3xTF32 split keeps, but
+//     kind::f16 runs at twice the rate (K = 16 per instruction at the cost of tf32's K = 8) and a sample
+//     needs 4 bytes of shared memory (hi + lo) instead of 8, which is what makes room for two window
+//     positions (below).  Products  hi*hi -> accumulator 0;  hi*lo' and lo'*hi -> accumulator 1 (both carry
+//     2^11);  y = acc0 + 2^-11 acc1;  lo*lo (2^-22 relative) is dropped as before.  Range: |x| < 65504
+//     (audio is +-1); a larger sample sets the context's range flag and the call reports it.
+//  3. The CTA keeps a stream group for all the blocks of the call.  A step = 16 streams x 8 rows (512
+//     samples); its window [H history rows | 8 new rows] lives at one of two positions of a 40-row tile
+//     (rows 0.. and rows 16..; for H = 16 they share rows 16-23, which travel through registers), so the
+//     loader warps fill the window of step k+1 while the tensor pipe works on step k and the epilogue warps
+//     drain step k-1 from TMEM (two accumulator sets).  History is read from the carried buffer only for the
+//     first steps of a call and written once at its end; in between the "history" is the previous blocks'
+//     input, re-read through L2.
+//
+// Cost model (measured): an M = 128, N = 64, K = 16 MMA takes max(32 clk pipe, 6 KB / 128 B/clk = 48 clk operand
+// fetch) = 48 clk;  a step is n_chunks x 4 k-steps x 3 products.  1001 taps: 204 MMAs = 9.8 kclk per 8192 samples.
+#pragma once
+#include <cstdint>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include "afp_fir_tc.cuh"
+
+namespace afp {
+
+constexpr int TC2_R = 64;                  // samples per row
+constexpr int TC2_STREAMS = 16;            // streams per work item (M = 128 = 16 x 8 rows)
+constexpr int TC2_ROWS = 41;               // rows per stream tile: 40 + 1 (row pitch 41 x 16 B = 16 mod 128: conflict-free loader stores)
+constexpr int TC2_POS_B = 16;              // first row of window position B
+constexpr int TC2_STEP = 8 * TC2_R;        // new samples per stream and step
+constexpr int TC2_LOADERS = 8, TC2_EPIS = 8;            // warps
+constexpr int TC2_THREADS = 32 * (1 + TC2_LOADERS + TC2_EPIS);
+constexpr int TC2_A_LBO = TC2_ROWS * 16;                 // bytes between column chunks (8 samples) of one stream tile
+constexpr int TC2_PITCH = (TC2_R / 8) * TC2_A_LBO;       // bytes per stream tile
+constexpr int TC2_TILE_BYTES = TC2_STREAMS * TC2_PITCH;  // one of hi / lo
+
+struct Tc2Params {
+    const float* hist_in;      // [n_streams][hist_pitch] carried samples, oldest first (the last hist_len of the past input)
+    float* hist_out;           // same layout: the last hist_len samples after this call
+    long long hist_pitch;
+    int hist_len;              // multiple of 8, <= hist_rows * 64
+    const float* in;           // block b, stream s, frame f: in[b * in_block_stride + s * in_pitch + f]
+    long long in_pitch, in_block_stride;
+    void* out;                 // same indexing in elements of the output format (bytes / 3 for packed int24)
+    long long out_pitch, out_block_stride;
+    const __half* w;           // [2][n_cores][8][8]: Hankel cores of the taps' high parts, then of the low parts * 2^11
+    int n_cores;
+    int n_streams, frames, n_blocks;
+    int n_chunks;              // D + 1
+    int hist_rows;             // H: 8 or 16
+    int n_groups;              // ceil(n_streams / 16)
+    unsigned int* range_flag;  // set to 1 when a sample does not fit FP16
+    // epilogue (same meaning as FirParams)
+    int fmt, dither, decim, fast_out;
+    unsigned long long seed, sample_base;
+    int stream_id0;
+    float gain, dither_lsb;
+};
+
+typedef void (*tc2_kern_t)(const Tc2Params);
+
+__host__ __device__ constexpr int tc2_n_cores(int n_chunks) { return 8 * (n_chunks + 1) - 1; }
+__host__ __device__ constexpr int tc2_smem_bytes(int n_chunks) { return 2 * TC2_TILE_BYTES + 2 * tc2_n_cores(n_chunks) * 128 + 256; }
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// instruction descriptor: D f32, A / B f16 K-major, M = 128
+__host__ __device__ constexpr uint32_t tc2_idesc(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
+
+// 8 consecutive samples -> the two 16-byte granules (hi, lo) of their row, element e = sample 7 - e
+__device__ __forceinline__ void tc2_split(const float4& a, const float4& b, uint4& hi, uint4& lo, float& amax) {
+    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const float x1 = x[7 - 2 * p], x0 = x[6 - 2 * p];          // elements 2p, 2p+1
+        amax = fmaxf(amax, fmaxf(fabsf(x1), fabsf(x0)));
+        const __half2 hh = __floats2half2_rn(x1, x0);
+        const float2 hf = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(__fmul_rn(__fsub_rn(x1, hf.x), 2048.0f), __fmul_rn(__fsub_rn(x0, hf.y), 2048.0f));
+        h[p] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[p] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(TC2_THREADS, 1)
+fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
+    extern __shared__ __align__(128) unsigned char tc2_smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned char* tile_hi = tc2_smem;
+    unsigned char* tile_lo = tile_hi + TC2_TILE_BYTES;
+    unsigned char* w_hi = tile_lo + TC2_TILE_BYTES;
+    unsigned char* w_lo = w_hi + P.n_cores * 128;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(w_lo + P.n_cores * 128);
+    uint64_t* win_direct = bars;        // [2] window position p: rows outside the shared rows are in place
+    uint64_t* win_staged = bars + 2;    // [2] ... and the shared rows too
+    uint64_t* mma_done = bars + 4;      // [2] accumulator set p final, window p read for the last time
+    uint64_t* acc_empty = bars + 6;     // [2] accumulator set p drained
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int H = P.hist_rows;
+    const bool shared_rows = H == 16;   // the two window positions overlap in rows 16..23
+    const int win_rows = H + 8;
+    const int steps_per_block = P.frames / TC2_STEP;
+    const int n_steps = steps_per_block * P.n_blocks;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&win_direct[i], TC2_LOADERS); mbar_init(&win_staged[i], TC2_LOADERS);
+            mbar_init(&mma_done[i], 1); mbar_init(&acc_empty[i], TC2_EPIS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {   // tap cores: global -> shared, once
+        const uint4* src = reinterpret_cast<const uint4*>(P.w);
+        uint4* dst = reinterpret_cast<uint4*>(w_hi);
+        for (int i = tid; i < 2 * P.n_cores * 8; i += TC2_THREADS) dst[i] = __ldg(src + i);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+
+    if (warp_u == 0) {
+        // ================= MMA issuer: one elected lane, operands warp-uniform =================
+        const uint64_t a_hi_d = umma_desc(smem_u32(tile_hi), TC2_A_LBO, TC2_PITCH), a_lo_d = umma_desc(smem_u32(tile_lo), TC2_A_LBO, TC2_PITCH);
+        const uint64_t w_hi_d = umma_desc(smem_u32(w_hi), 128, 128), w_lo_d = umma_desc(smem_u32(w_lo), 128, 128);
+        const uint32_t top_a = (uint32_t)(a_hi_d >> 32), top_w = (uint32_t)(w_hi_d >> 32);
+        const uint32_t idesc = tc2_idesc(TC2_R);
+        const int D = P.n_chunks - 1;
+        uint32_t kk = 0;                                       // steps issued by this CTA
+        for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x) {
+            for (int k = 0; k < n_steps; ++k, ++kk) {
+                const uint32_t p = kk & 1u, ph = (kk >> 1) & 1u;
+                const int pos = p ? TC2_POS_B : 0;
+                mbar_wait(&acc_empty[p], ph ^ 1u);             // (passes at once the first time round)
+                mbar_wait(&win_direct[p], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t acc0 = tmem_base + p * 128u, acc1 = acc0 + 64u;
+                bool staged_seen = !shared_rows;
+                bool first = true;
+                // chunk order, the same at both positions so that a step's rounding does not depend on where it ran:
+                // H = 16: 8 (touches no shared row at either position), D..9, 7..0;  H = 8: D..0
+                for (int idx = 0; idx <= D; ++idx) {
+                    int d;
+                    if (shared_rows) d = idx == 0 ? 8 : (idx <= D - 8 ? D + 1 - idx : D - idx);
+                    else d = D - idx;
+                    if (!staged_seen && (p ? d >= 9 : d <= 7)) {   // rows 16..23: the oldest rows of position B, the newest of A
+                        mbar_wait(&win_staged[p], ph);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        staged_seen = true;
+                    }
+                    if (elect_one()) {
+                        const uint32_t arow = (uint32_t)(pos + H - d);
+                        const uint32_t ah = (uint32_t)a_hi_d + arow, al = (uint32_t)a_lo_d + arow;
+                        const uint32_t wh = (uint32_t)w_hi_d + (uint32_t)(8 * d) * 8u, wl = (uint32_t)w_lo_d + (uint32_t)(8 * d) * 8u;
+#pragma unroll
+                        for (int ks = 0; ks < TC2_R / 16; ++ks) {
+                            const uint32_t ao = (uint32_t)(2 * ks * TC2_ROWS), wo = (uint32_t)(2 * ks) * 8u;
+                            const uint32_t f = (first && ks == 0) ? 0u : 1u;
+                            umma_f16(acc0, ah + ao, top_a, wh + wo, top_w, idesc, f);     // x_hi * W_hi
+                            umma_f16(acc1, ah + ao, top_a, wl + wo, top_w, idesc, f);     // x_hi * W_lo'
+                            umma_f16(acc1, al + ao, top_a, wh + wo, top_w, idesc, 1u);    // x_lo' * W_hi
+                        }
+                    }
+                    __syncwarp();
+                    first = false;
+                }
+                if (!staged_seen) mbar_wait(&win_staged[p], ph);   // (keeps the barrier phases in step; not reached for D >= 9)
+                if (elect_one()) umma_commit(&mma_done[p]);
+                __syncwarp();
+            }
+        }
+    } else if (warp_u <= TC2_LOADERS) {
+        // ================= loaders: global -> hi / lo granules of the next window =================
+        const int ltid = tid - 32, LT = 32 * TC2_LOADERS;
+        const int hist_span = H * TC2_R;                       // samples of a window before its new rows
+        uint32_t kk = 0;
+        float amax = 0.f;
+        for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x) {
+            const int s0 = grp * TC2_STREAMS;
+            for (int k = 0; k < n_steps; ++k, ++kk) {
+                const uint32_t p = kk & 1u;
+                const int pos = p ? TC2_POS_B : 0;
+                const bool last = k == n_steps - 1;
+                // the previous user of this position (step kk-2) must have been read for the last time
+                if (kk >= 2) mbar_wait(&mma_done[p], ((kk - 2) >> 1) & 1u);
+                // task = 8 consecutive samples of one stream; a warp takes 32 consecutive tasks (1 KB of one stream)
+                auto fetch = [&](int task, float4& a, float4& b) {
+                    const int sl = task / (win_rows * 8), gi = task - sl * (win_rows * 8);
+                    const int s = s0 + sl;
+                    const int t = k * TC2_STEP - hist_span + gi * 8;   // logical sample index: < 0 = carried history
+                    a = b = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (s < P.n_streams && t >= -P.hist_len) {
+                        const float* src;
+                        if (t < 0) src = P.hist_in + (long long)s * P.hist_pitch + (P.hist_len + t);
+                        else {
+                            const int b_ = t / P.frames, f = t - b_ * P.frames;
+                            src = P.in + (long long)b_ * P.in_block_stride + (long long)s * P.in_pitch + f;
+                        }
+                        a = __ldg(reinterpret_cast<const float4*>(src));
+                        b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                    }
+                };
+                auto place = [&](int task, const float4& a, const float4& b) {
+                    const int sl = task / (win_rows * 8), gi = task - sl * (win_rows * 8);
+                    const int row = gi >> 3, g = gi & 7;
+                    uint4 hi, lo;
+                    tc2_split(a, b, hi, lo, amax);
+                    const int off = sl * TC2_PITCH + (7 - g) * TC2_A_LBO + (pos + row) * 16;
+                    *reinterpret_cast<uint4*>(tile_hi + off) = hi;
+                    *reinterpret_cast<uint4*>(tile_lo + off) = lo;
+                    if (last) {   // the carried samples of the next call: the last hist_len samples of the window
+                        const int s = s0 + sl, wpos = gi * 8 - (win_rows * TC2_R - P.hist_len);
+                        if (s < P.n_streams && wpos >= 0) {
+                            float4* dst = reinterpret_cast<float4*>(P.hist_out + (long long)s * P.hist_pitch + wpos);
+                            dst[0] = a; dst[1] = b;
+                        }
+                    }
+                };
+                // rows shared by the two positions (buffer rows 16..23): window rows 16..23 at A, 0..7 at B
+                const int sh_lo = shared_rows ? (p ? 0 : 16) : -1;
+                const int n_tasks = TC2_STREAMS * win_rows * 8;
+                // the shared rows first into registers (their loads overlap everything below)
+                float4 sa[4], sb[4];
+                if (shared_rows) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int j = ltid + u * LT;                          // 0 .. 1023: (stream, row 0..7, granule)
+                        const int sl = j >> 6, r8 = j & 63;
+                        fetch(sl * (win_rows * 8) + sh_lo * 8 + r8, sa[u], sb[u]);
+                    }
+                }
+                // the other rows: straight to shared memory, 4 tasks in flight per thread
+                const int n_direct = shared_rows ? TC2_STREAMS * 16 * 8 : n_tasks;
+                for (int base = ltid; base < n_direct; base += 4 * LT) {
+                    float4 va[4], vb[4];
+                    int task[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int j = base + u * LT;
+                        task[u] = -1;
+                        if (j < n_direct) {
+                            if (shared_rows) {
+                                const int sl = j >> 7, r = j & 127;                  // 16 direct rows x 8 granules
+                                const int gi = p ? 64 + r : r;                        // A: window rows 0..15, B: 8..23
+                                task[u] = sl * (win_rows * 8) + gi;
+                            } else task[u] = j;
+                            fetch(task[u], va[u], vb[u]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (task[u] >= 0) place(task[u], va[u], vb[u]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&win_direct[p]);
+                if (shared_rows) {
+                    // rows 16..23 are still being read by step kk-1 (the other position)
+                    if (kk >= 1) mbar_wait(&mma_done[p ^ 1u], ((kk - 1) >> 1) & 1u);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int j = ltid + u * LT;
+                        const int sl = j >> 6, r8 = j & 63;
+                        place(sl * (win_rows * 8) + sh_lo * 8 + r8, sa[u], sb[u]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                }
+                if (lane == 0) mbar_arrive(&win_staged[p]);
+            }
+        }
+        if (amax > 65000.0f) atomicOr(P.range_flag, 1u);
+    } else {
+        // ================= epilogue: TMEM -> registers -> dither / quantise -> HBM =================
+        const int ew = warp_u - 1 - TC2_LOADERS;                // 0..7
+        const int quarter = warp_u & 3;                         // the TMEM lanes this warp may read
+        const int half = ew >> 2;                               // columns 32*half .. +31 of each 64-column accumulator
+        const int m = 32 * quarter + lane;                      // accumulator row: stream m/8 of the group, row m%8 of the step
+        struct EpiView {   // what store_row reads; out / sample_base move with the block
+            int fmt, dither, decim, fast_out;
+            float gain, dither_lsb;
+            void* out; long long out_pitch;
+            unsigned long long seed, sample_base;
+            int stream_id0;
+        } V = {P.fmt, P.dither, 1, P.fast_out, P.gain, P.dither_lsb, P.out, P.out_pitch, P.seed, P.sample_base, P.stream_id0};
+        const int eb = P.fmt == FMT_I16 ? 2 : (P.fmt == FMT_I24_PACKED ? 3 : 4);
+        uint32_t kk = 0;
+        for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x) {
+            const int s = grp * TC2_STREAMS + (m >> 3);
+            for (int k = 0; k < n_steps; ++k, ++kk) {
+                const uint32_t p = kk & 1u, ph = (kk >> 1) & 1u;
+                const int blk = k / steps_per_block, kb = k - blk * steps_per_block;
+                mbar_wait(&mma_done[p], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t taddr = tmem_base + ((uint32_t)(32 * quarter) << 16) + p * 128u + (uint32_t)(32 * half);
+                float y[32];
+#pragma unroll
+                for (int f = 0; f < 2; ++f) {
+                    uint32_t a[32];
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]),
+                          "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]),
+                          "=r"(a[16]), "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]),
+                          "=r"(a[24]), "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]), "=r"(a[31])
+                        : "r"(taddr + f * 64u));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        y[j] = f == 0 ? __uint_as_float(a[j]) : __fmaf_rn(__uint_as_float(a[j]), 4.8828125e-4f, y[j]);   // + 2^-11 acc1
+                }
+                // the accumulators are in registers: hand the set back before the (long) store
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[p]);
+                V.out = static_cast<unsigned char*>(P.out) + (long long)blk * P.out_block_stride * eb;
+                V.sample_base = P.sample_base + (unsigned long long)blk * (unsigned long long)P.frames;
+                const long long o_base = (long long)kb * TC2_STEP + (long long)(m & 7) * TC2_R + 32 * half;
+                store_row<32, EPI>(V, y, s, o_base, s < P.n_streams ? 32 : 0);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+}
+
+}  // namespace afp

@@ -1,0 +1,14 @@
+// fir_tc2_kernel (split-FP16 tcgen05 FIR with resident Hankel tap cores) instantiations; see afp_fir_tc2.cuh.
+#include "afp_kernel_table.cuh"
+#include "afp_fir_tc2.cuh"
+
+afp::tc2_kern_t afp_kernel_tc2(int epi) {
+    using namespace afp;
+    switch (epi) {
+        case kEpiF32: return (tc2_kern_t)fir_tc2_kernel<kEpiF32>;
+        case kEpiI24T: return (tc2_kern_t)fir_tc2_kernel<kEpiI24T>;
+        case kEpiI16T: return (tc2_kern_t)fir_tc2_kernel<kEpiI16T>;
+        case kEpiP24T: return (tc2_kern_t)fir_tc2_kernel<kEpiP24T>;
+        default: return (tc2_kern_t)fir_tc2_kernel<EPI_GENERIC>;
+    }
+}

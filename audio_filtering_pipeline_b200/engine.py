@@ -181,6 +181,35 @@ class BatchFirEngine:
                                          out.stride(0), frames, stream), self._ctx)
         return out
 
+    def process_blocks(self, x, out=None):
+        """``n`` consecutive blocks on device tensors: ``x`` float32 cuda [n, S, frames] (unit frame stride) ->
+        [n, S, out_cols].  Bit-identical to ``n`` calls of :meth:`process`; a chain that is one long U = 1 filter
+        runs as a single launch that keeps [history | block] in shared memory from block to block
+        (afp_process_blocks).  Asynchronous on torch's current stream."""
+        import torch
+        if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 3 or x.shape[1] != self.n_streams:
+            raise ValueError("x must be a float32 CUDA tensor of shape [n_blocks, n_streams, frames]")
+        if x.stride(2) != 1:
+            x = x.contiguous()
+        nb, _, frames = x.shape
+        cols = self._out_cols(frames)
+        if out is None:
+            out = torch.empty((nb, self.n_streams, cols), dtype=getattr(torch, _TORCH_DTYPE[self.fmt]), device=x.device)
+        elif (out.dim() != 3 or out.stride(2) != 1 or out.shape[0] != nb or out.shape[1] != self.n_streams
+              or out.shape[2] < cols or out.dtype != getattr(torch, _TORCH_DTYPE[self.fmt])):
+            raise ValueError("out has the wrong shape / stride / dtype")
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(self._lib.afp_process_blocks(self._ctx, x.data_ptr(), x.stride(1), x.stride(0), out.data_ptr(),
+                                                out.stride(1), out.stride(0), frames, nb, stream), self._ctx)
+        return out
+
+    def range_exceeded(self):
+        """True if the split-FP16 tensor path has seen a sample beyond +-65504 since the last check (waits for the
+        device; clears the flag).  The host-buffer calls raise ``AfpError`` (code 5) for this on their own."""
+        flag = C.c_int32(0)
+        _lib.check(self._lib.afp_range_status(self._ctx, C.byref(flag)), self._ctx)
+        return bool(flag.value)
+
     def process_host(self, x, out=None):
         """One block with host arrays (numpy float32 [S, frames]); returns a numpy array."""
         x = np.ascontiguousarray(x, dtype=np.float32)

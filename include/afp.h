@@ -40,6 +40,7 @@ extern "C" {
 #define AFP_ERR_CUDA 2      /* a CUDA runtime call failed; message has the CUDA error string */
 #define AFP_ERR_STATE 3     /* call made in the wrong state (e.g. process before set_taps) */
 #define AFP_ERR_NOMEM 4
+#define AFP_ERR_RANGE 5     /* an input sample is outside the range of the split-FP16 tensor path (|x| > 65504) */
 
 /* afp_config.chain */
 #define AFP_CHAIN_DAC 0        /* x -> [EQ] -> polyphase FIR(h, U) -> out at fs*U (the FIR is the interpolator) */
@@ -101,8 +102,10 @@ typedef struct afp_stage_info {
     int32_t grid;
     int32_t history;          /* carried samples per stream */
     int32_t kernel;           /* kernel of the last launch: 0 = packed-FFMA2 row-pair form, 1 = tcgen05 / TMEM
-                                 Toeplitz 3xTF32 (long single-table U = 1 filters, 256/512/1024-frame blocks),
-                                 2 = packed-FFMA2 single-row form (single-table stages, aligned buffers) */
+                                 Toeplitz 3xTF32 (long single-table U = 1 filters, 256-frame blocks, AFP_NO_TC2),
+                                 2 = packed-FFMA2 single-row form (single-table stages, aligned buffers),
+                                 3 = tcgen05 / TMEM split-FP16 form with resident Hankel tap cores (long single-table
+                                 U = 1 filters, blocks of a multiple of 512 frames) */
 } afp_stage_info;
 
 /* Automatic gain control of the input block (stream_process_AGC.py:43-89), per block and stateless like
@@ -145,6 +148,20 @@ int afp_set_gains(afp_ctx* ctx, const double* gains, int32_t n_bands);
  * (bytes for AFP_FMT_I24_PACKED output).  Output samples per stream: afp_out_frames(). */
 int afp_process(afp_ctx* ctx, const float* in_dev, int64_t in_pitch, void* out_dev, int64_t out_pitch,
                 int32_t frames, void* cuda_stream);
+/* n_blocks consecutive blocks (the buffers of n_blocks consecutive callbacks) in one call: block b of stream s
+ * starts at in_dev[b*in_block_stride + s*in_pitch] / out_dev[b*out_block_stride + s*out_pitch] (strides in
+ * elements, bytes for AFP_FMT_I24_PACKED).  Results are bit-identical to n_blocks afp_process calls.  For a chain
+ * that is a single long U = 1 filter (>= 400 taps; the collapsed reference chain included) with blocks of a multiple
+ * of 512 frames this is ONE launch: the CTA that owns 16 streams walks their blocks with [history | block] resident
+ * in shared memory, the carried history (the reference's sliding input_buffer, stream_process.py:45-46,97-98)
+ * is read once and written once.  Every other chain runs block by block. */
+int afp_process_blocks(afp_ctx* ctx, const float* in_dev, int64_t in_pitch, int64_t in_block_stride, void* out_dev,
+                       int64_t out_pitch, int64_t out_block_stride, int32_t frames, int32_t n_blocks, void* cuda_stream);
+/* The tensor path for long filters splits every sample into two FP16 numbers and therefore needs |x| <= 65504
+ * (float audio is +-1).  A larger sample makes the affected outputs invalid (inf / NaN) and sets a flag that the
+ * host-buffer entry points report as AFP_ERR_RANGE; after asynchronous afp_process / afp_process_blocks calls
+ * this function waits for the device, returns the flag in *exceeded and clears it. */
+int afp_range_status(afp_ctx* ctx, int32_t* exceeded);
 /* Same with host buffers (any host memory; pinned memory from afp_host_alloc is fastest).
  * Copies in, runs, copies out and waits.  Dense layout: in[S][frames], out[S][afp_out_frames]. */
 int afp_process_host(afp_ctx* ctx, const float* in_host, void* out_host, int32_t frames);

@@ -1,0 +1,187 @@
+"""Split-FP16 tensor kernel (csrc/afp_fir_tc2.cuh, kernel id 3) and afp_process_blocks: parity against the float64
+oracle of the reference's block loop (stream_process.py:96-107 as restated in oracle/reference_chain.py) at the
+filter lengths / block sizes that select its two window layouts, multi-block launches bit-identical to
+block-by-block feeding, small-signal accuracy of the hi + lo*2^-11 split, and the FP16 range flag."""
+import numpy as np
+import pytest
+
+from conftest import assert_parity
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from audio_filtering_pipeline_b200 import design  # noqa: E402
+from audio_filtering_pipeline_b200._lib import AfpError  # noqa: E402
+from audio_filtering_pipeline_b200.engine import BatchFirEngine  # noqa: E402
+from oracle import reference_chain as rc  # noqa: E402
+from oracle import dither_quant as dq  # noqa: E402
+
+
+def taps_for(N):
+    if N == 1001:
+        return design.create_fir_filter(method="remez", cutoff=20000, numtaps=1001, filter_type="lowpass", samplerate=176400)
+    return design.create_fir_filter(cutoff=9000, numtaps=N, window_type="kaiser", samplerate=96000)
+
+
+def noise(S, n, seed=1234, amp=0.1):
+    return np.stack([np.clip(amp * np.random.default_rng(seed + s).standard_normal(n), -1, 1)
+                     for s in range(S)]).astype(np.float32)
+
+
+def blocks_of(x, B):
+    S, n = x.shape
+    return np.ascontiguousarray(x.reshape(S, n // B, B).transpose(1, 0, 2))
+
+
+def unblock(y):
+    return np.concatenate(list(y), axis=1)
+
+
+# 401..512 taps: 8 history rows, two disjoint windows; 513..1025: 16 history rows, windows share rows 16-23
+@pytest.mark.parametrize("N,B,S,nb", [(1001, 512, 37, 5), (1025, 512, 16, 4), (513, 512, 3, 4), (512, 512, 17, 4),
+                                      (401, 512, 5, 3), (449, 1024, 9, 3), (641, 4096, 2, 2), (900, 1536, 1, 3),
+                                      (1001, 512, 160 * 16 + 3, 2)])
+def test_block_by_block_matches_oracle(N, B, S, nb):
+    h = taps_for(N)
+    x = noise(S, B * nb, amp=0.3)
+    xd = torch.from_numpy(x).cuda()
+    with BatchFirEngine(h, n_streams=S, max_frames=B) as eng:
+        ys = []
+        for i in range(nb):
+            ys.append(eng.process(xd[:, i * B:(i + 1) * B]).cpu().numpy())
+            assert eng.stage_info()[-1]["kernel"] == 3
+        assert not eng.range_exceeded()
+    y = np.concatenate(ys, axis=1)
+    for s in sorted({0, min(1, S - 1), S // 2, S - 1}):
+        assert_parity(y[s], rc.streaming_fir(h, x[s]).astype(np.float32), f"N={N} B={B} s={s}")
+
+
+@pytest.mark.parametrize("N,B,S,nb", [(1001, 512, 37, 16), (1001, 512, 16, 1), (1001, 512, 20, 2), (1001, 512, 20, 3),
+                                      (577, 1024, 33, 5), (449, 512, 18, 7)])
+@pytest.mark.parametrize("fmt,dither", [("f32", "none"), ("i24", "tpdf")])
+def test_process_blocks_is_bit_identical_to_block_by_block(N, B, S, nb, fmt, dither):
+    h = taps_for(N)
+    x = noise(S, B * nb * 2, amp=0.2)
+    xb = torch.from_numpy(blocks_of(x, B)).cuda()            # [2 nb, S, B]
+    kw = dict(n_streams=S, max_frames=B, out_format=fmt, dither=dither, seed=5, first_stream_id=3)
+    with BatchFirEngine(h, **kw) as eng:
+        y_one = torch.stack([eng.process(xb[i]) for i in range(2 * nb)]).cpu().numpy()
+    with BatchFirEngine(h, **kw) as eng:
+        y_a = eng.process_blocks(xb[:nb])                    # two calls: the carried state crosses a call boundary
+        y_b = eng.process_blocks(xb[nb:])
+        assert eng.stage_info()[-1]["kernel"] == 3
+        y_multi = torch.cat([y_a, y_b]).cpu().numpy()
+        assert eng.kernel_launches == 2
+    np.testing.assert_array_equal(y_multi, y_one)
+    if fmt == "f32":
+        y = unblock(y_multi)
+        for s in (0, S - 1):
+            assert_parity(y[s], rc.streaming_fir(h, x[s]).astype(np.float32), f"s={s}")
+
+
+def test_process_blocks_strided_views_and_int24():
+    """Non-contiguous block / stream strides (a [n, S, B] window of a larger buffer) and TPDF -> int24 against the
+    numpy statement of the Philox epilogue."""
+    h = taps_for(1001)
+    S, B, nb = 19, 512, 4
+    x = noise(S, B * nb, amp=0.4)
+    big = torch.zeros((nb, S + 5, B + 64), dtype=torch.float32, device="cuda")
+    xin = big[:, 2:2 + S, 32:32 + B]
+    xin.copy_(torch.from_numpy(blocks_of(x, B)))
+    obig = torch.zeros((nb, S + 3, B + 32), dtype=torch.int32, device="cuda")
+    with BatchFirEngine(h, n_streams=S, max_frames=B) as ef:
+        yf = ef.process_blocks(xin).cpu().numpy()
+    with BatchFirEngine(h, n_streams=S, max_frames=B, out_format="i24", dither="tpdf", seed=2024) as eq:
+        eq.process_blocks(xin, obig[:, 1:1 + S, 16:16 + B])
+    yq = obig[:, 1:1 + S, 16:16 + B].cpu().numpy()
+    ref = dq.epilogue(unblock(yf), dq.FMT_I24_IN_I32, dq.DITHER_TPDF, 2024, np.arange(S), 0)
+    np.testing.assert_array_equal(unblock(yq), ref)
+    assert int(obig[:, 0].abs().max()) == 0 and int(obig[:, :, :16].abs().max()) == 0   # nothing outside the window
+
+
+def test_process_blocks_falls_back_block_by_block_for_other_chains():
+    """A chain that is not one long U = 1 filter (here the 251-tap 4x interpolator) runs block by block behind the
+    same call."""
+    h = 4 * design.create_fir_filter(cutoff=[500, 8000], numtaps=251, window_type="kaiser", filter_type="bandpass",
+                                     samplerate=176400)
+    S, B, nb = 6, 1024, 3
+    x = noise(S, B * nb)
+    xb = torch.from_numpy(blocks_of(x, B)).cuda()
+    with BatchFirEngine(h, n_streams=S, max_frames=B, upsample=4, chain="dac") as eng:
+        y_one = torch.stack([eng.process(xb[i]) for i in range(nb)]).cpu().numpy()
+        eng.reset()
+        y_multi = eng.process_blocks(xb).cpu().numpy()
+        assert eng.stage_info()[-1]["kernel"] == 2
+    np.testing.assert_array_equal(y_multi, y_one)
+    assert_parity(unblock(y_multi)[0], rc.polyphase_upsample_whole(h, x[0], 4).astype(np.float32), "C1 DAC chain")
+
+
+def test_small_and_full_scale_signals():
+    """The split keeps 22 significant bits whatever the level: -120 dBFS noise and a 0.999 sine both stay within
+    2e-6 of the output peak (the FFMA2 kernel's own error level), far inside the parity tolerance."""
+    h = taps_for(1001)
+    n = 512 * 6
+    t = np.arange(n) / 176400.0
+    x = np.stack([0.999 * np.sin(2 * np.pi * 997.0 * t), 0.999 * np.sin(2 * np.pi * 15000.0 * t),
+                  1e-6 * np.random.default_rng(1).standard_normal(n), 3e-4 * np.random.default_rng(2).standard_normal(n),
+                  0.999 * np.sign(np.sin(2 * np.pi * 50.0 * t))]).astype(np.float32)
+    with BatchFirEngine(h, n_streams=5, max_frames=512) as eng:
+        y = unblock(eng.process_blocks(torch.from_numpy(blocks_of(x, 512)).cuda()).cpu().numpy())
+        assert eng.stage_info()[-1]["kernel"] == 3
+    for s in range(5):
+        ref = rc.streaming_fir(h, x[s])
+        assert_parity(y[s], ref.astype(np.float32), f"signal {s}")
+        assert np.abs(y[s] - ref).max() <= 2e-6 * np.abs(ref).max() + 1e-12, f"signal {s}: split precision lost"
+
+
+def test_state_roundtrip_across_process_blocks():
+    h = taps_for(1001)
+    S, B = 24, 512
+    x = noise(S, B * 8)
+    xb = torch.from_numpy(blocks_of(x, B)).cuda()
+    with BatchFirEngine(h, n_streams=S, max_frames=B, out_format="i24", dither="tpdf", seed=9) as e:
+        y_all = e.process_blocks(xb).cpu().numpy()
+        e.reset()
+        y1 = e.process_blocks(xb[:3]).cpu().numpy()
+        blob = e.get_state()
+        e.reset()
+        e.set_state(blob)
+        y2 = e.process_blocks(xb[3:]).cpu().numpy()
+    np.testing.assert_array_equal(np.concatenate([y1, y2]), y_all)
+
+
+def test_tensor2_and_other_kernels_share_history():
+    """512-multiples on kernel 3, 256 frames on kernel 1, other aligned sizes on the single-row FFMA2 kernel, odd sizes
+    on the row-pair kernel - all on one carried history."""
+    h = taps_for(1001)
+    sizes = [512, 100, 256, 1024, 37, 512, 2048]
+    x = noise(4, sum(sizes))
+    xd = torch.from_numpy(x).cuda()
+    outs, kernels, pos = [], [], 0
+    with BatchFirEngine(h, n_streams=4, max_frames=2048) as eng:
+        for n in sizes:
+            outs.append(eng.process(xd[:, pos:pos + n].contiguous()).cpu().numpy())
+            kernels.append(eng.stage_info()[-1]["kernel"])
+            pos += n
+    assert kernels == [3, 2, 1, 3, 0, 3, 3]
+    y = np.concatenate(outs, axis=1)
+    for s in range(4):
+        assert_parity(y[s], rc.streaming_fir(h, x[s]).astype(np.float32), f"stream {s}")
+
+
+def test_range_flag():
+    """A sample beyond FP16's range: the host-buffer call reports AFP_ERR_RANGE, the device call sets the flag."""
+    h = taps_for(1001)
+    x = noise(16, 512)
+    x[3, 100] = 1.0e6
+    with BatchFirEngine(h, n_streams=16, max_frames=512) as eng:
+        with pytest.raises(AfpError) as ei:
+            eng.process_host(x)
+        assert ei.value.code == 5
+        eng.reset()
+        eng.process(torch.from_numpy(x).cuda())
+        assert eng.range_exceeded()
+        assert not eng.range_exceeded()        # cleared by the query
+        x[3, 100] = 0.5
+        eng.reset()
+        eng.process_host(x)                    # in range again: no error

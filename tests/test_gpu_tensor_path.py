@@ -1,6 +1,8 @@
-"""Tensor-core path (tcgen05 / TMEM Toeplitz FIR, 3xTF32) parity: same tolerance as the FFMA2 kernel
-(1e-5 relative / -100 dBFS absolute against the float64 oracle), bit-exact integer epilogue, and
-interchangeability with the FFMA2 kernel block by block (shared history format)."""
+"""Tensor-core paths (tcgen05 / TMEM Toeplitz FIR: the split-FP16 form with resident Hankel tap cores, kernel 3,
+and the 3xTF32 form, kernel 1) parity: same tolerance as the FFMA2 kernel (1e-5 relative / -100 dBFS absolute
+against the float64 oracle), bit-exact integer epilogue, and interchangeability with the FFMA2 kernels block by
+block (shared history format).  Every test runs twice: with the default selection (kernel 3 for blocks of a
+multiple of 512 frames, kernel 1 for 256-frame blocks) and with AFP_NO_TC2=1 (kernel 1 only)."""
 import os
 
 import numpy as np
@@ -15,6 +17,19 @@ from audio_filtering_pipeline_b200 import design  # noqa: E402
 from audio_filtering_pipeline_b200.engine import BatchFirEngine  # noqa: E402
 from oracle import reference_chain as rc  # noqa: E402
 from oracle import dither_quant as dq  # noqa: E402
+
+
+@pytest.fixture(autouse=True, params=["tc2", "tc1"])
+def tensor_variant(request):
+    if request.param == "tc1":
+        os.environ["AFP_NO_TC2"] = "1"
+    yield request.param
+    os.environ.pop("AFP_NO_TC2", None)
+
+
+def TK(frames):
+    """kernel id a tensor-eligible stage reports for a block of `frames`"""
+    return 3 if frames % 512 == 0 and not os.environ.get("AFP_NO_TC2") else 1
 
 
 def remez1001():
@@ -45,7 +60,7 @@ def test_tensor_path_matches_lfilter(N, B, S):
     x = noise(S, B * 5, amp=0.3)
     with BatchFirEngine(h, n_streams=S, max_frames=B) as eng:
         y, kernels = run(eng, x, [B] * 5)
-    assert kernels == [1] * 5, "the tcgen05 kernel should have run"
+    assert kernels == [TK(B)] * 5, "the tcgen05 kernel should have run"
     for s in range(S):
         assert_parity(y[s], rc.streaming_fir(h, x[s]).astype(np.float32), f"N={N} B={B} s={s}")
 
@@ -61,7 +76,7 @@ def test_1024_frame_blocks_several_row_groups():
             y, kernels = run(eng, x, [1024] * 3)
     finally:
         del os.environ["AFP_TC_MIN_TAPS"]
-    assert kernels == [1, 1, 1]
+    assert kernels == [TK(1024)] * 3
     for s in range(7):
         assert_parity(y[s], rc.streaming_fir(h, x[s]).astype(np.float32), f"s={s}")
 
@@ -74,7 +89,7 @@ def test_full_scale_signal_stays_in_tolerance():
     x = np.stack([0.999 * np.sin(2 * np.pi * f * t) for f in (997.0, 5000.0, 15000.0)]).astype(np.float32)
     with BatchFirEngine(h, n_streams=3, max_frames=512) as eng:
         y, kernels = run(eng, x, [512] * 6)
-    assert kernels == [1] * 6
+    assert kernels == [TK(512)] * 6
     for s in range(3):
         assert_parity(y[s], rc.streaming_fir(h, x[s]).astype(np.float32), f"sine {s}")
 
@@ -88,7 +103,7 @@ def test_kernels_interchange_block_by_block():
     x = noise(4, sum(sizes))
     with BatchFirEngine(h, n_streams=4, max_frames=1024) as eng:
         y, kernels = run(eng, x, sizes)
-    assert kernels == [1, 2, 1, 1, 0, 1, 1]          # 1024 frames x 1001 taps: a chain of two 512-frame tensor launches
+    assert kernels == [TK(512), 2, 1, TK(512), 0, TK(1024), TK(512)]   # 1024 frames x 1001 taps on kernel 1: a chain of two 512-frame launches
     for s in range(4):
         assert_parity(y[s], rc.streaming_fir(h, x[s]).astype(np.float32), f"stream {s}")
 
@@ -104,7 +119,7 @@ def test_tensor_and_ffma_paths_agree():
             y_ff, k_ff = run(eng, x, [512] * 3)
     finally:
         del os.environ["AFP_NO_TC"]
-    assert k_tc == [1, 1, 1] and k_ff == [2, 2, 2]      # without the tensor path: the single-row FFMA2 kernel
+    assert k_tc == [TK(512)] * 3 and k_ff == [2, 2, 2]      # without the tensor path: the single-row FFMA2 kernel
     assert np.abs(y_tc - y_ff).max() < 2e-6
 
 
@@ -118,7 +133,7 @@ def test_tensor_path_epilogue_bit_exact(fmt, mode):
     with BatchFirEngine(h, n_streams=S, max_frames=512, out_format=fmt, dither=mode, seed=seed,
                         first_stream_id=sid0) as eq:
         yq, kq = run(eq, x, [512] * 3)
-    assert kf == [1] * 3 and kq == [1] * 3
+    assert kf == [TK(512)] * 3 and kq == [TK(512)] * 3
     fmt_code = {"f32": dq.FMT_F32, "i16": dq.FMT_I16, "i24": dq.FMT_I24_IN_I32, "i24_packed": dq.FMT_I24_PACKED}[fmt]
     mode_code = {"none": dq.DITHER_NONE, "tpdf": dq.DITHER_TPDF, "rpdf": dq.DITHER_RPDF}[mode]
     ref = dq.epilogue(yf, fmt_code, mode_code, seed, np.arange(S) + sid0, 0)
@@ -159,7 +174,7 @@ def test_long_fused_eq_runs_on_tensor_cores():
     x = noise(S, B * 4, amp=0.05)
     with BatchFirEngine(main, n_streams=S, max_frames=B, eq_bands=bank, eq_gains=gains, eq_mode="fused") as eng:
         y, _ = run(eng, x, [B] * 4)
-        assert [st["kernel"] for st in eng.stage_info()] == [1, 1]
+        assert [st["kernel"] for st in eng.stage_info()] == [TK(512), TK(512)]
     comb = design.combine_eq_taps(bank, gains)
     for s in range(S):
         ref = lfilter(main, 1.0, lfilter(comb, 1.0, x[s].astype(np.float64)).astype(np.float32).astype(np.float64))
@@ -180,7 +195,7 @@ def test_long_blocks_chain_through_the_tensor_kernel(fmt, dither):
         y_big, k_big = run(eng, x, [4096, 2048, 512, 4096])
     with BatchFirEngine(h, n_streams=S, max_frames=512, **kw) as eng:
         y_small, k_small = run(eng, x, [512] * (n // 512))
-    assert k_big == [1, 1, 1, 1] and set(k_small) == {1}
+    assert k_big == [TK(512)] * 4 and set(k_small) == {TK(512)}
     np.testing.assert_array_equal(y_big, y_small)
     if fmt == "f32":
         for s in range(0, S, 5):
