@@ -24,7 +24,7 @@ SYMBOLS = [
     "afp_out_elem_bytes", "afp_reset", "afp_state_size", "afp_get_state", "afp_set_state",
     "afp_get_stage_info", "afp_kernel_launches", "afp_host_alloc", "afp_host_free",
     "afp_measure_fma_peak", "afp_set_agc", "afp_agc_block", "afp_process_host_interleaved", "afp_swap_taps", "afp_spectrum_db",
-    "afp_process_blocks", "afp_range_status",
+    "afp_process_blocks", "afp_range_status", "afp_measure_tensor_peak",
 ]
 
 
@@ -108,6 +108,7 @@ def load():
     lib.afp_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     lib.afp_host_free.argtypes = [vp]
     lib.afp_measure_fma_peak.argtypes = [i32, dp, dp]
+    lib.afp_measure_tensor_peak.argtypes = [i32, i32, dp, dp, dp]
     lib.afp_spectrum_db.argtypes = [vp, vp, i64, vp, i64, i32, i32, vp]
     lib.afp_set_agc.argtypes = [vp, C.POINTER(AgcParams)]
     lib.afp_agc_block.argtypes = [vp, C.POINTER(AgcParams), vp, i64, vp, i64, i32, i32, vp]

@@ -300,26 +300,14 @@ int build_stage(afp_ctx* c, Stage& s, int kind, int U, const double* taps, int n
             AFP_CUDA(c, cudaMemcpy(s.tc_w[v], w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
             s.tc_chunks[v] = nc;
         }
-        // split-FP16 kernel (afp_fir_tc2.cuh): Hankel cores C_q[jj][e] = hp[8 q + jj + e], hp[t] = h[t - 63];
-        // h = hi + lo * 2^-11, hi = fp16(h), lo = fp16((h - hi) * 2^11): first all hi cores, then all lo cores
+        // split-FP16 kernel (afp_fir_tc2.cuh): Hankel tap cores, all high parts then all low parts
         if (s.tc2_w) { cudaFree(s.tc2_w); s.tc2_w = nullptr; }
-        const int D = (n + afp::TC2_R - 2) / afp::TC2_R;
-        if (D + 1 <= 17 && !env_flag("AFP_NO_TC2")) {
-            const int Q = afp::tc2_n_cores(D + 1);
-            std::vector<__half> w((size_t)2 * Q * 64);
-            for (int q = 0; q < Q; ++q)
-                for (int jj = 0; jj < 8; ++jj)
-                    for (int e = 0; e < 8; ++e) {
-                        const int k = 8 * q + jj + e - (afp::TC2_R - 1);
-                        const float hv = (k >= 0 && k < n) ? (float)taps[k] : 0.f;
-                        const __half hi = __float2half_rn(hv);
-                        const __half lo = __float2half_rn((hv - __half2float(hi)) * 2048.0f);
-                        w[(size_t)q * 64 + jj * 8 + e] = hi;
-                        w[(size_t)(Q + q) * 64 + jj * 8 + e] = lo;
-                    }
+        if ((n + afp::TC2_R - 2) / afp::TC2_R + 1 <= 17 && !env_flag("AFP_NO_TC2")) {
+            std::vector<__half> w;
+            s.tc2_chunks = afp::tc2_build_cores(taps, n, w);
+            s.tc2_cores = afp::tc2_n_cores(s.tc2_chunks);
             AFP_CUDA(c, cudaMalloc(&s.tc2_w, w.size() * sizeof(__half)));
             AFP_CUDA(c, cudaMemcpy(s.tc2_w, w.data(), w.size() * sizeof(__half), cudaMemcpyHostToDevice));
-            s.tc2_cores = Q; s.tc2_chunks = D + 1;
         }
     }
     // the memsets / copies above ran on the legacy stream; the kernels run on non-blocking streams that do
@@ -520,15 +508,14 @@ int launch_stage_tc2(afp_ctx* c, Stage& s, const float* in, long long in_pitch, 
     if ((long long)frames * n_blocks > (1 << 30)) return AFP_OK;
     const int eb = fmt == AFP_FMT_I16 ? 2 : (fmt == AFP_FMT_I24_PACKED ? 3 : 4);
     if (!aligned16(in) || in_pitch % 4 != 0 || in_bstride % 4 != 0 || s.hist_pitch % 4 != 0 || s.kq_pad % 8 != 0) return AFP_OK;
-    const int D = s.tc2_chunks - 1, H = D <= 8 ? 8 : 16;
-    if ((H + 8) * afp::TC2_R < s.kq_pad) return AFP_OK;
+    if (s.tc2_chunks > 17 || s.kq_pad > 24 * afp::TC2_R) return AFP_OK;
     afp::Tc2Params P{};
     P.hist_in = s.hist[s.cur] + (long long)s0 * s.hist_pitch; P.hist_out = s.hist[s.cur ^ 1] + (long long)s0 * s.hist_pitch;
     P.hist_pitch = s.hist_pitch; P.hist_len = s.kq_pad;
     P.in = in; P.in_pitch = in_pitch; P.in_block_stride = in_bstride;
     P.out = out; P.out_pitch = out_pitch; P.out_block_stride = out_bstride;
     P.w = static_cast<const __half*>(s.tc2_w); P.n_cores = s.tc2_cores;
-    P.n_streams = ns; P.frames = frames; P.n_blocks = n_blocks; P.n_chunks = s.tc2_chunks; P.hist_rows = H;
+    P.n_streams = ns; P.frames = frames; P.n_blocks = n_blocks; P.n_chunks = s.tc2_chunks;
     P.n_groups = (ns + afp::TC2_STREAMS - 1) / afp::TC2_STREAMS;
     P.range_flag = c->range_flag;
     P.fmt = fmt; P.dither = dither; P.decim = 1;

@@ -54,7 +54,7 @@ struct Tc2Params {
     const float* hist_in;      // [n_streams][hist_pitch] carried samples, oldest first (the last hist_len of the past input)
     float* hist_out;           // same layout: the last hist_len samples after this call
     long long hist_pitch;
-    int hist_len;              // multiple of 8, <= hist_rows * 64
+    int hist_len;              // multiple of 4, <= 1536
     const float* in;           // block b, stream s, frame f: in[b * in_block_stride + s * in_pitch + f]
     long long in_pitch, in_block_stride;
     void* out;                 // same indexing in elements of the output format (bytes / 3 for packed int24)
@@ -63,9 +63,9 @@ struct Tc2Params {
     int n_cores;
     int n_streams, frames, n_blocks;
     int n_chunks;              // D + 1
-    int hist_rows;             // H: 8 or 16
     int n_groups;              // ceil(n_streams / 16)
     unsigned int* range_flag;  // set to 1 when a sample does not fit FP16
+    long long* prof;           // nullptr, or [grid][8] cycle counters of the MMA warp (bench/microbench/tc2_probe.cu)
     // epilogue (same meaning as FirParams)
     int fmt, dither, decim, fast_out;
     unsigned long long seed, sample_base;
@@ -94,22 +94,92 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // instruction descriptor: D f32, A / B f16 K-major, M = 128
 __host__ __device__ constexpr uint32_t tc2_idesc(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
 
-// 8 consecutive samples -> the two 16-byte granules (hi, lo) of their row, element e = sample 7 - e
-__device__ __forceinline__ void tc2_split(const float4& a, const float4& b, uint4& hi, uint4& lo, float& amax) {
-    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    uint32_t h[4], l[4];
+// Host side: the Hankel core array of a filter.  C_q[jj][e] = hp[8 q + jj + e], hp[t] = h[t - (R-1)]; every tap
+// h = hi + lo * 2^-11 with hi = fp16(h), lo = fp16((h - hi) * 2^11).  Layout: all hi cores, then all lo cores,
+// 64 halves each.  Returns the chunk count D + 1.
+template <class VEC>
+inline int tc2_build_cores(const double* taps, int n, VEC& w) {
+    const int D = (n + TC2_R - 2) / TC2_R, Q = 8 * (D + 2) - 1;
+    w.assign((size_t)2 * Q * 64, __float2half_rn(0.f));
+    for (int q = 0; q < Q; ++q)
+        for (int jj = 0; jj < 8; ++jj)
+            for (int e = 0; e < 8; ++e) {
+                const int k = 8 * q + jj + e - (TC2_R - 1);
+                const float hv = (k >= 0 && k < n) ? (float)taps[k] : 0.f;
+                const __half hi = __float2half_rn(hv);
+                w[(size_t)q * 64 + jj * 8 + e] = hi;
+                w[(size_t)(Q + q) * 64 + jj * 8 + e] = __float2half_rn((hv - __half2float(hi)) * 2048.0f);
+            }
+    return D + 1;
+}
+
+// 4 consecutive samples (one float4, the low or high half of an 8-sample granule) -> 8 bytes of the hi tile and 8 of
+// the lo tile.  A granule holds its samples in reversed order (element e = sample 7 - e), so within the half the
+// words are (x3, x2), (x1, x0), the first of each pair in the low 16 bits.
+__device__ __forceinline__ void tc2_split4(const float4& v, uint2& hi, uint2& lo, float& amax) {
+    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    const __half2 h32 = __floats2half2_rn(v.w, v.z), h10 = __floats2half2_rn(v.y, v.x);
+    const float2 f32 = __half22float2(h32), f10 = __half22float2(h10);
+    const __half2 l32 = __floats2half2_rn(__fmul_rn(__fsub_rn(v.w, f32.x), 2048.0f), __fmul_rn(__fsub_rn(v.z, f32.y), 2048.0f));
+    const __half2 l10 = __floats2half2_rn(__fmul_rn(__fsub_rn(v.y, f10.x), 2048.0f), __fmul_rn(__fsub_rn(v.x, f10.y), 2048.0f));
+    hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h32), *reinterpret_cast<const uint32_t*>(&h10));
+    lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l32), *reinterpret_cast<const uint32_t*>(&l10));
+}
+
+// Where the window of a step lives and how it gets there - the same function in the three warp roles.
+// A window is 24 rows [16 history | 8 new] of the 40-row tile at row 0, 8 or 16.  Inside a stream group it slides:
+// position (first + 8 k) mod 24, so a step normally finds its history rows in place and loads only its 8 new
+// rows (SLIDE); coming back to row 0 it reloads all 24 rows (the history from the previous blocks' input, an L2
+// hit), and so does the first step of a group (FRESH).  A fresh window may share 8 rows at most with the window the
+// tensor pipe is still reading - rows 16..23, which wait in registers until that step is done - so a group starts
+// at row 0 after a group that ended at row 16 and at row 16 after one that ended at row 0; the start row is chosen
+// from (n_steps - 1) mod 3 so that no group ever ends at row 8.
+enum : int { TC2_SLIDE = 0, TC2_FRESH0 = 1, TC2_FRESH16 = 2 };
+struct Tc2Step { int pos, kind; };
+__device__ __forceinline__ Tc2Step tc2_step(int n_steps, int group_ordinal, int k) {
+    const int r = (n_steps - 1) % 3;
+    const int first = r == 0 ? ((group_ordinal & 1) ? 16 : 0) : (r == 1 ? 16 : 0);
+    const int pos = (first + 8 * k) % 24;
+    Tc2Step st;
+    st.pos = pos;
+    st.kind = k == 0 ? (first == 0 ? TC2_FRESH0 : TC2_FRESH16) : (pos == 0 ? TC2_FRESH0 : TC2_SLIDE);
+    return st;
+}
+
+// The carried samples of the next call: the last hist_len samples of [history | all blocks] of the 16 streams from s0
+// on, copied global -> global (L2 hits) by `nthreads` threads.  Loads go in batches of 8 ahead of their stores (the
+// compiler cannot reorder them itself: the buffers may alias).
+__device__ __forceinline__ void tc2_copy_history(const Tc2Params& P, int s0, int n_steps, int ltid, int nthreads) {
+    const int total = n_steps * TC2_STEP, q4 = P.hist_len >> 2, n_copy = TC2_STREAMS * q4;
+    for (int base = ltid; base < n_copy; base += 8 * nthreads) {
+        float4 v[8];
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        const float x1 = x[7 - 2 * p], x0 = x[6 - 2 * p];          // elements 2p, 2p+1
-        amax = fmaxf(amax, fmaxf(fabsf(x1), fabsf(x0)));
-        const __half2 hh = __floats2half2_rn(x1, x0);
-        const float2 hf = __half22float2(hh);
-        const __half2 ll = __floats2half2_rn(__fmul_rn(__fsub_rn(x1, hf.x), 2048.0f), __fmul_rn(__fsub_rn(x0, hf.y), 2048.0f));
-        h[p] = *reinterpret_cast<const uint32_t*>(&hh);
-        l[p] = *reinterpret_cast<const uint32_t*>(&ll);
+        for (int u = 0; u < 8; ++u) {
+            const int j = base + u * nthreads;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < n_copy) {
+                const int sl = j / q4, i4 = j - sl * q4, s = s0 + sl;
+                const int t = total - P.hist_len + 4 * i4;
+                if (s < P.n_streams) {
+                    const float* src;
+                    if (t < 0) src = P.hist_in + (long long)s * P.hist_pitch + (P.hist_len + t);
+                    else {
+                        const int b_ = t / P.frames, f = t - b_ * P.frames;
+                        src = P.in + (long long)b_ * P.in_block_stride + (long long)s * P.in_pitch + f;
+                    }
+                    v[u] = __ldg(reinterpret_cast<const float4*>(src));
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = base + u * nthreads;
+            if (j < n_copy) {
+                const int sl = j / q4, i4 = j - sl * q4, s = s0 + sl;
+                if (s < P.n_streams) reinterpret_cast<float4*>(P.hist_out + (long long)s * P.hist_pitch)[i4] = v[u];
+            }
+        }
     }
-    hi = make_uint4(h[0], h[1], h[2], h[3]);
-    lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 template <int EPI>
@@ -122,15 +192,13 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
     unsigned char* w_hi = tile_lo + TC2_TILE_BYTES;
     unsigned char* w_lo = w_hi + P.n_cores * 128;
     uint64_t* bars = reinterpret_cast<uint64_t*>(w_lo + P.n_cores * 128);
-    uint64_t* win_direct = bars;        // [2] window position p: rows outside the shared rows are in place
-    uint64_t* win_staged = bars + 2;    // [2] ... and the shared rows too
-    uint64_t* mma_done = bars + 4;      // [2] accumulator set p final, window p read for the last time
+    uint64_t* win_early = bars;         // [2] step parity p: the rows the first chunks read are in place
+    uint64_t* win_late = bars + 2;      // [2] ... and the rows only the later chunks read
+    uint64_t* mma_done = bars + 4;      // [2] accumulator set p final, window of the step read for the last time
     uint64_t* acc_empty = bars + 6;     // [2] accumulator set p drained
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
 
-    const int H = P.hist_rows;
-    const bool shared_rows = H == 16;   // the two window positions overlap in rows 16..23
-    const int win_rows = H + 8;
+    constexpr int H = 16;               // history rows of a window (covers 1025 taps; shorter filters skip the oldest)
     const int steps_per_block = P.frames / TC2_STEP;
     const int n_steps = steps_per_block * P.n_blocks;
 
@@ -140,7 +208,7 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
     }
     if (tid == 32) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&win_direct[i], TC2_LOADERS); mbar_init(&win_staged[i], TC2_LOADERS);
+            mbar_init(&win_early[i], TC2_LOADERS); mbar_init(&win_late[i], TC2_LOADERS);
             mbar_init(&mma_done[i], 1); mbar_init(&acc_empty[i], TC2_EPIS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -165,29 +233,40 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
         const uint32_t idesc = tc2_idesc(TC2_R);
         const int D = P.n_chunks - 1;
         uint32_t kk = 0;                                       // steps issued by this CTA
-        for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x) {
+        long long t_acc = 0, t_dir = 0, t_stg = 0, t_iss = 0;  // cycles waiting for: accumulators, early rows, late rows; issuing
+        const long long t_begin = clock64();
+        int ordinal = 0;
+        for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x, ++ordinal) {
             for (int k = 0; k < n_steps; ++k, ++kk) {
                 const uint32_t p = kk & 1u, ph = (kk >> 1) & 1u;
-                const int pos = p ? TC2_POS_B : 0;
+                const Tc2Step st = tc2_step(n_steps, ordinal, k);
+                const long long c0 = clock64();
                 mbar_wait(&acc_empty[p], ph ^ 1u);             // (passes at once the first time round)
-                mbar_wait(&win_direct[p], ph);
+                const long long c1 = clock64();
+                mbar_wait(&win_early[p], ph);
+                const long long c2 = clock64();
+                t_acc += c1 - c0; t_dir += c2 - c1;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t acc0 = tmem_base + p * 128u, acc1 = acc0 + 64u;
-                bool staged_seen = !shared_rows;
+                bool late_seen = false;
                 bool first = true;
-                // chunk order, the same at both positions so that a step's rounding does not depend on where it ran:
-                // H = 16: 8 (touches no shared row at either position), D..9, 7..0;  H = 8: D..0
+                // Chunk order, the same for every step so that rounding does not depend on where a step ran:
+                // 8, D..9, 7..0 (what exists of it).  Chunk d reads window rows 16-d .. 23-d: the chunks >= 8 only history
+                // rows - a sliding step starts them while its new rows are still on their way.
                 for (int idx = 0; idx <= D; ++idx) {
                     int d;
-                    if (shared_rows) d = idx == 0 ? 8 : (idx <= D - 8 ? D + 1 - idx : D - idx);
+                    if (D >= 8) d = idx == 0 ? 8 : (idx <= D - 8 ? D + 1 - idx : D - idx);
                     else d = D - idx;
-                    if (!staged_seen && (p ? d >= 9 : d <= 7)) {   // rows 16..23: the oldest rows of position B, the newest of A
-                        mbar_wait(&win_staged[p], ph);
+                    const bool late = st.kind == TC2_FRESH16 ? d >= 9 : d <= 7;
+                    if (late && !late_seen) {
+                        const long long w0 = clock64();
+                        mbar_wait(&win_late[p], ph);
+                        t_stg += clock64() - w0;
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        staged_seen = true;
+                        late_seen = true;
                     }
                     if (elect_one()) {
-                        const uint32_t arow = (uint32_t)(pos + H - d);
+                        const uint32_t arow = (uint32_t)(st.pos + H - d);
                         const uint32_t ah = (uint32_t)a_hi_d + arow, al = (uint32_t)a_lo_d + arow;
                         const uint32_t wh = (uint32_t)w_hi_d + (uint32_t)(8 * d) * 8u, wl = (uint32_t)w_lo_d + (uint32_t)(8 * d) * 8u;
 #pragma unroll
@@ -202,108 +281,97 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                     __syncwarp();
                     first = false;
                 }
-                if (!staged_seen) mbar_wait(&win_staged[p], ph);   // (keeps the barrier phases in step; not reached for D >= 9)
+                if (!late_seen) mbar_wait(&win_late[p], ph);   // (D < 9 at a window that starts at row 16: nothing was late)
                 if (elect_one()) umma_commit(&mma_done[p]);
                 __syncwarp();
+                t_iss += clock64() - c2;
             }
         }
+        if (P.prof && lane == 0) {
+            long long* o = P.prof + (size_t)blockIdx.x * 8;
+            o[0] = clock64() - t_begin; o[1] = t_acc; o[2] = t_dir; o[3] = t_stg; o[4] = t_iss; o[5] = kk;
+        }
     } else if (warp_u <= TC2_LOADERS) {
-        // ================= loaders: global -> hi / lo granules of the next window =================
-        const int ltid = tid - 32, LT = 32 * TC2_LOADERS;
-        const int hist_span = H * TC2_R;                       // samples of a window before its new rows
+        // ================= loaders: global -> hi / lo halves of the window rows =================
+        const int ltid = tid - 32;
+        constexpr int LT = 32 * TC2_LOADERS;
         uint32_t kk = 0;
         float amax = 0.f;
-        for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x) {
+        int ordinal = 0;
+        for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x, ++ordinal) {
             const int s0 = grp * TC2_STREAMS;
-            for (int k = 0; k < n_steps; ++k, ++kk) {
-                const uint32_t p = kk & 1u;
-                const int pos = p ? TC2_POS_B : 0;
-                const bool last = k == n_steps - 1;
-                // the previous user of this position (step kk-2) must have been read for the last time
-                if (kk >= 2) mbar_wait(&mma_done[p], ((kk - 2) >> 1) & 1u);
-                // task = 8 consecutive samples of one stream; a warp takes 32 consecutive tasks (1 KB of one stream)
-                auto fetch = [&](int task, float4& a, float4& b) {
-                    const int sl = task / (win_rows * 8), gi = task - sl * (win_rows * 8);
-                    const int s = s0 + sl;
-                    const int t = k * TC2_STEP - hist_span + gi * 8;   // logical sample index: < 0 = carried history
-                    a = b = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (s < P.n_streams && t >= -P.hist_len) {
-                        const float* src;
-                        if (t < 0) src = P.hist_in + (long long)s * P.hist_pitch + (P.hist_len + t);
-                        else {
-                            const int b_ = t / P.frames, f = t - b_ * P.frames;
-                            src = P.in + (long long)b_ * P.in_block_stride + (long long)s * P.in_pitch + f;
-                        }
-                        a = __ldg(reinterpret_cast<const float4*>(src));
-                        b = __ldg(reinterpret_cast<const float4*>(src) + 1);
-                    }
-                };
-                auto place = [&](int task, const float4& a, const float4& b) {
-                    const int sl = task / (win_rows * 8), gi = task - sl * (win_rows * 8);
-                    const int row = gi >> 3, g = gi & 7;
-                    uint4 hi, lo;
-                    tc2_split(a, b, hi, lo, amax);
-                    const int off = sl * TC2_PITCH + (7 - g) * TC2_A_LBO + (pos + row) * 16;
-                    *reinterpret_cast<uint4*>(tile_hi + off) = hi;
-                    *reinterpret_cast<uint4*>(tile_lo + off) = lo;
-                    if (last) {   // the carried samples of the next call: the last hist_len samples of the window
-                        const int s = s0 + sl, wpos = gi * 8 - (win_rows * TC2_R - P.hist_len);
-                        if (s < P.n_streams && wpos >= 0) {
-                            float4* dst = reinterpret_cast<float4*>(P.hist_out + (long long)s * P.hist_pitch + wpos);
-                            dst[0] = a; dst[1] = b;
-                        }
-                    }
-                };
-                // rows shared by the two positions (buffer rows 16..23): window rows 16..23 at A, 0..7 at B
-                const int sh_lo = shared_rows ? (p ? 0 : 16) : -1;
-                const int n_tasks = TC2_STREAMS * win_rows * 8;
-                // the shared rows first into registers (their loads overlap everything below)
-                float4 sa[4], sb[4];
-                if (shared_rows) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int j = ltid + u * LT;                          // 0 .. 1023: (stream, row 0..7, granule)
-                        const int sl = j >> 6, r8 = j & 63;
-                        fetch(sl * (win_rows * 8) + sh_lo * 8 + r8, sa[u], sb[u]);
-                    }
+            // one float4 (4 samples) of window row `wrow` (0..23) of local stream sl at step k
+            auto fetch = [&](int k, int sl, int wrow, int f4) -> float4 {
+                const int s = s0 + sl;
+                const int t = k * TC2_STEP - H * TC2_R + wrow * TC2_R + f4 * 4;   // logical sample index: < 0 = carried history
+                if (s >= P.n_streams || t < -P.hist_len) return make_float4(0.f, 0.f, 0.f, 0.f);
+                const float* src;
+                if (t < 0) src = P.hist_in + (long long)s * P.hist_pitch + (P.hist_len + t);
+                else {
+                    const int b_ = t / P.frames, f = t - b_ * P.frames;
+                    src = P.in + (long long)b_ * P.in_block_stride + (long long)s * P.in_pitch + f;
                 }
-                // the other rows: straight to shared memory, 4 tasks in flight per thread
-                const int n_direct = shared_rows ? TC2_STREAMS * 16 * 8 : n_tasks;
-                for (int base = ltid; base < n_direct; base += 4 * LT) {
-                    float4 va[4], vb[4];
-                    int task[4];
+                return __ldg(reinterpret_cast<const float4*>(src));
+            };
+            auto place = [&](int pos, int sl, int wrow, int f4, const float4& v) {
+                uint2 hi, lo;
+                tc2_split4(v, hi, lo, amax);
+                const int off = sl * TC2_PITCH + (7 - (f4 >> 1)) * TC2_A_LBO + (pos + wrow) * 16 + ((f4 & 1) ? 0 : 8);
+                *reinterpret_cast<uint2*>(tile_hi + off) = hi;
+                *reinterpret_cast<uint2*>(tile_lo + off) = lo;
+            };
+            // 8 window rows starting at r0 for all 16 streams: 2048 float4, 8 per thread; consecutive lanes take
+            // consecutive float4 of a stream's rows (rows are contiguous in memory)
+            auto rows8_fetch = [&](int k, int r0, float4 (&v)[8]) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int j = base + u * LT;
-                        task[u] = -1;
-                        if (j < n_direct) {
-                            if (shared_rows) {
-                                const int sl = j >> 7, r = j & 127;                  // 16 direct rows x 8 granules
-                                const int gi = p ? 64 + r : r;                        // A: window rows 0..15, B: 8..23
-                                task[u] = sl * (win_rows * 8) + gi;
-                            } else task[u] = j;
-                            fetch(task[u], va[u], vb[u]);
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) if (task[u] >= 0) place(task[u], va[u], vb[u]);
+                for (int u = 0; u < 8; ++u) {
+                    const int j = ltid + u * LT;
+                    v[u] = fetch(k, j >> 7, r0 + ((j >> 4) & 7), j & 15);
                 }
+            };
+            auto rows8_place = [&](int pos, int r0, const float4 (&v)[8]) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int j = ltid + u * LT;
+                    place(pos, j >> 7, r0 + ((j >> 4) & 7), j & 15, v[u]);
+                }
+            };
+            auto publish = [&](uint64_t* bar) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&win_direct[p]);
-                if (shared_rows) {
-                    // rows 16..23 are still being read by step kk-1 (the other position)
-                    if (kk >= 1) mbar_wait(&mma_done[p ^ 1u], ((kk - 1) >> 1) & 1u);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int j = ltid + u * LT;
-                        const int sl = j >> 6, r8 = j & 63;
-                        place(sl * (win_rows * 8) + sh_lo * 8 + r8, sa[u], sb[u]);
+                if (lane == 0) mbar_arrive(bar);
+            };
+            for (int k = 0; k < n_steps; ++k, ++kk) {
+                const uint32_t p = kk & 1u;
+                const Tc2Step st = tc2_step(n_steps, ordinal, k);
+                if (st.kind == TC2_SLIDE) {
+                    if (lane == 0) mbar_arrive(&win_early[p]);          // the history rows are where the last step left them
+                    float4 v[8];
+                    rows8_fetch(k, 16, v);
+                    // the new rows' place was last read by step kk-2 at the latest
+                    if (kk >= 2) mbar_wait(&mma_done[p], ((kk - 2) >> 1) & 1u);
+                    rows8_place(st.pos, 16, v);
+                    publish(&win_late[p]);
+                } else {
+                    // fresh window: rows 16..23 of the tile are shared with the window of step kk-1 (its oldest rows if
+                    // this window starts at row 0, its newest if at row 16): they wait in registers
+                    const int sh0 = st.kind == TC2_FRESH0 ? 16 : 0;      // window rows that live in tile rows 16..23
+                    const int d0 = st.kind == TC2_FRESH0 ? 0 : 8;        // first of the 16 other window rows
+                    {
+                        float4 v0[8], v1[8];                             // one round trip for the 16 rows
+                        rows8_fetch(k, d0, v0);
+                        rows8_fetch(k, d0 + 8, v1);
+                        if (kk >= 2) mbar_wait(&mma_done[p], ((kk - 2) >> 1) & 1u);
+                        rows8_place(st.pos, d0, v0);
+                        rows8_place(st.pos, d0 + 8, v1);
                     }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
+                    publish(&win_early[p]);
+                    float4 sv[8];
+                    rows8_fetch(k, sh0, sv);
+                    if (kk >= 1) mbar_wait(&mma_done[p ^ 1u], ((kk - 1) >> 1) & 1u);
+                    rows8_place(st.pos, sh0, sv);
+                    publish(&win_late[p]);
                 }
-                if (lane == 0) mbar_arrive(&win_staged[p]);
             }
         }
         if (amax > 65000.0f) atomicOr(P.range_flag, 1u);
@@ -357,6 +425,8 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                 const long long o_base = (long long)kb * TC2_STEP + (long long)(m & 7) * TC2_R + 32 * half;
                 store_row<32, EPI>(V, y, s, o_base, s < P.n_streams ? 32 : 0);
             }
+            // (the epilogue warps have the slack for this; in the loaders it would delay the next group's first window)
+            tc2_copy_history(P, grp * TC2_STREAMS, n_steps, tid - 32 * (1 + TC2_LOADERS), 32 * TC2_EPIS);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

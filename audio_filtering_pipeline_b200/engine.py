@@ -334,3 +334,12 @@ def measure_fma_peak(device=0):
     t, m = C.c_double(), C.c_double()
     _lib.check(lib.afp_measure_fma_peak(int(device), C.byref(t), C.byref(m)))
     return t.value, m.value
+
+
+def measure_tensor_peak(device=0, n_cols=256):
+    """Tensor-pipe roof (TFLOP/s, SM MHz, clocks per MMA) from a bare tcgen05.mma kind::f16 loop with M = 128, K = 16,
+    N = ``n_cols``; 64 is the split-FP16 FIR kernel's instruction shape (operand-fetch bound), 256 the pipe's rate."""
+    lib = _lib.load()
+    t, m, c = C.c_double(), C.c_double(), C.c_double()
+    _lib.check(lib.afp_measure_tensor_peak(int(device), int(n_cols), C.byref(t), C.byref(m), C.byref(c)))
+    return t.value, m.value, c.value

@@ -213,6 +213,12 @@ int afp_host_free(void* ptr);
  * FP32 entry in MEASURED_PEAKS.json).  Returns TFLOP/s and the SM clock seen during the loop. */
 int afp_measure_fma_peak(int32_t device, double* tflops, double* sm_mhz);
 
+/* Tensor-pipe roof of the device for the split-FP16 FIR kernel's roofline: a bare tcgen05.mma loop (kind::f16,
+ * M = 128, K = 16, N = n_cols in 16..256, operands in shared memory in the kernel's own un-swizzled layout).
+ * n_cols = 256: the pipe's rate; n_cols = 64: the kernel's instruction shape, bound by operand fetch.  Returns
+ * TFLOP/s, the SM clock during the loop and clocks per MMA. */
+int afp_measure_tensor_peak(int32_t device, int32_t n_cols, double* tflops, double* sm_mhz, double* clk_per_mma);
+
 #ifdef __cplusplus
 }
 #endif

@@ -301,6 +301,45 @@ def gen_stream_process_eq(soxr):
              outdata=outs, params=np.array([N, B, U, fs]))
 
 
+def gen_stream_process_eq_c3(soxr):
+    """BASELINE.json configs[2] at full size through the same callback (stream_process_EQ.audio_callback): 10 bands
+    (the GUIs' 9, stream_process_EQ_GUI.py:162-172, + 16-20 kHz) x 501 taps, 501-tap main low-pass, 48 kHz, U = 1,
+    1024-frame blocks, stereo = the mono callback run once per channel."""
+    import stream_process_EQ as sp
+    from fir_filter import create_fir_filter
+    N, B, U, fs, nblk = 501, 1024, 1, 48000, 4
+    bands = [(20, 60), (60, 120), (120, 250), (250, 500), (500, 1000), (1000, 2000), (2000, 4000), (4000, 8000),
+             (8000, 16000), (16000, 20000)]
+    gains = [1.2, 1.0, 0.8, 1.0, 1.5, 1.0, 0.5, 1.0, 1.3, 0.9]                      # SURVEY.md 8(d)
+    taps = create_fir_filter(method="window", cutoff=16000, numtaps=N, window_type="hamming", filter_type="lowpass",
+                             samplerate=fs * U)
+    eq = [(create_fir_filter(method="window", cutoff=b, numtaps=N, window_type="hamming", filter_type="bandpass",
+                             samplerate=fs * U), g) for b, g in zip(bands, gains)]
+    xs, pres, outs_all = [], [], []
+    for ch in range(2):
+        sp.SAMPLERATE, sp.UPSAMPLE_FACTOR, sp.UPSAMPLE_RATE = fs, U, fs * U
+        sp.BLOCKSIZE, sp.NUM_TAPS = B, N
+        sp.fir_coeff, sp.eq_filters = taps, eq
+        sp.input_buffer = np.zeros(N + B * U - 1, dtype=np.float32)
+        sp.audio_buffer.clear()
+        sp.silence_block = np.zeros(B, dtype=np.float32)
+        soxr.table = {}
+        soxr.log = []
+        x = sweep_and_noise(nblk * B, fs, seed=20 + ch)
+        pre, outs = [], np.zeros((nblk, B), dtype=np.float32)
+        for i in range(nblk):
+            indata = x[i * B:(i + 1) * B].reshape(B, 1).copy()
+            outdata = np.zeros((B, 1), dtype=np.float32)
+            np.random.seed(500 + 10 * ch + i)
+            sp.audio_callback(indata, outdata, B, None, None)
+            pre.append(np.array(sp.audio_buffer[-1], dtype=np.float64))
+            outs[i] = outdata[:, 0]
+        xs.append(x); pres.append(np.stack(pre)); outs_all.append(outs)
+    save("cb_stream_process_eq_n501_10band", x=np.stack(xs), taps=taps, eq_taps=np.stack([c for c, _ in eq]),
+         eq_gains=np.array(gains), pre_dither=np.stack(pres), outdata=np.stack(outs_all),
+         params=np.array([N, B, U, fs]))
+
+
 def gen_overlap_add():
     import stream_process_GUI_Presets as pr
     from fir_filter import create_fir_filter
@@ -485,10 +524,14 @@ def gen_agc():
 
 def main():
     soxr = install_stubs()
+    if "--only-eq-c3" in sys.argv:      # added in round 2: leaves the other fixtures (and the manifest) untouched
+        print("stream_process_EQ, C3 size ..."); gen_stream_process_eq_c3(soxr)
+        return
     print("design ...");            gen_design()
     print("min phase ...");         gen_min_phase()
     print("stream_process ...");    gen_stream_process(soxr)
     print("stream_process_EQ ..."); gen_stream_process_eq(soxr)
+    print("stream_process_EQ, C3 size ..."); gen_stream_process_eq_c3(soxr)
     print("overlap-add ...");       gen_overlap_add()
     print("waterfall ...");         gen_waterfall(soxr)
     print("EQ_GUI worker ...");     gen_eq_gui_worker()

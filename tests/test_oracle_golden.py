@@ -50,6 +50,19 @@ def test_sliding_block_eq_matches_stream_process_eq(tag):
         np.testing.assert_allclose(y, g["pre_dither"][i], rtol=0, atol=1e-9)
 
 
+def test_sliding_block_eq_c3_size():
+    """BASELINE.json configs[2] at full size: 10 bands x 501 taps + 501-tap main, 1024-frame blocks, both channels
+    of the stereo pair (fixture: the reference's stream_process_EQ.audio_callback, run per channel)."""
+    g = load_golden("cb_stream_process_eq_n501_10band")
+    N, B, U, fs = (int(v) for v in g["params"])
+    assert (N, B, U, fs) == (501, 1024, 1, 48000) and g["eq_taps"].shape == (10, 501)
+    for ch in range(2):
+        orc = rc.SlidingBlockEq(g["taps"], list(zip(g["eq_taps"], g["eq_gains"])), B, U)
+        for i in range(g["pre_dither"].shape[1]):
+            y = orc.step(g["x"][ch, i * B:(i + 1) * B], B)
+            np.testing.assert_allclose(y, g["pre_dither"][ch, i], rtol=0, atol=1e-9)
+
+
 @pytest.mark.parametrize("tag", ["n129_l2048", "n1001_l512", "n51_l256"])
 def test_overlap_add_matches_presets_class(tag):
     g = load_golden(f"ola_{tag}")
