@@ -4,22 +4,27 @@
     python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm
     python bench.py --impl reference [--gpus N] [--steps K] ...     # the reference's CPU path
 
-Workload (BASELINE.json configs[1], "C2"): 1001-tap Remez low-pass at 176.4 kHz, stereo sessions
-batched as independent streams, 512-frame blocks, TPDF dither to int24.  One step = one pass of the
-hot path over one batch = BLOCKS_PER_STEP consecutive 512-frame blocks for every stream of the rank
-(16384 streams per GPU by default).  Streams are partitioned across GPUs by stream id (weak
-scaling, no collective on the data path); torch.distributed is used only for the barrier and the
-max-over-ranks time.
+Headline workload (BASELINE.json configs[1], "C2"): 1001-tap Remez low-pass at 176.4 kHz, stereo sessions batched as
+independent streams, 512-frame blocks, TPDF dither to int24.  One step = one pass of the hot path over one batch =
+BLOCKS_PER_STEP consecutive 512-frame blocks for every stream of the rank (16384 streams per GPU by default), handed
+over in ONE afp_process_blocks call.  Streams are partitioned across GPUs by stream id (weak scaling, no collective on
+the data path); torch.distributed is used only for the barrier and the max-over-ranks time.
 
-`value`   : device-resident input and output (HBM), CUDA events around exactly K steps.
-`e2e`     : same metric through the host API (engine.process_host_blocks): pinned host input,
-            H2D + kernels + D2H inside the timed region.
-`roofline`: the kernel is FP32-FMA bound (2*N flop per output sample); the peak is the
-            FMA issue rate measured in this run with a packed-FFMA2 loop (MEASURED_PEAKS.json has no
-            FP32 entry); HBM numbers are reported beside it.
-`cpu_baseline`: the reference's block loop (sliding float32 buffer -> scipy oaconvolve 'valid' ->
-            apply_dither, stream_process.py:96-113) as restated in oracle/, on all host cores, on a
-            bounded sample of the same workload.
+`value`           device-resident input and output (HBM), CUDA events around exactly K steps.
+`value_sustained` the same loop run back to back for --sustain-seconds, with the clocks seen under it.
+`e2e`             the same metric through the host API (engine.process_host_blocks): pinned host input, H2D + kernels +
+                  D2H inside the timed region; `ceiling_gbs` is a concurrent pinned H2D + D2H copy probe run by all ranks
+                  at once, `frac` the e2e's bytes per second per direction against it.
+`roofline`        C2 runs on the tensor pipe (split-FP16 tcgen05 kernel): achieved = algorithmic flop (2 N per output
+                  sample) per second against MEASURED_PEAKS.json's bf16 figure; `tensor` adds the MMA flop
+                  actually issued (3 products x Toeplitz padding) against tensor roofs measured in this run, and
+                  `fp32_fma_equiv` the north star's FP32-FMA framing as a plain speed-up, not a fraction.
+`cpu_baseline`    the reference's block loop (sliding float32 buffer -> scipy oaconvolve 'valid' -> apply_dither,
+                  stream_process.py:96-113) as restated in oracle/, on all host cores and on one pinned core
+                  (stream_process.py:17), on a bounded sample of the same workload.
+`configs`         C1 / C3 (per-band and fused) / C4 of BASELINE.json, each with value, e2e, roofline and cpu_baseline.
+`c5_sweep`        BASELINE.json configs[4]: {1k, 4k, 16k, 64k} streams x {51, 251, 1001} taps x {1, 2, 4}x up-sampling,
+                  streams sharded over the ranks of the run, with the CPU figure of each filter beside it.
 """
 from __future__ import annotations
 
@@ -45,6 +50,9 @@ METRIC = "output Msamples/s (batched streams)"
 N_TAPS, FS, FRAMES = 1001, 176400, 512
 DEFAULT_STREAMS = 16384          # per GPU: 8192 stereo sessions
 BLOCKS_PER_STEP = 16
+EQ_BANDS_10 = [(20, 60), (60, 120), (120, 250), (250, 500), (500, 1000), (1000, 2000), (2000, 4000), (4000, 8000),
+               (8000, 16000), (16000, 20000)]
+EQ_GAINS_10 = [1.2, 1.0, 0.8, 1.0, 1.5, 1.0, 0.5, 1.0, 1.3, 0.9]
 
 
 def c2_taps():
@@ -65,47 +73,89 @@ def workload_config(streams, n_gpus, blocks):
     }
 
 
-# --------------------------------------------------------------------------- CPU reference arm
-def _cpu_worker(args):
-    """Reference block loop for `n_streams` streams x `n_blocks` blocks on one core."""
-    taps, n_streams, n_blocks, seed = args
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
-    from oracle.reference_chain import SlidingBlockFir, apply_dither_scale
+# --------------------------------------------------------------------------- CPU legs (oracle port of the reference)
+# A job = (kind, params, n_streams, n_blocks, seed) run on one core; returns (seconds, output samples).
+def _cpu_job(args):
+    kind, prm, n_streams, n_blocks, seed = args
+    from oracle import reference_chain as rc
     rng = np.random.default_rng(seed)
-    x = (0.1 * rng.standard_normal((n_blocks, FRAMES))).astype(np.float32)
-    filt = [SlidingBlockFir(taps, FRAMES, 1) for _ in range(n_streams)]
-    out = np.empty(FRAMES, dtype=np.float32)
-    t0 = time.perf_counter()
-    for b in range(n_blocks):
-        for f in filt:
-            y = f.step(x[b], FRAMES)                                        # stream_process.py:96-107
-            out[:] = apply_dither_scale(y, np.random.random(FRAMES), 24)    # :61-64, :113
-    return time.perf_counter() - t0
-
-
-def cpu_reference(taps, seconds_target=12.0, pool=None, cores=None):
-    """Times the oracle port of the reference loop on all host cores.  Returns (Msamples/s, cores,
-    sample description)."""
-    import multiprocessing as mp
-    cores = cores or len(os.sched_getaffinity(0))
-    own_pool = pool is None
-    if own_pool:
-        pool = mp.get_context("fork").Pool(cores)
-    try:
-        # calibrate: 4 streams x 8 blocks per core
-        t = max(pool.map(_cpu_worker, [(taps, 4, 8, i) for i in range(cores)]))
-        per_sb = t / 32.0
-        n_streams = 8
-        n_blocks = int(max(8, min(4096, seconds_target / (per_sb * n_streams))))
+    B = prm["frames"]
+    x = (0.1 * rng.standard_normal((n_blocks, B))).astype(np.float32)
+    out = np.empty(B * prm.get("out_mult", 1), dtype=np.float32)
+    if kind == "fir":                 # stream_process.py:96-113 at U = 1 (C2, C5 U = 1)
+        st = [rc.SlidingBlockFir(prm["taps"], B, 1) for _ in range(n_streams)]
         t0 = time.perf_counter()
-        pool.map(_cpu_worker, [(taps, n_streams, n_blocks, 100 + i) for i in range(cores)])
+        for b in range(n_blocks):
+            for f in st:
+                out[:] = rc.apply_dither_scale(f.step(x[b], B), np.random.random(B), 24)
+    elif kind == "reference_chain":   # up-sample -> FIR at fs*U -> [::U] -> dither (C1; the callback of stream_process.py)
+        U = prm["upsample"]
+        st = [(rc.PolyphaseUpsampler(prm["up_taps"], U), rc.SlidingBlockFir(prm["taps"], B, U)) for _ in range(n_streams)]
+        t0 = time.perf_counter()
+        for b in range(n_blocks):
+            for up, f in st:
+                out[:] = rc.apply_dither_scale(f.step(up.step(x[b]), B), np.random.random(B), 24)
+    elif kind == "eq":                # stream_process_EQ.py:119-148 (C3)
+        st = [rc.SlidingBlockEq(prm["taps"], list(zip(prm["eq_taps"], prm["eq_gains"])), B, 1) for _ in range(n_streams)]
+        t0 = time.perf_counter()
+        for b in range(n_blocks):
+            for f in st:
+                out[:] = rc.apply_dither_scale(f.step(x[b], B), np.random.random(B), 24)
+    elif kind == "interp":            # polyphase interpolator with carried state, output at fs*U (C4, C5 U > 1)
+        U = prm["upsample"]
+        st = [rc.PolyphaseUpsampler(prm["taps"], U) for _ in range(n_streams)]
+        t0 = time.perf_counter()
+        for b in range(n_blocks):
+            for f in st:
+                out[:] = f.step(x[b])
+    else:
+        raise ValueError(kind)
+    return time.perf_counter() - t0, n_streams * n_blocks * out.size
+
+
+def _pin_first_core():
+    os.sched_setaffinity(0, {min(os.sched_getaffinity(0))})   # stream_process.py:17 pins the callback to one core
+
+
+class CpuLegs:
+    """One pool over all host cores and one single-core pool pinned like the reference."""
+
+    def __init__(self):
+        import multiprocessing as mp
+        self.cores = len(os.sched_getaffinity(0))
+        ctx = mp.get_context("fork")
+        self.pool = ctx.Pool(self.cores)
+        self.pool1 = ctx.Pool(1, initializer=_pin_first_core)
+        warm = ("fir", {"taps": np.ones(8) / 8, "frames": 64}, 1, 2, 0)     # imports scipy in every worker before anything is timed
+        self.pool.map(_cpu_job, [warm] * (2 * self.cores))
+        self.pool1.apply(_cpu_job, (warm,))
+
+    def close(self):
+        for p in (self.pool, self.pool1):
+            p.close()
+            p.join()
+
+    def measure(self, kind, prm, seconds=3.0, one_core=True, n_streams=4):
+        """Msamples/s on all cores (and on one pinned core, best of 3) for a bounded sample sized from a calibration run."""
+        t, n = self.pool1.apply(_cpu_job, ((kind, prm, 2, 4, 1),))
+        per_block_stream = t / 8.0
+        n_blocks = int(max(4, min(2048, seconds / (per_block_stream * n_streams))))
+        job = [(kind, prm, n_streams, n_blocks, 100 + i) for i in range(self.cores)]
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_job, job)
         wall = time.perf_counter() - t0
-    finally:
-        if own_pool:
-            pool.close()
-            pool.join()
-    samples = cores * n_streams * n_blocks * FRAMES
-    return samples / wall / 1e6, cores, f"{cores * n_streams} streams x {n_blocks} blocks of {FRAMES} frames"
+        samples = sum(r[1] for r in res)
+        out = {"value": round(samples / wall / 1e6, 3), "unit": "Msamples/s", "cores": self.cores, "kind": "port",
+               "sample": f"{self.cores * n_streams} streams x {n_blocks} blocks of {prm['frames']} frames"}
+        if one_core:
+            nb1 = max(4, n_blocks // 3)
+            best = 0.0
+            for rep in range(3):
+                t1, n1 = self.pool1.apply(_cpu_job, ((kind, prm, n_streams, nb1, 200 + rep),))
+                best = max(best, n1 / t1 / 1e6)
+            out["one_core"] = {"value": round(best, 3), "cores": 1, "pinned": True, "best_of": 3,
+                               "sample": f"{n_streams} streams x {nb1} blocks"}
+        return out
 
 
 def run_reference(args):
@@ -115,18 +165,18 @@ def run_reference(args):
     if rank != 0:
         return 0
     import multiprocessing as mp
-    taps = c2_taps()
+    prm = {"taps": c2_taps(), "frames": FRAMES}
     cores = len(os.sched_getaffinity(0))
     pool = mp.get_context("fork").Pool(cores)
     # per core per step: a bounded sample of the workload, long enough (~0.2 s) that the pool dispatch and the
     # per-call set-up inside the worker stay a few per cent of the step - the reference is not undersold
     n_streams, n_blocks = 8, 256
-    job = [(taps, n_streams, n_blocks, i) for i in range(cores)]
+    job = [("fir", prm, n_streams, n_blocks, i) for i in range(cores)]
     for _ in range(args.warmup):
-        pool.map(_cpu_worker, job)
+        pool.map(_cpu_job, job)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        pool.map(_cpu_worker, job)
+        pool.map(_cpu_job, job)
     wall = time.perf_counter() - t0
     pool.close()
     pool.join()
@@ -155,7 +205,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index, period=0.01):
         super().__init__(daemon=True)
         self.index, self.period = index, period
-        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
         self._stop_evt = threading.Event()
         self.ok = False
         try:
@@ -183,6 +233,10 @@ class ClockSampler(threading.Thread):
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                except Exception:
+                    pass
+                try:
                     mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
                     mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -198,7 +252,7 @@ class ClockSampler(threading.Thread):
         self.join(timeout=2)
         mhz = int(np.median(self.samples)) if self.samples else None
         return {"sm_mhz": mhz, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(self.samples)}
+                "samples": len(self.samples), "power_w_max": round(max(self.power), 1) if self.power else None}
 
 
 def bind_to_gpu_numa_node(index):
@@ -222,220 +276,306 @@ def bind_to_gpu_numa_node(index):
         return prev, f"unavailable ({type(exc).__name__})"
 
 
-# --------------------------------------------------------------------------- our arm
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from audio_filtering_pipeline_b200.engine import BatchFirEngine, PinnedArray, measure_fma_peak
-    from audio_filtering_pipeline_b200.sharding import max_over_ranks
+# --------------------------------------------------------------------------- helpers of our arm
+class Dist:
+    """Rank plumbing: barrier and max-over-ranks (NCCL); no collective ever touches the audio data."""
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
-    prev_affinity, numa_note = bind_to_gpu_numa_node(local)
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    if args.gpus != world and rank == 0 and world > 1:
-        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
 
-    S, NB, K, W = args.streams, args.blocks, args.steps, args.warmup
-    taps = c2_taps()
-    eng = BatchFirEngine(taps, n_streams=S, max_frames=FRAMES, upsample=1, chain="dac", out_format="i24",
-                         dither="tpdf", seed=2024, device=local, first_stream_id=rank * S)
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def max(self, v):
+        from audio_filtering_pipeline_b200.sharding import max_over_ranks
+        return max_over_ranks(v, self.dev)
 
-    # synthetic input, resident in HBM: NB distinct blocks [NB][S][FRAMES], sigma = 0.1 noise
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    x = torch.empty((NB, S, FRAMES), device=dev, dtype=torch.float32)
-    x.normal_(0.0, 0.1, generator=g).clamp_(-1.0, 1.0)
-    y = torch.empty((NB, S, FRAMES), device=dev, dtype=torch.int32)
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
 
-    def step():
-        for b in range(NB):
-            eng.process(x[b], y[b])
 
-    fma_peak_tflops, fma_mhz = measure_fma_peak(local)
-    for _ in range(max(W, 3)):
+def timed_steps(D, step, steps, warmup):
+    """CUDA events around exactly `steps` calls of step() after `warmup` calls; returns this rank's ms and the max over ranks."""
+    torch = D.torch
+    for _ in range(warmup):
         step()
-    barrier()
-    l0 = eng.kernel_launches
-    sampler = ClockSampler(local)
-    sampler.start()
+    D.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(K):
+    for _ in range(steps):
         step()
     e1.record()
-    barrier()
-    clocks = sampler.stop()
-    launches = eng.kernel_launches - l0
-    ms_total = e0.elapsed_time(e1)
-    ms_total_max = max_over_ranks(ms_total, dev)
-    samples_rank = S * FRAMES * NB * K
-    value = samples_rank * world / (ms_total_max * 1e-3) / 1e6
+    D.barrier()
+    ms = e0.elapsed_time(e1)
+    return ms, D.max(ms)
 
-    # roofline of the dominant (only) kernel, from this rank's own launches
-    ms_launch = ms_total / launches
-    flops_launch = 2.0 * N_TAPS * S * FRAMES
-    bytes_launch = S * FRAMES * (4 + 4)
-    achieved_tf = flops_launch / (ms_launch * 1e-3) / 1e12
-    traffic = None
-    prof = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(prof):
-        try:
-            traffic = json.load(open(prof)).get("c2_dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    info = eng.stage_info()[-1]
-    tensor = None
-    if info.get("kernel") == 1:
-        # tcgen05 path: MMA work actually issued per launch (3xTF32: x_hi*[W_hi|W_lo] as one N=128 MMA +
-        # x_lo*W_hi as one N=64 MMA per K=8 step, 64-sample Toeplitz chunks), against the nominal dense TF32 peak
-        R = 64
-        n_chunks = (N_TAPS + R - 2) // R + 1
-        items = (S + 15) // 16
-        mma_flops = 2.0 * items * n_chunks * (R // 8) * (FRAMES // (8 * R)) * (128 * 2 * R * 8 + 128 * R * 8)
-        tensor = {"kind": "tcgen05.mma kind::tf32, FP32 accumulators in TMEM, 3xTF32 split",
-                  "issued_tflops": round(mma_flops / (ms_launch * 1e-3) / 1e12, 1), "nominal_tf32_dense_peak_tflops": 1125.0,
-                  "note": "roofline.frac stays relative to the FP32-FMA roof of the north star (2N flop per sample); "
-                          "it can exceed 1 because the work runs on the tensor pipe"}
-        kernel_name = "afp::fir_tc_kernel<EPI_I24_TPDF, 1, 64> (tcgen05 / TMEM Toeplitz FIR)"
-    else:
-        kernel_name = ("afp::fir_row_kernel<1,16,256> (packed FFMA2, single row)" if info.get("kernel") == 2
-                       else "afp::fir_stream_kernel<1,16,256> (packed FFMA2, row pair)")
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    roofline = {
-        "bound": "fp32_fma", "achieved": round(achieved_tf, 2), "peak": round(fma_peak_tflops, 2),
-        "unit": "TFLOP/s", "frac": round(achieved_tf / fma_peak_tflops, 4), "traffic": traffic,
-        "peak_source": f"packed-FFMA2 issue loop measured in this run at {fma_mhz:.0f} MHz "
-                       "(MEASURED_PEAKS.json has no FP32 entry; nominal 148 SM x 128 x 2 x 1.965 GHz = 74.4)",
-        "kernel": kernel_name, "flop_per_sample": 2 * N_TAPS,
-        "ms_per_launch": round(ms_launch, 5),
-        "tensor": tensor,
-        "hbm": {"achieved_gbs": round(bytes_launch / (ms_launch * 1e-3) / 1e9, 1), "peak_gbs": hbm_peak,
-                "frac": round(bytes_launch / (ms_launch * 1e-3) / 1e9 / hbm_peak, 4),
-                "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
-    }
 
-    # end to end through the host API: pinned host buffers, H2D + kernels + D2H in the timed region
-    hx = PinnedArray((NB, S, FRAMES), np.float32)
-    hy = PinnedArray((NB, S, FRAMES), np.int32)
-    hx.a[...] = x.cpu().numpy()
+def pcie_probe(D, mbytes=256):
+    """Concurrent pinned H2D + D2H copies of `mbytes` MiB each on two streams, all ranks at once: GB/s per direction."""
+    torch = D.torch
+    n = mbytes * 2**20 // 4
+    h_in = torch.empty(n, dtype=torch.float32).pin_memory()
+    h_out = torch.empty(n, dtype=torch.float32).pin_memory()
+    d_in, d_out = torch.empty(n, dtype=torch.float32, device=D.dev), torch.zeros(n, dtype=torch.float32, device=D.dev)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    best = 0.0
+    for rep in range(4):
+        D.barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = D.max(time.perf_counter() - t0)
+        if rep:
+            best = max(best, mbytes * 2**20 / dt / 1e9)
+    return best
+
+
+def e2e_leg(D, eng, hx, hy, steps, in_bytes, out_bytes, samples_per_step, ceiling):
+    """Host API (afp_process_host_blocks), pinned host memory, H2D + kernels + D2H inside the timed region."""
     eng.reset()
-    Ke = max(2, min(K, args.e2e_steps))
     for _ in range(2):
-        eng.process_host_blocks(hx.a, hy.a)
-    barrier()
+        eng.process_host_blocks(hx, hy)
+    D.barrier()
     t0 = time.perf_counter()
-    for _ in range(Ke):
-        eng.process_host_blocks(hx.a, hy.a)
-    torch.cuda.synchronize()
-    te = max_over_ranks(time.perf_counter() - t0, dev)
-    e2e_value = S * FRAMES * NB * Ke * world / te / 1e6
-    e2e = {"value": round(e2e_value, 2), "unit": "Msamples/s", "h2d_bytes_per_step": S * FRAMES * NB * 4,
-           "d2h_bytes_per_step": S * FRAMES * NB * 4, "steps": Ke,
-           "api": "BatchFirEngine.process_host_blocks (afp_process_host_blocks), pinned host memory"}
-    checksum = int(np.bitwise_xor.reduce(hy.a.ravel()[:: 4099]))
-
-    line = None
-    os.sched_setaffinity(0, prev_affinity)      # the CPU legs use every core the process was given
-    e2e["host_affinity"] = numa_note
-    if rank == 0:
-        sweep = agc = None
-        if world == 1 and not args.no_sweep:
-            del x, y
-            torch.cuda.empty_cache()
-            sweep = c5_sweep(local, hbm_peak, fma_peak_tflops)
-            agc = agc_points(local, hbm_peak)
-        cpu_val, cores, sample = cpu_reference(taps, seconds_target=args.cpu_seconds)
-        line = {
-            "metric": METRIC, "value": round(value, 2), "unit": "Msamples/s", "n_gpus": world,
-            "steps": K, "warmup": max(W, 3), "ms_per_step": round(ms_total_max / K, 4),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(S, world, NB),
-            "roofline": roofline,
-            "cpu_baseline": {"value": round(cpu_val, 3), "unit": "Msamples/s", "cores": cores, "kind": "port",
-                             "sample": sample},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "stage": eng.stage_info(), "checksum": checksum,
-            "c5_sweep_kernel_only": sweep, "agc_kernel_only": agc,
-        }
-        print(json.dumps(line))
-    hx.free()
-    hy.free()
-    eng.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    return 0
-
-
-def c5_sweep(local, hbm_peak_gbs, fma_peak_tflops, iters=10):
-    """Kernel-only points of BASELINE.json configs[4] (batch sweep: {51,101,251,1001} taps x {1,2,4}x up-sampling,
-    f32 out, 1024-frame blocks - 512 for the 1001-tap U=1 case, the tensor kernel's block), device-resident I/O rotated over 3 buffer pairs (0.8-2 GB, far beyond L2),
-    CUDA events.  Work per output sample: 2*ceil(N/U) flop, 4/U + 4 bytes; the relevant roof
-    is the lower of the two."""
-    import torch
-    from audio_filtering_pipeline_b200.engine import BatchFirEngine
-    dev = torch.device("cuda", local)
-    out = []
-    for n_taps, up, streams, B in [(51, 1, 65536, 1024), (51, 2, 32768, 1024), (51, 4, 32768, 1024),
-                                   (101, 1, 32768, 1024), (101, 2, 32768, 1024), (101, 4, 32768, 1024),
-                                   (251, 1, 16384, 1024), (251, 2, 16384, 1024), (251, 4, 16384, 1024),
-                                   (1001, 1, 16384, 512), (1001, 2, 8192, 1024), (1001, 4, 8192, 1024)]:
-        rng = np.random.default_rng(n_taps * 8 + up)
-        h = up * rng.standard_normal(n_taps) / n_taps
-        eng = BatchFirEngine(h, n_streams=streams, max_frames=B, upsample=up, device=local)
-        xs = [0.1 * torch.randn(streams, B, device=dev) for _ in range(3)]
-        ys = [torch.empty(streams, B * up, device=dev) for _ in range(3)]
-        for i in range(3):
-            eng.process(xs[i], ys[i])
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(iters):
-            eng.process(xs[i % 3], ys[i % 3])
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / iters
-        n_out = streams * B * up
-        gs = n_out / ms / 1e6
-        flop, byts = 2.0 * -(-n_taps // up), 4.0 / up + 4.0
-        roof_fma, roof_hbm = fma_peak_tflops * 1e3 / flop, hbm_peak_gbs / byts     # Gsamples/s
-        bound = "hbm" if roof_hbm < roof_fma else "fp32_fma"
-        info = eng.stage_info()[-1]
-        out.append({"taps": n_taps, "upsample": up, "streams": streams, "frames": B, "gsamples_s": round(gs, 1),
-                    "tflops": round(gs * flop / 1e3, 1), "alg_gbs": round(gs * byts, 0), "bound": bound,
-                    "frac": round(gs / min(roof_fma, roof_hbm), 3), "kernel": info["kernel"], "tile": info["tile_taps"]})
-        eng.close()
-        del xs, ys
+    for _ in range(steps):
+        eng.process_host_blocks(hx, hy)
+    D.torch.cuda.synchronize()
+    te = D.max(time.perf_counter() - t0)
+    val = samples_per_step * steps * D.world / te / 1e6
+    gbs = max(in_bytes, out_bytes) * steps / te / 1e9                 # the busier direction, per rank
+    out = {"value": round(val, 2), "unit": "Msamples/s", "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(out_bytes),
+           "steps": steps, "api": "BatchFirEngine.process_host_blocks (afp_process_host_blocks), pinned host memory"}
+    if ceiling:
+        out["ceiling_gbs"] = round(ceiling, 1)
+        out["ceiling"] = f"concurrent pinned H2D + D2H copy probe, GB/s per direction per rank, all {D.world} ranks at once"
+        out["achieved_gbs"] = round(gbs, 1)
+        out["frac"] = round(gbs / ceiling, 3)
     return out
 
 
-def agc_points(local, hbm_peak_gbs, iters=10):
-    """Kernel-only points of the AGC kernel (csrc/afp_agc.cuh): HBM-bound by design,
-    4 bytes in + 4 bytes out per sample; 3 rotating input buffers (0.2-0.8 GB, beyond L2), CUDA events."""
-    import torch
+def kernel_names(info):
+    k = info.get("kernel")
+    return {0: "afp::fir_stream_kernel (packed FFMA2, row pair)", 1: "afp::fir_tc_kernel (tcgen05 / TMEM Toeplitz FIR, 3xTF32)",
+            2: "afp::fir_row_kernel (packed FFMA2, single row)",
+            3: "afp::fir_tc2_kernel (tcgen05 / TMEM Toeplitz FIR, split FP16, resident Hankel tap cores)"}.get(k, str(k))
+
+
+def tensor_block(n_taps, samples_per_s, peaks_run, peaks_file):
+    """MMA work the split-FP16 kernel issues for `samples_per_s` outputs of an n_taps filter: 3 products (hi*hi, hi*lo, lo*hi)
+    over ceil-padded 64-sample Toeplitz chunks; against the tensor roofs measured in this run."""
+    n_chunks = (n_taps + 62) // 64 + 1
+    issued = 3.0 * 2.0 * n_chunks * 64 * samples_per_s / 1e12
+    out = {"kind": "tcgen05.mma kind::f16, M=128 N=64 K=16, FP32 accumulators in TMEM, split FP16 (hi + lo*2^-11), 3 products",
+           "issued_tflops": round(issued, 1), "issued_over_algorithmic": round(3.0 * n_chunks * 64 / n_taps, 3)}
+    if peaks_run:
+        out["measured_roof_n64_tflops"] = round(peaks_run["n64"][0], 1)
+        out["measured_roof_n256_tflops"] = round(peaks_run["n256"][0], 1)
+        out["frac_of_n64_roof"] = round(issued / peaks_run["n64"][0], 3)
+        out["frac_of_n256_roof"] = round(issued / peaks_run["n256"][0], 3)
+        out["roof_note"] = ("bare tcgen05.mma loops measured in this run (afp_measure_tensor_peak): N=256 is the pipe's rate, N=64 the "
+                            "kernel's instruction shape, bound by the 6 KB operand fetch per MMA from shared memory at 128 B/clk "
+                            f"({peaks_run['n64'][2]:.1f} clk per MMA at {peaks_run['n64'][1]:.0f} MHz)")
+    if "bf16_tflops" in peaks_file:
+        out["frac_of_measured_bf16_peak"] = round(issued / peaks_file["bf16_tflops"], 3)
+    return out
+
+
+def roofline_for(eng, n_taps_exec, upsample, out_bytes, samples_per_s, ms_per_launch, fma_peak, peaks_run, peaks_file, traffic=None,
+                 flop_per_sample=None, stage=-1):
+    """Roofline block of the stage that did the work.  Algorithmic work per output sample:
+    2*ceil(N/U) flop, 4/U + out_bytes bytes."""
+    info = eng.stage_info()[stage]
+    flop = flop_per_sample if flop_per_sample is not None else 2.0 * -(-n_taps_exec // upsample)
+    byts = 4.0 / upsample + out_bytes
+    tf = samples_per_s * flop / 1e12
+    gbs = samples_per_s * byts / 1e9
+    hbm_peak = peaks_file.get("hbm_gbs", 6650.0)
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks_file else "fallback 6650 GB/s"
+    r = {"kernel": kernel_names(info), "flop_per_sample": flop, "bytes_per_sample": byts, "ms_per_launch": round(ms_per_launch, 5),
+         "traffic": traffic,
+         "hbm": {"achieved_gbs": round(gbs, 1), "peak_gbs": hbm_peak, "frac": round(gbs / hbm_peak, 4), "peak_source": hbm_src}}
+    if info.get("kernel") in (1, 3):
+        bf16 = peaks_file.get("bf16_tflops", 1590.0)
+        r.update({"bound": "tensor", "achieved": round(tf, 2), "peak": bf16, "unit": "TFLOP/s", "frac": round(tf / bf16, 4),
+                  "peak_source": ("MEASURED_PEAKS.json bf16_tflops (cuBLAS burst; kind::f16 runs at the bf16 rate)" if "bf16_tflops" in peaks_file
+                                  else "fallback 1590 TFLOP/s"),
+                  "note": "achieved counts the ALGORITHMIC 2N flop per output sample; the split-precision Toeplitz form issues "
+                          "issued_over_algorithmic x that on the tensor pipe (see tensor)"})
+        if info.get("kernel") == 3:
+            r["tensor"] = tensor_block(n_taps_exec, samples_per_s, peaks_run, peaks_file)
+        r["fp32_fma_equiv"] = {"speedup_over_fma_roof": round(tf / fma_peak, 3), "fma_roof_tflops": round(fma_peak, 2),
+                               "note": "north-star framing (>= 70 % of the FP32-FMA roof for >= 251 taps): the same work on the "
+                                       "FFMA2 kernels cannot exceed 1.0; a speed-up, not a roofline fraction"}
+    else:
+        roof_fma, roof_hbm = fma_peak * 1e12 / flop, hbm_peak * 1e9 / byts          # samples/s
+        if roof_hbm < roof_fma:
+            r.update({"bound": "hbm", "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(gbs / hbm_peak, 4),
+                      "peak_source": hbm_src})
+        else:
+            r.update({"bound": "fp32_fma", "achieved": round(tf, 2), "peak": round(fma_peak, 2), "unit": "TFLOP/s",
+                      "frac": round(tf / fma_peak, 4),
+                      "peak_source": "packed-FFMA2 issue loop measured in this run (MEASURED_PEAKS.json has no FP32 entry; nominal 74.4)"})
+    return r
+
+
+# --------------------------------------------------------------------------- BASELINE.json configs C1 / C3 / C4
+def config_points(D, args, cpu, fma_peak, peaks_run, peaks_file, ceiling):
+    """value / e2e / roofline / cpu_baseline for C1, C3 (per band and fused) and C4, streams sharded like the headline."""
+    torch = D.torch
+    from audio_filtering_pipeline_b200 import design
+    from audio_filtering_pipeline_b200.engine import BatchFirEngine, PinnedArray
+    out = {}
+    bank = [design.create_fir_filter(cutoff=b, numtaps=501, window_type="hamming", filter_type="bandpass", samplerate=48000)
+            for b in EQ_BANDS_10]
+    main48 = design.create_fir_filter(cutoff=16000, numtaps=501, window_type="hamming", filter_type="lowpass", samplerate=48000)
+    h1 = design.create_fir_filter(cutoff=[500, 8000], numtaps=251, window_type="kaiser", filter_type="bandpass", samplerate=176400)
+    up4 = design.design_upsampler(4, 44100)
+    h4 = design.apply_min_phase(design.create_fir_filter(cutoff=1000, numtaps=501, window_type="boxcar", filter_type="highpass",
+                                                         samplerate=88200), 88200)
+    specs = {
+        "C1": dict(desc="251-tap Kaiser band-pass 500-8000 Hz designed at 176.4 kHz, 44.1 kHz streams, 4x up-sample -> FIR -> [::4] "
+                        "(reference chain, collapsed to one base-rate FIR), 1024-frame blocks, RPDF float dither",
+                   S=8192, B=1024, NB=8, eng=dict(taps=h1, upsample=4, chain="reference", upsampler_taps=up4, dither="rpdf"),
+                   n_exec=-(-(len(h1) + len(up4) - 1) // 4), U=1, out_mult=1, out_bytes=4,
+                   cpu=("reference_chain", {"taps": h1, "up_taps": up4, "upsample": 4, "frames": 1024})),
+        "C3_per_band": dict(desc="10-band EQ (9 reference bands + 16-20 kHz) x 501 taps accumulated band by band, then 501-tap low-pass, "
+                                 "48 kHz stereo sessions, 1024-frame blocks",
+                            S=4096, B=1024, NB=4, eng=dict(taps=main48, eq_bands=bank, eq_gains=EQ_GAINS_10, eq_mode="per_band"),
+                            n_exec=501, U=1, out_mult=1, out_bytes=4, flop=2.0 * (10 * 501 + 501), stage=0,
+                            cpu=("eq", {"taps": main48, "eq_taps": bank, "eq_gains": EQ_GAINS_10, "frames": 1024})),
+        "C3_fused": dict(desc="the same EQ in the fused form (taps-domain sum, stream_process_EQ_GUI.py:86-90) folded into the main "
+                              "filter: one 1001-tap FIR",
+                         S=4096, B=1024, NB=4, eng=dict(taps=main48, eq_bands=bank, eq_gains=EQ_GAINS_10, eq_mode="fused"),
+                         n_exec=1001, U=1, out_mult=1, out_bytes=4,
+                         cpu=("eq", {"taps": main48, "eq_taps": bank, "eq_gains": EQ_GAINS_10, "frames": 1024})),
+        "C4": dict(desc=f"501-tap boxcar high-pass -> minimum phase ({len(h4)} taps) as the 2x polyphase interpolator, 4096 streams, "
+                        "1024-frame blocks, output at 2 fs",
+                   S=4096, B=1024, NB=8, eng=dict(taps=2 * h4, upsample=2, chain="dac"),
+                   n_exec=len(h4), U=2, out_mult=2, out_bytes=4,
+                   cpu=("interp", {"taps": 2 * h4, "upsample": 2, "frames": 1024, "out_mult": 2})),
+    }
+    for name, sp in specs.items():
+        S, B, NB = sp["S"], sp["B"], sp["NB"]
+        eng = BatchFirEngine(n_streams=S, max_frames=B, device=D.local, first_stream_id=D.rank * S, seed=2024, **sp["eng"])
+        cols = eng._out_cols(B)
+        x = torch.empty((NB, S, B), device=D.dev).normal_(0.0, 0.1).clamp_(-1.0, 1.0)
+        y = torch.empty((NB, S, cols), device=D.dev, dtype=torch.float32)
+        l0 = eng.kernel_launches
+        ms, ms_max = timed_steps(D, lambda: eng.process_blocks(x, y), 10, 3)
+        launches = (eng.kernel_launches - l0) // 13
+        n_out = S * cols * NB
+        value = n_out * 10 * D.world / (ms_max * 1e-3) / 1e6
+        # the stage that dominates: the last one; per-launch figures from this rank's own clock
+        per_s = n_out * 10 / (ms * 1e-3)
+        roof = roofline_for(eng, sp["n_exec"], sp["U"], sp["out_bytes"], per_s, ms / 10 / max(launches, 1), fma_peak, peaks_run, peaks_file,
+                            flop_per_sample=sp.get("flop"), stage=sp.get("stage", -1))
+        roof["launches_per_step"] = launches
+        hx, hy = PinnedArray((NB, S, B), np.float32), PinnedArray((NB, S, cols), np.float32)
+        hx.a[...] = x.cpu().numpy()
+        e2e = e2e_leg(D, eng, hx.a, hy.a, 3, S * B * NB * 4, n_out * 4, n_out, ceiling)
+        hx.free(); hy.free()
+        stage = eng.stage_info()
+        eng.close()
+        del x, y
+        torch.cuda.empty_cache()
+        entry = {"workload": sp["desc"], "streams_per_gpu": S, "frames_per_block": B, "blocks_per_step": NB,
+                 "value": round(value, 1), "unit": "Msamples/s", "ms_per_step": round(ms_max / 10, 4), "e2e": e2e, "roofline": roof,
+                 "stage": [{k: st[k] for k in ("kind", "n_taps", "kernel", "upsample")} for st in stage]}
+        if cpu is not None:
+            entry["cpu_baseline"] = cpu.measure(*sp["cpu"], seconds=args.cpu_seconds / 4)
+        out[name] = entry
+    return out
+
+
+# --------------------------------------------------------------------------- C5 sweep
+def c5_sweep(D, cpu, hbm_peak_gbs, fma_peak, iters=8):
+    """BASELINE.json configs[4]: {1k, 4k, 16k, 64k} streams x {51, 251, 1001} taps x {1, 2, 4}x up-sampling, f32 out, 1024-frame
+    blocks, device-resident I/O rotated over 3 buffer pairs, CUDA events, max over ranks.  The streams of a point are sharded
+    over the ranks of the run (sharding.partition_streams - the helper the gloo test covers), so at N GPUs a point is the same
+    total batch on N devices.  Work per output sample: 2*ceil(N/U) flop, 4/U + 4 bytes; `frac` is against the
+    lower of the FP32-FMA and HBM roofs, except on the tensor kernels (kernel 1 / 3), where it is the speed-up over the FMA roof."""
+    torch = D.torch
     from audio_filtering_pipeline_b200.engine import BatchFirEngine
-    dev = torch.device("cuda", local)
+    from audio_filtering_pipeline_b200.sharding import partition_streams
+    B = 1024
+    cpu_rate = {}
     out = []
-    with BatchFirEngine([1.0], n_streams=1, max_frames=1, device=local) as eng:
+    for n_taps in (51, 251, 1001):
+        for up in (1, 2, 4):
+            rng = np.random.default_rng(n_taps * 8 + up)
+            h = up * rng.standard_normal(n_taps) / n_taps
+            if cpu is not None:
+                kind = "fir" if up == 1 else "interp"
+                cpu_rate[(n_taps, up)] = cpu.measure(kind, {"taps": h, "upsample": up, "frames": B, "out_mult": up}, seconds=1.0,
+                                                     one_core=False)
+            for total in (1024, 4096, 16384, 65536):
+                first, count = partition_streams(total, D.world, D.rank)
+                ms = 0.0
+                info = {"kernel": None, "tile_taps": None}
+                if count > 0:
+                    eng = BatchFirEngine(h, n_streams=count, max_frames=B, upsample=up, device=D.local, first_stream_id=first)
+                    xs = [0.1 * torch.randn(count, B, device=D.dev) for _ in range(3)]
+                    ys = [torch.empty(count, B * up, device=D.dev) for _ in range(3)]
+                    for i in range(3):
+                        eng.process(xs[i], ys[i])
+                D.barrier()
+                if count > 0:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for i in range(iters):
+                        eng.process(xs[i % 3], ys[i % 3])
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ms = e0.elapsed_time(e1) / iters
+                    info = eng.stage_info()[-1]
+                    eng.close()
+                    del xs, ys
+                ms = D.max(ms)
+                gs = total * B * up / ms / 1e6
+                flop, byts = 2.0 * -(-n_taps // up), 4.0 / up + 4.0
+                roof_fma, roof_hbm = fma_peak * 1e3 / flop, hbm_peak_gbs / byts     # Gsamples/s per GPU
+                bound = "hbm" if roof_hbm < roof_fma else "fp32_fma"
+                row = {"taps": n_taps, "upsample": up, "streams_total": total, "streams_per_gpu": count, "frames": B,
+                       "gsamples_s": round(gs, 1), "tflops": round(gs * flop / 1e3, 1), "alg_gbs": round(gs * byts, 0), "bound": bound,
+                       "frac": round(gs / (min(roof_fma, roof_hbm) * D.world), 3), "kernel": info["kernel"], "tile": info["tile_taps"]}
+                if info["kernel"] in (1, 3):
+                    row["bound"] = "tensor (frac = speed-up over the FP32-FMA roof)"
+                if (n_taps, up) in cpu_rate:
+                    c = cpu_rate[(n_taps, up)]
+                    row["cpu_msamples_s"] = c["value"]
+                    row["cpu_cores"] = c["cores"]
+                    row["gpu_over_cpu"] = round(gs * 1e3 / c["value"], 0)
+                out.append(row)
+    return out
+
+
+def aux_points(D, hbm_peak_gbs, iters=10):
+    """Kernel-only points of the AGC kernel and the waterfall-row kernel: HBM-bound by design
+    (AGC 4 B in + 4 B out per sample; waterfall row 4 B in + ~2 B out per input sample)."""
+    torch = D.torch
+    from audio_filtering_pipeline_b200.engine import BatchFirEngine
+    agc, spec = [], []
+    with BatchFirEngine([1.0], n_streams=1, max_frames=1, device=D.local) as eng:
         for streams, frames, window in [(16384, 1024, 512), (65536, 1024, 512), (16384, 512, 256)]:
-            xs = [0.05 * torch.randn(streams, frames, device=dev) for _ in range(3)]
+            xs = [0.05 * torch.randn(streams, frames, device=D.dev) for _ in range(3)]
             y = torch.empty_like(xs[0])
             for i in range(3):
                 eng.agc_block(xs[i], out=y, window_size=window)
@@ -448,10 +588,159 @@ def agc_points(local, hbm_peak_gbs, iters=10):
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / iters
             gs = streams * frames / ms / 1e6
-            out.append({"streams": streams, "frames": frames, "window": window, "gsamples_s": round(gs, 1),
+            agc.append({"streams": streams, "frames": frames, "window": window, "gsamples_s": round(gs, 1),
                         "alg_gbs": round(gs * 8, 0), "bound": "hbm", "frac": round(gs * 8 / hbm_peak_gbs, 3)})
             del xs, y
-    return out
+        for streams, frames in [(16384, 1024), (65536, 1024), (16384, 4096)]:
+            xs = [0.05 * torch.randn(streams, frames, device=D.dev) for _ in range(3)]
+            y = torch.empty((streams, frames // 2 + 1), device=D.dev)
+            for i in range(3):
+                eng.spectrum_db(xs[i], out=y)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(iters):
+                eng.spectrum_db(xs[i % 3], out=y)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            gs = streams * frames / ms / 1e6
+            byts = 4.0 + 4.0 * (frames // 2 + 1) / frames
+            spec.append({"streams": streams, "frames": frames, "g_input_samples_s": round(gs, 1), "alg_gbs": round(gs * byts, 0),
+                         "bound": "hbm", "frac": round(gs * byts / hbm_peak_gbs, 3)})
+            del xs, y
+    return agc, spec
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    from audio_filtering_pipeline_b200.engine import BatchFirEngine, PinnedArray, measure_fma_peak, measure_tensor_peak
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    prev_affinity, numa_note = bind_to_gpu_numa_node(local)
+    D = Dist()
+    rank, world, dev = D.rank, D.world, D.dev
+    if args.gpus != world and rank == 0 and world > 1:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+
+    S, NB, K, W = args.streams, args.blocks, args.steps, max(args.warmup, 3)
+    taps = c2_taps()
+    eng = BatchFirEngine(taps, n_streams=S, max_frames=FRAMES, upsample=1, chain="dac", out_format="i24",
+                         dither="tpdf", seed=2024, device=local, first_stream_id=rank * S)
+
+    # synthetic input, resident in HBM: NB distinct blocks [NB][S][FRAMES], sigma = 0.1 noise
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = torch.empty((NB, S, FRAMES), device=dev, dtype=torch.float32)
+    x.normal_(0.0, 0.1, generator=g).clamp_(-1.0, 1.0)
+    y = torch.empty((NB, S, FRAMES), device=dev, dtype=torch.int32)
+
+    def step():
+        eng.process_blocks(x, y)
+
+    fma_peak, fma_mhz = measure_fma_peak(local)
+    peaks_run = {"n64": measure_tensor_peak(local, 64), "n256": measure_tensor_peak(local, 256)}
+    peaks_file = {}
+    try:
+        peaks_file = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks_file.get("hbm_gbs", 6650.0)
+
+    for _ in range(W):
+        step()
+    D.barrier()
+    l0 = eng.kernel_launches
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        step()
+    e1.record()
+    D.barrier()
+    clocks = sampler.stop()
+    launches = eng.kernel_launches - l0
+    ms_total = e0.elapsed_time(e1)
+    ms_total_max = D.max(ms_total)
+    samples_rank = S * FRAMES * NB * K
+    value = samples_rank * world / (ms_total_max * 1e-3) / 1e6
+
+    # sustained: the same step back to back for >= sustain_seconds (power / clock behaviour of a long run)
+    sustained = None
+    if args.sustain_seconds > 0:
+        n_sus = max(K, int(args.sustain_seconds * 1e3 / max(ms_total / K, 1e-3)) + 1)
+        sampler2 = ClockSampler(local, period=0.05)
+        D.barrier()
+        sampler2.start()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(n_sus):
+            step()
+        s1.record()
+        D.barrier()
+        ck = sampler2.stop()
+        ms_sus = D.max(s0.elapsed_time(s1))
+        sustained = {"value": round(S * FRAMES * NB * n_sus * world / (ms_sus * 1e-3) / 1e6, 2), "unit": "Msamples/s",
+                     "seconds": round(ms_sus * 1e-3, 2), "steps": n_sus, "clocks": ck}
+
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("c2_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    ms_launch = ms_total / max(launches, 1)
+    roofline = roofline_for(eng, N_TAPS, 1, 4, samples_rank / (ms_total * 1e-3), ms_launch, fma_peak, peaks_run, peaks_file, traffic)
+    roofline["algorithmic_bytes_per_launch"] = S * FRAMES * NB * 8
+    roofline["fma_peak_source"] = f"packed-FFMA2 issue loop measured in this run at {fma_mhz:.0f} MHz"
+
+    # end to end through the host API: pinned host buffers, H2D + kernels + D2H in the timed region
+    ceiling = pcie_probe(D)
+    hx = PinnedArray((NB, S, FRAMES), np.float32)
+    hy = PinnedArray((NB, S, FRAMES), np.int32)
+    hx.a[...] = x.cpu().numpy()
+    Ke = max(2, min(K, args.e2e_steps))
+    e2e = e2e_leg(D, eng, hx.a, hy.a, Ke, S * FRAMES * NB * 4, S * FRAMES * NB * 4, S * FRAMES * NB, ceiling)
+    e2e["host_affinity"] = numa_note
+    checksum = int(np.bitwise_xor.reduce(hy.a.ravel()[:: 4099]))
+    stage = eng.stage_info()
+    hx.free()
+    hy.free()
+    eng.close()
+    del x, y
+    torch.cuda.empty_cache()
+
+    os.sched_setaffinity(0, prev_affinity)      # the CPU legs use every core the process was given
+    cpu = CpuLegs() if rank == 0 else None
+    configs = sweep = agc = spec = None
+    if not args.no_configs:
+        configs = config_points(D, args, cpu, fma_peak, peaks_run, peaks_file, ceiling)
+    if not args.no_sweep:
+        sweep = c5_sweep(D, cpu, hbm_peak, fma_peak)
+        if rank == 0:
+            agc, spec = aux_points(D, hbm_peak)
+    if rank == 0:
+        cpu_base = cpu.measure("fir", {"taps": taps, "frames": FRAMES}, seconds=args.cpu_seconds, n_streams=8)
+        cpu.close()
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": "Msamples/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": round(ms_total_max / K, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(S, world, NB),
+            "value_sustained": sustained,
+            "roofline": roofline,
+            "cpu_baseline": cpu_base,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "stage": stage, "checksum": checksum,
+            "configs": configs, "c5_sweep": sweep, "agc_kernel_only": agc, "waterfall_rows_kernel_only": spec,
+        }
+        print(json.dumps(line))
+    D.close()
+    return 0
 
 
 def main():
@@ -464,7 +753,9 @@ def main():
     ap.add_argument("--blocks", type=int, default=BLOCKS_PER_STEP, help="512-frame blocks per step")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--no-sweep", action="store_true", help="skip the short-filter kernel-only sweep (N = 1 only)")
+    ap.add_argument("--sustain-seconds", type=float, default=2.0, help="length of the back-to-back run behind value_sustained (0 = skip)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the C5 batch sweep and the AGC / waterfall kernel points")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1 / C3 / C4 blocks")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -25,6 +25,17 @@ KEYS = [
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st.sum",
     "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum",
+    # tensor pipe (tcgen05 kernels): SURVEY.md 8d's required evidence
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tensor.sum", "sm__inst_executed_pipe_tensor_subpipe_hmma.sum",
+    "sm__inst_executed_pipe_uniform.sum", "smsp__inst_executed_pipe_uniform.sum",
+    "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum",
+    "sm__cycles_elapsed.avg.per_second",
 ]
 
 
