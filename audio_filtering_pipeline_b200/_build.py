@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libafp_b200.so")
 SOURCES = ["afp_abi.cu", "afp_kernels_u1.cu", "afp_kernels_u2.cu", "afp_kernels_u3.cu", "afp_kernels_u4.cu", "afp_kernels_tc.cu", "afp_kernels_tc2.cu",
            "afp_kernels_row_u1.cu", "afp_kernels_row_u2.cu", "afp_kernels_row_u3.cu", "afp_kernels_row_u4.cu",
-           "afp_kernels_agc.cu", "afp_kernels_peak.cu"]
+           "afp_kernels_agc.cu", "afp_kernels_peak.cu", "afp_kernels_grouped.cu"]
 DEPS = SOURCES + ["afp_fir_kernel.cuh", "afp_kernel_table.cuh", "afp_fir_tc.cuh", "afp_fir_tc2.cuh", "afp_philox.cuh", "afp_fir_row.cuh", "afp_kernels_row.cuh", "afp_agc.cuh", "afp_spectrum.cuh",
                   os.path.join("..", "..", "include", "afp.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -25,6 +25,7 @@ SYMBOLS = [
     "afp_get_stage_info", "afp_kernel_launches", "afp_host_alloc", "afp_host_free",
     "afp_measure_fma_peak", "afp_set_agc", "afp_agc_block", "afp_process_host_interleaved", "afp_swap_taps", "afp_spectrum_db",
     "afp_process_blocks", "afp_range_status", "afp_measure_tensor_peak",
+    "afp_assign_groups", "afp_set_gains_group", "afp_set_taps_group",
 ]
 
 
@@ -88,6 +89,9 @@ def load():
     lib.afp_swap_taps.argtypes = [vp, dp, i32]
     lib.afp_set_eq.argtypes = [vp, dp, C.POINTER(i32), i32, dp]
     lib.afp_set_gains.argtypes = [vp, dp, i32]
+    lib.afp_assign_groups.argtypes = [vp, C.POINTER(i32), i32]
+    lib.afp_set_gains_group.argtypes = [vp, i32, dp, i32]
+    lib.afp_set_taps_group.argtypes = [vp, i32, dp, i32]
     lib.afp_process.argtypes = [vp, vp, i64, vp, i64, i32, vp]
     lib.afp_process_blocks.argtypes = [vp, vp, i64, i64, vp, i64, i64, i32, i32, vp]
     lib.afp_range_status.argtypes = [vp, C.POINTER(i32)]

@@ -23,6 +23,7 @@
 #include <map>
 
 afp::tc2_kern_t afp_kernel_tc2(int epi);                                    // afp_kernels_tc2.cu
+afp::tc2_kern_t afp_kernel_tc2_grouped();
 afp::agc_kern_t afp_kernel_agc(int variant, int scan_blocks, int team);   // afp_kernels_agc.cu: variant AGC_*, scan_blocks 1 / 2, team 1 / 2
 
 using afp::FirParams;
@@ -37,7 +38,7 @@ constexpr uint32_t kStateMagic = 0x41465031u;  // "AFP1"
 enum StageKind { ST_INTERP = 0, ST_EQ = 1, ST_MAIN = 2 };
 
 struct Geometry {
-    int nt = 0, tg_log2 = 0, smem = 0, grid = 0, segs_per_stream = 0;
+    int nt = 0, tg_log2 = 0, smem = 0, grid = 0, segs_per_stream = 0, resident = 0;
     int key_nq = -1, key_ns = -1;   // launch shape this geometry was computed for
 };
 
@@ -183,6 +184,17 @@ struct afp_ctx {
     cudaStream_t own_stream = nullptr, s_in = nullptr, s_out = nullptr;
     FirParams params{};              // scratch for the kernel-parameter block of the launch being prepared
     unsigned int* range_flag = nullptr;   // device word: set by the split-FP16 tensor kernel when a sample exceeds FP16's range
+    // per-stream-group filters (afp_assign_groups): every session of a batch with its own EQ gains / main taps, the way
+    // each reference process reads its own sliders per block (stream_process_EQ_GUI.py:86-90).  Empty = one filter set.
+    struct GroupDef { std::vector<double> gains, taps; };   // empty = the context-level gains / main taps
+    std::vector<int> group_of_stream;
+    std::vector<GroupDef> groups;
+    bool groups_dirty = false, groups_pair_aligned = false;
+    int* d_group_of_stream = nullptr;
+    float* d_gtaps = nullptr;        // [G][gtaps_stride] per-group tables of the chain's single stage (layout of Stage::table)
+    long long gtaps_stride = 0;
+    void* d_gcores = nullptr;        // [G][gcores_stride] halves: per-group Hankel tap cores for the split-FP16 tensor kernel
+    long long gcores_stride = 0;
 };
 
 namespace {
@@ -321,10 +333,10 @@ int build_stage(afp_ctx* c, Stage& s, int kind, int U, const double* taps, int n
 // A thread group (tg threads) owns one segment of tg*T positions.  Small groups mean many independent
 // groups per SM (one group's load/epilogue hides behind the others' FMAs) but re-load the halo more
 // often; the halo is kept <= 1/4 of a segment unless the block itself is shorter.
-Geometry pick_geometry(int T, int kq_pad, int n_q, int n_streams) {
+Geometry pick_geometry(int T, int kq_pad, int n_q, int n_streams, int nt_min = 128) {
     Geometry best;
     double best_score = -1;
-    for (int nt = 256; nt >= 128; nt >>= 1) {
+    for (int nt = 256; nt >= nt_min; nt >>= 1) {
         int cover = 3;                                   // smallest group that covers the whole block
         while ((1 << cover) * T < n_q && (1 << cover) < nt) ++cover;
         int halo = 5;                                    // smallest warp-or-larger group with halo <= 25 %
@@ -504,6 +516,7 @@ int launch_stage_tc2(afp_ctx* c, Stage& s, const float* in, long long in_pitch, 
                      unsigned long long sample_base, int s0, int ns, cudaStream_t stream, bool* done) {
     *done = false;
     if (!s.tc2_w || s.U != 1 || env_flag("AFP_NO_TC2")) return AFP_OK;
+    if (!c->group_of_stream.empty()) return AFP_OK;   // per-group filters: launch_stage_tc2_grouped / the row-pair kernel
     if (frames < afp::TC2_STEP || frames % afp::TC2_STEP != 0 || n_blocks < 1) return AFP_OK;
     if ((long long)frames * n_blocks > (1 << 30)) return AFP_OK;
     const int eb = fmt == AFP_FMT_I16 ? 2 : (fmt == AFP_FMT_I24_PACKED ? 3 : 4);
@@ -526,6 +539,46 @@ int launch_stage_tc2(afp_ctx* c, Stage& s, const float* in, long long in_pitch, 
     if (smem > kMaxSmem) return AFP_OK;
     const int grid = P.n_groups < c->n_sm ? P.n_groups : c->n_sm;
     afp_kernel_tc2(afp::epi_code(fmt, dither))<<<grid, afp::TC2_THREADS, smem, stream>>>(P);
+    AFP_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    s.last_kernel = 3;
+    s.geo.nt = afp::TC2_THREADS; s.geo.tg_log2 = 4; s.geo.smem = smem; s.geo.grid = grid; s.geo.key_nq = -1;
+    *done = true;
+    return AFP_OK;
+}
+
+// The same kernel with per-stream tap cores (afp_assign_groups): a work item is one stream, whose blocks fill the 16 tile
+// slots as 16 consecutive runs - so the call must bring a multiple of 16 x 512 frames per stream.
+int launch_stage_tc2_grouped(afp_ctx* c, Stage& s, const float* in, long long in_pitch, long long in_bstride, void* out,
+                             long long out_pitch, long long out_bstride, int frames, int n_blocks, int fmt, int dither,
+                             unsigned long long sample_base, int s0, int ns, cudaStream_t stream, bool* done) {
+    *done = false;
+    if (!s.tc2_w || !c->d_gcores || s.U != 1 || env_flag("AFP_NO_TC2")) return AFP_OK;
+    if (frames < afp::TC2_STEP || frames % afp::TC2_STEP != 0 || n_blocks < 1) return AFP_OK;
+    const long long steps = (long long)(frames / afp::TC2_STEP) * n_blocks;
+    if (steps % afp::TC2_STREAMS != 0 || (long long)frames * n_blocks > (1 << 30)) return AFP_OK;
+    const int eb = fmt == AFP_FMT_I16 ? 2 : (fmt == AFP_FMT_I24_PACKED ? 3 : 4);
+    if (!aligned16(in) || in_pitch % 4 != 0 || in_bstride % 4 != 0 || s.hist_pitch % 4 != 0 || s.kq_pad % 8 != 0) return AFP_OK;
+    if (s.tc2_chunks > 17 || s.kq_pad > 24 * afp::TC2_R) return AFP_OK;
+    afp::Tc2Params P{};
+    P.hist_in = s.hist[s.cur] + (long long)s0 * s.hist_pitch; P.hist_out = s.hist[s.cur ^ 1] + (long long)s0 * s.hist_pitch;
+    P.hist_pitch = s.hist_pitch; P.hist_len = s.kq_pad;
+    P.in = in; P.in_pitch = in_pitch; P.in_block_stride = in_bstride;
+    P.out = out; P.out_pitch = out_pitch; P.out_block_stride = out_bstride;
+    P.w = static_cast<const __half*>(s.tc2_w); P.n_cores = s.tc2_cores;
+    P.n_streams = ns; P.frames = frames; P.n_blocks = n_blocks; P.n_chunks = s.tc2_chunks;
+    P.n_groups = ns;                                   // work items = streams
+    P.steps_per_slot = (int)(steps / afp::TC2_STREAMS);
+    P.gw = static_cast<const __half*>(c->d_gcores); P.gw_stride = c->gcores_stride; P.group_of_stream = c->d_group_of_stream + s0;
+    P.range_flag = c->range_flag;
+    P.fmt = fmt; P.dither = dither; P.decim = 1;
+    P.fast_out = (aligned16(out) && (out_pitch * eb) % 16 == 0 && (out_bstride * eb) % 16 == 0) ? 1 : 0;
+    P.seed = c->cfg.seed; P.sample_base = sample_base; P.stream_id0 = c->cfg.first_stream_id + s0;
+    P.gain = 1.0f; P.dither_lsb = std::ldexp(1.0f, -(c->dither_bits - 1));
+    const int smem = afp::tc2_smem_bytes(s.tc2_chunks);
+    if (smem > kMaxSmem) return AFP_OK;
+    const int grid = ns < c->n_sm ? ns : c->n_sm;
+    afp_kernel_tc2_grouped()<<<grid, afp::TC2_THREADS, smem, stream>>>(P);
     AFP_CUDA(c, cudaGetLastError());
     c->launches += 1;
     s.last_kernel = 3;
@@ -648,21 +701,19 @@ int launch_stage_row(afp_ctx* c, Stage& s, const StageIO& io, const Align& al, c
 }
 
 int launch_stage(afp_ctx* c, Stage& s, const StageIO& io, cudaStream_t stream) {
-    {
+    const bool grouped = !c->group_of_stream.empty();   // per-group tap tables: the row-pair kernel reads them per work item
+    const Align al = alignment_of(s, io);
+    if (!grouped) {
         bool done = false;
         int rc = launch_stage_tc(c, s, io, stream, &done);
         if (rc || done) return rc;
-    }
-    const Align al = alignment_of(s, io);
-    {
-        bool done = false;
-        int rc = launch_stage_row(c, s, io, al, stream, &done);
+        rc = launch_stage_row(c, s, io, al, stream, &done);
         if (rc || done) return rc;
-        s.last_kernel = 0; s.last_T = s.T;
     }
+    s.last_kernel = 0; s.last_T = s.T;
     const int S = io.ns;
     if (s.geo.key_nq != io.n_q || s.geo.key_ns != S) {
-        Geometry g = pick_geometry(s.T, s.kq_pad, io.n_q, S);
+        Geometry g = pick_geometry(s.T, s.kq_pad, io.n_q, S, grouped ? 256 : 128);
         if (g.nt == 0) return fail(c, AFP_ERR_INVALID, "filter/block combination does not fit in shared memory");
         // persistent grid: no more CTAs than fit on the device at once (items are dealt round-robin)
         int per_sm = 0;
@@ -674,6 +725,7 @@ int launch_stage(afp_ctx* c, Stage& s, const StageIO& io, cudaStream_t stream) {
         const long long n_pairs = ((long long)S * g.segs_per_stream + 1) / 2;
         const int resident = per_sm * c->n_sm;
         g.grid = (int)(n_pairs < resident ? n_pairs : resident);
+        g.resident = resident;
         g.key_nq = io.n_q; g.key_ns = S;
         s.geo = g;
     }
@@ -689,9 +741,24 @@ int launch_stage(afp_ctx* c, Stage& s, const StageIO& io, cudaStream_t stream) {
     std::memset(P.taps, 0, sizeof(P.taps));
     std::memcpy(P.taps, s.table.data(), s.table.size() * sizeof(float));
     const int epi = io.decim == 1 ? afp::epi_code(io.fmt, io.dither) : afp::EPI_GENERIC;
-    kern_t k = kernel_for(s.U, s.T, g.nt, s.n_sub > 1, epi);
+    kern_t k = nullptr;
+    int grid = g.grid;
+    if (grouped) {
+        if (s.n_sub != 1 || !c->d_gtaps || c->gtaps_stride != (long long)s.kq_pad * s.U)
+            return fail(c, AFP_ERR_STATE, "per-group filters are not built for this stage");
+        k = afp_kernel_grouped(s.U, s.T);
+        P.gtaps = c->d_gtaps; P.gstride = c->gtaps_stride; P.group_of_stream = c->d_group_of_stream + io.s0;
+        // the two rows of a work item share their taps: pairs of segments of one stream, or of two streams of one group
+        P.pair_single = (g.segs_per_stream % 2 == 1 && !c->groups_pair_aligned) ? 1 : 0;
+        if (P.pair_single) {
+            P.n_pairs = P.n_seg_total;
+            grid = P.n_pairs < g.resident ? P.n_pairs : g.resident;
+        }
+    } else {
+        k = kernel_for(s.U, s.T, g.nt, s.n_sub > 1, epi);
+    }
     if (!k) return fail(c, AFP_ERR_INVALID, "no kernel for this stage shape");
-    k<<<g.grid, g.nt, g.smem, stream>>>(P);
+    k<<<grid, g.nt, g.smem, stream>>>(P);
     AFP_CUDA(c, cudaGetLastError());
     c->launches += 1;
     return AFP_OK;
@@ -721,7 +788,7 @@ int run_streaming(afp_ctx* c, Stage& s, const float* in, long long in_pitch, int
         int rc = launch_stage_tc2(c, s, in, in_pitch, 0, out, out_pitch, 0, len, 1, fmt, dither, sample_base, s0, ns, stream, &done);
         if (rc || done) return rc;
     }
-    const int sub = (decim == 1 && !env_flag("AFP_NO_TC_CHAIN")) ? tc_max_block(s) : 0;
+    const int sub = (decim == 1 && c->group_of_stream.empty() && !env_flag("AFP_NO_TC_CHAIN")) ? tc_max_block(s) : 0;
     if (sub > 0 && len > sub && len % sub == 0 && aligned16(in) && in_pitch % 4 == 0) {
         if (!s.hist_scratch) {
             const size_t bytes = (size_t)c->cfg.n_streams * s.hist_pitch * sizeof(float);
@@ -941,10 +1008,19 @@ int afp_create(const afp_config* cfg, afp_ctx** out_ctx) {
                 e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
                 if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, tensor path)");
             }
+    for (int U = 1; U <= 4; ++U)
+        for (int ti = 0; ti < 3 && kTiles[U][ti]; ++ti) {
+            kern_t k = afp_kernel_grouped(U, kTiles[U][ti]);
+            if (!k) continue;
+            e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+            if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, grouped kernel)");
+        }
     for (int epi : kAllEpi) {
         e = cudaFuncSetAttribute((const void*)afp_kernel_tc2(epi), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
         if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, split-FP16 tensor path)");
     }
+    e = cudaFuncSetAttribute((const void*)afp_kernel_tc2_grouped(), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, split-FP16 tensor path, grouped)");
     for (int variant : {afp::AGC_FAST, afp::AGC_EXACT, afp::AGC_CHECKED})
         for (int sb : {1, 2})
             for (int team : {1, 2}) {
@@ -973,6 +1049,9 @@ int afp_destroy(afp_ctx* c) {
     free_stage(c->up); free_stage(c->eq); free_stage(c->mainf); free_stage(c->fused);
     if (c->tmp_agc) cudaFree(c->tmp_agc);
     if (c->range_flag) cudaFree(c->range_flag);
+    if (c->d_group_of_stream) cudaFree(c->d_group_of_stream);
+    if (c->d_gtaps) cudaFree(c->d_gtaps);
+    if (c->d_gcores) cudaFree(c->d_gcores);
     for (auto& kv : c->spec_tables) cudaFree(kv.second);
     if (c->d_il_in) cudaFree(c->d_il_in);
     if (c->d_il_out) cudaFree(c->d_il_out);
@@ -1015,6 +1094,7 @@ static std::vector<double> convolve(const std::vector<double>& a, const std::vec
 }
 
 static int rebuild_fused(afp_ctx* c, bool keep_state = false) {
+    c->groups_dirty = !c->group_of_stream.empty();   // every filter change goes through here: per-group tables follow lazily
     const int U = c->cfg.upsample;
     const bool ref_up = c->cfg.chain == AFP_CHAIN_REFERENCE && U > 1;
     const bool eq_ok = c->cfg.eq_mode == AFP_EQ_NONE || (c->cfg.eq_mode == AFP_EQ_FUSED && c->eq.active);
@@ -1035,6 +1115,159 @@ static int rebuild_fused(afp_ctx* c, bool keep_state = false) {
         if (2 * afp::TC_STREAMS * (kq64 + 256) * 4 + 2 * 8192 + 512 > kMaxSmem) { free_stage(c->fused); return AFP_OK; }
     }
     return build_stage(c, c->fused, ST_MAIN, 1, g0.data(), (int)g0.size(), 1, keep_state);
+}
+
+// ---- per-stream-group filters ------------------------------------------------------------------------------------
+// The one stage of a chain that is a single filter, AGC or not ahead of it (see single_stage below for the launch side).
+static Stage* grouped_stage(afp_ctx* c) {
+    if (c->fused.active) return &c->fused;
+    if (c->cfg.chain == AFP_CHAIN_REFERENCE && c->cfg.upsample > 1) return nullptr;
+    if (c->eq.active || c->cfg.eq_mode != AFP_EQ_NONE) return nullptr;
+    return c->mainf.active ? &c->mainf : nullptr;
+}
+
+// EQ table sum_b g_b h_b with the bands aligned on their 'same' centres (the layout of rebuild_eq, fused form)
+static std::vector<double> eq_table_for(const afp_ctx* c, const double* gains, int only_band = -1) {
+    int cmax = 0, nall = 0;
+    for (auto& b : c->bands) cmax = std::max(cmax, ((int)b.size() - 1) / 2);
+    for (auto& b : c->bands) nall = std::max(nall, cmax - ((int)b.size() - 1) / 2 + (int)b.size());
+    std::vector<double> tab(nall, 0.0);
+    for (size_t i = 0; i < c->bands.size(); ++i) {
+        if (only_band >= 0 && (int)i != only_band) continue;
+        const int off = cmax - ((int)c->bands[i].size() - 1) / 2;
+        const double g = only_band >= 0 ? 1.0 : gains[i];
+        for (size_t k = 0; k < c->bands[i].size(); ++k) tab[off + k] += g * c->bands[i][k];
+    }
+    return tab;
+}
+
+// Taps of the chain's single stage for a main filter and an EQ table: what rebuild_fused computes for the context's own.
+static std::vector<double> single_stage_taps(const afp_ctx* c, const std::vector<double>& main, const std::vector<double>* eq) {
+    if (!c->fused.active) return main;
+    const int U = c->cfg.upsample;
+    const bool ref_up = c->cfg.chain == AFP_CHAIN_REFERENCE && U > 1;
+    std::vector<double> g = main;
+    if (c->cfg.eq_mode == AFP_EQ_FUSED && eq) g = convolve(*eq, g);
+    if (ref_up) g = convolve(c->up.taps, g);
+    const int step = ref_up ? U : 1;
+    std::vector<double> g0((g.size() + step - 1) / step);
+    for (size_t j = 0; j < g0.size(); ++j) g0[j] = g[j * step];
+    return g0;
+}
+
+static int rebuild_groups(afp_ctx* c) {
+    c->groups_dirty = false;
+    if (c->group_of_stream.empty()) return AFP_OK;
+    AFP_CUDA(c, cudaSetDevice(c->cfg.device));
+    Stage* s = grouped_stage(c);
+    if (!s || s->n_sub != 1)
+        return fail(c, AFP_ERR_STATE, "per-group filters need a chain that is ONE filter: eq_mode none or fused (U = 1 or the collapsed "
+                                      "reference chain)");
+    const int G = (int)c->groups.size(), n = s->n_taps;
+    const bool eq = c->fused.active && c->cfg.eq_mode == AFP_EQ_FUSED;
+    const size_t stride = (size_t)s->kq_pad * s->U;
+    AFP_CUDA(c, cudaDeviceSynchronize());      // launches in flight still read the old tables
+    if (c->d_gtaps) { cudaFree(c->d_gtaps); c->d_gtaps = nullptr; }
+    if (c->d_gcores) { cudaFree(c->d_gcores); c->d_gcores = nullptr; }
+    AFP_CUDA(c, cudaMalloc(&c->d_gtaps, (size_t)G * stride * sizeof(float)));
+    c->gtaps_stride = (long long)stride;
+    const bool cores = s->tc2_w != nullptr;
+    const size_t cstride = cores ? (size_t)2 * s->tc2_cores * 64 : 0;
+    if (cores) AFP_CUDA(c, cudaMalloc(&c->d_gcores, (size_t)G * cstride * sizeof(__half)));
+    c->gcores_stride = (long long)cstride;
+    // sessions that only differ in their gains: the stage filter is linear in them, sum_b g_b F_b with F_b the stage
+    // filter of band b alone - ten convolutions for the whole batch instead of one per group
+    std::vector<std::vector<double>> band_stage;
+    if (eq)
+        for (size_t b = 0; b < c->bands.size(); ++b) {
+            const std::vector<double> e1 = eq_table_for(c, nullptr, (int)b);
+            band_stage.push_back(single_stage_taps(c, c->mainf.taps, &e1));
+        }
+    const int chunk = 64;
+    std::vector<float> tab((size_t)chunk * stride);
+    std::vector<__half> cw, cbuf;
+    if (cores) cbuf.resize((size_t)chunk * cstride);
+    for (int g0 = 0; g0 < G; g0 += chunk) {
+        const int gn = std::min(chunk, G - g0);
+        std::fill(tab.begin(), tab.end(), 0.f);
+        for (int gi = 0; gi < gn; ++gi) {
+            const afp_ctx::GroupDef& gd = c->groups[g0 + gi];
+            const double* gains = gd.gains.empty() ? c->gains.data() : gd.gains.data();
+            std::vector<double> t;
+            if (eq && gd.taps.empty()) {
+                t.assign(band_stage[0].size(), 0.0);
+                for (size_t b = 0; b < band_stage.size(); ++b)
+                    for (size_t k = 0; k < t.size(); ++k) t[k] += gains[b] * band_stage[b][k];
+            } else {
+                const std::vector<double>& main = gd.taps.empty() ? c->mainf.taps : gd.taps;
+                if (eq) { const std::vector<double> e = eq_table_for(c, gains); t = single_stage_taps(c, main, &e); }
+                else t = single_stage_taps(c, main, nullptr);
+            }
+            if ((int)t.size() != n)
+                return fail(c, AFP_ERR_INVALID, "a group's filter has another length than the context's: all groups share one stage shape");
+            for (int k = 0; k < n; ++k) tab[(size_t)gi * stride + k] = (float)t[k];
+            if (cores) {
+                afp::tc2_build_cores(t.data(), n, cw);
+                std::memcpy(cbuf.data() + (size_t)gi * cstride, cw.data(), cstride * sizeof(__half));
+            }
+        }
+        AFP_CUDA(c, cudaMemcpy(c->d_gtaps + (size_t)g0 * stride, tab.data(), (size_t)gn * stride * sizeof(float), cudaMemcpyHostToDevice));
+        if (cores)
+            AFP_CUDA(c, cudaMemcpy(static_cast<__half*>(c->d_gcores) + (size_t)g0 * cstride, cbuf.data(), (size_t)gn * cstride * sizeof(__half),
+                                   cudaMemcpyHostToDevice));
+    }
+    if (!c->d_group_of_stream) AFP_CUDA(c, cudaMalloc(&c->d_group_of_stream, (size_t)c->cfg.n_streams * sizeof(int)));
+    AFP_CUDA(c, cudaMemcpy(c->d_group_of_stream, c->group_of_stream.data(), (size_t)c->cfg.n_streams * sizeof(int), cudaMemcpyHostToDevice));
+    AFP_CUDA(c, cudaDeviceSynchronize());
+    s->geo = Geometry();
+    return AFP_OK;
+}
+
+int afp_assign_groups(afp_ctx* c, const int32_t* group_of_stream, int32_t n_streams) {
+    if (!c) return AFP_ERR_INVALID;
+    if (!group_of_stream) {   // back to one filter set for the whole batch
+        c->group_of_stream.clear(); c->groups.clear(); c->groups_dirty = false;
+        for (Stage* s : {&c->fused, &c->mainf}) s->geo = Geometry();
+        return AFP_OK;
+    }
+    if (n_streams != c->cfg.n_streams) return fail(c, AFP_ERR_INVALID, "afp_assign_groups needs one entry per stream");
+    int gmax = 0;
+    for (int i = 0; i < n_streams; ++i) {
+        if (group_of_stream[i] < 0 || group_of_stream[i] >= (1 << 20)) return fail(c, AFP_ERR_INVALID, "group index outside 0..2^20-1");
+        gmax = std::max(gmax, (int)group_of_stream[i]);
+    }
+    c->group_of_stream.assign(group_of_stream, group_of_stream + n_streams);
+    c->groups.resize((size_t)gmax + 1);
+    c->groups_pair_aligned = true;
+    for (int i = 0; i + 1 < n_streams; i += 2)
+        if (group_of_stream[i] != group_of_stream[i + 1]) c->groups_pair_aligned = false;
+    c->groups_dirty = true;
+    return AFP_OK;
+}
+
+int afp_set_gains_group(afp_ctx* c, int32_t group, const double* gains, int32_t n_bands) {
+    if (!c) return AFP_ERR_INVALID;
+    if (group < 0 || group >= (int)c->groups.size()) return fail(c, AFP_ERR_INVALID, "no such group (afp_assign_groups first)");
+    if (!gains) { c->groups[group].gains.clear(); c->groups_dirty = true; return AFP_OK; }
+    if ((size_t)n_bands != c->bands.size()) return fail(c, AFP_ERR_INVALID, "gain count does not match the EQ bank");
+    for (int b = 0; b < n_bands; ++b)
+        if (!std::isfinite(gains[b])) return fail(c, AFP_ERR_INVALID, "non-finite gain");
+    c->groups[group].gains.assign(gains, gains + n_bands);
+    c->groups_dirty = true;
+    return AFP_OK;
+}
+
+int afp_set_taps_group(afp_ctx* c, int32_t group, const double* taps, int32_t n_taps) {
+    if (!c) return AFP_ERR_INVALID;
+    if (group < 0 || group >= (int)c->groups.size()) return fail(c, AFP_ERR_INVALID, "no such group (afp_assign_groups first)");
+    if (!taps) { c->groups[group].taps.clear(); c->groups_dirty = true; return AFP_OK; }
+    if (!c->mainf.active || n_taps != c->mainf.n_taps)
+        return fail(c, AFP_ERR_INVALID, "a group's main filter must have the length of the context's (afp_set_taps)");
+    for (int i = 0; i < n_taps; ++i)
+        if (!std::isfinite(taps[i])) return fail(c, AFP_ERR_INVALID, "non-finite filter tap");
+    c->groups[group].taps.assign(taps, taps + n_taps);
+    c->groups_dirty = true;
+    return AFP_OK;
 }
 
 int afp_set_taps(afp_ctx* c, const double* taps, int32_t n) {
@@ -1274,6 +1507,9 @@ static int check_ready(afp_ctx* c, int32_t frames) {
         return fail(c, AFP_ERR_INVALID, "a fixed same_buffer_len needs frames == max_frames on every call");
     if (((long long)frames * c->cfg.upsample) % c->decim != 0)
         return fail(c, AFP_ERR_INVALID, "frames * upsample is not a multiple of the decimation factor");
+    if (c->groups_dirty) return rebuild_groups(c);
+    if (!c->group_of_stream.empty() && !grouped_stage(c))
+        return fail(c, AFP_ERR_STATE, "per-group filters need a chain that is ONE filter (eq_mode none or fused)");
     return AFP_OK;
 }
 
@@ -1349,8 +1585,9 @@ int afp_process_blocks(afp_ctx* c, const float* in, int64_t in_pitch, int64_t in
         // shared memory; the carried history is read once and written once
         bool done = false;
         if (s->U == 1 && c->decim == 1) {
-            rc = launch_stage_tc2(c, *s, in, in_pitch, in_block_stride, out, out_pitch / unit, out_block_stride / unit, frames, n_blocks,
-                                  c->cfg.out_format, c->cfg.dither, c->out_samples, 0, S, st, &done);
+            auto launch = c->group_of_stream.empty() ? launch_stage_tc2 : launch_stage_tc2_grouped;
+            rc = launch(c, *s, in, in_pitch, in_block_stride, out, out_pitch / unit, out_block_stride / unit, frames, n_blocks,
+                        c->cfg.out_format, c->cfg.dither, c->out_samples, 0, S, st, &done);
             if (rc) return rc;
         }
         if (done) {

@@ -70,6 +70,12 @@ struct FirParams {
     int fast_all;                // every 4-sample group of every region is aligned and lies in one source
     float gain;                  // applied to the accumulators before the epilogue (1.0 = none)
     float dither_lsb;            // float-output dither: value of one LSB (2^-(bits-1))
+    // per-stream-group filters (GROUPED instantiation): the taps of stream s are gtaps + group_of_stream[s] * gstride,
+    // same layout as `taps`; pair_single = 1: one row per work item (the two rows of a pair must share their taps)
+    const float* gtaps;
+    const int* group_of_stream;
+    long long gstride;
+    int pair_single;
     alignas(16) float taps[MAX_TAPS];
 };
 
@@ -392,7 +398,7 @@ struct RowItem {
 // (measured slower), T = 16 needs all 128
 __host__ __device__ constexpr int min_ctas(int T, int NT) { return NT == 256 ? (T == 4 ? 3 : 2) : (T == 4 ? 6 : 4); }
 
-template <int U, int T, int NT, bool MULTI, int EPI>
+template <int U, int T, int NT, bool MULTI, int EPI, bool GROUPED = false>
 __global__ void __launch_bounds__(NT, min_ctas(T, NT))
 fir_stream_kernel(const __grid_constant__ FirParams P) {
     extern __shared__ float4 smem[];
@@ -416,14 +422,15 @@ fir_stream_kernel(const __grid_constant__ FirParams P) {
         // ---- which two rows
         RowItem it[2];
         {
-            const unsigned segA = 2u * (unsigned)pair_idx;
+            const unsigned segA = (GROUPED && P.pair_single) ? (unsigned)pair_idx : 2u * (unsigned)pair_idx;
             unsigned sA, gA;
             if (P.segs_shift >= 0) { sA = segA >> P.segs_shift; gA = segA & ((1u << P.segs_shift) - 1u); }
             else { sA = segA / (unsigned)P.segs_per_stream; gA = segA - sA * (unsigned)P.segs_per_stream; }
             unsigned sB = sA, gB = gA + 1;
             if (gB == (unsigned)P.segs_per_stream) { gB = 0; sB = sA + 1; }
             it[0].stream = (int)sA; it[0].seg = (int)gA; it[0].valid = true;
-            it[1].stream = (int)sB; it[1].seg = (int)gB; it[1].valid = (int)(segA + 1) < P.n_seg_total;
+            it[1].stream = (int)sB; it[1].seg = (int)gB;
+            it[1].valid = (int)(segA + 1) < P.n_seg_total && !(GROUPED && P.pair_single);
             if (!it[1].valid) { it[1].stream = (int)sA; it[1].seg = (int)gA; }   // keep addresses in range
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
@@ -510,7 +517,7 @@ fir_stream_kernel(const __grid_constant__ FirParams P) {
         // ---- L2 prefetch of the next item's rows (lanes 0..3 of the group: row A/B x src0/src1).
         // Only worth its instructions when a region is large (long filters: history >> block).
         if (T == 16 && lt < 4 && pair_idx + stride < P.n_pairs) {
-            const int seg = 2 * (pair_idx + stride) + (lt >> 1);
+            const int seg = (GROUPED && P.pair_single) ? (pair_idx + stride) : 2 * (pair_idx + stride) + (lt >> 1);
             if (seg < P.n_seg_total) {
                 const int s_ = seg / P.segs_per_stream, g_ = seg - s_ * P.segs_per_stream;
                 const int n0 = P.q_begin + g_ * lq - kq, n1 = n0 + region_pairs;   // logical range
@@ -533,7 +540,9 @@ fir_stream_kernel(const __grid_constant__ FirParams P) {
         // taps in uniform registers (LDCU + FFMA2 ..., UR.F32, ...).
         const int n_sub = MULTI ? P.n_sub : 1;
         for (int sb = 0; sb < n_sub; ++sb) {
-            const float* tp = MULTI ? P.taps + sb * P.sub_stride : P.taps;
+            // GROUPED: the item's own table in global memory (every lane reads the same address: one L1 broadcast per load)
+            const float* tp = GROUPED ? P.gtaps + (long long)__ldg(P.group_of_stream + it[0].stream) * P.gstride
+                                      : (MULTI ? P.taps + sb * P.sub_stride : P.taps);
             load_block<T>(wb, region, b0);
             int c = 0;
             for (; c + 2 <= P.n_chunks; c += 2) {

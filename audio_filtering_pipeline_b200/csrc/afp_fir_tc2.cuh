@@ -66,6 +66,13 @@ struct Tc2Params {
     int n_groups;              // ceil(n_streams / 16)
     unsigned int* range_flag;  // set to 1 when a sample does not fit FP16
     long long* prof;           // nullptr, or [grid][8] cycle counters of the MMA warp (bench/microbench/tc2_probe.cu)
+    // GROUPED instantiation (per-stream filters, afp_assign_groups): a work item is ONE stream; its 16 tile slots are 16
+    // consecutive runs of steps_per_slot steps of that stream (slot v starts where slot v-1 ends), so all 16 share the
+    // stream's tap cores gw + group_of_stream[s] * gw_stride, which the loaders bring in when the group changes
+    const __half* gw;
+    long long gw_stride;
+    const int* group_of_stream;
+    int steps_per_slot;
     // epilogue (same meaning as FirParams)
     int fmt, dither, decim, fast_out;
     unsigned long long seed, sample_base;
@@ -149,8 +156,8 @@ __device__ __forceinline__ Tc2Step tc2_step(int n_steps, int group_ordinal, int 
 // The carried samples of the next call: the last hist_len samples of [history | all blocks] of the 16 streams from s0
 // on, copied global -> global (L2 hits) by `nthreads` threads.  Loads go in batches of 8 ahead of their stores (the
 // compiler cannot reorder them itself: the buffers may alias).
-__device__ __forceinline__ void tc2_copy_history(const Tc2Params& P, int s0, int n_steps, int ltid, int nthreads) {
-    const int total = n_steps * TC2_STEP, q4 = P.hist_len >> 2, n_copy = TC2_STREAMS * q4;
+__device__ __forceinline__ void tc2_copy_history(const Tc2Params& P, int s0, int n_rows, int total, int ltid, int nthreads) {
+    const int q4 = P.hist_len >> 2, n_copy = n_rows * q4;
     for (int base = ltid; base < n_copy; base += 8 * nthreads) {
         float4 v[8];
 #pragma unroll
@@ -182,7 +189,7 @@ __device__ __forceinline__ void tc2_copy_history(const Tc2Params& P, int s0, int
     }
 }
 
-template <int EPI>
+template <int EPI, bool GROUPED = false>
 __global__ void __launch_bounds__(TC2_THREADS, 1)
 fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
     extern __shared__ __align__(128) unsigned char tc2_smem[];
@@ -199,8 +206,7 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
 
     constexpr int H = 16;               // history rows of a window (covers 1025 taps; shorter filters skip the oldest)
-    const int steps_per_block = P.frames / TC2_STEP;
-    const int n_steps = steps_per_block * P.n_blocks;
+    const int n_steps = GROUPED ? P.steps_per_slot : (P.frames / TC2_STEP) * P.n_blocks;   // steps of one work item
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(256u) : "memory");
@@ -297,13 +303,14 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
         constexpr int LT = 32 * TC2_LOADERS;
         uint32_t kk = 0;
         float amax = 0.f;
-        int ordinal = 0;
+        int ordinal = 0, cur_group = -1;
         for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x, ++ordinal) {
             const int s0 = grp * TC2_STREAMS;
             // one float4 (4 samples) of window row `wrow` (0..23) of local stream sl at step k
             auto fetch = [&](int k, int sl, int wrow, int f4) -> float4 {
-                const int s = s0 + sl;
-                const int t = k * TC2_STEP - H * TC2_R + wrow * TC2_R + f4 * 4;   // logical sample index: < 0 = carried history
+                const int s = GROUPED ? grp : s0 + sl;
+                // logical sample index of the stream: < 0 = carried history
+                const int t = ((GROUPED ? sl * n_steps : 0) + k) * TC2_STEP - H * TC2_R + wrow * TC2_R + f4 * 4;
                 if (s >= P.n_streams || t < -P.hist_len) return make_float4(0.f, 0.f, 0.f, 0.f);
                 const float* src;
                 if (t < 0) src = P.hist_in + (long long)s * P.hist_pitch + (P.hist_len + t);
@@ -341,10 +348,50 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar);
             };
+            // GROUPED: this stream's tap cores replace the previous stream's unless they share a group
+            bool new_taps = false;
+            const uint4* wsrc = nullptr;
+            if (GROUPED) {
+                const int g = __ldg(P.group_of_stream + grp);
+                new_taps = g != cur_group;
+                cur_group = g;
+                wsrc = reinterpret_cast<const uint4*>(P.gw + (long long)g * P.gw_stride);
+            }
             for (int k = 0; k < n_steps; ++k, ++kk) {
                 const uint32_t p = kk & 1u;
                 const Tc2Step st = tc2_step(n_steps, ordinal, k);
-                if (st.kind == TC2_SLIDE) {
+                if (GROUPED && k == 0 && new_taps) {
+                    // fresh window AND new taps: every MMA of the step needs the taps, and they can only be replaced once
+                    // the previous step is done - so the whole window is published then; the loads are all in flight before
+                    const int sh0 = st.kind == TC2_FRESH0 ? 16 : 0, d0 = st.kind == TC2_FRESH0 ? 0 : 8;
+                    {
+                        float4 v0[8], v1[8];
+                        rows8_fetch(k, d0, v0);
+                        rows8_fetch(k, d0 + 8, v1);
+                        if (kk >= 2) mbar_wait(&mma_done[p], ((kk - 2) >> 1) & 1u);
+                        rows8_place(st.pos, d0, v0);
+                        rows8_place(st.pos, d0 + 8, v1);
+                    }
+                    float4 sv[8];
+                    rows8_fetch(k, sh0, sv);
+                    constexpr int WPT = (2 * tc2_n_cores(17) * 8 + LT - 1) / LT;     // uint4 of tap cores per thread (9)
+                    uint4 wv[WPT];
+                    const int n_w = 2 * P.n_cores * 8;
+#pragma unroll
+                    for (int u = 0; u < WPT; ++u) {
+                        const int j = ltid + u * LT;
+                        wv[u] = j < n_w ? __ldg(wsrc + j) : make_uint4(0u, 0u, 0u, 0u);
+                    }
+                    if (kk >= 1) mbar_wait(&mma_done[p ^ 1u], ((kk - 1) >> 1) & 1u);
+#pragma unroll
+                    for (int u = 0; u < WPT; ++u) {
+                        const int j = ltid + u * LT;
+                        if (j < n_w) reinterpret_cast<uint4*>(w_hi)[j] = wv[u];
+                    }
+                    rows8_place(st.pos, sh0, sv);
+                    publish(&win_early[p]);
+                    publish(&win_late[p]);
+                } else if (st.kind == TC2_SLIDE) {
                     if (lane == 0) mbar_arrive(&win_early[p]);          // the history rows are where the last step left them
                     float4 v[8];
                     rows8_fetch(k, 16, v);
@@ -391,10 +438,12 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
         const int eb = P.fmt == FMT_I16 ? 2 : (P.fmt == FMT_I24_PACKED ? 3 : 4);
         uint32_t kk = 0;
         for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x) {
-            const int s = grp * TC2_STREAMS + (m >> 3);
+            const int s = GROUPED ? grp : grp * TC2_STREAMS + (m >> 3);
             for (int k = 0; k < n_steps; ++k, ++kk) {
                 const uint32_t p = kk & 1u, ph = (kk >> 1) & 1u;
-                const int blk = k / steps_per_block, kb = k - blk * steps_per_block;
+                // first output sample of this thread's 32 within the call: slot m/8 runs through its own steps (GROUPED)
+                const int idx = ((GROUPED ? (m >> 3) * n_steps : 0) + k) * TC2_STEP + (m & 7) * TC2_R + 32 * half;
+                const int blk = idx / P.frames;
                 mbar_wait(&mma_done[p], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t taddr = tmem_base + ((uint32_t)(32 * quarter) << 16) + p * 128u + (uint32_t)(32 * half);
@@ -422,11 +471,11 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                 if (lane == 0) mbar_arrive(&acc_empty[p]);
                 V.out = static_cast<unsigned char*>(P.out) + (long long)blk * P.out_block_stride * eb;
                 V.sample_base = P.sample_base + (unsigned long long)blk * (unsigned long long)P.frames;
-                const long long o_base = (long long)kb * TC2_STEP + (long long)(m & 7) * TC2_R + 32 * half;
-                store_row<32, EPI>(V, y, s, o_base, s < P.n_streams ? 32 : 0);
+                store_row<32, EPI>(V, y, s, (long long)(idx - blk * P.frames), s < P.n_streams ? 32 : 0);
             }
             // (the epilogue warps have the slack for this; in the loaders it would delay the next group's first window)
-            tc2_copy_history(P, grp * TC2_STREAMS, n_steps, tid - 32 * (1 + TC2_LOADERS), 32 * TC2_EPIS);
+            if (GROUPED) tc2_copy_history(P, grp, 1, TC2_STREAMS * n_steps * TC2_STEP, tid - 32 * (1 + TC2_LOADERS), 32 * TC2_EPIS);
+            else tc2_copy_history(P, grp * TC2_STREAMS, TC2_STREAMS, n_steps * TC2_STEP, tid - 32 * (1 + TC2_LOADERS), 32 * TC2_EPIS);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

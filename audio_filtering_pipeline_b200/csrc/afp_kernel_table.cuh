@@ -32,6 +32,10 @@ kern_t pick_kernel(int nt, bool multi, int epi) {
     }
 }
 
+// per-stream-group filters: taps from a per-item table in global memory; generic epilogue, 256-thread CTAs
+template <int U, int T>
+kern_t pick_grouped_kernel() { return (kern_t)fir_stream_kernel<U, T, 256, false, EPI_GENERIC, true>; }
+
 }  // namespace afp
 
 namespace afp { struct TcParams; typedef void (*tc_kern_t)(const TcParams); }
@@ -47,3 +51,4 @@ afp::kern_t afp_kernel_u1(int T, int nt, bool multi, int epi);
 afp::kern_t afp_kernel_u2(int T, int nt, bool multi, int epi);
 afp::kern_t afp_kernel_u3(int T, int nt, bool multi, int epi);
 afp::kern_t afp_kernel_u4(int T, int nt, bool multi, int epi);
+afp::kern_t afp_kernel_grouped(int U, int T);   // afp_kernels_grouped.cu

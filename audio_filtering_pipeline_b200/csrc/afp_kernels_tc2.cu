@@ -12,3 +12,6 @@ afp::tc2_kern_t afp_kernel_tc2(int epi) {
         default: return (tc2_kern_t)fir_tc2_kernel<EPI_GENERIC>;
     }
 }
+
+// per-stream filters (afp_assign_groups): one stream per work item, generic epilogue
+afp::tc2_kern_t afp_kernel_tc2_grouped() { return (afp::tc2_kern_t)afp::fir_tc2_kernel<afp::EPI_GENERIC, true>; }

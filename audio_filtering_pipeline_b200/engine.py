@@ -110,6 +110,33 @@ class BatchFirEngine:
         g, gp = _dbl(gains)
         _lib.check(self._lib.afp_set_gains(self._ctx, gp, len(g)), self._ctx)
 
+    # -- per-stream-group filters ---------------------------------------------------------------
+    def assign_groups(self, group_of_stream):
+        """Give every stream a filter group (``None``: back to one filter set): sessions with their own EQ gains or
+        main taps inside one batch, as every reference process reads its own sliders per block
+        (stream_process_EQ_GUI.py:86-90).  The chain must be one filter per stream (eq_mode 'none' or 'fused')."""
+        if group_of_stream is None:
+            _lib.check(self._lib.afp_assign_groups(self._ctx, None, 0), self._ctx)
+            return
+        g = np.ascontiguousarray(group_of_stream, dtype=np.int32).ravel()
+        _lib.check(self._lib.afp_assign_groups(self._ctx, g.ctypes.data_as(C.POINTER(C.c_int32)), len(g)), self._ctx)
+
+    def set_group_gains(self, group, gains):
+        """EQ gains of one group (``None``: the engine-level gains); takes effect at the next block, state kept."""
+        if gains is None:
+            _lib.check(self._lib.afp_set_gains_group(self._ctx, int(group), None, 0), self._ctx)
+            return
+        a, p = _dbl(gains)
+        _lib.check(self._lib.afp_set_gains_group(self._ctx, int(group), p, len(a)), self._ctx)
+
+    def set_group_taps(self, group, taps):
+        """Main filter of one group, same length as the engine's (``None``: the engine-level taps)."""
+        if taps is None:
+            _lib.check(self._lib.afp_set_taps_group(self._ctx, int(group), None, 0), self._ctx)
+            return
+        a, p = _dbl(taps)
+        _lib.check(self._lib.afp_set_taps_group(self._ctx, int(group), p, len(a)), self._ctx)
+
     def set_agc(self, enabled=True, **params):
         """Switch the input AGC on (keyword arguments of ``apply_agc`` plus ``clip``) or off
         (``set_agc(False)``).  Takes effect at the next block."""

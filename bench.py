@@ -458,14 +458,19 @@ def config_points(D, args, cpu, fma_peak, peaks_run, peaks_file, ceiling):
                    cpu=("reference_chain", {"taps": h1, "up_taps": up4, "upsample": 4, "frames": 1024})),
         "C3_per_band": dict(desc="10-band EQ (9 reference bands + 16-20 kHz) x 501 taps accumulated band by band, then 501-tap low-pass, "
                                  "48 kHz stereo sessions, 1024-frame blocks",
-                            S=4096, B=1024, NB=4, eng=dict(taps=main48, eq_bands=bank, eq_gains=EQ_GAINS_10, eq_mode="per_band"),
+                            S=8192, B=1024, NB=8, eng=dict(taps=main48, eq_bands=bank, eq_gains=EQ_GAINS_10, eq_mode="per_band"),
                             n_exec=501, U=1, out_mult=1, out_bytes=4, flop=2.0 * (10 * 501 + 501), stage=0,
                             cpu=("eq", {"taps": main48, "eq_taps": bank, "eq_gains": EQ_GAINS_10, "frames": 1024})),
         "C3_fused": dict(desc="the same EQ in the fused form (taps-domain sum, stream_process_EQ_GUI.py:86-90) folded into the main "
                               "filter: one 1001-tap FIR",
-                         S=4096, B=1024, NB=4, eng=dict(taps=main48, eq_bands=bank, eq_gains=EQ_GAINS_10, eq_mode="fused"),
+                         S=8192, B=1024, NB=16, eng=dict(taps=main48, eq_bands=bank, eq_gains=EQ_GAINS_10, eq_mode="fused"),
                          n_exec=1001, U=1, out_mult=1, out_bytes=4,
                          cpu=("eq", {"taps": main48, "eq_taps": bank, "eq_gains": EQ_GAINS_10, "frames": 1024})),
+        "C3_fused_4096_gain_sets": dict(
+            desc="C3 fused with per-session gains: 4096 stereo sessions, each with its own 10 gains (afp_assign_groups / "
+                 "afp_set_gains_group) - one 1001-tap filter per session, per-stream Hankel tap cores on the tensor kernel",
+            S=8192, B=1024, NB=16, eng=dict(taps=main48, eq_bands=bank, eq_gains=EQ_GAINS_10, eq_mode="fused"), groups=4096,
+            n_exec=1001, U=1, out_mult=1, out_bytes=4, cpu=None),
         "C4": dict(desc=f"501-tap boxcar high-pass -> minimum phase ({len(h4)} taps) as the 2x polyphase interpolator, 4096 streams, "
                         "1024-frame blocks, output at 2 fs",
                    S=4096, B=1024, NB=8, eng=dict(taps=2 * h4, upsample=2, chain="dac"),
@@ -475,6 +480,12 @@ def config_points(D, args, cpu, fma_peak, peaks_run, peaks_file, ceiling):
     for name, sp in specs.items():
         S, B, NB = sp["S"], sp["B"], sp["NB"]
         eng = BatchFirEngine(n_streams=S, max_frames=B, device=D.local, first_stream_id=D.rank * S, seed=2024, **sp["eng"])
+        if sp.get("groups"):
+            G = sp["groups"]
+            eng.assign_groups(np.arange(S) * G // S)
+            gg = np.round(np.random.default_rng(7).uniform(0.4, 1.6, (G, len(EQ_GAINS_10))), 3)
+            for gi in range(G):
+                eng.set_group_gains(gi, gg[gi])
         cols = eng._out_cols(B)
         x = torch.empty((NB, S, B), device=D.dev).normal_(0.0, 0.1).clamp_(-1.0, 1.0)
         y = torch.empty((NB, S, cols), device=D.dev, dtype=torch.float32)
@@ -499,7 +510,7 @@ def config_points(D, args, cpu, fma_peak, peaks_run, peaks_file, ceiling):
         entry = {"workload": sp["desc"], "streams_per_gpu": S, "frames_per_block": B, "blocks_per_step": NB,
                  "value": round(value, 1), "unit": "Msamples/s", "ms_per_step": round(ms_max / 10, 4), "e2e": e2e, "roofline": roof,
                  "stage": [{k: st[k] for k in ("kind", "n_taps", "kernel", "upsample")} for st in stage]}
-        if cpu is not None:
+        if cpu is not None and sp["cpu"] is not None:
             entry["cpu_baseline"] = cpu.measure(*sp["cpu"], seconds=args.cpu_seconds / 4)
         out[name] = entry
     return out

@@ -108,6 +108,23 @@ typedef struct afp_stage_info {
                                  U = 1 filters, blocks of a multiple of 512 frames) */
 } afp_stage_info;
 
+/* Per-stream-group filters: sessions with their own EQ gains (or their own main filter) inside ONE batch - what every
+ * reference process does when it reads its own sliders per block (stream_process_EQ_GUI.py:86-90,
+ * stream_process_GUI_Presets.py:603-607) and swaps its filter under filter_lock (:380-385).
+ *   afp_assign_groups     group_of_stream[s] in 0..G-1 for every stream (NULL: back to one filter set).  Two streams of
+ *                         one session (stereo) normally share a group.
+ *   afp_set_gains_group   EQ gains of one group (NULL: the context's gains, afp_set_eq / afp_set_gains)
+ *   afp_set_taps_group    main filter of one group, same length as the context's (NULL: the context's taps)
+ * The chain must be one filter per stream: eq_mode AFP_EQ_NONE or AFP_EQ_FUSED with U = 1 or the collapsed reference
+ * chain (for stream s it is  (h_up * sum_b g_{group(s),b} h_b * h_{group(s)})[::U]).  Tables are rebuilt at the next
+ * process call; the carried samples are kept (they are input samples, valid for any taps), so a change of gains
+ * between two blocks is the reference's live filter swap.  Per-group tables live in device memory and are read per
+ * work item by the packed-FFMA2 row-pair kernel; long U = 1 filters in afp_process_blocks calls of a multiple of
+ * 16 x 512 frames run on the tensor cores with per-stream Hankel tap cores. */
+int afp_assign_groups(afp_ctx* ctx, const int32_t* group_of_stream, int32_t n_streams);
+int afp_set_gains_group(afp_ctx* ctx, int32_t group, const double* gains, int32_t n_bands);
+int afp_set_taps_group(afp_ctx* ctx, int32_t group, const double* taps, int32_t n_taps);
+
 /* Automatic gain control of the input block (stream_process_AGC.py:43-89), per block and stateless like
  * the reference.  Defaults of apply_agc / of its call site in comments. */
 typedef struct afp_agc_params {
