@@ -10,7 +10,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/afp.h"
@@ -24,7 +26,7 @@
 
 afp::tc2_kern_t afp_kernel_tc2(int epi);                                    // afp_kernels_tc2.cu
 afp::tc2_kern_t afp_kernel_tc2_grouped();
-afp::agc_kern_t afp_kernel_agc(int variant, int scan_blocks, int team);   // afp_kernels_agc.cu: variant AGC_*, scan_blocks 1 / 2, team 1 / 2
+afp::agc_kern_t afp_kernel_agc(int variant);   // afp_kernels_agc.cu: variant AGC_*
 
 using afp::FirParams;
 
@@ -142,6 +144,8 @@ int tile_for(int U, int n_taps) {
 
 }  // namespace
 
+struct AgcPlanEntry { int group = 0, grid = 0; size_t smem = 0; };
+
 struct afp_ctx {
     afp_config cfg{};
     std::string err;
@@ -176,6 +180,7 @@ struct afp_ctx {
     unsigned char* d_out[kSlots] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_in[kSlots] = {}, ev_k[kSlots] = {}, ev_out[kSlots] = {};
     int slot_streams = 0;            // streams per staging slot
+    std::map<std::pair<int, int>, AgcPlanEntry> agc_plans;   // launch shape of the AGC kernel per (variant, streams)
     // afp_spectrum_db: per block length n, device tables [window n floats | twiddles n/2 float2]
     std::map<int, float*> spec_tables;
     // afp_process_host_interleaved: frame-major device copies of one block in / out
@@ -367,52 +372,32 @@ Geometry pick_geometry(int T, int kq_pad, int n_q, int n_streams, int nt_min = 1
     return best;
 }
 
-// ---- AGC (afp_agc.cuh).  Shared memory per CTA: one float row per stream of the work item (pitch 4 x odd)
-// + one float64 prefix-sum row per warp or warp pair + a flag per stream.  Two (short blocks: three) CTAs per SM when at
-// least 8 streams fit in that share of an SM's shared memory (one CTA's serial recurrence phase overlaps
-// the others' memory phases), else one CTA with as many streams as fit.
-struct AgcPlan { int warps = 0, team = 1, group = 0, pitch = 0, ctas_per_sm = 0, scratch = 0; size_t smem = 0; };   // warps = prefix rows (teams)
-bool plan_agc(int frames, int n_streams, int n_sm, AgcPlan& pl) {
-    const int pitch = 4 * (((frames + 3) / 4) | 1);   // an odd number of 16-byte units
-    const size_t row = (size_t)pitch * sizeof(float) + sizeof(int);
-    struct Try { size_t budget; int warps, min_group, ctas; };
-    const Try tries[] = {{74 * 1024, 4, 8, 3}, {112 * 1024, 4, 8, 2}, {224 * 1024, 4, 4, 1}, {224 * 1024, 2, 1, 1}, {224 * 1024, 1, 1, 1}};
-    // three smaller CTAs per SM pay for short blocks (measured, 16384 streams: 512 frames 192 vs 160
-    // Gsamples/s, 256 frames 140 vs 113; 1024 frames 165 vs 169)
-    const int plan_from = frames <= 512 ? 0 : 1;
-    for (int ti = plan_from; ti < 5; ++ti) {
-        const Try& t = tries[ti];
-        const int scratch = afp::agc_phys(frames) + 2;   // prefix sums 0..frames, one pad double per 16
-        const size_t fixed = (size_t)t.warps * (scratch + 1) * sizeof(double) + 16;
-        if (fixed + row * t.min_group > t.budget) continue;
-        long long g = (long long)((t.budget - fixed) / row);
-        if (g > 32 * t.warps) g = 32 * t.warps;
-        // equal work per CTA: with `rounds` items per CTA the group that covers the batch exactly (also spreads
-        // a small batch over all SMs instead of filling a few CTAs)
-        const long long grid = (long long)n_sm * t.ctas;
-        const long long items = (n_streams + g - 1) / g, rounds = (items + grid - 1) / grid;
-        const long long even = (n_streams + rounds * grid - 1) / (rounds * grid);
-        if (g > even) g = even < 1 ? 1 : even;
-        pl.warps = t.warps; pl.group = (int)g; pl.pitch = pitch; pl.ctas_per_sm = t.ctas;
-        pl.scratch = scratch;
-        pl.smem = ((((size_t)g * pitch * sizeof(float)) + 7) & ~(size_t)7) + (size_t)t.warps * (scratch + 1) * sizeof(double) +
-                  (size_t)g * sizeof(int);
-        // two warps per prefix row above 512 frames (measured, 16384 streams: 1024 frames 211 vs 175 Gsamples/s,
-        // 2048: 136 vs 103, 4096: 58 vs 47; 512 frames 115 vs 199 - three 4-warp CTAs per SM win there);
-        // AFP_AGC_TEAM=1|2 overrides for A/B runs
-        pl.team = frames > 512 ? 2 : 1;
-        if (const char* v = std::getenv("AFP_AGC_TEAM")) pl.team = std::atoi(v) == 2 ? 2 : 1;
-        return true;
+// ---- AGC (afp_agc.cuh).  A work item is `group` streams x the whole block, one 256-sample row per stream in shared
+// memory, at most 32 streams per item (one lane each in the recurrence phase).  Items are dealt round-robin over a
+// persistent grid, every item takes the same time, and the recurrence runs at 13.5 clk per sample and lane whatever the
+// group size - so the group is chosen for the fullest last wave (65536 streams: 32 per item are 2.3 waves of 888 CTAs,
+// 22 per item 2.9 waves of 1036), and a small batch is spread over every SM.
+using AgcPlan = AgcPlanEntry;
+int plan_agc(afp_ctx* c, afp::agc_kern_t k, int n_streams, AgcPlan& pl) {
+    double best = -1.0;
+    for (int g = afp::AGC_MAX_GROUP; g >= 8; --g) {
+        const size_t smem = afp::agc_smem_bytes(g);
+        int per_sm = 0;
+        AFP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, afp::AGC_THREADS, smem));
+        if (per_sm < 1) continue;
+        const long long slots = (long long)c->n_sm * per_sm, items = (n_streams + g - 1) / g;
+        const long long waves = (items + slots - 1) / slots;
+        // time ~ waves x (phases of one item, nearly independent of g); streams per SM in flight = per_sm x g
+        const double eff = (double)items / (double)(waves * slots);
+        const double score = (items >= slots ? eff : eff * 0.5 + 0.5 * (double)std::min<long long>(items, c->n_sm) / c->n_sm) + 1e-4 * g;
+        if (score > best) { best = score; pl.group = g; pl.grid = (int)std::min(items, slots); pl.smem = smem; }
     }
-    return false;
+    return best < 0 ? fail(c, AFP_ERR_INVALID, "AGC kernel does not fit on an SM") : AFP_OK;
 }
 
 int launch_agc(afp_ctx* c, const afp_agc_params& a, const float* in, long long in_pitch, float* out, long long out_pitch,
                int ns, int frames, cudaStream_t stream) {
     if (ns < 1 || frames < 1) return AFP_OK;
-    AgcPlan pl;
-    if (!plan_agc(frames, ns, c->n_sm, pl))
-        return fail(c, AFP_ERR_INVALID, "AGC: the block is too long for one SM's shared memory (about 19000 frames)");
     afp::AgcParams P{};
     P.in = in; P.in_pitch = in_pitch; P.out = out; P.out_pitch = out_pitch;
     P.n_streams = ns; P.frames = frames;
@@ -422,25 +407,37 @@ int launch_agc(afp_ctx* c, const afp_agc_params& a, const float* in, long long i
     P.passthrough = (W < 1 || W > frames) ? 1 : 0;
     P.window = W < 1 ? 1 : W; P.left = P.window / 2; P.right = (P.window - 1) / 2;   // np.convolve 'same' centring
     P.inv_window = (float)(1.0 / P.window);
-    P.group = pl.group; P.pitch = pl.pitch; P.n_items = (ns + pl.group - 1) / pl.group;
     P.target = (float)a.target_level; P.max_gain = (float)a.max_gain; P.min_gain = 0.1f;   // :83
     P.clip = (float)a.clip;
     const int att_n = (int)(a.attack * (double)W), rel_n = (int)(a.release * (double)W);   // :56-57
     P.att_ok = att_n != 0; P.rel_ok = rel_n != 0;
     const double aa = P.att_ok ? 1.0 - std::exp(-1.0 / att_n) : 0.0, ar = P.rel_ok ? 1.0 - std::exp(-1.0 / rel_n) : 0.0;   // :73-78
     P.a_att = (float)aa; P.c_att = (float)(1.0 - aa); P.a_rel = (float)ar; P.c_rel = (float)(1.0 - ar);
-    P.scratch = pl.scratch;
     // The reference divides by (rms + 1e-10).  Wherever the gain is not clamped to max_gain, rms exceeds
     // target/max_gain; if that is >= 1e-4 the epsilon moves the gain by < 1e-6 relative and the kernel may
     // use target*rsqrt(mean) (a zero window then gives +inf -> max_gain, as the reference's 1e9 clip does).
     const bool fast = a.target_level > 0 && a.max_gain > 0 && a.target_level / a.max_gain >= 1e-4;
     P.fast_scale = (float)(a.target_level * std::sqrt((double)P.window));
-    const int variant = !(P.att_ok && P.rel_ok) ? afp::AGC_CHECKED : (fast ? afp::AGC_FAST : afp::AGC_EXACT);
-    const int part = pl.team == 2 ? (((frames + 1) / 2 + 15) & ~15) : frames;   // samples per warp in the gain phase
-    afp::agc_kern_t k = afp_kernel_agc(variant, part > 512 ? 2 : 1, pl.team);
-    int grid = c->n_sm * pl.ctas_per_sm;
-    if (grid > P.n_items) grid = P.n_items;
-    k<<<grid, 32 * pl.warps * pl.team, pl.smem, stream>>>(P);
+    int variant = !(P.att_ok && P.rel_ok) ? afp::AGC_CHECKED : (fast ? afp::AGC_FAST : afp::AGC_EXACT);
+    P.probe = std::getenv("AFP_AGC_PROBE") ? std::atoi(std::getenv("AFP_AGC_PROBE")) : 0;   // timing probes, not a product path
+    if (variant == afp::AGC_FAST && (P.probe & 1)) variant = afp::AGC_PROBE_F32;
+    afp::agc_kern_t k = afp_kernel_agc(variant);
+    AgcPlan& pl = c->agc_plans[{variant, ns}];
+    if (!pl.group) {
+        if (int rc = plan_agc(c, k, ns, pl)) return rc;
+        if (const char* v = std::getenv("AFP_AGC_GROUP")) {   // tuning experiments
+            const int g = std::atoi(v);
+            if (g >= 1 && g <= afp::AGC_MAX_GROUP) {
+                int per_sm = 1;
+                pl.group = g; pl.smem = afp::agc_smem_bytes(g);
+                AFP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, afp::AGC_THREADS, pl.smem));
+                pl.grid = (int)std::min<long long>((ns + g - 1) / g, (long long)c->n_sm * std::max(per_sm, 1));
+            }
+        }
+    }
+    P.group = pl.group;
+    P.n_items = (ns + P.group - 1) / P.group;
+    k<<<pl.grid, afp::AGC_THREADS, pl.smem, stream>>>(P);
     AFP_CUDA(c, cudaGetLastError());
     c->launches++;
     return AFP_OK;
@@ -1021,12 +1018,10 @@ int afp_create(const afp_config* cfg, afp_ctx** out_ctx) {
     }
     e = cudaFuncSetAttribute((const void*)afp_kernel_tc2_grouped(), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, split-FP16 tensor path, grouped)");
-    for (int variant : {afp::AGC_FAST, afp::AGC_EXACT, afp::AGC_CHECKED})
-        for (int sb : {1, 2})
-            for (int team : {1, 2}) {
-                e = cudaFuncSetAttribute((const void*)afp_kernel_agc(variant, sb, team), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-                if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, AGC)");
-            }
+    for (int variant : {afp::AGC_FAST, afp::AGC_EXACT, afp::AGC_CHECKED, afp::AGC_PROBE_F32}) {
+        e = cudaFuncSetAttribute((const void*)afp_kernel_agc(variant), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+        if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, AGC)");
+    }
     afp_ctx* c = new (std::nothrow) afp_ctx();
     if (!c) return fail(nullptr, AFP_ERR_NOMEM, "out of host memory");
     c->cfg = *cfg;
