@@ -25,7 +25,7 @@ SYMBOLS = [
     "afp_get_stage_info", "afp_kernel_launches", "afp_host_alloc", "afp_host_free",
     "afp_measure_fma_peak", "afp_set_agc", "afp_agc_block", "afp_process_host_interleaved", "afp_swap_taps", "afp_spectrum_db",
     "afp_process_blocks", "afp_range_status", "afp_measure_tensor_peak",
-    "afp_assign_groups", "afp_set_gains_group", "afp_set_taps_group",
+    "afp_assign_groups", "afp_set_gains_group", "afp_set_taps_group", "afp_host_alloc_wc",
 ]
 
 
@@ -110,6 +110,7 @@ def load():
     lib.afp_kernel_launches.argtypes = [vp]
     lib.afp_kernel_launches.restype = i64
     lib.afp_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    lib.afp_host_alloc_wc.argtypes = [C.POINTER(vp), C.c_size_t]
     lib.afp_host_free.argtypes = [vp]
     lib.afp_measure_fma_peak.argtypes = [i32, dp, dp]
     lib.afp_measure_tensor_peak.argtypes = [i32, i32, dp, dp, dp]

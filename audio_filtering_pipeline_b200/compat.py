@@ -27,7 +27,7 @@ from . import design
 from .engine import BatchFirEngine
 
 __all__ = ["make_audio_callback", "OverlapAddFilter", "process_audio_block", "apply_dither",
-           "safe_upsample", "safe_downsample", "apply_agc", "StreamChain"]
+           "safe_upsample", "safe_downsample", "apply_agc", "StreamChain", "Resampler", "close_helpers"]
 
 
 class StreamChain:
@@ -191,8 +191,18 @@ def process_audio_block(gui, upsampled_block):
     return current_eq_sum
 
 
-# --- helper shims (module-level state like the reference's globals) --------------------------------
+# --- helper shims ------------------------------------------------------------------------------------
+# The reference's helpers are plain functions, called from the audio thread and from GUI worker threads alike, and its
+# resampler (soxr.resample per block) keeps nothing between calls.  The engines behind the shims are cached per shape,
+# so: one lock serialises their use (a context is single-owner), and a call WITHOUT a `state` object starts from a
+# cleared history - two streams, channels or threads that happen to share a block length never see each other's
+# samples.  Streaming use (history carried from block to block, what StreamChain does internally) takes an explicit
+# per-stream Resampler.
+import atexit
+import threading
+
 _ENGINES = {}
+_LOCK = threading.RLock()
 
 
 def _cached(key, factory):
@@ -202,14 +212,56 @@ def _cached(key, factory):
     return eng
 
 
+def close_helpers():
+    """Release the engines the helper shims have created (also runs at interpreter exit)."""
+    with _LOCK:
+        for eng in _ENGINES.values():
+            try:
+                eng.close()
+            except Exception:                                                  # noqa: BLE001
+                pass
+        _ENGINES.clear()
+
+
+atexit.register(close_helpers)
+
+
+class Resampler:
+    """Per-stream state for :func:`safe_upsample` / :func:`safe_downsample`: an integer-factor polyphase interpolator
+    (``up=True``) or anti-alias decimator with its own carried history.  One object per stream and direction."""
+
+    def __init__(self, factor, sr=44100, blocksize=4096, up=True, device=0):
+        self.factor, self.sr, self.blocksize, self.up = int(factor), int(sr), int(blocksize), bool(up)
+        taps = design.design_upsampler(self.factor, self.sr)
+        if up:
+            self.engine = BatchFirEngine(taps, n_streams=1, max_frames=self.blocksize, upsample=self.factor, chain="dac", device=device)
+        else:
+            self.engine = BatchFirEngine(taps / self.factor, n_streams=1, max_frames=self.blocksize, upsample=1, chain="dac",
+                                         decimate=self.factor, device=device)
+        self._lock = threading.Lock()
+
+    def process(self, x):
+        with self._lock:
+            return self.engine.process_host(np.ascontiguousarray(x, dtype=np.float32)[None, :])[0]
+
+    def reset(self):
+        with self._lock:
+            self.engine.reset()
+
+    def close(self):
+        self.engine.close()
+
+
 def apply_dither(audio, bit_depth=24):
     """``audio + uniform(-0.5, 0.5) LSB`` at LSB = 2/2**bit_depth (stream_process.py:61-64), drawn
-    from the engine's Philox stream instead of numpy's global RNG.  Returns float32."""
+    from the engine's Philox stream instead of numpy's global RNG (successive calls continue the stream; every
+    block length has its own seed).  Returns float32."""
     a = np.asarray(audio, dtype=np.float32)
     flat = a.reshape(1, -1)
-    eng = _cached(("dither", flat.shape[1], int(bit_depth)), lambda: BatchFirEngine(
-        [1.0], n_streams=1, max_frames=flat.shape[1], dither="rpdf", dither_bits=int(bit_depth), seed=0x5EED))
-    return eng.process_host(flat).reshape(a.shape)
+    with _LOCK:
+        eng = _cached(("dither", flat.shape[1], int(bit_depth)), lambda: BatchFirEngine(
+            [1.0], n_streams=1, max_frames=flat.shape[1], dither="rpdf", dither_bits=int(bit_depth), seed=0x5EED + len(_ENGINES)))
+        return eng.process_host(flat).reshape(a.shape)
 
 
 def apply_agc(signal, target_level=0.1, window_size=512, alpha=0.01, max_gain=10.0, attack=0.01, release=0.1):
@@ -221,51 +273,72 @@ def apply_agc(signal, target_level=0.1, window_size=512, alpha=0.01, max_gain=10
     import torch
     sig = np.asarray(signal, dtype=np.float32)
     sig = np.atleast_2d(sig).T if sig.ndim == 1 else sig                       # :52-53
-    # (outside the try: a missing library or device must raise, not look like the reference's pass-through)
-    eng = _cached(("agc",), lambda: BatchFirEngine([1.0], n_streams=1, max_frames=1))
-    try:
-        x = np.ascontiguousarray(sig[:, 0])[None, :]
-        xd = torch.from_numpy(x).cuda(eng.device)
-        y = eng.agc_block(xd, target_level=target_level, window_size=window_size, max_gain=max_gain,
-                          attack=attack, release=release, clip=0.0)
-        return y.cpu().numpy()[0][:, None]
-    except Exception as exc:                                                   # noqa: BLE001 (:87-89)
-        print(f"AGC error: {exc}, shape={sig.shape}")
-        return sig
+    with _LOCK:
+        # (outside the try: a missing library or device must raise, not look like the reference's pass-through)
+        eng = _cached(("agc",), lambda: BatchFirEngine([1.0], n_streams=1, max_frames=1))
+        try:
+            x = np.ascontiguousarray(sig[:, 0])[None, :]
+            xd = torch.from_numpy(x).cuda(eng.device)
+            y = eng.agc_block(xd, target_level=target_level, window_size=window_size, max_gain=max_gain,
+                              attack=attack, release=release, clip=0.0)
+            return y.cpu().numpy()[0][:, None]
+        except Exception as exc:                                               # noqa: BLE001 (:87-89)
+            print(f"AGC error: {exc}, shape={sig.shape}")
+            return sig
 
 
-def safe_upsample(data, sr=44100, upsr=176400):
-    """Interpolation by ``upsr/sr`` (1..4).  Streaming polyphase FIR with carried state in place of the
-    reference's one-shot ``soxr.resample`` per block; zeros on failure like :75-77."""
+def safe_upsample(data, sr=44100, upsr=176400, state=None):
+    """Interpolation by ``upsr/sr`` (1..4) with the polyphase FIR of ``design.design_upsampler``; zeros on failure like
+    stream_process.py:75-77.  Without ``state`` every call is on its own, like the reference's one-shot ``soxr.resample``
+    per block (the block starts from silence); with a :class:`Resampler` the history is carried from block to block
+    (what a streaming interpolator should do, and what StreamChain does)."""
     x = np.asarray(data, dtype=np.float32)
     x = x[:, 0] if x.ndim > 1 else x                                           # :70
     if upsr == sr:
         return x.astype(np.float32)                                            # stream_process_EQ_GUI.py:422-423
     if upsr < sr:
-        return safe_downsample(x, sr, upsr, int(round(len(x) * upsr / sr)))
+        return safe_downsample(x, sr, upsr, int(round(len(x) * upsr / sr)), state=state)
     factor = int(round(upsr / sr))
-    # (outside the try: a missing library or device must raise, not turn into the reference's block of zeros)
-    eng = _cached(("up", factor, len(x), int(sr)), lambda: BatchFirEngine(
-        design.design_upsampler(factor, sr), n_streams=1, max_frames=len(x), upsample=factor, chain="dac"))
-    try:
-        return eng.process_host(x[None, :])[0]
-    except Exception as exc:                                                   # noqa: BLE001
-        print(f"Upsample error: {exc}")
-        return np.zeros(int(len(data) * upsr / sr), dtype=np.float32)
+    if state is not None:
+        try:
+            return state.process(x)
+        except Exception as exc:                                               # noqa: BLE001
+            print(f"Upsample error: {exc}")
+            return np.zeros(int(len(data) * upsr / sr), dtype=np.float32)
+    with _LOCK:
+        # (outside the try: a missing library or device must raise, not turn into the reference's block of zeros)
+        eng = _cached(("up", factor, len(x), int(sr)), lambda: BatchFirEngine(
+            design.design_upsampler(factor, sr), n_streams=1, max_frames=len(x), upsample=factor, chain="dac"))
+        try:
+            eng.reset()
+            return eng.process_host(x[None, :])[0]
+        except Exception as exc:                                               # noqa: BLE001
+            print(f"Upsample error: {exc}")
+            return np.zeros(int(len(data) * upsr / sr), dtype=np.float32)
 
 
-def safe_downsample(data, upsr, sr, expected_len):
-    """Anti-alias FIR + keep every ``upsr/sr``-th sample (stream_process_EQ_GUI.py:429-436)."""
+def safe_downsample(data, upsr, sr, expected_len, state=None):
+    """Anti-alias FIR + keep every ``upsr/sr``-th sample (stream_process_EQ_GUI.py:429-436); ``state`` as in
+    :func:`safe_upsample` (a ``Resampler(..., up=False)``)."""
     x = np.asarray(data, dtype=np.float32).ravel()
     if upsr == sr:
         return x
     factor = int(round(upsr / sr))
-    eng = _cached(("down", factor, len(x), int(sr)), lambda: BatchFirEngine(
-        design.design_upsampler(factor, sr) / factor, n_streams=1, max_frames=len(x), upsample=1,
-        chain="dac", decimate=factor))                                         # (raises without library / device)
-    try:
-        y = eng.process_host(x[None, :])[0]
-        return np.resize(y, expected_len) if len(y) != expected_len else y
-    except Exception as exc:                                                   # noqa: BLE001
-        print(f"Downsample error: {exc}")
-        return np.zeros(expected_len, dtype=np.float32)
+    if state is not None:
+        try:
+            y = state.process(x)
+            return np.resize(y, expected_len) if len(y) != expected_len else y
+        except Exception as exc:                                               # noqa: BLE001
+            print(f"Downsample error: {exc}")
+            return np.zeros(expected_len, dtype=np.float32)
+    with _LOCK:
+        eng = _cached(("down", factor, len(x), int(sr)), lambda: BatchFirEngine(
+            design.design_upsampler(factor, sr) / factor, n_streams=1, max_frames=len(x), upsample=1,
+            chain="dac", decimate=factor))                                     # (raises without library / device)
+        try:
+            eng.reset()
+            y = eng.process_host(x[None, :])[0]
+            return np.resize(y, expected_len) if len(y) != expected_len else y
+        except Exception as exc:                                               # noqa: BLE001
+            print(f"Downsample error: {exc}")
+            return np.zeros(expected_len, dtype=np.float32)

@@ -168,6 +168,7 @@ struct afp_ctx {
     float* xhist[2] = {nullptr, nullptr};
     long long xhist_pitch = 0;
     int xhist_len = -1, xhist_cur = 0;
+    bool xhist_migrate = false, xhist_reset = false;   // next ensure_tmp: keep (afp_swap_taps) / clear (afp_set_taps) the sliding buffer
     int eq_centre = 0;               // (N_eq-1)//2 of the widest band: 'same' centring
     unsigned long long out_samples = 0;   // kept output samples per stream since reset
     long long launches = 0;
@@ -869,13 +870,28 @@ int ensure_tmp(afp_ctx* c) {
         const int hm = c->cfg.same_buffer_len > 0 ? c->cfg.same_buffer_len - (int)rate_len : c->mainf.n_taps - 1;
         if (hm < c->mainf.n_taps - 1)
             return fail(c, AFP_ERR_INVALID, "same_buffer_len is shorter than max_frames*rate + N_main - 1");
-        if (c->xhist_len != hm) {
-            for (int i = 0; i < 2; ++i) { if (c->xhist[i]) cudaFree(c->xhist[i]); c->xhist[i] = nullptr; }
+        if (c->xhist_len != hm || c->xhist_reset) {
+            // afp_swap_taps with another filter length: the carried samples move over right-aligned (a row is the last
+            // xhist_len processing-rate input samples, oldest first); afp_set_taps: cleared like every other state
+            float* old = (c->xhist_migrate && !c->xhist_reset && c->xhist[c->xhist_cur]) ? c->xhist[c->xhist_cur] : nullptr;
+            const long long old_pitch = c->xhist_pitch;
+            const int old_len = c->xhist_len;
+            for (int i = 0; i < 2; ++i) { if (c->xhist[i] && c->xhist[i] != old) cudaFree(c->xhist[i]); c->xhist[i] = nullptr; }
             c->xhist_pitch = (hm + 3) / 4 * 4 + 4;
             for (int i = 0; i < 2; ++i) {
-                AFP_CUDA(c, cudaMalloc(&c->xhist[i], (size_t)S * c->xhist_pitch * sizeof(float)));
-                AFP_CUDA(c, cudaMemset(c->xhist[i], 0, (size_t)S * c->xhist_pitch * sizeof(float)));
+                cudaError_t e = cudaMalloc(&c->xhist[i], (size_t)S * c->xhist_pitch * sizeof(float));
+                if (e == cudaSuccess) e = cudaMemset(c->xhist[i], 0, (size_t)S * c->xhist_pitch * sizeof(float));
+                if (e != cudaSuccess) { if (old) cudaFree(old); return cuda_fail(c, e, "sliding-buffer allocation"); }
             }
+            if (old) {
+                const int k = old_len < hm ? old_len : hm;
+                cudaError_t e = k > 0 ? cudaMemcpy2D(c->xhist[0] + (hm - k), (size_t)c->xhist_pitch * sizeof(float), old + (old_len - k),
+                                                     (size_t)old_pitch * sizeof(float), (size_t)k * sizeof(float), (size_t)S,
+                                                     cudaMemcpyDeviceToDevice) : cudaSuccess;
+                cudaFree(old);
+                if (e != cudaSuccess) return cuda_fail(c, e, "sliding-buffer migration");
+            }
+            c->xhist_migrate = c->xhist_reset = false;
             AFP_CUDA(c, cudaDeviceSynchronize());   // (legacy-stream memsets vs. the non-blocking streams of the kernels)
             c->xhist_len = hm; c->xhist_cur = 0;
             if (c->tmp_b) { cudaFree(c->tmp_b); c->tmp_b = nullptr; }
@@ -1095,21 +1111,52 @@ static int rebuild_fused(afp_ctx* c, bool keep_state = false) {
     const bool eq_ok = c->cfg.eq_mode == AFP_EQ_NONE || (c->cfg.eq_mode == AFP_EQ_FUSED && c->eq.active);
     const bool shape_ok = ref_up ? (c->decim == U && c->up.active) : (U == 1 && c->decim == 1 && c->cfg.eq_mode == AFP_EQ_FUSED);
     const bool want = eq_ok && shape_ok && c->mainf.active && !env_flag("AFP_NO_COLLAPSE");
-    if (!want) { free_stage(c->fused); return AFP_OK; }
+    // The collapsed form carries INPUT samples; so does the first stage of the staged form (interpolator, or the fused EQ
+    // at U = 1).  A keep-state rebuild that changes form hands them over (right-aligned): collapsed -> staged seeds the
+    // first stage and clears the later ones (their state is intermediate signal that was never computed - a restart
+    // transient of the later stages' length); staged -> collapsed is exact.
+    Stage* first = ref_up ? &c->up : &c->eq;
+    auto leave_collapsed = [&]() -> int {
+        if (keep_state && c->fused.active && c->fused.hist[c->fused.cur] && first->active && first->hist[0]) {
+            const long long k = std::min(c->fused.hist_pitch, first->hist_pitch);
+            AFP_CUDA(c, cudaDeviceSynchronize());
+            for (Stage* s : {&c->up, &c->eq, &c->mainf})
+                if (s->active)
+                    for (int i = 0; i < 2; ++i)
+                        if (s->hist[i]) AFP_CUDA(c, cudaMemset(s->hist[i], 0, (size_t)c->cfg.n_streams * s->hist_pitch * sizeof(float)));
+            AFP_CUDA(c, cudaMemcpy2D(first->hist[first->cur] + (first->hist_pitch - k), (size_t)first->hist_pitch * sizeof(float),
+                                     c->fused.hist[c->fused.cur] + (c->fused.hist_pitch - k), (size_t)c->fused.hist_pitch * sizeof(float),
+                                     (size_t)k * sizeof(float), (size_t)c->cfg.n_streams, cudaMemcpyDeviceToDevice));
+            AFP_CUDA(c, cudaDeviceSynchronize());
+        }
+        free_stage(c->fused);
+        return AFP_OK;
+    };
+    if (!want) return leave_collapsed();
     std::vector<double> g = c->mainf.taps;
     if (c->cfg.eq_mode == AFP_EQ_FUSED) g = convolve(c->eq.taps, g);
     if (ref_up) g = convolve(c->up.taps, g);
     const int step = ref_up ? U : 1;
     std::vector<double> g0((g.size() + step - 1) / step);
     for (size_t j = 0; j < g0.size(); ++j) g0[j] = g[j * step];
-    if ((long long)g0.size() + 16 > afp::MAX_TAPS) { free_stage(c->fused); return AFP_OK; }   // too long for one table: stay staged
+    if ((long long)g0.size() + 16 > afp::MAX_TAPS) return leave_collapsed();   // too long for one table: stay staged
     // two tensor-kernel stages beat one FFMA2 stage: do not merge EQ and main FIR into a filter that is too
     // long for the tensor kernel's shared memory (16 streams x [history | 256 frames], hi + lo, + tap ring)
     if (!ref_up) {
         const long long kq64 = ((long long)g0.size() + 63) / 64 * 64;
-        if (2 * afp::TC_STREAMS * (kq64 + 256) * 4 + 2 * 8192 + 512 > kMaxSmem) { free_stage(c->fused); return AFP_OK; }
+        if (2 * afp::TC_STREAMS * (kq64 + 256) * 4 + 2 * 8192 + 512 > kMaxSmem) return leave_collapsed();
     }
-    return build_stage(c, c->fused, ST_MAIN, 1, g0.data(), (int)g0.size(), 1, keep_state);
+    const bool entering = keep_state && !c->fused.active && first->active && first->hist[first->cur];
+    int rc = build_stage(c, c->fused, ST_MAIN, 1, g0.data(), (int)g0.size(), 1, keep_state);
+    if (rc || !entering) return rc;
+    // staged -> collapsed with the state kept: the first stage's carried input samples become the collapsed filter's
+    const long long k = std::min(c->fused.hist_pitch, first->hist_pitch);
+    AFP_CUDA(c, cudaDeviceSynchronize());
+    AFP_CUDA(c, cudaMemcpy2D(c->fused.hist[c->fused.cur] + (c->fused.hist_pitch - k), (size_t)c->fused.hist_pitch * sizeof(float),
+                             first->hist[first->cur] + (first->hist_pitch - k), (size_t)first->hist_pitch * sizeof(float),
+                             (size_t)k * sizeof(float), (size_t)c->cfg.n_streams, cudaMemcpyDeviceToDevice));
+    AFP_CUDA(c, cudaDeviceSynchronize());
+    return AFP_OK;
 }
 
 // ---- per-stream-group filters ------------------------------------------------------------------------------------
@@ -1270,6 +1317,7 @@ int afp_set_taps(afp_ctx* c, const double* taps, int32_t n) {
     AFP_CUDA(c, cudaSetDevice(c->cfg.device));
     const int U = c->cfg.chain == AFP_CHAIN_DAC ? c->cfg.upsample : 1;
     int rc = build_stage(c, c->mainf, ST_MAIN, U, taps, n);
+    c->xhist_reset = true;
     return rc ? rc : rebuild_fused(c);
 }
 
@@ -1280,6 +1328,7 @@ int afp_swap_taps(afp_ctx* c, const double* taps, int32_t n) {
     AFP_CUDA(c, cudaDeviceSynchronize());   // blocks in flight still read the current history rows
     const int U = c->cfg.chain == AFP_CHAIN_DAC ? c->cfg.upsample : 1;
     int rc = build_stage(c, c->mainf, ST_MAIN, U, taps, n, 1, true);
+    c->xhist_migrate = true;
     return rc ? rc : rebuild_fused(c, true);
 }
 
@@ -1820,6 +1869,13 @@ int afp_host_alloc(void** ptr, size_t bytes) {
     if (!ptr) return AFP_ERR_INVALID;
     cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocDefault);
     if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaHostAlloc");
+    return AFP_OK;
+}
+
+int afp_host_alloc_wc(void** ptr, size_t bytes) {
+    if (!ptr) return AFP_ERR_INVALID;
+    cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocWriteCombined);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaHostAlloc(write-combined)");
     return AFP_OK;
 }
 

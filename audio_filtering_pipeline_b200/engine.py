@@ -189,6 +189,13 @@ class BatchFirEngine:
         n = self.out_frames(frames)
         return n * 3 if self.fmt == 3 else n
 
+    def _check_out(self, out, shape):
+        """A caller-supplied host output buffer goes to C as a bare pointer: it must be exactly the array the library writes."""
+        if not isinstance(out, np.ndarray) or out.dtype != _NP_DTYPE[self.fmt] or not out.flags.c_contiguous or \
+                not out.flags.writeable or out.size != int(np.prod(shape)):
+            raise ValueError(f"out must be a writable C-contiguous {np.dtype(_NP_DTYPE[self.fmt]).name} array of {int(np.prod(shape))} "
+                             f"elements (shape {tuple(shape)})")
+
     def process(self, x, out=None):
         """One block for all streams on device tensors: ``x`` float32 cuda [S, frames] (row stride
         arbitrary, unit column stride).  Asynchronous on torch's current stream."""
@@ -245,6 +252,8 @@ class BatchFirEngine:
         frames = x.shape[1]
         if out is None:
             out = np.empty((self.n_streams, self._out_cols(frames)), dtype=_NP_DTYPE[self.fmt])
+        else:
+            self._check_out(out, (self.n_streams, self._out_cols(frames)))
         _lib.check(self._lib.afp_process_host(self._ctx, x.ctypes.data, out.ctypes.data, frames), self._ctx)
         return out
 
@@ -278,6 +287,8 @@ class BatchFirEngine:
         nb, _, frames = x.shape
         if out is None:
             out = np.empty((nb, self.n_streams, self._out_cols(frames)), dtype=_NP_DTYPE[self.fmt])
+        else:
+            self._check_out(out, (nb, self.n_streams, self._out_cols(frames)))
         _lib.check(self._lib.afp_process_host_blocks(self._ctx, x.ctypes.data, out.ctypes.data, frames, nb),
                    self._ctx)
         return out
@@ -331,14 +342,16 @@ class BatchFirEngine:
 
 class PinnedArray:
     """Page-locked host memory from afp_host_alloc with a numpy view in ``.a`` (keep the object
-    alive while the view is in use; ``free()`` or garbage collection releases it)."""
+    alive while the view is in use; ``free()`` or garbage collection releases it).  ``write_combined``: for
+    buffers the host only writes (input staging); reading such memory from the host is very slow."""
 
-    def __init__(self, shape, dtype):
+    def __init__(self, shape, dtype, write_combined=False):
         self._lib = _lib.load()
         dtype = np.dtype(dtype)
         count = int(np.prod(shape))
         self._ptr = C.c_void_p()
-        _lib.check(self._lib.afp_host_alloc(C.byref(self._ptr), max(count * dtype.itemsize, 1)))
+        alloc = self._lib.afp_host_alloc_wc if write_combined else self._lib.afp_host_alloc
+        _lib.check(alloc(C.byref(self._ptr), max(count * dtype.itemsize, 1)))
         buf = (C.c_uint8 * max(count * dtype.itemsize, 1)).from_address(self._ptr.value)
         self.a = np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
 

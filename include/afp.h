@@ -153,7 +153,11 @@ int afp_set_taps(afp_ctx* ctx, const double* taps, int32_t n_taps);
 /* Replace the main filter between two blocks WITHOUT touching the carried samples - the reference's swap
  * of active_filter_params under filter_lock (stream_process_EQ_GUI.py:380-385; deferred form
  * stream_process_AGC.py:27-29,102-108), which leaves input_buffer alone: the next block is the new filter
- * over the true past input, no restart transient.  A longer filter sees zeros beyond what was carried. */
+ * over the true past input, no restart transient.  A longer filter sees zeros beyond what was carried.  This holds
+ * for the stage the call rebuilds, for the sliding buffer of the AFP_EQ_BUFFER_SAME* modes (migrated right-aligned
+ * when the filter length changes) and when the chain enters its collapsed one-filter form.  When a swap makes the
+ * collapsed form impossible (the combined filter no longer fits one launch), the staged chain restarts from the
+ * carried INPUT samples: its first stage continues, the later stages start from zero state. */
 int afp_swap_taps(afp_ctx* ctx, const double* taps, int32_t n_taps);
 int afp_set_upsampler(afp_ctx* ctx, const double* taps, int32_t n_taps);
 int afp_set_eq(afp_ctx* ctx, const double* band_taps, const int32_t* band_len, int32_t n_bands,
@@ -222,8 +226,10 @@ int afp_set_state(afp_ctx* ctx, const void* host_buf, size_t bytes);
 int afp_get_stage_info(const afp_ctx* ctx, int32_t stage, afp_stage_info* info);   /* AFP_ERR_INVALID past the end */
 int64_t afp_kernel_launches(const afp_ctx* ctx);
 
-/* Pinned host memory for afp_process_host. */
+/* Pinned host memory for afp_process_host.  afp_host_alloc_wc: write-combined pinned memory for buffers the host only
+ * WRITES (input staging: no cache snooping on the device's reads; host reads of it are very slow). */
 int afp_host_alloc(void** ptr, size_t bytes);
+int afp_host_alloc_wc(void** ptr, size_t bytes);
 int afp_host_free(void* ptr);
 
 /* FP32 FMA roof of the device, measured with a packed-FFMA2 issue loop (there is no

@@ -264,3 +264,40 @@ def test_decimate_option_and_gain_update(collapse, monkeypatch):
             eq = np.concatenate([e1[:2048], e2[2048:]]).astype(np.float32).astype(np.float64)
             ref = lfilter(h, 1.0, eq)
         assert_parity(np.concatenate([ya[s], yb[s]]), ref.astype(np.float32), "gain swap")
+
+
+def test_helper_shims_are_stateless_unless_given_a_state():
+    """The reference's safe_upsample is a one-shot soxr call per block (stream_process.py:66-77): nothing is carried.  Two
+    streams with the same block length through the shim must not see each other's samples; streaming use takes an explicit
+    per-stream compat.Resampler, which then equals the whole-signal interpolation."""
+    r = np.random.default_rng(17)
+    a, b = (0.1 * r.standard_normal((2, 2048))).astype(np.float32)
+    h = design.design_upsampler(2, 44100)
+    a0 = compat.safe_upsample(a[:1024], 44100, 88200)
+    compat.safe_upsample(b[:1024], 44100, 88200)                       # another stream, same shape
+    a0_again = compat.safe_upsample(a[:1024], 44100, 88200)
+    assert np.array_equal(a0, a0_again)
+    assert_parity(a0, rc.polyphase_upsample_whole(h, a[:1024], 2).astype(np.float32), "one-shot")
+    st_a, st_b = compat.Resampler(2, 44100, 1024), compat.Resampler(2, 44100, 1024)
+    ya, yb = [], []
+    for i in range(2):                                                # interleaved streams, each with its own state
+        ya.append(compat.safe_upsample(a[i * 1024:(i + 1) * 1024], 44100, 88200, state=st_a))
+        yb.append(compat.safe_upsample(b[i * 1024:(i + 1) * 1024], 44100, 88200, state=st_b))
+    assert_parity(np.concatenate(ya), rc.polyphase_upsample_whole(h, a, 2).astype(np.float32), "streaming a")
+    assert_parity(np.concatenate(yb), rc.polyphase_upsample_whole(h, b, 2).astype(np.float32), "streaming b")
+    dn = compat.Resampler(2, 44100, 2048, up=False)
+    d = compat.safe_downsample(np.concatenate(ya)[:2048], 88200, 44100, 1024, state=dn)
+    assert d.shape == (1024,)
+    for s in (st_a, st_b, dn):
+        s.close()
+    # dither: successive calls continue the Philox stream, different lengths use different seeds
+    z = np.zeros(256, dtype=np.float32)
+    d1, d2 = compat.apply_dither(z), compat.apply_dither(z)
+    assert not np.array_equal(d1, d2)
+    assert not np.array_equal(compat.apply_dither(np.zeros(255, dtype=np.float32)), d1[:255])
+    # caller-supplied host output buffers are validated before they reach C
+    with BatchFirEngine([1.0], n_streams=2, max_frames=64) as e:
+        with pytest.raises(ValueError):
+            e.process_host(np.zeros((2, 64), np.float32), out=np.zeros((2, 32), np.float32))
+        with pytest.raises(ValueError):
+            e.process_host_blocks(np.zeros((3, 2, 64), np.float32), out=np.zeros((3, 2, 64), np.float64))
