@@ -24,7 +24,7 @@ from collections import deque
 import numpy as np
 
 from . import design
-from .engine import BatchFirEngine
+from .engine import BatchFirEngine, PinnedArray
 
 __all__ = ["make_audio_callback", "OverlapAddFilter", "process_audio_block", "apply_dither",
            "safe_upsample", "safe_downsample", "apply_agc", "StreamChain", "Resampler", "close_helpers"]
@@ -71,16 +71,35 @@ class StreamChain:
         self.waterfall_data = deque(maxlen=50)                                # :112
         self.audio_buffer = deque(maxlen=4)                                   # stream_process.py:50
         self.silence_block = np.zeros((self.blocksize, self.channels), dtype=np.float32)
-        self._planar = np.zeros((self.channels, self.blocksize), dtype=np.float32)
+        # Everything the callback touches per block exists from here on (pinned staging, no allocation in
+        # the call): page-locked in / out blocks in the [frames, channels] wire format, and the last-good blocks as a
+        # ring of five buffers of which audio_buffer (maxlen 4) holds views - the slot being written is never in it.
+        self._pin_in = PinnedArray((self.blocksize, self.channels), np.float32)
+        self._pin_out = PinnedArray((self.engine.out_frames(self.blocksize), self.channels), np.float32)
+        self._good = np.zeros((5, self.blocksize, self.channels), dtype=np.float32)
+        self._good_i = 0
 
     def process(self, indata):
-        """indata float32 [frames, channels] (or [frames]) -> float32 [frames, channels]."""
-        x = np.asarray(indata, dtype=np.float32)
+        """indata float32 [frames, channels] (or [frames]) -> float32 [frames, channels]: a view of the chain's pinned
+        output block, valid until the next call."""
+        x = np.asarray(indata)
         if x.ndim == 1:
             x = x[:, None]
         frames = x.shape[0]
+        if frames > self.blocksize:
+            raise ValueError(f"{frames} frames exceed the chain's blocksize {self.blocksize}")
         # [frames, channels] goes to the device as it is; the (de)interleave runs there
-        return self.engine.process_host_interleaved(x[:, :self.channels])[:frames]
+        xin = self._pin_in.a[:frames]
+        np.copyto(xin, x[:, :self.channels], casting="same_kind")
+        out = self._pin_out.a[:self.engine.out_frames(frames)]
+        return self.engine.process_host_interleaved(xin, out=out)[:frames]
+
+    def keep_good(self, y):
+        """``audio_buffer.append(processed.copy())`` (stream_process.py:110) without the allocation."""
+        slot = self._good[self._good_i][:y.shape[0], :y.shape[1]]
+        np.copyto(slot, y)
+        self.audio_buffer.append(slot)
+        self._good_i = (self._good_i + 1) % 5
 
     def waterfall_row(self, column):
         """``20*log10(|rfft(column * hanning)| + 1e-12)`` of one output column on the GPU
@@ -91,6 +110,8 @@ class StreamChain:
 
     def close(self):
         self.engine.close()
+        self._pin_in.free()
+        self._pin_out.free()
 
 
 def make_audio_callback(chain, verbose=True):
@@ -106,7 +127,7 @@ def make_audio_callback(chain, verbose=True):
             y = chain.process(indata)                                          # :89-113
             if y.shape[0] != frames:
                 y = np.resize(y, (frames, y.shape[1]))                         # :106-107
-            chain.audio_buffer.append(y.copy())                                # :110
+            chain.keep_good(y)                                                 # :110
             outdata[:, :y.shape[1]] = y
             if chain.show_waterfall:                                           # stream_process_GUI_Waterfall.py:471-478
                 try:

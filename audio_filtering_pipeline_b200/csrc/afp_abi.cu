@@ -32,7 +32,9 @@ using afp::FirParams;
 
 namespace {
 
-std::string g_create_error;
+// message of the last failed context-free call (afp_create, afp_host_alloc, ...) of THIS thread: contexts are created one
+// per caller thread (one per GPU), so the slot is per thread too
+thread_local std::string g_create_error;
 
 constexpr int kMaxSmem = 227 * 1024;
 constexpr uint32_t kStateMagic = 0x41465031u;  // "AFP1"
@@ -190,6 +192,7 @@ struct afp_ctx {
     cudaStream_t own_stream = nullptr, s_in = nullptr, s_out = nullptr;
     FirParams params{};              // scratch for the kernel-parameter block of the launch being prepared
     unsigned int* range_flag = nullptr;   // device word: set by the split-FP16 tensor kernel when a sample exceeds FP16's range
+    bool range_dirty = false;             // a split-FP16 launch has run since the flag was last read
     // per-stream-group filters (afp_assign_groups): every session of a batch with its own EQ gains / main taps, the way
     // each reference process reads its own sliders per block (stream_process_EQ_GUI.py:86-90).  Empty = one filter set.
     struct GroupDef { std::vector<double> gains, taps; };   // empty = the context-level gains / main taps
@@ -539,6 +542,7 @@ int launch_stage_tc2(afp_ctx* c, Stage& s, const float* in, long long in_pitch, 
     afp_kernel_tc2(afp::epi_code(fmt, dither))<<<grid, afp::TC2_THREADS, smem, stream>>>(P);
     AFP_CUDA(c, cudaGetLastError());
     c->launches += 1;
+    c->range_dirty = true;
     s.last_kernel = 3;
     s.geo.nt = afp::TC2_THREADS; s.geo.tg_log2 = 4; s.geo.smem = smem; s.geo.grid = grid; s.geo.key_nq = -1;
     *done = true;
@@ -579,6 +583,7 @@ int launch_stage_tc2_grouped(afp_ctx* c, Stage& s, const float* in, long long in
     afp_kernel_tc2_grouped()<<<grid, afp::TC2_THREADS, smem, stream>>>(P);
     AFP_CUDA(c, cudaGetLastError());
     c->launches += 1;
+    c->range_dirty = true;
     s.last_kernel = 3;
     s.geo.nt = afp::TC2_THREADS; s.geo.tg_log2 = 4; s.geo.smem = smem; s.geo.grid = grid; s.geo.key_nq = -1;
     *done = true;
@@ -1325,7 +1330,9 @@ int afp_swap_taps(afp_ctx* c, const double* taps, int32_t n) {
     if (!c || !taps) return fail(c, AFP_ERR_INVALID, "null argument");
     if (!c->mainf.active) return fail(c, AFP_ERR_STATE, "afp_set_taps has not been called");
     AFP_CUDA(c, cudaSetDevice(c->cfg.device));
-    AFP_CUDA(c, cudaDeviceSynchronize());   // blocks in flight still read the current history rows
+    // blocks in flight still read the current history rows - on the context's own streams or on whatever stream the
+    // caller passed to afp_process, which the context does not know: hence the device-wide wait (a swap is a GUI event)
+    AFP_CUDA(c, cudaDeviceSynchronize());
     const int U = c->cfg.chain == AFP_CHAIN_DAC ? c->cfg.upsample : 1;
     int rc = build_stage(c, c->mainf, ST_MAIN, U, taps, n, 1, true);
     c->xhist_migrate = true;
@@ -1587,7 +1594,9 @@ static Stage* single_stage(afp_ctx* c) {
 }
 
 // the split-FP16 tensor kernel saw a sample beyond FP16's range since the last check: report and clear
-static int check_range(afp_ctx* c) {
+static int check_range(afp_ctx* c, bool force = false) {
+    if (!c->range_dirty && !force) return AFP_OK;      // no split-FP16 launch since the last look: nothing can have set it
+    c->range_dirty = false;
     unsigned int flag = 0;
     AFP_CUDA(c, cudaMemcpy(&flag, c->range_flag, sizeof(flag), cudaMemcpyDeviceToHost));
     if (!flag) return AFP_OK;
@@ -1600,7 +1609,7 @@ static int check_range(afp_ctx* c) {
 int afp_range_status(afp_ctx* c, int32_t* exceeded) {
     if (!c || !exceeded) return AFP_ERR_INVALID;
     AFP_CUDA(c, cudaSetDevice(c->cfg.device));
-    const int rc = check_range(c);
+    const int rc = check_range(c, true);
     *exceeded = rc == AFP_ERR_RANGE ? 1 : 0;
     return rc == AFP_ERR_RANGE ? AFP_OK : rc;
 }
@@ -1697,6 +1706,17 @@ int afp_process_host_blocks(afp_ctx* c, const float* in, void* out, int32_t fram
     const size_t in_row = (size_t)frames * sizeof(float), out_row = (size_t)out_n * eb;
     const unsigned char* hin = reinterpret_cast<const unsigned char*>(in);
     unsigned char* hout = static_cast<unsigned char*>(out);
+    if (n_blocks == 1 && c->slot_streams >= S) {
+        // one unit (the sounddevice callback: one small block): nothing to overlap, so copy in, run and copy out on ONE
+        // stream - no cross-stream event hops on the audio thread's critical path
+        AFP_CUDA(c, cudaMemcpyAsync(c->d_in[0], hin, (size_t)S * in_row, cudaMemcpyHostToDevice, c->own_stream));
+        rc = process_block_range(c, c->d_in[0], frames, c->d_out[0], (int64_t)out_n * (eb == 3 ? 3 : 1), frames, 0, S, c->own_stream);
+        if (rc) return rc;
+        AFP_CUDA(c, cudaMemcpyAsync(hout, c->d_out[0], (size_t)S * out_row, cudaMemcpyDeviceToHost, c->own_stream));
+        finish_block(c, frames);
+        AFP_CUDA(c, cudaStreamSynchronize(c->own_stream));
+        return check_range(c);
+    }
     long long unit = 0;
     for (int b = 0; b < n_blocks; ++b) {
         for (int s0 = 0; s0 < S; s0 += c->slot_streams, ++unit) {
@@ -1751,23 +1771,49 @@ int afp_process_host_interleaved(afp_ctx* c, const float* in, void* out, int32_t
         AFP_CUDA(c, cudaMalloc(&c->d_il_in, (size_t)S * c->cfg.max_frames * sizeof(float)));
         AFP_CUDA(c, cudaMalloc(&c->d_il_out, (size_t)S * afp_out_frames(c, c->cfg.max_frames) * eb));
     }
-    cudaStream_t st = c->own_stream;
-    const size_t in_bytes = (size_t)S * frames * sizeof(float), out_bytes = (size_t)S * out_n * eb;
-    AFP_CUDA(c, cudaMemcpyAsync(c->d_il_in, in, in_bytes, cudaMemcpyHostToDevice, st));
+    // Sessions travel in chunks through three streams (H2D | de-interleave, chain, interleave | D2H), like the planar
+    // entry point: chunk i+1 is copied in while chunk i is computed and chunk i-1 is copied out.  Every chunk has its own
+    // region of the (whole-batch) device buffers, so nothing is reused inside a call and the events only order the streams.
+    int chunk_streams = pick_slot_streams(c, frames, 1);
+    const int unit = channels % 2 == 0 ? channels : 2 * channels;          // whole sessions, and row pairs stay inside a chunk
+    chunk_streams = (chunk_streams + unit - 1) / unit * unit;
     auto grid_for = [&](long long total) { long long g = (total + 255) / 256; return (int)(g < 1 ? 1 : (g > 8LL * c->n_sm ? 8LL * c->n_sm : g)); };
-    deinterleave_kernel<<<grid_for((long long)sessions * frames), 256, 0, st>>>(c->d_il_in, c->d_in[0], sessions, frames, channels, frames);
-    AFP_CUDA(c, cudaGetLastError());
-    rc = process_block_range(c, c->d_in[0], frames, c->d_out[0], (int64_t)out_n * (eb == 3 ? 3 : 1), frames, 0, S, st);
-    if (rc) return rc;
-    const long long pitch_bytes = (long long)out_n * eb;
-    const int g = grid_for((long long)sessions * out_n);
-    if (eb == 4) interleave_kernel<4><<<g, 256, 0, st>>>(c->d_out[0], c->d_il_out, sessions, out_n, channels, pitch_bytes);
-    else if (eb == 2) interleave_kernel<2><<<g, 256, 0, st>>>(c->d_out[0], c->d_il_out, sessions, out_n, channels, pitch_bytes);
-    else interleave_kernel<3><<<g, 256, 0, st>>>(c->d_out[0], c->d_il_out, sessions, out_n, channels, pitch_bytes);
-    AFP_CUDA(c, cudaGetLastError());
-    c->launches += 2;
-    AFP_CUDA(c, cudaMemcpyAsync(out, c->d_il_out, out_bytes, cudaMemcpyDeviceToHost, st));
-    AFP_CUDA(c, cudaStreamSynchronize(st));
+    const size_t in_row = (size_t)frames * sizeof(float), out_row = (size_t)out_n * eb;   // bytes per stream
+    const unsigned char* hin = reinterpret_cast<const unsigned char*>(in);
+    unsigned char* hout = static_cast<unsigned char*>(out);
+    const bool one = chunk_streams >= S;     // a single chunk (the callback's one small block): everything on one stream
+    cudaStream_t st_in = one ? c->own_stream : c->s_in, st_out = one ? c->own_stream : c->s_out;
+    int i = 0;
+    for (int s0 = 0; s0 < S; s0 += chunk_streams, ++i) {
+        const int ns = S - s0 < chunk_streams ? S - s0 : chunk_streams, se = ns / channels, k = i % afp_ctx::kSlots;
+        float* il_in = c->d_il_in + (size_t)s0 * frames;
+        unsigned char* il_out = c->d_il_out + (size_t)s0 * out_row;
+        float* pl_in = c->d_in[0] + (size_t)s0 * frames;
+        unsigned char* pl_out = c->d_out[0] + (size_t)s0 * out_row;
+        AFP_CUDA(c, cudaMemcpyAsync(il_in, hin + (size_t)s0 * in_row, (size_t)ns * in_row, cudaMemcpyHostToDevice, st_in));
+        if (!one) {
+            AFP_CUDA(c, cudaEventRecord(c->ev_in[k], c->s_in));
+            AFP_CUDA(c, cudaStreamWaitEvent(c->own_stream, c->ev_in[k], 0));
+        }
+        deinterleave_kernel<<<grid_for((long long)se * frames), 256, 0, c->own_stream>>>(il_in, pl_in, se, frames, channels, frames);
+        AFP_CUDA(c, cudaGetLastError());
+        rc = process_block_range(c, pl_in, frames, pl_out, (int64_t)out_n * (eb == 3 ? 3 : 1), frames, s0, ns, c->own_stream);
+        if (rc) return rc;
+        const long long pitch_bytes = (long long)out_n * eb;
+        const int g = grid_for((long long)se * out_n);
+        if (eb == 4) interleave_kernel<4><<<g, 256, 0, c->own_stream>>>(pl_out, il_out, se, out_n, channels, pitch_bytes);
+        else if (eb == 2) interleave_kernel<2><<<g, 256, 0, c->own_stream>>>(pl_out, il_out, se, out_n, channels, pitch_bytes);
+        else interleave_kernel<3><<<g, 256, 0, c->own_stream>>>(pl_out, il_out, se, out_n, channels, pitch_bytes);
+        AFP_CUDA(c, cudaGetLastError());
+        c->launches += 2;
+        if (!one) {
+            AFP_CUDA(c, cudaEventRecord(c->ev_k[k], c->own_stream));
+            AFP_CUDA(c, cudaStreamWaitEvent(c->s_out, c->ev_k[k], 0));
+        }
+        AFP_CUDA(c, cudaMemcpyAsync(hout + (size_t)s0 * out_row, il_out, (size_t)ns * out_row, cudaMemcpyDeviceToHost, st_out));
+    }
+    if (!one) AFP_CUDA(c, cudaStreamSynchronize(c->s_out));
+    AFP_CUDA(c, cudaStreamSynchronize(c->own_stream));
     finish_block(c, frames);
     return check_range(c);
 }
@@ -1897,8 +1943,11 @@ int afp_measure_fma_peak(int32_t device, double* tflops, double* sm_mhz) {
     float *out = nullptr, *in = nullptr; long long* cyc = nullptr;
     if (cudaMalloc(&out, sizeof(float) * grid * threads) != cudaSuccess ||
         cudaMalloc(&in, sizeof(float) * 4096) != cudaSuccess ||
-        cudaMalloc(&cyc, sizeof(long long) * grid) != cudaSuccess)
+        cudaMalloc(&cyc, sizeof(long long) * grid) != cudaSuccess) {
+        cudaFree(out); cudaFree(in); cudaFree(cyc);      // (cudaFree(nullptr) is a no-op)
+        cudaGetLastError();
         return fail(nullptr, AFP_ERR_NOMEM, "cudaMalloc failed in afp_measure_fma_peak");
+    }
     cudaMemset(in, 0, sizeof(float) * 4096);
     fma_peak_kernel<8><<<grid, threads>>>(out, in, 100, cyc);
     cudaEvent_t e0, e1;

@@ -303,6 +303,10 @@ class Dist:
         from audio_filtering_pipeline_b200.sharding import max_over_ranks
         return max_over_ranks(v, self.dev)
 
+    def sum(self, v):
+        from audio_filtering_pipeline_b200.sharding import sum_over_ranks
+        return sum_over_ranks(v, self.dev)
+
     def close(self):
         if self.world > 1:
             self.dist.barrier()
@@ -552,6 +556,7 @@ def c5_sweep(D, cpu, hbm_peak_gbs, fma_peak, iters=8):
                                                      one_core=False)
             for total in (1024, 4096, 16384, 65536):
                 first, count = partition_streams(total, D.world, D.rank)
+                assert int(D.sum(count)) == total, "the ranks' shards do not add up to the point's batch"
                 ms = 0.0
                 info = {"kernel": None, "tile_taps": None}
                 if count > 0:
@@ -690,7 +695,7 @@ def run_ours(args):
     ms_total = e0.elapsed_time(e1)
     ms_total_max = D.max(ms_total)
     samples_rank = S * FRAMES * NB * K
-    value = samples_rank * world / (ms_total_max * 1e-3) / 1e6
+    value = D.sum(samples_rank) / (ms_total_max * 1e-3) / 1e6        # units all ranks processed / max-over-ranks time
 
     # sustained: the same step back to back for >= sustain_seconds (power / clock behaviour of a long run)
     sustained = None

@@ -301,3 +301,48 @@ def test_helper_shims_are_stateless_unless_given_a_state():
             e.process_host(np.zeros((2, 64), np.float32), out=np.zeros((2, 32), np.float32))
         with pytest.raises(ValueError):
             e.process_host_blocks(np.zeros((3, 2, 64), np.float32), out=np.zeros((3, 2, 64), np.float64))
+
+
+@pytest.mark.parametrize("channels", [1, 2])
+def test_callback_allocates_no_block_buffers(channels):
+    """the per-block callback runs on PortAudio's audio thread - pinned staging, no allocation in the call.
+    After the first blocks, 50 callbacks must not allocate anything of a block's size (tracemalloc sees numpy's buffers);
+    what remains are the small transient Python objects of the call itself."""
+    import tracemalloc
+    B = 4096                                                         # the reference's own blocksize (stream_process.py:23)
+    chain = compat.StreamChain(samplerate=44100, upsample_factor=4, blocksize=B, numtaps=251, cutoff=[500, 8000],
+                               window_type="kaiser", filter_type="bandpass", channels=channels)
+    cb = compat.make_audio_callback(chain, verbose=False)
+    x = (0.1 * np.random.default_rng(4).standard_normal((60, B, channels))).astype(np.float32)
+    out = np.zeros((B, channels), dtype=np.float32)
+    for i in range(10):
+        cb(x[i], out, B, None, None)
+    tracemalloc.start()
+    base, _ = tracemalloc.get_traced_memory()
+    tracemalloc.reset_peak()
+    for i in range(10, 60):
+        cb(x[i], out, B, None, None)
+    cur, peak = tracemalloc.get_traced_memory()
+    tracemalloc.stop()
+    block_bytes = B * channels * 4
+    assert peak - base < block_bytes // 2, f"the callback allocated {peak - base} bytes at its peak (a block is {block_bytes})"
+    assert cur - base < 4096
+    assert np.abs(out).max() > 0 and len(chain.audio_buffer) == 4
+    assert np.array_equal(chain.audio_buffer[-1], out)
+    chain.close()
+
+
+def test_interleaved_entry_point_pipelines_session_chunks():
+    """Large batches go through afp_process_host_interleaved in chunks of sessions on three streams; the result is the planar
+    path's, whatever the chunking (4096 stereo sessions = 8 chunks)."""
+    S, B, ch = 8192, 512, 2
+    h = design.create_fir_filter(cutoff=5000, numtaps=101, samplerate=48000)
+    x = (0.1 * np.random.default_rng(6).standard_normal((S // ch, B, ch))).astype(np.float32)
+    with BatchFirEngine(h, n_streams=S, max_frames=B) as e:
+        y = e.process_host_interleaved(x)
+        e.reset()
+        planar = np.ascontiguousarray(x.transpose(0, 2, 1)).reshape(S, B)
+        yp = e.process_host(planar)
+    assert np.array_equal(y.transpose(0, 2, 1).reshape(S, B), yp)
+    for s in (0, 1, 4097, 8191):
+        assert_parity(yp[s], rc.streaming_fir(h, planar[s]), f"stream {s}")
