@@ -40,7 +40,7 @@ class StreamChain:
                  window_type="hamming", filter_type="lowpass", method="window", channels=1,
                  eq_bands=None, eq_gains=None, eq_numtaps=None, eq_mode="buffer_same_per_band",
                  min_phase=False, dither=True, bit_depth=24, seed=0, device=0, upsampler_taps=None,
-                 fir_coeff=None, agc=None, show_waterfall=False):
+                 fir_coeff=None, agc=None, show_waterfall=False, upsampler_quality="fast"):
         self.samplerate, self.upsample_factor, self.blocksize = int(samplerate), int(upsample_factor), int(blocksize)
         self.channels = int(channels)
         up_rate = self.samplerate * self.upsample_factor                     # stream_process.py:20
@@ -60,7 +60,7 @@ class StreamChain:
             if eq_gains is None:
                 eq_gains = [1.0] * len(bands)
         if upsampler_taps is None and self.upsample_factor > 1:
-            upsampler_taps = design.design_upsampler(self.upsample_factor, self.samplerate)
+            upsampler_taps = design.design_upsampler(self.upsample_factor, self.samplerate, quality=upsampler_quality)
         self.engine = BatchFirEngine(
             self.fir_coeff, n_streams=self.channels, max_frames=self.blocksize,
             upsample=self.upsample_factor, chain="reference", out_format="f32",

@@ -186,6 +186,7 @@ struct afp_ctx {
     std::map<std::pair<int, int>, AgcPlanEntry> agc_plans;   // launch shape of the AGC kernel per (variant, streams)
     // afp_spectrum_db: per block length n, device tables [window n floats | twiddles n/2 float2]
     std::map<int, float*> spec_tables;
+    int spw_per_sm = 0;              // resident CTAs per SM of the warp-per-row spectrum kernel
     // afp_process_host_interleaved: frame-major device copies of one block in / out
     float* d_il_in = nullptr;
     unsigned char* d_il_out = nullptr;
@@ -247,10 +248,15 @@ int build_stage(afp_ctx* c, Stage& s, int kind, int U, const double* taps, int n
     // Long single-table U = 1 filters can also run on the tensor cores (afp_fir_tc.cuh).  Both kernels
     // then share one history format: the last kq_pad samples with kq_pad a multiple of 32 (the tensor
     // kernel's row length), so a stage may switch kernel from one block to the next.
-    // (crossover against the single-row FFMA2 kernel measured at 16384 streams: equal at 385 taps / 512-frame
-    // blocks, +13 % at 385 / 1024, +27 % at 501 / 1024 - measured with bench/quick_perf.py, AFP_TC_MIN_TAPS=300 vs 5000)
+    // Crossovers against the single-row FFMA2 kernel, measured at 16384 streams (bench/quick_perf.py with AFP_TC_MIN_TAPS
+    // 32 vs 5000, bench/gpu_calls/r02_tcmin*.sh): the split-FP16 kernel (afp_fir_tc2.cuh) runs at 165-210 Gsamples/s
+    // whatever the length (its loaders and epilogue, not the MMAs, bound it below ~400 taps) - equal at 160 taps, +18 %
+    // at 192, +45 % at 251, 2.1x at 385; the 3xTF32 kernel (afp_fir_tc.cuh, 256-frame blocks) only from 385 taps up.
     const int tc_min = std::getenv("AFP_TC_MIN_TAPS") ? std::atoi(std::getenv("AFP_TC_MIN_TAPS")) : 400;
-    const bool tc_ok = U == 1 && n_sub == 1 && n >= tc_min && !env_flag("AFP_NO_TC");
+    const int tc2_min = std::getenv("AFP_TC_MIN_TAPS") ? std::atoi(std::getenv("AFP_TC_MIN_TAPS")) : 176;
+    const bool tc_any = U == 1 && n_sub == 1 && !env_flag("AFP_NO_TC");
+    const bool tc1_ok = tc_any && n >= tc_min, tc2_ok = tc_any && n >= tc2_min && !env_flag("AFP_NO_TC2");
+    const bool tc_ok = tc1_ok || tc2_ok;
     // History length = padded taps per phase.  A multiple of 16 (every tile size divides it, so the two
     // FFMA2 kernels share one history format and a stage may switch kernel from block to block), with room
     // for the extra tap slot the single-row kernel's U = 1 form needs (afp_fir_row.cuh).
@@ -294,7 +300,7 @@ int build_stage(afp_ctx* c, Stage& s, int kind, int U, const double* taps, int n
     for (int b = 0; b < n_sub; ++b)
         for (int i = 0; i < n; ++i) s.table[(size_t)b * s.kq_pad * U + i] = (float)taps[(size_t)b * n + i];
     for (int i = 0; i < 2; ++i) { if (s.tc_w[i]) cudaFree(s.tc_w[i]); s.tc_w[i] = nullptr; s.tc_chunks[i] = 0; }
-    if (tc_ok) {
+    if (tc1_ok) {
         // W slices for both row lengths R: chunk d, k-step ks, column chunk cc, row (0..R-1: hi, j = row;
         // R..2R-1: lo, j = row-R), 4 floats:  W[j][i] = h[R d + j - i],  i = 8 ks + 4 cc + e;
         // hi = the value with its 13 low mantissa bits cleared, lo = value - hi
@@ -321,9 +327,11 @@ int build_stage(afp_ctx* c, Stage& s, int kind, int U, const double* taps, int n
             AFP_CUDA(c, cudaMemcpy(s.tc_w[v], w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
             s.tc_chunks[v] = nc;
         }
+    }
+    if (s.tc2_w) { cudaFree(s.tc2_w); s.tc2_w = nullptr; s.tc2_cores = s.tc2_chunks = 0; }
+    if (tc2_ok) {
         // split-FP16 kernel (afp_fir_tc2.cuh): Hankel tap cores, all high parts then all low parts
-        if (s.tc2_w) { cudaFree(s.tc2_w); s.tc2_w = nullptr; }
-        if ((n + afp::TC2_R - 2) / afp::TC2_R + 1 <= 17 && !env_flag("AFP_NO_TC2")) {
+        if ((n + afp::TC2_R - 2) / afp::TC2_R + 1 <= 17) {
             std::vector<__half> w;
             s.tc2_chunks = afp::tc2_build_cores(taps, n, w);
             s.tc2_cores = afp::tc2_n_cores(s.tc2_chunks);
@@ -1426,6 +1434,22 @@ int afp_spectrum_db(afp_ctx* c, const float* in, int64_t in_pitch, float* out, i
     P.in = in; P.in_pitch = in_pitch; P.out = out; P.out_pitch = out_pitch;
     P.window = tab; P.twiddle = reinterpret_cast<const float2*>(tab + frames);
     P.n_streams = n_streams; P.n = frames; P.log2n = log2n;
+    if (frames == afp::SPW_N && !env_flag("AFP_SPEC_NO_WARP")) {
+        // one warp per row, radix-8 passes in registers (afp_spectrum.cuh): the GUI's default block length
+        if (!c->spw_per_sm) {
+            int per_sm = 0;
+            AFP_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)afp::spectrum_db_warp_kernel,
+                                                                      32 * afp::SPW_WARPS, afp::SPW_SMEM));
+            c->spw_per_sm = per_sm < 1 ? 1 : per_sm;
+        }
+        long long grid_w = (long long)c->n_sm * c->spw_per_sm;
+        const long long want = (n_streams + afp::SPW_WARPS - 1) / afp::SPW_WARPS;
+        if (grid_w > want) grid_w = want;
+        afp::spectrum_db_warp_kernel<<<(int)grid_w, 32 * afp::SPW_WARPS, afp::SPW_SMEM, (cudaStream_t)cuda_stream>>>(P);
+        AFP_CUDA(c, cudaGetLastError());
+        c->launches++;
+        return AFP_OK;
+    }
     const size_t smem = (size_t)(afp::spec_pad(frames / 2) + frames / 4) * sizeof(float2);   // padded packed samples + twiddle copy
     const int per_sm = frames <= 1024 ? 8 : (frames <= 2048 ? 4 : 2);
     int grid = c->n_sm * per_sm;

@@ -187,16 +187,44 @@ def apply_min_phase(h, fs, min_phase=True, force=False, normalize=True):
     return normalize_filter(h, fs) if normalize else h
 
 
-def design_upsampler(factor, samplerate, numtaps=None, window_type="kaiser"):
+# libsoxr's quality recipes (soxr.h / soxr_quality_spec of libsoxr 0.1.3, the library behind the reference's
+# soxr.resample(..., 'VHQ'), stream_process.py:66-77 - restated from its published source, not runnable here):
+# 'HQ' = 20-bit, 'VHQ' = 28-bit precision; stop-band rejection = bits * 6.02 dB; the stop band begins AT the Nyquist
+# frequency of the lower rate; the pass band ends at 1 - 0.05 / TO_3dB(rejection) of it, TO_3dB(a) = (1.6e-6 a - 7.5e-4) a + 0.646.
+_SOXR_BITS = {"hq": 20, "vhq": 28}
+
+
+def upsampler_spec(quality):
+    """(stop-band rejection in dB, pass-band end as a fraction of the base-rate Nyquist frequency) of a soxr recipe."""
+    bits = _SOXR_BITS[quality]
+    rej = bits * 20.0 * np.log10(2.0)
+    return rej, 1.0 - 0.05 / ((1.6e-6 * rej - 7.5e-4) * rej + 0.646)
+
+
+def design_upsampler(factor, samplerate, numtaps=None, window_type="kaiser", quality="fast"):
     """Anti-imaging prototype for the polyphase interpolator that replaces the per-block
-    ``soxr.resample`` call (stream_process.py:66-77).  Builder-defined (soxr parity is unpinned,
-    SURVEY.md F7): Kaiser windowed-sinc low-pass at ``samplerate/2`` designed at
-    ``samplerate*factor`` with the reference's own designer, scaled by ``factor`` so the passband
-    gain after zero-stuffing is 1.  ``factor == 1`` gives the identity ``[1.0]``.
+    ``soxr.resample`` call (stream_process.py:66-77), scaled by ``factor`` so the passband gain after
+    zero-stuffing is 1.  ``factor == 1`` gives the identity ``[1.0]``.  Builder-defined (soxr parity is
+    unpinned); what each choice guarantees is tested in tests/test_design.py:
+
+    ``quality='fast'`` (default): 32*factor+1 taps, Kaiser windowed-sinc low-pass at ``samplerate/2`` from the
+        reference's own designer: flat to 0.001 dB up to 0.8 Nyquist, -0.5 dB at 0.91 Nyquist, -6 dB at Nyquist,
+        images beyond 1.2 Nyquist below -88 dB.  Short on purpose (a live callback's latency: 16 base-rate samples).
+    ``quality='hq'`` / ``'vhq'``: Kaiser designs to libsoxr's HQ / VHQ recipes (``upsampler_spec``): pass band flat
+        (< 1e-4 dB) to 0.913 Nyquist, stop band from Nyquist on at -120 dB (365 / 727 taps for 2x / 4x) or -160 dB
+        (507 / 1013 taps; -150 dB with the float32 taps the device holds).  In the collapsed reference chain the extra
+        taps cost a quarter of their number at 4x: (1013 + N - 1) / 4 base-rate taps.
     """
     factor = int(factor)
     if factor <= 1:
         return np.ones(1)
+    if quality != "fast":
+        from scipy import signal
+        rej, pass_end = upsampler_spec(quality)
+        nyq, rate = samplerate / 2.0, float(samplerate * factor)
+        n, beta = signal.kaiserord(rej, (1.0 - pass_end) * nyq / (0.5 * rate))
+        n = int(numtaps) if numtaps is not None else (n | 1)
+        return factor * signal.firwin(n, 0.5 * (pass_end + 1.0) * nyq, window=("kaiser", beta), fs=rate)
     if numtaps is None:
         numtaps = 32 * factor + 1
     h = create_fir_filter(method="window", cutoff=samplerate / 2, numtaps=numtaps,

@@ -172,7 +172,7 @@ int afp_process(afp_ctx* ctx, const float* in_dev, int64_t in_pitch, void* out_d
 /* n_blocks consecutive blocks (the buffers of n_blocks consecutive callbacks) in one call: block b of stream s
  * starts at in_dev[b*in_block_stride + s*in_pitch] / out_dev[b*out_block_stride + s*out_pitch] (strides in
  * elements, bytes for AFP_FMT_I24_PACKED).  Results are bit-identical to n_blocks afp_process calls.  For a chain
- * that is a single long U = 1 filter (>= 400 taps; the collapsed reference chain included) with blocks of a multiple
+ * that is a single long U = 1 filter (>= 176 taps; the collapsed reference chain included) with blocks of a multiple
  * of 512 frames this is ONE launch: the CTA that owns 16 streams walks their blocks with [history | block] resident
  * in shared memory, the carried history (the reference's sliding input_buffer, stream_process.py:45-46,97-98)
  * is read once and written once.  Every other chain runs block by block. */

@@ -346,3 +346,19 @@ def test_interleaved_entry_point_pipelines_session_chunks():
     assert np.array_equal(y.transpose(0, 2, 1).reshape(S, B), yp)
     for s in (0, 1, 4097, 8191):
         assert_parity(yp[s], rc.streaming_fir(h, planar[s]), f"stream {s}")
+
+
+def test_reference_chain_with_the_soxr_grade_interpolator():
+    """C1's chain with the 1013-tap 'vhq' prototype (libsoxr's VHQ recipe, design.design_upsampler): collapsed to one
+    (1013 + 251 - 1) / 4 = 316-tap base-rate filter; oracle = up-sample the whole signal, FIR at 4 fs, keep every 4th."""
+    S, B, nblk, U, fs = 4, 1024, 4, 4, 44100
+    up = design.design_upsampler(U, fs, quality="vhq")
+    h = design.create_fir_filter(cutoff=[500, 8000], numtaps=251, window_type="kaiser", filter_type="bandpass", samplerate=fs * U)
+    x = (0.1 * np.random.default_rng(31).standard_normal((S, nblk * B))).astype(np.float32)
+    with BatchFirEngine(h, n_streams=S, max_frames=B, upsample=U, chain="reference", upsampler_taps=up) as e:
+        y = run_host(e, x, B)
+        info = e.stage_info()
+    assert len(info) == 1 and info[0]["n_taps"] == (len(up) + len(h) - 1 + U - 1) // U
+    for s in range(S):
+        u = rc.polyphase_upsample_whole(up, x[s], U)
+        assert_parity(y[s], rc.streaming_fir(h, u, U), f"stream {s}")

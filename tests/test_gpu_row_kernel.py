@@ -19,6 +19,13 @@ from oracle import dither_quant as dq  # noqa: E402
 ROW, PAIR = 2, 0
 
 
+@pytest.fixture(autouse=True)
+def _ffma2_kernels_only(monkeypatch):
+    """These tests are about the two packed-FFMA2 kernels: U = 1 filters of 176 taps and more would otherwise run on the
+    split-FP16 tensor kernel whenever the block is a multiple of 512 frames (tests/test_gpu_tensor2.py covers that)."""
+    monkeypatch.setenv("AFP_NO_TC2", "1")
+
+
 def noise(S, n, seed=99, amp=0.1):
     return np.stack([np.clip(amp * np.random.default_rng(seed + s).standard_normal(n), -1, 1)
                      for s in range(S)]).astype(np.float32)
