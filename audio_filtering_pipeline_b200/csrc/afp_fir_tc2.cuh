@@ -65,7 +65,9 @@ struct Tc2Params {
     int n_chunks;              // D + 1
     int n_groups;              // ceil(n_streams / 16)
     unsigned int* range_flag;  // set to 1 when a sample does not fit FP16
-    long long* prof;           // nullptr, or [grid][8] cycle counters of the MMA warp (bench/microbench/tc2_probe.cu)
+    long long* prof;           // nullptr, or [grid][16] cycle counters (bench/microbench/tc2_probe.cu): 0-5 MMA warp (total, waits for
+                               // accumulators / early rows / late rows, issue, steps), 6-8 loader warp 1 (load latency, wait for the
+                               // window slot, split + store), 9-11 epilogue warp 0 (wait for the MMAs, TMEM read, store)
     // GROUPED instantiation (per-stream filters, afp_assign_groups): a work item is ONE stream; its 16 tile slots are 16
     // consecutive runs of steps_per_slot steps of that stream (slot v starts where slot v-1 ends), so all 16 share the
     // stream's tap cores gw + group_of_stream[s] * gw_stride, which the loaders bring in when the group changes
@@ -294,7 +296,7 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
             }
         }
         if (P.prof && lane == 0) {
-            long long* o = P.prof + (size_t)blockIdx.x * 8;
+            long long* o = P.prof + (size_t)blockIdx.x * 16;
             o[0] = clock64() - t_begin; o[1] = t_acc; o[2] = t_dir; o[3] = t_stg; o[4] = t_iss; o[5] = kk;
         }
     } else if (warp_u <= TC2_LOADERS) {
@@ -303,6 +305,7 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
         constexpr int LT = 32 * TC2_LOADERS;
         uint32_t kk = 0;
         float amax = 0.f;
+        long long t_ld = 0, t_slot = 0, t_place = 0;       // probe counters (P.prof)
         int ordinal = 0, cur_group = -1;
         for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x, ++ordinal) {
             const int s0 = grp * TC2_STREAMS;
@@ -394,11 +397,19 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                 } else if (st.kind == TC2_SLIDE) {
                     if (lane == 0) mbar_arrive(&win_early[p]);          // the history rows are where the last step left them
                     float4 v[8];
+                    const long long q0 = P.prof ? clock64() : 0;
                     rows8_fetch(k, 16, v);
+                    if (P.prof) {                                       // (probe only: make the loads land here)
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) asm volatile("" ::"f"(v[u].x), "f"(v[u].w));
+                    }
+                    const long long q1 = P.prof ? clock64() : 0;
                     // the new rows' place was last read by step kk-2 at the latest
                     if (kk >= 2) mbar_wait(&mma_done[p], ((kk - 2) >> 1) & 1u);
+                    const long long q2 = P.prof ? clock64() : 0;
                     rows8_place(st.pos, 16, v);
                     publish(&win_late[p]);
+                    if (P.prof) { t_ld += q1 - q0; t_slot += q2 - q1; t_place += clock64() - q2; }
                 } else {
                     // fresh window: rows 16..23 of the tile are shared with the window of step kk-1 (its oldest rows if
                     // this window starts at row 0, its newest if at row 16): they wait in registers
@@ -422,6 +433,7 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
             }
         }
         if (amax > 65000.0f) atomicOr(P.range_flag, 1u);
+        if (P.prof && tid == 32) { long long* o = P.prof + (size_t)blockIdx.x * 16; o[6] = t_ld; o[7] = t_slot; o[8] = t_place; }
     } else {
         // ================= epilogue: TMEM -> registers -> dither / quantise -> HBM =================
         const int ew = warp_u - 1 - TC2_LOADERS;                // 0..7
@@ -437,6 +449,7 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
         } V = {P.fmt, P.dither, 1, P.fast_out, P.gain, P.dither_lsb, P.out, P.out_pitch, P.seed, P.sample_base, P.stream_id0};
         const int eb = P.fmt == FMT_I16 ? 2 : (P.fmt == FMT_I24_PACKED ? 3 : 4);
         uint32_t kk = 0;
+        long long e_wait = 0, e_tmem = 0, e_store = 0;      // probe counters (P.prof)
         for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x) {
             const int s = GROUPED ? grp : grp * TC2_STREAMS + (m >> 3);
             for (int k = 0; k < n_steps; ++k, ++kk) {
@@ -444,7 +457,9 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                 // first output sample of this thread's 32 within the call: slot m/8 runs through its own steps (GROUPED)
                 const int idx = ((GROUPED ? (m >> 3) * n_steps : 0) + k) * TC2_STEP + (m & 7) * TC2_R + 32 * half;
                 const int blk = idx / P.frames;
+                const long long r0 = P.prof ? clock64() : 0;
                 mbar_wait(&mma_done[p], ph);
+                const long long r1 = P.prof ? clock64() : 0;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t taddr = tmem_base + ((uint32_t)(32 * quarter) << 16) + p * 128u + (uint32_t)(32 * half);
                 float y[32];
@@ -469,14 +484,17 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[p]);
+                const long long r2 = P.prof ? clock64() : 0;
                 V.out = static_cast<unsigned char*>(P.out) + (long long)blk * P.out_block_stride * eb;
                 V.sample_base = P.sample_base + (unsigned long long)blk * (unsigned long long)P.frames;
                 store_row<32, EPI>(V, y, s, (long long)(idx - blk * P.frames), s < P.n_streams ? 32 : 0);
+                if (P.prof) { e_wait += r1 - r0; e_tmem += r2 - r1; e_store += clock64() - r2; }
             }
             // (the epilogue warps have the slack for this; in the loaders it would delay the next group's first window)
             if (GROUPED) tc2_copy_history(P, grp, 1, TC2_STREAMS * n_steps * TC2_STEP, tid - 32 * (1 + TC2_LOADERS), 32 * TC2_EPIS);
             else tc2_copy_history(P, grp * TC2_STREAMS, TC2_STREAMS, n_steps * TC2_STEP, tid - 32 * (1 + TC2_LOADERS), 32 * TC2_EPIS);
         }
+        if (P.prof && tid == 32 * (1 + TC2_LOADERS)) { long long* o = P.prof + (size_t)blockIdx.x * 16; o[9] = e_wait; o[10] = e_tmem; o[11] = e_store; }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();

@@ -470,7 +470,7 @@ def config_points(D, args, cpu, fma_peak, peaks_run, peaks_file):
     specs = {
         "C1": dict(desc="251-tap Kaiser band-pass 500-8000 Hz designed at 176.4 kHz, 44.1 kHz streams, 4x up-sample -> FIR -> [::4] "
                         "(reference chain, collapsed to one base-rate FIR), 1024-frame blocks, RPDF float dither",
-                   S=8192, B=1024, NB=8, eng=dict(taps=h1, upsample=4, chain="reference", upsampler_taps=up4, dither="rpdf"),
+                   S=16384, B=1024, NB=8, eng=dict(taps=h1, upsample=4, chain="reference", upsampler_taps=up4, dither="rpdf"),
                    n_exec=-(-(len(h1) + len(up4) - 1) // 4), U=1, out_mult=1, out_bytes=4,
                    cpu=("reference_chain", {"taps": h1, "up_taps": up4, "upsample": 4, "frames": 1024})),
         "C3_per_band": dict(desc="10-band EQ (9 reference bands + 16-20 kHz) x 501 taps accumulated band by band, then 501-tap low-pass, "
@@ -643,6 +643,11 @@ def aux_points(D, hbm_peak_gbs, iters=10):
 
 # --------------------------------------------------------------------------- our arm
 def run_ours(args):
+    # stdout must carry exactly ONE JSON line: whatever libraries print there meanwhile (NCCL's version banner comes
+    # from C, past sys.stdout) goes to stderr - file descriptor 1 is pointed at stderr until the line is written
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     from audio_filtering_pipeline_b200.engine import BatchFirEngine, PinnedArray, measure_fma_peak, measure_tensor_peak
 
@@ -774,8 +779,12 @@ def run_ours(args):
             "stage": stage, "checksum": checksum,
             "configs": configs, "c5_sweep": sweep, "agc_kernel_only": agc, "waterfall_rows_kernel_only": spec,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     D.close()
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    os.close(real_stdout)
     return 0
 
 

@@ -29,11 +29,11 @@ int main(int argc, char** argv) {
     const int n_groups = (S + 15) / 16, grid = std::min(n_groups, prop.multiProcessorCount);
     CK(cudaMalloc(&d_hist, hist.size() * 4)); CK(cudaMalloc(&d_hout, hist.size() * 4));
     CK(cudaMalloc(&d_in, in.size() * 4)); CK(cudaMalloc(&d_out, in.size() * 4));
-    CK(cudaMalloc(&d_w, w.size() * 2)); CK(cudaMalloc(&d_flag, 4)); CK(cudaMalloc(&d_prof, sizeof(long long) * 8 * grid));
+    CK(cudaMalloc(&d_w, w.size() * 2)); CK(cudaMalloc(&d_flag, 4)); CK(cudaMalloc(&d_prof, sizeof(long long) * 16 * grid));
     CK(cudaMemcpy(d_hist, hist.data(), hist.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_in, in.data(), in.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_w, w.data(), w.size() * 2, cudaMemcpyHostToDevice));
-    CK(cudaMemset(d_flag, 0, 4)); CK(cudaMemset(d_prof, 0, sizeof(long long) * 8 * grid));
+    CK(cudaMemset(d_flag, 0, 4)); CK(cudaMemset(d_prof, 0, sizeof(long long) * 16 * grid));
     afp::Tc2Params P{};
     P.hist_in = d_hist; P.hist_out = d_hout; P.hist_pitch = hist_len; P.hist_len = hist_len;
     P.in = d_in; P.in_pitch = frames; P.in_block_stride = (long long)S * frames;
@@ -76,16 +76,20 @@ int main(int argc, char** argv) {
     for (int i = 0; i < iters; ++i) kern<<<grid, afp::TC2_THREADS, smem>>>(P);
     cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
     float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
-    std::vector<long long> prof((size_t)8 * grid);
+    std::vector<long long> prof((size_t)16 * grid);
     CK(cudaMemcpy(prof.data(), d_prof, prof.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-    double tot = 0, acc = 0, dir = 0, stg = 0, iss = 0, steps = 0; long long tmax = 0;
+    double tot = 0, acc = 0, dir = 0, stg = 0, iss = 0, steps = 0, ld = 0, slot = 0, place = 0, ew = 0, et = 0, es = 0; long long tmax = 0;
     for (int b = 0; b < grid; ++b) {
-        tot += prof[b * 8]; acc += prof[b * 8 + 1]; dir += prof[b * 8 + 2]; stg += prof[b * 8 + 3]; iss += prof[b * 8 + 4]; steps += prof[b * 8 + 5];
-        tmax = std::max(tmax, prof[b * 8]);
+        const long long* o = &prof[(size_t)b * 16];
+        tot += o[0]; acc += o[1]; dir += o[2]; stg += o[3]; iss += o[4]; steps += o[5];
+        ld += o[6]; slot += o[7]; place += o[8]; ew += o[9]; et += o[10]; es += o[11];
+        tmax = std::max(tmax, o[0]);
     }
     const double mma_clk = 48.0 * n_chunks * 4 * 3;
     printf("{\"taps\": %d, \"streams\": %d, \"frames\": %d, \"blocks\": %d, \"ms\": %.4f, \"gsamples_s\": %.1f, \"sm_mhz_from_clk\": %.0f, "
-           "\"clk_per_step\": %.0f, \"model_mma_clk_per_step\": %.0f, \"wait_acc\": %.0f, \"wait_window\": %.0f, \"wait_shared_rows\": %.0f, \"issue\": %.0f}\n",
-           N, S, frames, NB, ms, (double)S * frames * NB / ms / 1e6, tmax / (ms * 1e-3) / 1e6, tot / steps, mma_clk, acc / steps, dir / steps, stg / steps, iss / steps);
+           "\"clk_per_step\": %.0f, \"model_mma_clk_per_step\": %.0f, \"wait_acc\": %.0f, \"wait_window\": %.0f, \"wait_shared_rows\": %.0f, \"issue\": %.0f, "
+           "\"loader_load\": %.0f, \"loader_wait_slot\": %.0f, \"loader_split_store\": %.0f, \"epi_wait_mma\": %.0f, \"epi_tmem\": %.0f, \"epi_store\": %.0f}\n",
+           N, S, frames, NB, ms, (double)S * frames * NB / ms / 1e6, tmax / (ms * 1e-3) / 1e6, tot / steps, mma_clk, acc / steps, dir / steps, stg / steps, iss / steps,
+           ld / steps, slot / steps, place / steps, ew / steps, et / steps, es / steps);
     return 0;
 }
