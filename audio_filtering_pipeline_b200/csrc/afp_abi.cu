@@ -248,12 +248,15 @@ int build_stage(afp_ctx* c, Stage& s, int kind, int U, const double* taps, int n
     // Long single-table U = 1 filters can also run on the tensor cores (afp_fir_tc.cuh).  Both kernels
     // then share one history format: the last kq_pad samples with kq_pad a multiple of 32 (the tensor
     // kernel's row length), so a stage may switch kernel from one block to the next.
-    // Crossovers against the single-row FFMA2 kernel, measured at 16384 streams (bench/quick_perf.py with AFP_TC_MIN_TAPS
-    // 32 vs 5000, bench/gpu_calls/r02_tcmin*.sh): the split-FP16 kernel (afp_fir_tc2.cuh) runs at 165-210 Gsamples/s
-    // whatever the length (its loaders and epilogue, not the MMAs, bound it below ~400 taps) - equal at 160 taps, +18 %
-    // at 192, +45 % at 251, 2.1x at 385; the 3xTF32 kernel (afp_fir_tc.cuh, 256-frame blocks) only from 385 taps up.
+    // Crossovers against the single-row FFMA2 kernel, measured at 16384 streams (bench/quick_perf.py and
+    // bench/microbench/tc2_probe with AFP_TC_MIN_TAPS 32 vs 5000, bench/gpu_calls/r02_tcmin*.sh, r02_tc2_ring.sh): the
+    // split-FP16 kernel (afp_fir_tc2.cuh) is bound by its loaders and epilogue, not by the MMAs, below ~400 taps - one
+    // 1024-frame block per launch: 295 / 286 / 243 / 208 Gsamples/s at 51 / 101 / 251 / 385 taps (FFMA2: 388 / 243 / 123 /
+    // 83); 16 blocks of 512 frames per launch: 494 / 424 / 325 at 51 / 251 / 449 taps.  So cores are built from 48 taps
+    // up and launch_stage_tc2 decides per call (>= 8 steps of 512 frames: from 48 taps, else from 112).  The 3xTF32
+    // kernel (afp_fir_tc.cuh, 256-frame blocks) only wins from 385 taps up.
     const int tc_min = std::getenv("AFP_TC_MIN_TAPS") ? std::atoi(std::getenv("AFP_TC_MIN_TAPS")) : 400;
-    const int tc2_min = std::getenv("AFP_TC_MIN_TAPS") ? std::atoi(std::getenv("AFP_TC_MIN_TAPS")) : 176;
+    const int tc2_min = std::getenv("AFP_TC_MIN_TAPS") ? std::atoi(std::getenv("AFP_TC_MIN_TAPS")) : 48;
     const bool tc_any = U == 1 && n_sub == 1 && !env_flag("AFP_NO_TC");
     const bool tc1_ok = tc_any && n >= tc_min, tc2_ok = tc_any && n >= tc2_min && !env_flag("AFP_NO_TC2");
     const bool tc_ok = tc1_ok || tc2_ok;
@@ -528,6 +531,8 @@ int launch_stage_tc2(afp_ctx* c, Stage& s, const float* in, long long in_pitch, 
     if (!c->group_of_stream.empty()) return AFP_OK;   // per-group filters: launch_stage_tc2_grouped / the row-pair kernel
     if (frames < afp::TC2_STEP || frames % afp::TC2_STEP != 0 || n_blocks < 1) return AFP_OK;
     if ((long long)frames * n_blocks > (1 << 30)) return AFP_OK;
+    // short filters: only when a stream group's window start is amortised over enough steps (see build_stage)
+    if (!std::getenv("AFP_TC_MIN_TAPS") && s.n_taps < 112 && (long long)(frames / afp::TC2_STEP) * n_blocks < 8) return AFP_OK;
     const int eb = fmt == AFP_FMT_I16 ? 2 : (fmt == AFP_FMT_I24_PACKED ? 3 : 4);
     if (!aligned16(in) || in_pitch % 4 != 0 || in_bstride % 4 != 0 || s.hist_pitch % 4 != 0 || s.kq_pad % 8 != 0) return AFP_OK;
     if (s.tc2_chunks > 17 || s.kq_pad > 24 * afp::TC2_R) return AFP_OK;
@@ -544,7 +549,9 @@ int launch_stage_tc2(afp_ctx* c, Stage& s, const float* in, long long in_pitch, 
     P.fast_out = (aligned16(out) && (out_pitch * eb) % 16 == 0 && (out_bstride * eb) % 16 == 0) ? 1 : 0;
     P.seed = c->cfg.seed; P.sample_base = sample_base; P.stream_id0 = c->cfg.first_stream_id + s0;
     P.gain = 1.0f; P.dither_lsb = std::ldexp(1.0f, -(c->dither_bits - 1));
-    const int smem = afp::tc2_smem_bytes(s.tc2_chunks);
+    // transposed epilogue stores when the staging tiles fit beside the window tile and the tap cores (filters up to ~640 taps)
+    P.epi_stage = afp::tc2_smem_bytes(s.tc2_chunks, true) <= kMaxSmem && !env_flag("AFP_TC2_NO_STAGE") ? 1 : 0;
+    const int smem = afp::tc2_smem_bytes(s.tc2_chunks, P.epi_stage != 0);
     if (smem > kMaxSmem) return AFP_OK;
     const int grid = P.n_groups < c->n_sm ? P.n_groups : c->n_sm;
     afp_kernel_tc2(afp::epi_code(fmt, dither))<<<grid, afp::TC2_THREADS, smem, stream>>>(P);
@@ -585,7 +592,8 @@ int launch_stage_tc2_grouped(afp_ctx* c, Stage& s, const float* in, long long in
     P.fast_out = (aligned16(out) && (out_pitch * eb) % 16 == 0 && (out_bstride * eb) % 16 == 0) ? 1 : 0;
     P.seed = c->cfg.seed; P.sample_base = sample_base; P.stream_id0 = c->cfg.first_stream_id + s0;
     P.gain = 1.0f; P.dither_lsb = std::ldexp(1.0f, -(c->dither_bits - 1));
-    const int smem = afp::tc2_smem_bytes(s.tc2_chunks);
+    P.epi_stage = afp::tc2_smem_bytes(s.tc2_chunks, true) <= kMaxSmem && !env_flag("AFP_TC2_NO_STAGE") ? 1 : 0;
+    const int smem = afp::tc2_smem_bytes(s.tc2_chunks, P.epi_stage != 0);
     if (smem > kMaxSmem) return AFP_OK;
     const int grid = ns < c->n_sm ? ns : c->n_sm;
     afp_kernel_tc2_grouped()<<<grid, afp::TC2_THREADS, smem, stream>>>(P);

@@ -22,12 +22,11 @@
 //     2^11);  y = acc0 + 2^-11 acc1;  lo*lo (2^-22 relative) is dropped as before.  Range: |x| < 65504
 //     (audio is +-1); a larger sample sets the context's range flag and the call reports it.
 //  3. The CTA keeps a stream group for all the blocks of the call.  A step = 16 streams x 8 rows (512
-//     samples); its window [H history rows | 8 new rows] lives at one of two positions of a 40-row tile
-//     (rows 0.. and rows 16..; for H = 16 they share rows 16-23, which travel through registers), so the
-//     loader warps fill the window of step k+1 while the tensor pipe works on step k and the epilogue warps
-//     drain step k-1 from TMEM (two accumulator sets).  History is read from the carried buffer only for the
-//     first steps of a call and written once at its end; in between the "history" is the previous blocks'
-//     input, re-read through L2.
+//     samples); its window [H history rows | 8 new rows] slides over a ring of 32 tile rows (tc2_step), so the
+//     loader warps bring in only the 8 new rows of step k+1 while the tensor pipe works on step k and the epilogue
+//     warps drain step k-1 from TMEM (two accumulator sets).  History is read from the carried buffer only for the
+//     first step of a call and written once at its end; in between the "history" is the previous blocks' input,
+//     still in shared memory.
 //
 // Cost model (measured): an M = 128, N = 64, K = 16 MMA takes max(32 clk pipe, 6 KB / 128 B/clk = 48 clk operand
 // fetch) = 48 clk;  a step is n_chunks x 4 k-steps x 3 products.  1001 taps: 204 MMAs = 9.8 kclk per 8192 samples.
@@ -41,8 +40,7 @@ namespace afp {
 
 constexpr int TC2_R = 64;                  // samples per row
 constexpr int TC2_STREAMS = 16;            // streams per work item (M = 128 = 16 x 8 rows)
-constexpr int TC2_ROWS = 41;               // rows per stream tile: 40 + 1 (row pitch 41 x 16 B = 16 mod 128: conflict-free loader stores)
-constexpr int TC2_POS_B = 16;              // first row of window position B
+constexpr int TC2_ROWS = 41;               // rows per stream tile: a ring of 32, its first 8 repeated, + 1 (row pitch 41 x 16 B = 16 mod 128: conflict-free loader stores)
 constexpr int TC2_STEP = 8 * TC2_R;        // new samples per stream and step
 constexpr int TC2_LOADERS = 8, TC2_EPIS = 8;            // warps
 constexpr int TC2_THREADS = 32 * (1 + TC2_LOADERS + TC2_EPIS);
@@ -75,6 +73,7 @@ struct Tc2Params {
     long long gw_stride;
     const int* group_of_stream;
     int steps_per_slot;
+    int epi_stage;             // 1: the launch carries TC2_STAGE_BYTES of shared memory for the epilogue's transposed stores
     // epilogue (same meaning as FirParams)
     int fmt, dither, decim, fast_out;
     unsigned long long seed, sample_base;
@@ -85,7 +84,11 @@ struct Tc2Params {
 typedef void (*tc2_kern_t)(const Tc2Params);
 
 __host__ __device__ constexpr int tc2_n_cores(int n_chunks) { return 8 * (n_chunks + 1) - 1; }
-__host__ __device__ constexpr int tc2_smem_bytes(int n_chunks) { return 2 * TC2_TILE_BYTES + 2 * tc2_n_cores(n_chunks) * 128 + 256; }
+constexpr int TC2_STAGE_STRIDE = 9;                                  // granules per staged row: 8 + 1 (odd: conflict-free)
+constexpr int TC2_STAGE_BYTES = TC2_EPIS * 32 * TC2_STAGE_STRIDE * 16;  // one 32-row tile per epilogue warp
+__host__ __device__ constexpr int tc2_smem_bytes(int n_chunks, bool stage = false) {
+    return 2 * TC2_TILE_BYTES + 2 * tc2_n_cores(n_chunks) * 128 + 256 + (stage ? TC2_STAGE_BYTES : 0);
+}
 
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
                                          uint32_t accumulate) {
@@ -135,23 +138,24 @@ __device__ __forceinline__ void tc2_split4(const float4& v, uint2& hi, uint2& lo
     lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l32), *reinterpret_cast<const uint32_t*>(&l10));
 }
 
-// Where the window of a step lives and how it gets there - the same function in the three warp roles.
-// A window is 24 rows [16 history | 8 new] of the 40-row tile at row 0, 8 or 16.  Inside a stream group it slides:
-// position (first + 8 k) mod 24, so a step normally finds its history rows in place and loads only its 8 new
-// rows (SLIDE); coming back to row 0 it reloads all 24 rows (the history from the previous blocks' input, an L2
-// hit), and so does the first step of a group (FRESH).  A fresh window may share 8 rows at most with the window the
-// tensor pipe is still reading - rows 16..23, which wait in registers until that step is done - so a group starts
-// at row 0 after a group that ended at row 16 and at row 16 after one that ended at row 0; the start row is chosen
-// from (n_steps - 1) mod 3 so that no group ever ends at row 8.
-enum : int { TC2_SLIDE = 0, TC2_FRESH0 = 1, TC2_FRESH16 = 2 };
-struct Tc2Step { int pos, kind; };
-__device__ __forceinline__ Tc2Step tc2_step(int n_steps, int group_ordinal, int k) {
-    const int r = (n_steps - 1) % 3;
-    const int first = r == 0 ? ((group_ordinal & 1) ? 16 : 0) : (r == 1 ? 16 : 0);
-    const int pos = (first + 8 * k) % 24;
+// Where the window of a step lives - the same function in the MMA and the loader role.
+// A window is 24 rows [16 history | 8 new].  The stream tile is a RING of 32 rows (physical rows 32..39 repeat rows 0..7, so
+// the eight consecutive rows an MMA reads never wrap): step k of a stream group has its window at ring rows 8 k .. 8 k + 23
+// (mod 32) and writes only its 8 NEW rows, into the eight rows that are not part of the previous step's window - the oldest
+// rows of the step before that, free once that step's MMAs are done.  Only the first step of a group loads a whole window,
+// and of that only the rows its MMAs read (chunk d reads window rows 16 - d .. 23 - d: a 251-tap filter 12 rows, not 24).
+// (The first version walked three fixed positions of a 40-row tile and reloaded all 24 rows on every third step; the
+// probe counters showed the MMA warp waiting for exactly those reloads: 6.1 of 8.0 kclk per step at 51 taps.)
+constexpr int TC2_RING = 32;
+struct Tc2Step { int pos; bool fresh; };
+// Window start of the next step given the previous step's: +8 inside a group; a new group starts 24 rows on, so that
+// its eight OLDEST rows are the ring rows the previous step's window does not cover - they can be written while that step's
+// MMAs still run (long filters only read them; the other sixteen rows wait for those MMAs).  `w` starts at 8.
+__device__ __forceinline__ Tc2Step tc2_step(int& w, int k) {
+    w = (w + (k == 0 ? 24 : 8)) & (TC2_RING - 1);
     Tc2Step st;
-    st.pos = pos;
-    st.kind = k == 0 ? (first == 0 ? TC2_FRESH0 : TC2_FRESH16) : (pos == 0 ? TC2_FRESH0 : TC2_SLIDE);
+    st.pos = w;
+    st.fresh = k == 0;
     return st;
 }
 
@@ -191,6 +195,40 @@ __device__ __forceinline__ void tc2_copy_history(const Tc2Params& P, int s0, int
     }
 }
 
+// Epilogue store sink: warp transpose through shared memory.  A lane owns one row's run of NB words (one 128-byte line for
+// 4-byte samples), and the 32 rows of a warp lie 256 bytes apart: stored straight from registers, every STG.128 puts 16
+// bytes into 32 different lines - the partial-line traffic slowed the loaders' reads as much as the epilogue itself
+// (probe without the stores: 383 -> 545 Gsamples/s at 51 taps).  Here the lanes park their runs in the warp's tile and
+// read them back so that eight consecutive lanes store one row's eight granules: every instruction writes four whole
+// lines.  Row addresses travel by shuffle; rows outside the batch carry a null address.
+struct RowTransposeSink {
+    static constexpr bool kAllFull = true;    // (store_row's aligned full-run path; the caller checks fast_out)
+    uint4* tile;
+    bool ok;
+    template <int NB>
+    __device__ __forceinline__ void put(void* dst, const uint32_t (&w)[NB]) const {
+        constexpr int G = NB / 4;                               // granules per row
+        if (NB % 4 != 0 || G > 8 || 32 % G != 0) {              // (packed int24: 6 granules - straight from registers)
+            if (ok) store_words<NB>(dst, w);
+            return;
+        }
+        const int lane = threadIdx.x & 31;
+        __syncwarp();                                           // the previous read-back is done
+#pragma unroll
+        for (int i = 0; i < G; ++i)
+            tile[lane * TC2_STAGE_STRIDE + i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+        __syncwarp();
+        const unsigned long long d = ok ? reinterpret_cast<unsigned long long>(dst) : 0ull;
+        const unsigned dlo = (unsigned)d, dhi = (unsigned)(d >> 32);
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            const int r = i * (32 / G) + lane / G, g = lane % G;
+            const unsigned long long p = ((unsigned long long)__shfl_sync(0xffffffffu, dhi, r) << 32) | __shfl_sync(0xffffffffu, dlo, r);
+            if (p) reinterpret_cast<uint4*>(p)[g] = tile[r * TC2_STAGE_STRIDE + g];
+        }
+    }
+};
+
 template <int EPI, bool GROUPED = false>
 __global__ void __launch_bounds__(TC2_THREADS, 1)
 fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
@@ -216,7 +254,7 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
     }
     if (tid == 32) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&win_early[i], TC2_LOADERS); mbar_init(&win_late[i], TC2_LOADERS);
+            mbar_init(&win_early[i], TC2_LOADERS / 2); mbar_init(&win_late[i], TC2_LOADERS / 2);   // the owning loader group's warps
             mbar_init(&mma_done[i], 1); mbar_init(&acc_empty[i], TC2_EPIS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -241,13 +279,13 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
         const uint32_t idesc = tc2_idesc(TC2_R);
         const int D = P.n_chunks - 1;
         uint32_t kk = 0;                                       // steps issued by this CTA
+        int wpos = 8;
         long long t_acc = 0, t_dir = 0, t_stg = 0, t_iss = 0;  // cycles waiting for: accumulators, early rows, late rows; issuing
         const long long t_begin = clock64();
-        int ordinal = 0;
-        for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x, ++ordinal) {
+        for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x) {
             for (int k = 0; k < n_steps; ++k, ++kk) {
                 const uint32_t p = kk & 1u, ph = (kk >> 1) & 1u;
-                const Tc2Step st = tc2_step(n_steps, ordinal, k);
+                const Tc2Step st = tc2_step(wpos, k);
                 const long long c0 = clock64();
                 mbar_wait(&acc_empty[p], ph ^ 1u);             // (passes at once the first time round)
                 const long long c1 = clock64();
@@ -265,7 +303,7 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                     int d;
                     if (D >= 8) d = idx == 0 ? 8 : (idx <= D - 8 ? D + 1 - idx : D - idx);
                     else d = D - idx;
-                    const bool late = st.kind == TC2_FRESH16 ? d >= 9 : d <= 7;
+                    const bool late = d <= 7;              // reads new rows (a first step publishes both barriers together)
                     if (late && !late_seen) {
                         const long long w0 = clock64();
                         mbar_wait(&win_late[p], ph);
@@ -274,7 +312,7 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                         late_seen = true;
                     }
                     if (elect_one()) {
-                        const uint32_t arow = (uint32_t)(st.pos + H - d);
+                        const uint32_t arow = (uint32_t)((st.pos + H - d) & (TC2_RING - 1));
                         const uint32_t ah = (uint32_t)a_hi_d + arow, al = (uint32_t)a_lo_d + arow;
                         const uint32_t wh = (uint32_t)w_hi_d + (uint32_t)(8 * d) * 8u, wl = (uint32_t)w_lo_d + (uint32_t)(8 * d) * 8u;
 #pragma unroll
@@ -289,7 +327,7 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                     __syncwarp();
                     first = false;
                 }
-                if (!late_seen) mbar_wait(&win_late[p], ph);   // (D < 9 at a window that starts at row 16: nothing was late)
+                if (!late_seen) mbar_wait(&win_late[p], ph);
                 if (elect_one()) umma_commit(&mma_done[p]);
                 __syncwarp();
                 t_iss += clock64() - c2;
@@ -301,13 +339,18 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
         }
     } else if (warp_u <= TC2_LOADERS) {
         // ================= loaders: global -> hi / lo halves of the window rows =================
+        // Two groups of four warps; group g owns the steps of parity g (the accumulator set and barrier pair of that
+        // parity), so while one group splits and stores the rows of step k the other already waits for the loads of step
+        // k+1: a global-memory round trip (2-3.5 kclk under load) overlaps the other group's arithmetic instead of
+        // sitting between two steps.
         const int ltid = tid - 32;
-        constexpr int LT = 32 * TC2_LOADERS;
+        const int lg = ltid >> 7, lt = ltid & 127;
+        constexpr int LT = 32 * TC2_LOADERS / 2;
         uint32_t kk = 0;
         float amax = 0.f;
         long long t_ld = 0, t_slot = 0, t_place = 0;       // probe counters (P.prof)
-        int ordinal = 0, cur_group = -1;
-        for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x, ++ordinal) {
+        int cur_group = -1, wpos = 8;
+        for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x) {
             const int s0 = grp * TC2_STREAMS;
             // one float4 (4 samples) of window row `wrow` (0..23) of local stream sl at step k
             auto fetch = [&](int k, int sl, int wrow, int f4) -> float4 {
@@ -326,25 +369,27 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
             auto place = [&](int pos, int sl, int wrow, int f4, const float4& v) {
                 uint2 hi, lo;
                 tc2_split4(v, hi, lo, amax);
-                const int off = sl * TC2_PITCH + (7 - (f4 >> 1)) * TC2_A_LBO + (pos + wrow) * 16 + ((f4 & 1) ? 0 : 8);
+                const int row = (pos + wrow) & (TC2_RING - 1);
+                const int off = sl * TC2_PITCH + (7 - (f4 >> 1)) * TC2_A_LBO + row * 16 + ((f4 & 1) ? 0 : 8);
                 *reinterpret_cast<uint2*>(tile_hi + off) = hi;
                 *reinterpret_cast<uint2*>(tile_lo + off) = lo;
-            };
-            // 8 window rows starting at r0 for all 16 streams: 2048 float4, 8 per thread; consecutive lanes take
-            // consecutive float4 of a stream's rows (rows are contiguous in memory)
-            auto rows8_fetch = [&](int k, int r0, float4 (&v)[8]) {
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int j = ltid + u * LT;
-                    v[u] = fetch(k, j >> 7, r0 + ((j >> 4) & 7), j & 15);
+                if (row < 8) {                             // rows 0..7 are repeated after row 31
+                    *reinterpret_cast<uint2*>(tile_hi + off + TC2_RING * 16) = hi;
+                    *reinterpret_cast<uint2*>(tile_lo + off + TC2_RING * 16) = lo;
                 }
             };
-            auto rows8_place = [&](int pos, int r0, const float4 (&v)[8]) {
+            // 8 window rows starting at r0 for all 16 streams: 2048 float4, 16 per thread of the owning group.  Thread lt takes
+            // float4 (lt & 15) of row (lt >> 4) & 7 of EVERY stream (consecutive lanes: consecutive float4 of a stream's rows,
+            // which are contiguous in memory), so row, column and - one filter set per batch - the block and frame of the
+            // samples are the same for its 16 loads: one address computation per batch, then a stream pitch per load.
+            const int prow = (lt >> 4) & 7, pf4 = lt & 15;
+            auto rows8_fetch = [&](int k, int r0, float4 (&v)[16]) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int j = ltid + u * LT;
-                    place(pos, j >> 7, r0 + ((j >> 4) & 7), j & 15, v[u]);
-                }
+                for (int u = 0; u < 16; ++u) v[u] = fetch(k, u, r0 + prow, pf4);
+            };
+            auto rows8_place = [&](int pos, int r0, const float4 (&v)[16]) {
+#pragma unroll
+                for (int u = 0; u < 16; ++u) place(pos, u, r0 + prow, pf4, v[u]);
             };
             auto publish = [&](uint64_t* bar) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -360,75 +405,64 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                 cur_group = g;
                 wsrc = reinterpret_cast<const uint4*>(P.gw + (long long)g * P.gw_stride);
             }
+            const int D = P.n_chunks - 1;
             for (int k = 0; k < n_steps; ++k, ++kk) {
                 const uint32_t p = kk & 1u;
-                const Tc2Step st = tc2_step(n_steps, ordinal, k);
-                if (GROUPED && k == 0 && new_taps) {
-                    // fresh window AND new taps: every MMA of the step needs the taps, and they can only be replaced once
-                    // the previous step is done - so the whole window is published then; the loads are all in flight before
-                    const int sh0 = st.kind == TC2_FRESH0 ? 16 : 0, d0 = st.kind == TC2_FRESH0 ? 0 : 8;
-                    {
-                        float4 v0[8], v1[8];
-                        rows8_fetch(k, d0, v0);
-                        rows8_fetch(k, d0 + 8, v1);
-                        if (kk >= 2) mbar_wait(&mma_done[p], ((kk - 2) >> 1) & 1u);
-                        rows8_place(st.pos, d0, v0);
-                        rows8_place(st.pos, d0 + 8, v1);
-                    }
-                    float4 sv[8];
-                    rows8_fetch(k, sh0, sv);
-                    constexpr int WPT = (2 * tc2_n_cores(17) * 8 + LT - 1) / LT;     // uint4 of tap cores per thread (9)
-                    uint4 wv[WPT];
-                    const int n_w = 2 * P.n_cores * 8;
+                const Tc2Step st = tc2_step(wpos, k);
+                float4 v[16];
+                if (st.fresh) {
+                    // First step of a group: the window rows its MMAs read, [16 - D, 24), in batches of 8 rows.  Both loader
+                    // groups work on it (a thread takes one float4 position of every second stream), the two newest batches
+                    // in flight together and before the tile is free (every earlier MMA done); the oldest batch only exists
+                    // for filters of more than 513 taps.  GROUPED: this stream's tap cores replace the previous ones here too.
+                    // The groups meet at a named barrier, then the owning group publishes.
+                    if (D >= 9) {
+                        // the oldest batch lies outside the previous step's window: free once step kk-2 is done
 #pragma unroll
-                    for (int u = 0; u < WPT; ++u) {
-                        const int j = ltid + u * LT;
-                        wv[u] = j < n_w ? __ldg(wsrc + j) : make_uint4(0u, 0u, 0u, 0u);
+                        for (int u = 0; u < 8; ++u) v[u] = fetch(k, 2 * u + lg, prow, pf4);
+                        if (kk >= 2) mbar_wait(&mma_done[p], ((kk - 2) >> 1) & 1u);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) place(st.pos, 2 * u + lg, prow, pf4, v[u]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        v[u] = fetch(k, 2 * u + lg, 16 + prow, pf4);
+                        v[8 + u] = D >= 1 ? fetch(k, 2 * u + lg, 8 + prow, pf4) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                     if (kk >= 1) mbar_wait(&mma_done[p ^ 1u], ((kk - 1) >> 1) & 1u);
-#pragma unroll
-                    for (int u = 0; u < WPT; ++u) {
-                        const int j = ltid + u * LT;
-                        if (j < n_w) reinterpret_cast<uint4*>(w_hi)[j] = wv[u];
+                    if (GROUPED && new_taps) {
+                        const int n_w = 2 * P.n_cores * 8;
+                        for (int j = ltid; j < n_w; j += 2 * LT) reinterpret_cast<uint4*>(w_hi)[j] = __ldg(wsrc + j);
                     }
-                    rows8_place(st.pos, sh0, sv);
-                    publish(&win_early[p]);
-                    publish(&win_late[p]);
-                } else if (st.kind == TC2_SLIDE) {
-                    if (lane == 0) mbar_arrive(&win_early[p]);          // the history rows are where the last step left them
-                    float4 v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        place(st.pos, 2 * u + lg, 16 + prow, pf4, v[u]);
+                        if (D >= 1) place(st.pos, 2 * u + lg, 8 + prow, pf4, v[8 + u]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("bar.sync 1, %0;" ::"r"(32 * TC2_LOADERS) : "memory");
+                    if ((int)p == lg && lane == 0) { mbar_arrive(&win_early[p]); mbar_arrive(&win_late[p]); }
+                    continue;
+                }
+                if ((int)p != lg) continue;                 // the other group's step
+                {
                     const long long q0 = P.prof ? clock64() : 0;
                     rows8_fetch(k, 16, v);
                     if (P.prof) {                                       // (probe only: make the loads land here)
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) asm volatile("" ::"f"(v[u].x), "f"(v[u].w));
+                        for (int u = 0; u < 16; ++u) asm volatile("" ::"f"(v[u].x), "f"(v[u].w));
                     }
                     const long long q1 = P.prof ? clock64() : 0;
-                    // the new rows' place was last read by step kk-2 at the latest
+                    // the new rows replace the oldest rows of step kk-2
                     if (kk >= 2) mbar_wait(&mma_done[p], ((kk - 2) >> 1) & 1u);
+                    // The history rows are where the last steps left them.  (Not before the wait above: this group comes
+                    // here straight from step kk-2, and an arrival that completes this barrier's phase kk before the MMA
+                    // warp has looked at phase kk-2 would make that wait see the old parity again - a deadlock.)
+                    if (lane == 0) mbar_arrive(&win_early[p]);
                     const long long q2 = P.prof ? clock64() : 0;
                     rows8_place(st.pos, 16, v);
                     publish(&win_late[p]);
                     if (P.prof) { t_ld += q1 - q0; t_slot += q2 - q1; t_place += clock64() - q2; }
-                } else {
-                    // fresh window: rows 16..23 of the tile are shared with the window of step kk-1 (its oldest rows if
-                    // this window starts at row 0, its newest if at row 16): they wait in registers
-                    const int sh0 = st.kind == TC2_FRESH0 ? 16 : 0;      // window rows that live in tile rows 16..23
-                    const int d0 = st.kind == TC2_FRESH0 ? 0 : 8;        // first of the 16 other window rows
-                    {
-                        float4 v0[8], v1[8];                             // one round trip for the 16 rows
-                        rows8_fetch(k, d0, v0);
-                        rows8_fetch(k, d0 + 8, v1);
-                        if (kk >= 2) mbar_wait(&mma_done[p], ((kk - 2) >> 1) & 1u);
-                        rows8_place(st.pos, d0, v0);
-                        rows8_place(st.pos, d0 + 8, v1);
-                    }
-                    publish(&win_early[p]);
-                    float4 sv[8];
-                    rows8_fetch(k, sh0, sv);
-                    if (kk >= 1) mbar_wait(&mma_done[p ^ 1u], ((kk - 1) >> 1) & 1u);
-                    rows8_place(st.pos, sh0, sv);
-                    publish(&win_late[p]);
                 }
             }
         }
@@ -448,6 +482,7 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
             int stream_id0;
         } V = {P.fmt, P.dither, 1, P.fast_out, P.gain, P.dither_lsb, P.out, P.out_pitch, P.seed, P.sample_base, P.stream_id0};
         const int eb = P.fmt == FMT_I16 ? 2 : (P.fmt == FMT_I24_PACKED ? 3 : 4);
+        uint4* stage_tile = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(bars) + 256) + ew * 32 * TC2_STAGE_STRIDE;
         uint32_t kk = 0;
         long long e_wait = 0, e_tmem = 0, e_store = 0;      // probe counters (P.prof)
         for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x) {
@@ -487,7 +522,12 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                 const long long r2 = P.prof ? clock64() : 0;
                 V.out = static_cast<unsigned char*>(P.out) + (long long)blk * P.out_block_stride * eb;
                 V.sample_base = P.sample_base + (unsigned long long)blk * (unsigned long long)P.frames;
-                store_row<32, EPI>(V, y, s, (long long)(idx - blk * P.frames), s < P.n_streams ? 32 : 0);
+                if (!(P.prof && P.gain == 0.f)) {    // (probe: gain 0 = run without the stores)
+                    if (P.epi_stage && P.fast_out)
+                        store_row<32, EPI>(V, y, s, (long long)(idx - blk * P.frames), 32, RowTransposeSink{stage_tile, s < P.n_streams});
+                    else
+                        store_row<32, EPI>(V, y, s, (long long)(idx - blk * P.frames), s < P.n_streams ? 32 : 0);
+                }
                 if (P.prof) { e_wait += r1 - r0; e_tmem += r2 - r1; e_store += clock64() - r2; }
             }
             // (the epilogue warps have the slack for this; in the loaders it would delay the next group's first window)
