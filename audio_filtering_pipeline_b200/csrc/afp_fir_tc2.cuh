@@ -416,11 +416,17 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                     // in flight together and before the tile is free (every earlier MMA done); the oldest batch only exists
                     // for filters of more than 513 taps.  GROUPED: this stream's tap cores replace the previous ones here too.
                     // The groups meet at a named barrier, then the owning group publishes.
+                    // Who may wait for what: an mbarrier wait names a phase by its PARITY, so a thread must never ask about a
+                    // phase while the barrier is still two uses behind it (the answer would be the completed phase of equal
+                    // parity, two steps too early).  Each loader group follows the barrier of its own step parity use by use
+                    // (it waits on it at every step it owns), but not the other one.  So here the group that owns step kk-1
+                    // waits for it, the group that owns step kk-2 for that, and a named barrier carries the news across.
                     if (D >= 9) {
                         // the oldest batch lies outside the previous step's window: free once step kk-2 is done
 #pragma unroll
                         for (int u = 0; u < 8; ++u) v[u] = fetch(k, 2 * u + lg, prow, pf4);
-                        if (kk >= 2) mbar_wait(&mma_done[p], ((kk - 2) >> 1) & 1u);
+                        if ((int)p == lg && kk >= 2) mbar_wait(&mma_done[p], ((kk - 2) >> 1) & 1u);
+                        asm volatile("bar.sync 2, %0;" ::"r"(32 * TC2_LOADERS) : "memory");
 #pragma unroll
                         for (int u = 0; u < 8; ++u) place(st.pos, 2 * u + lg, prow, pf4, v[u]);
                     }
@@ -429,7 +435,8 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                         v[u] = fetch(k, 2 * u + lg, 16 + prow, pf4);
                         v[8 + u] = D >= 1 ? fetch(k, 2 * u + lg, 8 + prow, pf4) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                    if (kk >= 1) mbar_wait(&mma_done[p ^ 1u], ((kk - 1) >> 1) & 1u);
+                    if ((int)p != lg && kk >= 1) mbar_wait(&mma_done[p ^ 1u], ((kk - 1) >> 1) & 1u);
+                    asm volatile("bar.sync 3, %0;" ::"r"(32 * TC2_LOADERS) : "memory");
                     if (GROUPED && new_taps) {
                         const int n_w = 2 * P.n_cores * 8;
                         for (int j = ltid; j < n_w; j += 2 * LT) reinterpret_cast<uint4*>(w_hi)[j] = __ldg(wsrc + j);

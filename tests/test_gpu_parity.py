@@ -227,9 +227,12 @@ def test_quantise_bit_exact_no_dither(fmt, bits, U):
 
 @pytest.mark.parametrize("mode,fmt", [("tpdf", "i24"), ("tpdf", "i16"), ("rpdf", "i24"), ("tpdf", "f32"),
                                       ("tpdf", "i24_packed")])
-def test_dither_matches_philox_oracle(mode, fmt):
+def test_dither_matches_philox_oracle(mode, fmt, monkeypatch):
     """Kernel (5): Philox4x32-10 TPDF/RPDF dither is bit-exact against the numpy statement for a
-    fixed seed, and independent of the block size."""
+    fixed seed, and independent of the block size.  (Bit-exactness needs ONE arithmetic for the float values: the
+    4096-frame blocks would otherwise run on the split-FP16 tensor kernel, whose results differ from the FFMA2 kernels'
+    in the last bits; its epilogue is checked the same way in tests/test_gpu_tensor2.py.)"""
+    monkeypatch.setenv("AFP_NO_TC2", "1")
     h = design.create_fir_filter(cutoff=9000, numtaps=101, samplerate=44100)
     S, n, seed, sid0 = 4, 4096, 2024, 7
     x = synth(S, n, "sweep")

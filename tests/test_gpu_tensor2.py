@@ -187,3 +187,46 @@ def test_range_flag():
         x[3, 100] = 0.5
         eng.reset()
         eng.process_host(x)                    # in range again: no error
+
+
+# Ring-buffered window: every step count modulo the ring (1..9 steps per group, 16, 33), every number of history batches a
+# group start loads (D = 1: one, D = 2..8: two, D >= 9: three), several groups per CTA (more than 148 x 16 streams) with a
+# ragged last group, output formats on the transposed-store path (f32 / int24 in int32 / int16) and off it (packed int24).
+@pytest.mark.parametrize("N,B,nb", [(51, 512, 1), (51, 512, 2), (64, 512, 3), (65, 1024, 2), (129, 512, 5), (251, 512, 7),
+                                    (251, 1024, 4), (385, 512, 9), (513, 512, 6), (577, 1536, 3), (640, 512, 16),
+                                    (1001, 512, 33)])
+@pytest.mark.parametrize("S", [21, 148 * 16 * 2 + 5])
+def test_ring_window_all_step_counts(N, B, nb, S, monkeypatch):
+    monkeypatch.setenv("AFP_TC_MIN_TAPS", "32")              # short filters and single steps on the tensor kernel too
+    if S > 1000 and (nb > 7 or N > 600):
+        pytest.skip("large batch x long run: covered by the small batch")
+    h = taps_for(N)
+    x = noise(min(S, 64), B * nb * 2, amp=0.25, seed=N + nb)
+    x = np.tile(x, ((S + x.shape[0] - 1) // x.shape[0], 1))[:S] * np.linspace(0.5, 1.0, S, dtype=np.float32)[:, None]
+    xb = torch.from_numpy(blocks_of(np.ascontiguousarray(x), B)).cuda()
+    with BatchFirEngine(h, n_streams=S, max_frames=B) as eng:
+        y = torch.cat([eng.process_blocks(xb[:nb]), eng.process_blocks(xb[nb:])]).cpu().numpy()
+        assert eng.stage_info()[-1]["kernel"] == 3 and eng.kernel_launches == 2
+    y = unblock(y)
+    for s in sorted({0, 1, 15, 16, S // 2, S - 6, S - 1}):
+        assert_parity(y[s], rc.streaming_fir(h, x[s]).astype(np.float32), f"N={N} B={B} nb={nb} s={s}")
+
+
+@pytest.mark.parametrize("fmt,dither", [("i24", "tpdf"), ("i16", "tpdf"), ("i24_packed", "tpdf"), ("f32", "rpdf")])
+def test_short_filter_epilogues_bit_exact(fmt, dither, monkeypatch):
+    """The transposed-store epilogue (4- and 2-byte samples) and the direct one (packed int24) against the numpy statement of
+    the Philox / quantiser epilogue, applied to the kernel's own float output."""
+    monkeypatch.setenv("AFP_TC_MIN_TAPS", "32")
+    N, B, nb, S = 251, 512, 6, 40
+    h = taps_for(N)
+    x = noise(S, B * nb, amp=0.3, seed=77)
+    xb = torch.from_numpy(blocks_of(x, B)).cuda()
+    with BatchFirEngine(h, n_streams=S, max_frames=B) as eng:
+        yf = unblock(eng.process_blocks(xb).cpu().numpy())
+    with BatchFirEngine(h, n_streams=S, max_frames=B, out_format=fmt, dither=dither, seed=11, first_stream_id=5) as eng:
+        yq = unblock(eng.process_blocks(xb).cpu().numpy())
+        assert eng.stage_info()[-1]["kernel"] == 3
+    code = {"f32": dq.FMT_F32, "i16": dq.FMT_I16, "i24": dq.FMT_I24_IN_I32, "i24_packed": dq.FMT_I24_PACKED}[fmt]
+    # the per-block layout of packed samples is 3 bytes per sample: compare block by block through the oracle's own packing
+    ref = dq.epilogue(yf, code, {"tpdf": dq.DITHER_TPDF, "rpdf": dq.DITHER_RPDF}[dither], 11, np.arange(S) + 5, 0)
+    np.testing.assert_array_equal(yq, ref)
