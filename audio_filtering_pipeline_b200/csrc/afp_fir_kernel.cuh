@@ -168,9 +168,27 @@ __device__ __forceinline__ void hist_store4(const FirParams& P, float* hrow, int
 }
 
 // ---- epilogue ---------------------------------------------------------------------------------
-template <int NOUT, int MODE>
+template <int NOUT, int MODE, bool SIDE_BY_SIDE = false>
 __device__ __forceinline__ void dither_values(float (&d)[NOUT], unsigned long long seed, uint32_t sid, unsigned long long idx0) {
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    if (SIDE_BY_SIDE && NOUT % 16 == 0 && (idx0 & 3ull) == 0) {     // four calls at a time, round by round
+#pragma unroll
+        for (int i0 = 0; i0 < NOUT; i0 += 16) {
+            uint32_t c0[4], c1[4], c2[4], c3[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned long long c = (idx0 + i0 + 4 * j) >> 2;
+                c0[j] = (uint32_t)c; c1[j] = (uint32_t)(c >> 32); c2[j] = sid; c3[j] = 0u;
+            }
+            philox4x32_10_multi<4>(c0, c1, c2, c3, k0, k1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                d[i0 + 4 * j] = dither_lsb<MODE>(c0[j]); d[i0 + 4 * j + 1] = dither_lsb<MODE>(c1[j]);
+                d[i0 + 4 * j + 2] = dither_lsb<MODE>(c2[j]); d[i0 + 4 * j + 3] = dither_lsb<MODE>(c3[j]);
+            }
+        }
+        return;
+    }
     if (NOUT % 4 == 0 && (idx0 & 3ull) == 0) {     // the normal case: one Philox call per four samples
 #pragma unroll
         for (int i = 0; i < NOUT; i += 4) {
@@ -220,6 +238,7 @@ __host__ __device__ constexpr int epi_code(int fmt, int dither) { return fmt * 4
 // Where a thread's finished, format-converted words go.  DirectSink: vector stores from registers.
 // (afp_fir_row.cuh adds a sink that stages them in shared memory and hands them to the bulk-copy engine.)
 struct DirectSink {
+    static constexpr bool kPhiloxSideBySide = false;
     static constexpr bool kAllFull = false;   // true: the caller guarantees n_valid == NOUT and aligned output on every lane
     template <int NB>
     __device__ __forceinline__ void put(void* dst, const uint32_t (&w)[NB]) const { store_words<NB>(dst, w); }
@@ -247,8 +266,8 @@ __device__ __forceinline__ void store_row(const PT& P_, float (&y)[NOUT], int st
     if (P.decim == 1) {
         float d[NOUT];
         const unsigned long long idx0 = P.sample_base + (unsigned long long)o_base;
-        if (P.dither == DITHER_TPDF) dither_values<NOUT, DITHER_TPDF>(d, P.seed, (uint32_t)(P.stream_id0 + stream), idx0);
-        else if (P.dither == DITHER_RPDF) dither_values<NOUT, DITHER_RPDF>(d, P.seed, (uint32_t)(P.stream_id0 + stream), idx0);
+        if (P.dither == DITHER_TPDF) dither_values<NOUT, DITHER_TPDF, SINK::kPhiloxSideBySide>(d, P.seed, (uint32_t)(P.stream_id0 + stream), idx0);
+        else if (P.dither == DITHER_RPDF) dither_values<NOUT, DITHER_RPDF, SINK::kPhiloxSideBySide>(d, P.seed, (uint32_t)(P.stream_id0 + stream), idx0);
         else {
 #pragma unroll
             for (int i = 0; i < NOUT; ++i) d[i] = 0.f;

@@ -174,6 +174,7 @@ __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bu
 // alternative (5.8-6.4 TB/s for 128-byte runs in isolation, but slower than the transposed stores inside
 // the kernel and poor for 64-byte runs).
 struct BulkSink {
+    static constexpr bool kPhiloxSideBySide = false;
     static constexpr bool kAllFull = false;
     float4* stage;     // this thread's staging row (16-byte aligned)
     template <int NB>
@@ -197,6 +198,7 @@ struct BulkSink {
 // read-back has lane l fetch granule i*32+l of the tile in global order and store it: one STG.128 covers
 // 512 contiguous bytes.
 struct TransposeSink {
+    static constexpr bool kPhiloxSideBySide = false;
     static constexpr bool kAllFull = true;   // keeps the warp barriers below in uniform control flow
     float4* tile;      // the warp's tile: 32 rows of stage_stride_g(run bytes) granules
     template <int NB>

@@ -18,8 +18,13 @@
 //     the same for the taps: 11 + 11 significant bits per operand, exactly what the 3xTF32 split keeps, but
 //     kind::f16 runs at twice the rate (K = 16 per instruction at the cost of tf32's K = 8) and a sample
 //     needs 4 bytes of shared memory (hi + lo) instead of 8, which is what makes room for two window
-//     positions (below).  Products  hi*hi -> accumulator 0;  hi*lo' and lo'*hi -> accumulator 1 (both carry
-//     2^11);  y = acc0 + 2^-11 acc1;  lo*lo (2^-22 relative) is dropped as before.  Range: |x| < 65504
+//     positions (below).  Products  hi*hi and hi*lo' come out of ONE N = 128 instruction: the core array holds the
+//     high and the low core of every index side by side (slot 2q / 2q + 1), so a B descriptor that walks the slots
+//     one by one (stride 128 B) sees [hi core q | lo core q | hi core q+1 | ...] - accumulator A, column 16 g + c =
+//     x_hi * W_hi column 8 g + c, column 16 g + 8 + c = x_hi * W_lo' of the same column.  lo'*hi is an N = 64
+//     instruction over the high cores alone (stride 256 B) into accumulator B.  y = A_hh + 2^-11 (A_hl + B);
+//     lo*lo (2^-22 relative) is dropped as before.  An MMA costs its operand bytes at 128 B/clk (umma_peak):
+//     8 KB + 6 KB = 112 clk per chunk and k-step where three N = 64 instructions took 144.  Range: |x| < 65504
 //     (audio is +-1); a larger sample sets the context's range flag and the call reports it.
 //  3. The CTA keeps a stream group for all the blocks of the call.  A step = 16 streams x 8 rows (512
 //     samples); its window [H history rows | 8 new rows] slides over a ring of 32 tile rows (tc2_step), so the
@@ -28,8 +33,8 @@
 //     first step of a call and written once at its end; in between the "history" is the previous blocks' input,
 //     still in shared memory.
 //
-// Cost model (measured): an M = 128, N = 64, K = 16 MMA takes max(32 clk pipe, 6 KB / 128 B/clk = 48 clk operand
-// fetch) = 48 clk;  a step is n_chunks x 4 k-steps x 3 products.  1001 taps: 204 MMAs = 9.8 kclk per 8192 samples.
+// Cost model (measured): an M = 128, K = 16 MMA takes max(pipe, operand bytes / 128 B/clk): N = 64 48 clk, N = 128
+// 64 clk;  a step is n_chunks x 4 k-steps x (64 + 48) clk.  1001 taps: 17 x 4 x 112 = 7.6 kclk per 8192 samples.
 #pragma once
 #include <cstdint>
 #include <cuda_fp16.h>
@@ -42,7 +47,7 @@ constexpr int TC2_R = 64;                  // samples per row
 constexpr int TC2_STREAMS = 16;            // streams per work item (M = 128 = 16 x 8 rows)
 constexpr int TC2_ROWS = 41;               // rows per stream tile: a ring of 32, its first 8 repeated, + 1 (row pitch 41 x 16 B = 16 mod 128: conflict-free loader stores)
 constexpr int TC2_STEP = 8 * TC2_R;        // new samples per stream and step
-constexpr int TC2_LOADERS = 8, TC2_EPIS = 8;            // warps
+constexpr int TC2_LOADERS = 16, TC2_EPIS = 8;           // warps (loaders: a warp keeps ~4 128-bit loads in flight whatever it issues - bench/microbench/stream_mlp.cu - so HBM reads scale with the number of loading warps)
 constexpr int TC2_THREADS = 32 * (1 + TC2_LOADERS + TC2_EPIS);
 constexpr int TC2_A_LBO = TC2_ROWS * 16;                 // bytes between column chunks (8 samples) of one stream tile
 constexpr int TC2_PITCH = (TC2_R / 8) * TC2_A_LBO;       // bytes per stream tile
@@ -57,7 +62,7 @@ struct Tc2Params {
     long long in_pitch, in_block_stride;
     void* out;                 // same indexing in elements of the output format (bytes / 3 for packed int24)
     long long out_pitch, out_block_stride;
-    const __half* w;           // [2][n_cores][8][8]: Hankel cores of the taps' high parts, then of the low parts * 2^11
+    const __half* w;           // [n_cores][2][8][8]: Hankel core q of the taps' high parts, then core q of the low parts * 2^11
     int n_cores;
     int n_streams, frames, n_blocks;
     int n_chunks;              // D + 1
@@ -107,8 +112,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __host__ __device__ constexpr uint32_t tc2_idesc(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
 
 // Host side: the Hankel core array of a filter.  C_q[jj][e] = hp[8 q + jj + e], hp[t] = h[t - (R-1)]; every tap
-// h = hi + lo * 2^-11 with hi = fp16(h), lo = fp16((h - hi) * 2^11).  Layout: all hi cores, then all lo cores,
-// 64 halves each.  Returns the chunk count D + 1.
+// h = hi + lo * 2^-11 with hi = fp16(h), lo = fp16((h - hi) * 2^11).  Layout: hi core q in slot 2 q, lo core q in
+// slot 2 q + 1, 64 halves each.  Returns the chunk count D + 1.
 template <class VEC>
 inline int tc2_build_cores(const double* taps, int n, VEC& w) {
     const int D = (n + TC2_R - 2) / TC2_R, Q = 8 * (D + 2) - 1;
@@ -119,8 +124,8 @@ inline int tc2_build_cores(const double* taps, int n, VEC& w) {
                 const int k = 8 * q + jj + e - (TC2_R - 1);
                 const float hv = (k >= 0 && k < n) ? (float)taps[k] : 0.f;
                 const __half hi = __float2half_rn(hv);
-                w[(size_t)q * 64 + jj * 8 + e] = hi;
-                w[(size_t)(Q + q) * 64 + jj * 8 + e] = __float2half_rn((hv - __half2float(hi)) * 2048.0f);
+                w[(size_t)(2 * q) * 64 + jj * 8 + e] = hi;
+                w[(size_t)(2 * q + 1) * 64 + jj * 8 + e] = __float2half_rn((hv - __half2float(hi)) * 2048.0f);
             }
     return D + 1;
 }
@@ -202,13 +207,14 @@ __device__ __forceinline__ void tc2_copy_history(const Tc2Params& P, int s0, int
 // read them back so that eight consecutive lanes store one row's eight granules: every instruction writes four whole
 // lines.  Row addresses travel by shuffle; rows outside the batch carry a null address.
 struct RowTransposeSink {
+    static constexpr bool kPhiloxSideBySide = true;
     static constexpr bool kAllFull = true;    // (store_row's aligned full-run path; the caller checks fast_out)
     uint4* tile;
     bool ok;
     template <int NB>
     __device__ __forceinline__ void put(void* dst, const uint32_t (&w)[NB]) const {
-        constexpr int G = NB / 4;                               // granules per row
-        if (NB % 4 != 0 || G > 8 || 32 % G != 0) {              // (packed int24: 6 granules - straight from registers)
+        constexpr int G = NB / 4;                               // granules per row (packed int24: 3 per 16 samples)
+        if (NB % 4 != 0 || G > 8) {
             if (ok) store_words<NB>(dst, w);
             return;
         }
@@ -222,7 +228,7 @@ struct RowTransposeSink {
         const unsigned dlo = (unsigned)d, dhi = (unsigned)(d >> 32);
 #pragma unroll
         for (int i = 0; i < G; ++i) {
-            const int r = i * (32 / G) + lane / G, g = lane % G;
+            const int l = i * 32 + lane, r = l / G, g = l - r * G;   // the warp's 32 G granules in row-major order, 32 per instruction
             const unsigned long long p = ((unsigned long long)__shfl_sync(0xffffffffu, dhi, r) << 32) | __shfl_sync(0xffffffffu, dlo, r);
             if (p) reinterpret_cast<uint4*>(p)[g] = tile[r * TC2_STAGE_STRIDE + g];
         }
@@ -236,9 +242,8 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned char* tile_hi = tc2_smem;
     unsigned char* tile_lo = tile_hi + TC2_TILE_BYTES;
-    unsigned char* w_hi = tile_lo + TC2_TILE_BYTES;
-    unsigned char* w_lo = w_hi + P.n_cores * 128;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(w_lo + P.n_cores * 128);
+    unsigned char* w_hi = tile_lo + TC2_TILE_BYTES;       // core slots: [hi q | lo q], 256 B per index
+    uint64_t* bars = reinterpret_cast<uint64_t*>(w_hi + 2 * P.n_cores * 128);
     uint64_t* win_early = bars;         // [2] step parity p: the rows the first chunks read are in place
     uint64_t* win_late = bars + 2;      // [2] ... and the rows only the later chunks read
     uint64_t* mma_done = bars + 4;      // [2] accumulator set p final, window of the step read for the last time
@@ -249,7 +254,7 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
     const int n_steps = GROUPED ? P.steps_per_slot : (P.frames / TC2_STEP) * P.n_blocks;   // steps of one work item
 
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(256u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 32) {
@@ -271,12 +276,16 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
 
+    // (Tried: roles in whole warpgroups and setmaxnreg 56 / 104 for loaders / epilogue - the loaders' spills at 56 registers cost
+    // more than the epilogue gained: 553 -> 461 Gsamples/s at 51 taps.  25 warps compile to 72 registers each.)
     if (warp_u == 0) {
         // ================= MMA issuer: one elected lane, operands warp-uniform =================
         const uint64_t a_hi_d = umma_desc(smem_u32(tile_hi), TC2_A_LBO, TC2_PITCH), a_lo_d = umma_desc(smem_u32(tile_lo), TC2_A_LBO, TC2_PITCH);
-        const uint64_t w_hi_d = umma_desc(smem_u32(w_hi), 128, 128), w_lo_d = umma_desc(smem_u32(w_lo), 128, 128);
-        const uint32_t top_a = (uint32_t)(a_hi_d >> 32), top_w = (uint32_t)(w_hi_d >> 32);
-        const uint32_t idesc = tc2_idesc(TC2_R);
+        // B: the next core in K is the next index (256 B on); in N the wide product walks the slots (hi q, lo q, hi q+1, ...),
+        // the narrow one the high cores only
+        const uint64_t w_wide_d = umma_desc(smem_u32(w_hi), 256, 128), w_hi_d = umma_desc(smem_u32(w_hi), 256, 256);
+        const uint32_t top_a = (uint32_t)(a_hi_d >> 32), top_ww = (uint32_t)(w_wide_d >> 32), top_wh = (uint32_t)(w_hi_d >> 32);
+        const uint32_t idesc_wide = tc2_idesc(2 * TC2_R), idesc = tc2_idesc(TC2_R);
         const int D = P.n_chunks - 1;
         uint32_t kk = 0;                                       // steps issued by this CTA
         int wpos = 8;
@@ -293,7 +302,7 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                 const long long c2 = clock64();
                 t_acc += c1 - c0; t_dir += c2 - c1;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t acc0 = tmem_base + p * 128u, acc1 = acc0 + 64u;
+                const uint32_t acc_a = tmem_base + p * 256u, acc_b = acc_a + 128u;
                 bool late_seen = false;
                 bool first = true;
                 // Chunk order, the same for every step so that rounding does not depend on where a step ran:
@@ -314,14 +323,13 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                     if (elect_one()) {
                         const uint32_t arow = (uint32_t)((st.pos + H - d) & (TC2_RING - 1));
                         const uint32_t ah = (uint32_t)a_hi_d + arow, al = (uint32_t)a_lo_d + arow;
-                        const uint32_t wh = (uint32_t)w_hi_d + (uint32_t)(8 * d) * 8u, wl = (uint32_t)w_lo_d + (uint32_t)(8 * d) * 8u;
+                        const uint32_t ww = (uint32_t)w_wide_d + (uint32_t)(8 * d) * 16u, wh = (uint32_t)w_hi_d + (uint32_t)(8 * d) * 16u;
 #pragma unroll
                         for (int ks = 0; ks < TC2_R / 16; ++ks) {
-                            const uint32_t ao = (uint32_t)(2 * ks * TC2_ROWS), wo = (uint32_t)(2 * ks) * 8u;
+                            const uint32_t ao = (uint32_t)(2 * ks * TC2_ROWS), wo = (uint32_t)(2 * ks) * 16u;
                             const uint32_t f = (first && ks == 0) ? 0u : 1u;
-                            umma_f16(acc0, ah + ao, top_a, wh + wo, top_w, idesc, f);     // x_hi * W_hi
-                            umma_f16(acc1, ah + ao, top_a, wl + wo, top_w, idesc, f);     // x_hi * W_lo'
-                            umma_f16(acc1, al + ao, top_a, wh + wo, top_w, idesc, 1u);    // x_lo' * W_hi
+                            umma_f16(acc_a, ah + ao, top_a, ww + wo, top_ww, idesc_wide, f);   // x_hi * [W_hi | W_lo'] (interleaved by 8 columns)
+                            umma_f16(acc_b, al + ao, top_a, wh + wo, top_wh, idesc, f);        // x_lo' * W_hi
                         }
                     }
                     __syncwarp();
@@ -344,17 +352,25 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
         // k+1: a global-memory round trip (2-3.5 kclk under load) overlaps the other group's arithmetic instead of
         // sitting between two steps.
         const int ltid = tid - 32;
-        const int lg = ltid >> 7, lt = ltid & 127;
-        constexpr int LT = 32 * TC2_LOADERS / 2;
+        constexpr int LT = 32 * TC2_LOADERS / 2;           // threads of a loader group: 256
+        const int lg = ltid / LT, lt = ltid % LT;
+        const int sh = lt >> 7;                            // which streams of a pair this thread takes
         uint32_t kk = 0;
         float amax = 0.f;
-        long long t_ld = 0, t_slot = 0, t_place = 0;       // probe counters (P.prof)
+        float4 v[8];                                       // this thread's loads: in flight from one own step to the next
+        bool pre_fresh = false;                            // v holds this thread's share of the next group's first window
+        long long t_ld = 0, t_slot = 0, t_place = 0;       // probe counters (P.prof): remaining load latency, wait for the slot, split + store
         int cur_group = -1, wpos = 8;
         for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x) {
-            const int s0 = grp * TC2_STREAMS;
+            const int D = P.n_chunks - 1;
+            // 8 window rows for all 16 streams: 2048 float4, 8 per thread of the owning group.  Thread lt takes float4 (lt & 15)
+            // of row (lt >> 4) & 7 of every second stream (consecutive lanes: consecutive float4 of a stream's rows, which are
+            // contiguous in memory), so row, column and - one filter set per batch - the block and frame of the samples are the
+            // same for its 8 loads: one address computation per batch, then a stream pitch per load.
+            const int prow = (lt >> 4) & 7, pf4 = lt & 15;
             // one float4 (4 samples) of window row `wrow` (0..23) of local stream sl at step k
-            auto fetch = [&](int k, int sl, int wrow, int f4) -> float4 {
-                const int s = GROUPED ? grp : s0 + sl;
+            auto fetch_of = [&](int g, int k, int sl, int wrow, int f4) -> float4 {
+                const int s = GROUPED ? g : g * TC2_STREAMS + sl;
                 // logical sample index of the stream: < 0 = carried history
                 const int t = ((GROUPED ? sl * n_steps : 0) + k) * TC2_STEP - H * TC2_R + wrow * TC2_R + f4 * 4;
                 if (s >= P.n_streams || t < -P.hist_len) return make_float4(0.f, 0.f, 0.f, 0.f);
@@ -365,6 +381,14 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                     src = P.in + (long long)b_ * P.in_block_stride + (long long)s * P.in_pitch + f;
                 }
                 return __ldg(reinterpret_cast<const float4*>(src));
+            };
+            auto fetch = [&](int k, int sl, int wrow, int f4) -> float4 { return fetch_of(grp, k, sl, wrow, f4); };
+            // a first window is loaded by both groups: this thread's streams there are fs + 4 u; its share of the two newest
+            // batches: rows 16.. in v[0..3], rows 8.. in v[4..7]
+            const int fs = 2 * lg + sh;
+            const int grp_next = grp + gridDim.x;
+            auto fresh_fetch_next = [&](int u) -> float4 {
+                return u < 4 ? fetch_of(grp_next, 0, 4 * u + fs, 16 + prow, pf4) : fetch_of(grp_next, 0, 4 * (u - 4) + fs, 8 + prow, pf4);
             };
             auto place = [&](int pos, int sl, int wrow, int f4, const float4& v) {
                 uint2 hi, lo;
@@ -378,23 +402,23 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                     *reinterpret_cast<uint2*>(tile_lo + off + TC2_RING * 16) = lo;
                 }
             };
-            // 8 window rows starting at r0 for all 16 streams: 2048 float4, 16 per thread of the owning group.  Thread lt takes
-            // float4 (lt & 15) of row (lt >> 4) & 7 of EVERY stream (consecutive lanes: consecutive float4 of a stream's rows,
-            // which are contiguous in memory), so row, column and - one filter set per batch - the block and frame of the
-            // samples are the same for its 16 loads: one address computation per batch, then a stream pitch per load.
-            const int prow = (lt >> 4) & 7, pf4 = lt & 15;
-            auto rows8_fetch = [&](int k, int r0, float4 (&v)[16]) {
-#pragma unroll
-                for (int u = 0; u < 16; ++u) v[u] = fetch(k, u, r0 + prow, pf4);
-            };
-            auto rows8_place = [&](int pos, int r0, const float4 (&v)[16]) {
-#pragma unroll
-                for (int u = 0; u < 16; ++u) place(pos, u, r0 + prow, pf4, v[u]);
-            };
             auto publish = [&](uint64_t* bar) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar);
+            };
+            // What this thread loads next, issued right after it has published a step (never in front of a publication: under
+            // load the issue of sixteen loads itself takes kclk): the rows of its group's next own step `kn`, or - none left -
+            // its share of the next stream group's first window, which then finds its two newest batches on their way.
+            auto next_loads = [&](int kn) {
+                if (kn < n_steps) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = fetch(kn, 2 * u + sh, 16 + prow, pf4);
+                } else if (grp_next < P.n_groups && D < 9) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = fresh_fetch_next(u);
+                    pre_fresh = true;
+                }
             };
             // GROUPED: this stream's tap cores replace the previous stream's unless they share a group
             bool new_taps = false;
@@ -405,11 +429,11 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                 cur_group = g;
                 wsrc = reinterpret_cast<const uint4*>(P.gw + (long long)g * P.gw_stride);
             }
-            const int D = P.n_chunks - 1;
+            // The loads of a step are issued as soon as the thread's registers are free: right after the publication of its
+            // previous own step (next_loads), so they travel while the other group works.
             for (int k = 0; k < n_steps; ++k, ++kk) {
                 const uint32_t p = kk & 1u;
                 const Tc2Step st = tc2_step(wpos, k);
-                float4 v[16];
                 if (st.fresh) {
                     // First step of a group: the window rows its MMAs read, [16 - D, 24), in batches of 8 rows.  Both loader
                     // groups work on it (a thread takes one float4 position of every second stream), the two newest batches
@@ -423,41 +447,47 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                     // waits for it, the group that owns step kk-2 for that, and a named barrier carries the news across.
                     if (D >= 9) {
                         // the oldest batch lies outside the previous step's window: free once step kk-2 is done
+                        // (its loads use the registers a prefetched window would sit in: next_loads prefetches for D < 9 only)
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) v[u] = fetch(k, 2 * u + lg, prow, pf4);
+                        for (int u = 0; u < 4; ++u) v[u] = fetch(k, 4 * u + fs, prow, pf4);
                         if ((int)p == lg && kk >= 2) mbar_wait(&mma_done[p], ((kk - 2) >> 1) & 1u);
                         asm volatile("bar.sync 2, %0;" ::"r"(32 * TC2_LOADERS) : "memory");
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) place(st.pos, 2 * u + lg, prow, pf4, v[u]);
+                        for (int u = 0; u < 4; ++u) place(st.pos, 4 * u + fs, prow, pf4, v[u]);
                     }
+                    if (!pre_fresh) {
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        v[u] = fetch(k, 2 * u + lg, 16 + prow, pf4);
-                        v[8 + u] = D >= 1 ? fetch(k, 2 * u + lg, 8 + prow, pf4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int u = 0; u < 4; ++u) {
+                            v[u] = fetch(k, 4 * u + fs, 16 + prow, pf4);
+                            v[4 + u] = fetch(k, 4 * u + fs, 8 + prow, pf4);
+                        }
                     }
+                    pre_fresh = false;
                     if ((int)p != lg && kk >= 1) mbar_wait(&mma_done[p ^ 1u], ((kk - 1) >> 1) & 1u);
                     asm volatile("bar.sync 3, %0;" ::"r"(32 * TC2_LOADERS) : "memory");
                     if (GROUPED && new_taps) {
                         const int n_w = 2 * P.n_cores * 8;
                         for (int j = ltid; j < n_w; j += 2 * LT) reinterpret_cast<uint4*>(w_hi)[j] = __ldg(wsrc + j);
                     }
+                    // this group's next own step: k + 1 for the group that does not own the fresh step, k + 2 for the owner
+                    const int kn = (int)p == lg ? k + 2 : k + 1;
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        place(st.pos, 2 * u + lg, 16 + prow, pf4, v[u]);
-                        if (D >= 1) place(st.pos, 2 * u + lg, 8 + prow, pf4, v[8 + u]);
+                    for (int u = 0; u < 4; ++u) {
+                        place(st.pos, 4 * u + fs, 16 + prow, pf4, v[u]);
+                        place(st.pos, 4 * u + fs, 8 + prow, pf4, v[4 + u]);
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     asm volatile("bar.sync 1, %0;" ::"r"(32 * TC2_LOADERS) : "memory");
                     if ((int)p == lg && lane == 0) { mbar_arrive(&win_early[p]); mbar_arrive(&win_late[p]); }
+                    next_loads(kn);
                     continue;
                 }
                 if ((int)p != lg) continue;                 // the other group's step
                 {
                     const long long q0 = P.prof ? clock64() : 0;
-                    rows8_fetch(k, 16, v);
                     if (P.prof) {                                       // (probe only: make the loads land here)
 #pragma unroll
-                        for (int u = 0; u < 16; ++u) asm volatile("" ::"f"(v[u].x), "f"(v[u].w));
+                        for (int u = 0; u < 8; ++u) asm volatile("" ::"f"(v[u].x), "f"(v[u].w));
                     }
                     const long long q1 = P.prof ? clock64() : 0;
                     // the new rows replace the oldest rows of step kk-2
@@ -467,14 +497,16 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                     // warp has looked at phase kk-2 would make that wait see the old parity again - a deadlock.)
                     if (lane == 0) mbar_arrive(&win_early[p]);
                     const long long q2 = P.prof ? clock64() : 0;
-                    rows8_place(st.pos, 16, v);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) place(st.pos, 2 * u + sh, 16 + prow, pf4, v[u]);
                     publish(&win_late[p]);
                     if (P.prof) { t_ld += q1 - q0; t_slot += q2 - q1; t_place += clock64() - q2; }
+                    next_loads(k + 2);
                 }
             }
         }
         if (amax > 65000.0f) atomicOr(P.range_flag, 1u);
-        if (P.prof && tid == 32) { long long* o = P.prof + (size_t)blockIdx.x * 16; o[6] = t_ld; o[7] = t_slot; o[8] = t_place; }
+        if (P.prof && ltid == 0) { long long* o = P.prof + (size_t)blockIdx.x * 16; o[6] = t_ld; o[7] = t_slot; o[8] = t_place; }
     } else {
         // ================= epilogue: TMEM -> registers -> dither / quantise -> HBM =================
         const int ew = warp_u - 1 - TC2_LOADERS;                // 0..7
@@ -503,39 +535,98 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                 mbar_wait(&mma_done[p], ph);
                 const long long r1 = P.prof ? clock64() : 0;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t taddr = tmem_base + ((uint32_t)(32 * quarter) << 16) + p * 128u + (uint32_t)(32 * half);
-                float y[32];
-#pragma unroll
-                for (int f = 0; f < 2; ++f) {
-                    uint32_t a[32];
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                        : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]),
-                          "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]),
-                          "=r"(a[16]), "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]),
-                          "=r"(a[24]), "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]), "=r"(a[31])
-                        : "r"(taddr + f * 64u));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        y[j] = f == 0 ? __uint_as_float(a[j]) : __fmaf_rn(__uint_as_float(a[j]), 4.8828125e-4f, y[j]);   // + 2^-11 acc1
-                }
-                // the accumulators are in registers: hand the set back before the (long) store
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[p]);
-                const long long r2 = P.prof ? clock64() : 0;
+                // accumulator A columns 64 half .. +63 (this half's 32 output columns, hi*hi and hi*lo' interleaved by 8),
+                // accumulator B columns 32 half .. +31, 16 output columns at a time
+                const uint32_t taddr = tmem_base + ((uint32_t)(32 * quarter) << 16) + p * 256u;
                 V.out = static_cast<unsigned char*>(P.out) + (long long)blk * P.out_block_stride * eb;
                 V.sample_base = P.sample_base + (unsigned long long)blk * (unsigned long long)P.frames;
-                if (!(P.prof && P.gain == 0.f)) {    // (probe: gain 0 = run without the stores)
-                    if (P.epi_stage && P.fast_out)
-                        store_row<32, EPI>(V, y, s, (long long)(idx - blk * P.frames), 32, RowTransposeSink{stage_tile, s < P.n_streams});
-                    else
-                        store_row<32, EPI>(V, y, s, (long long)(idx - blk * P.frames), s < P.n_streams ? 32 : 0);
+                long long r2 = r1;
+                constexpr bool kWholeRow = EPI == epi_code(FMT_F32, DITHER_NONE);
+                if (kWholeRow) {
+                    // plain float output: the row's 32 columns at once - one 128-byte line per row and instruction in the
+                    // transposed store (553 vs 409 Gsamples/s at 51 taps against the two-pass form below)
+                    float y[32];
+#pragma unroll
+                    for (int f = 0; f < 2; ++f) {
+                        uint32_t b[16];
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                            : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]),
+                              "=r"(b[8]), "=r"(b[9]), "=r"(b[10]), "=r"(b[11]), "=r"(b[12]), "=r"(b[13]), "=r"(b[14]), "=r"(b[15])
+                            : "r"(taddr + 128u + (uint32_t)(32 * half + 16 * f)));
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            uint32_t a[16];
+                            asm volatile(
+                                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                                : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]),
+                                  "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15])
+                                : "r"(taddr + (uint32_t)(64 * half + 32 * f + 16 * g)));
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                            for (int c = 0; c < 8; ++c)                                    // y = A_hh + 2^-11 (A_hl + B)
+                                y[16 * f + 8 * g + c] = __fmaf_rn(__fadd_rn(__uint_as_float(a[8 + c]), __uint_as_float(b[8 * g + c])),
+                                                                  4.8828125e-4f, __uint_as_float(a[c]));
+                        }
+                    }
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[p]);
+                    if (P.prof) r2 = clock64();
+                    if (!(P.prof && P.gain == 0.f)) {
+                        if (P.epi_stage && P.fast_out)
+                            store_row<32, EPI>(V, y, s, (long long)(idx - blk * P.frames), 32, RowTransposeSink{stage_tile, s < P.n_streams});
+                        else
+                            store_row<32, EPI>(V, y, s, (long long)(idx - blk * P.frames), s < P.n_streams ? 32 : 0);
+                    }
+                } else {
+                    // 16 output columns at a time, each finished (dither, codes, stores) before the next is read: a row's 32 floats
+                    // next to the dither values and codes do not fit the 72 registers 25 warps leave a thread, and a spilled value
+                    // costs an L1 round trip behind the kernel's own global traffic (ncu: long-scoreboard stalls on the reloads).
+                    // The accumulator set goes back to the MMA warp after the second read.
+#pragma unroll
+                    for (int f = 0; f < 2; ++f) {
+                        const long long t0 = P.prof ? clock64() : 0;
+                        float y[16];
+                        uint32_t b[16];
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                            : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]),
+                              "=r"(b[8]), "=r"(b[9]), "=r"(b[10]), "=r"(b[11]), "=r"(b[12]), "=r"(b[13]), "=r"(b[14]), "=r"(b[15])
+                            : "r"(taddr + 128u + (uint32_t)(32 * half + 16 * f)));
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            uint32_t a[16];
+                            asm volatile(
+                                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                                : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]),
+                                  "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15])
+                                : "r"(taddr + (uint32_t)(64 * half + 32 * f + 16 * g)));
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                            for (int c = 0; c < 8; ++c)                                    // y = A_hh + 2^-11 (A_hl + B)
+                                y[8 * g + c] = __fmaf_rn(__fadd_rn(__uint_as_float(a[8 + c]), __uint_as_float(b[8 * g + c])),
+                                                         4.8828125e-4f, __uint_as_float(a[c]));
+                        }
+                        if (f == 1) {
+                            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&acc_empty[p]);
+                        }
+                        if (P.prof) r2 += clock64() - t0;
+                        if (!(P.prof && P.gain == 0.f)) {    // (probe: gain 0 = run without the stores)
+                            if (P.epi_stage && P.fast_out)
+                                store_row<16, EPI>(V, y, s, (long long)(idx - blk * P.frames + 16 * f), 16, RowTransposeSink{stage_tile, s < P.n_streams});
+                            else
+                                store_row<16, EPI>(V, y, s, (long long)(idx - blk * P.frames + 16 * f), s < P.n_streams ? 16 : 0);
+                        }
+                    }
                 }
-                if (P.prof) { e_wait += r1 - r0; e_tmem += r2 - r1; e_store += clock64() - r2; }
+                if (P.prof) { e_wait += r1 - r0; e_tmem += r2 - r1; e_store += clock64() - r1 - (r2 - r1); }
             }
             // (the epilogue warps have the slack for this; in the loaders it would delay the next group's first window)
             if (GROUPED) tc2_copy_history(P, grp, 1, TC2_STREAMS * n_steps * TC2_STEP, tid - 32 * (1 + TC2_LOADERS), 32 * TC2_EPIS);
@@ -546,7 +637,7 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
 }  // namespace afp

@@ -37,6 +37,28 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
     return o;
 }
 
+// The same function for NC independent counters, round by round: the ten rounds of one call are a chain of dependent
+// multiplies (ncu on the tensor kernel's epilogue warps: fixed-latency `wait` stalls, 0.2 instructions per clock and warp),
+// NC chains side by side fill the gaps, and the round keys are computed once for all of them.  Bit-identical results.
+template <int NC>
+__device__ __forceinline__ void philox4x32_10_multi(uint32_t (&c0)[NC], uint32_t (&c1)[NC], uint32_t (&c2)[NC], uint32_t (&c3)[NC],
+                                                    uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, c0[i]), lo0 = 0xD2511F53u * c0[i];
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2[i]), lo1 = 0xCD9E8D57u * c2[i];
+            c0[i] = hi1 ^ c1[i] ^ k0;
+            c1[i] = lo1;
+            c2[i] = hi0 ^ c3[i] ^ k1;
+            c3[i] = lo0;
+        }
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+
 // Dither value in LSB units from one 32-bit word (two 16-bit uniforms).
 // The integer (a+b or 2a+1, < 2^18) becomes a float by planting it in the mantissa of 2^23 - one integer
 // add instead of an I2F conversion - and the offset and the power-of-two scale fold into one FMA whose
