@@ -24,7 +24,7 @@
 #include "afp_spectrum.cuh"
 #include <map>
 
-afp::tc2_kern_t afp_kernel_tc2(int epi);                                    // afp_kernels_tc2.cu
+afp::tc2_kern_t afp_kernel_tc2(int epi, int up);                                    // afp_kernels_tc2.cu
 afp::tc2_kern_t afp_kernel_tc2_grouped();
 afp::agc_kern_t afp_kernel_agc(int variant);   // afp_kernels_agc.cu: variant AGC_*
 
@@ -68,7 +68,7 @@ struct Stage {
     int tc_chunks[2] = {0, 0};
     // split-FP16 tensor kernel (afp_fir_tc2.cuh): Hankel tap cores [2][n_cores][8][8] halves, chunk count D + 1
     void* tc2_w = nullptr;
-    int tc2_cores = 0, tc2_chunks = 0;
+    int tc2_cores = 0, tc2_chunks = 0;     // (U = 2 / 4: the polyphase form of the same kernel)
     int last_kernel = 0;           // 0 = row-pair FFMA2, 1 = tcgen05 (3xTF32), 2 = single-row FFMA2, 3 = tcgen05 (split FP16)
     int last_T = 0;                // tile of the last launch (the single-row kernel picks its own)
     // per-launch host work of the single-row kernel that only depends on the stage: its tap-table image
@@ -258,7 +258,11 @@ int build_stage(afp_ctx* c, Stage& s, int kind, int U, const double* taps, int n
     const int tc_min = std::getenv("AFP_TC_MIN_TAPS") ? std::atoi(std::getenv("AFP_TC_MIN_TAPS")) : 400;
     const int tc2_min = std::getenv("AFP_TC_MIN_TAPS") ? std::atoi(std::getenv("AFP_TC_MIN_TAPS")) : 48;
     const bool tc_any = U == 1 && n_sub == 1 && !env_flag("AFP_NO_TC");
-    const bool tc1_ok = tc_any && n >= tc_min, tc2_ok = tc_any && n >= tc2_min && !env_flag("AFP_NO_TC2");
+    // Polyphase interpolators (U = 2 / 4) run on the same kernel with wider Toeplitz rows (tc2_build_cores): from 40 taps per
+    // phase up (below, the FFMA2 row kernel is already at 0.7-0.9 of the HBM roof).
+    const bool tc2_up = (U == 2 || U == 4) && n_sub == 1 && !env_flag("AFP_NO_TC") && !env_flag("AFP_NO_TC2_UP") &&
+                        n >= (std::getenv("AFP_TC_MIN_TAPS") ? std::atoi(std::getenv("AFP_TC_MIN_TAPS")) : 40 * U);
+    const bool tc1_ok = tc_any && n >= tc_min, tc2_ok = (tc_any && n >= tc2_min || tc2_up) && !env_flag("AFP_NO_TC2");
     const bool tc_ok = tc1_ok || tc2_ok;
     // History length = padded taps per phase.  A multiple of 16 (every tile size divides it, so the two
     // FFMA2 kernels share one history format and a stage may switch kernel from block to block), with room
@@ -334,10 +338,10 @@ int build_stage(afp_ctx* c, Stage& s, int kind, int U, const double* taps, int n
     if (s.tc2_w) { cudaFree(s.tc2_w); s.tc2_w = nullptr; s.tc2_cores = s.tc2_chunks = 0; }
     if (tc2_ok) {
         // split-FP16 kernel (afp_fir_tc2.cuh): Hankel tap cores, all high parts then all low parts
-        if ((n + afp::TC2_R - 2) / afp::TC2_R + 1 <= 17) {
+        if ((n - 1 + (afp::TC2_R - 1) * U) / (afp::TC2_R * U) + 1 <= 17) {
             std::vector<__half> w;
-            s.tc2_chunks = afp::tc2_build_cores(taps, n, w);
-            s.tc2_cores = afp::tc2_n_cores(s.tc2_chunks);
+            s.tc2_chunks = afp::tc2_build_cores(taps, n, w, U);
+            s.tc2_cores = afp::tc2_n_cores(s.tc2_chunks, U);
             AFP_CUDA(c, cudaMalloc(&s.tc2_w, w.size() * sizeof(__half)));
             AFP_CUDA(c, cudaMemcpy(s.tc2_w, w.data(), w.size() * sizeof(__half), cudaMemcpyHostToDevice));
         }
@@ -527,12 +531,12 @@ int launch_stage_tc2(afp_ctx* c, Stage& s, const float* in, long long in_pitch, 
                      long long out_pitch, long long out_bstride, int frames, int n_blocks, int fmt, int dither,
                      unsigned long long sample_base, int s0, int ns, cudaStream_t stream, bool* done) {
     *done = false;
-    if (!s.tc2_w || s.U != 1 || env_flag("AFP_NO_TC2")) return AFP_OK;
+    if (!s.tc2_w || (s.U != 1 && s.U != 2 && s.U != 4) || env_flag("AFP_NO_TC2")) return AFP_OK;
     if (!c->group_of_stream.empty()) return AFP_OK;   // per-group filters: launch_stage_tc2_grouped / the row-pair kernel
     if (frames < afp::TC2_STEP || frames % afp::TC2_STEP != 0 || n_blocks < 1) return AFP_OK;
     if ((long long)frames * n_blocks > (1 << 30)) return AFP_OK;
     // short filters: only when a stream group's window start is amortised over enough steps (see build_stage)
-    if (!std::getenv("AFP_TC_MIN_TAPS") && s.n_taps < 112 && (long long)(frames / afp::TC2_STEP) * n_blocks < 8) return AFP_OK;
+    if (!std::getenv("AFP_TC_MIN_TAPS") && s.U == 1 && s.n_taps < 112 && (long long)(frames / afp::TC2_STEP) * n_blocks < 8) return AFP_OK;
     const int eb = fmt == AFP_FMT_I16 ? 2 : (fmt == AFP_FMT_I24_PACKED ? 3 : 4);
     if (!aligned16(in) || in_pitch % 4 != 0 || in_bstride % 4 != 0 || s.hist_pitch % 4 != 0 || s.kq_pad % 8 != 0) return AFP_OK;
     if (s.tc2_chunks > 17 || s.kq_pad > 24 * afp::TC2_R) return AFP_OK;
@@ -550,11 +554,11 @@ int launch_stage_tc2(afp_ctx* c, Stage& s, const float* in, long long in_pitch, 
     P.seed = c->cfg.seed; P.sample_base = sample_base; P.stream_id0 = c->cfg.first_stream_id + s0;
     P.gain = 1.0f; P.dither_lsb = std::ldexp(1.0f, -(c->dither_bits - 1));
     // transposed epilogue stores when the staging tiles fit beside the window tile and the tap cores (filters up to ~640 taps)
-    P.epi_stage = afp::tc2_smem_bytes(s.tc2_chunks, true) <= kMaxSmem && !env_flag("AFP_TC2_NO_STAGE") ? 1 : 0;
-    const int smem = afp::tc2_smem_bytes(s.tc2_chunks, P.epi_stage != 0);
+    P.epi_stage = afp::tc2_smem_bytes(s.tc2_chunks, true, s.U) <= kMaxSmem && !env_flag("AFP_TC2_NO_STAGE") ? 1 : 0;
+    const int smem = afp::tc2_smem_bytes(s.tc2_chunks, P.epi_stage != 0, s.U);
     if (smem > kMaxSmem) return AFP_OK;
     const int grid = P.n_groups < c->n_sm ? P.n_groups : c->n_sm;
-    afp_kernel_tc2(afp::epi_code(fmt, dither))<<<grid, afp::TC2_THREADS, smem, stream>>>(P);
+    afp_kernel_tc2(afp::epi_code(fmt, dither), s.U)<<<grid, afp::TC2_THREADS, smem, stream>>>(P);
     AFP_CUDA(c, cudaGetLastError());
     c->launches += 1;
     c->range_dirty = true;
@@ -1050,8 +1054,10 @@ int afp_create(const afp_config* cfg, afp_ctx** out_ctx) {
             if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, grouped kernel)");
         }
     for (int epi : kAllEpi) {
-        e = cudaFuncSetAttribute((const void*)afp_kernel_tc2(epi), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-        if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, split-FP16 tensor path)");
+        for (int up : {1, 2, 4}) {
+            e = cudaFuncSetAttribute((const void*)afp_kernel_tc2(epi, up), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+            if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, split-FP16 tensor path)");
+        }
     }
     e = cudaFuncSetAttribute((const void*)afp_kernel_tc2_grouped(), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, split-FP16 tensor path, grouped)");
@@ -1669,7 +1675,7 @@ int afp_process_blocks(afp_ctx* c, const float* in, int64_t in_pitch, int64_t in
         // one launch for all the blocks: the CTA that owns a stream group walks its blocks with the window in
         // shared memory; the carried history is read once and written once
         bool done = false;
-        if (s->U == 1 && c->decim == 1) {
+        if ((s->U == 1 || ((s->U == 2 || s->U == 4) && c->group_of_stream.empty())) && c->decim == 1) {
             auto launch = c->group_of_stream.empty() ? launch_stage_tc2 : launch_stage_tc2_grouped;
             rc = launch(c, *s, in, in_pitch, in_block_stride, out, out_pitch / unit, out_block_stride / unit, frames, n_blocks,
                         c->cfg.out_format, c->cfg.dither, c->out_samples, 0, S, st, &done);

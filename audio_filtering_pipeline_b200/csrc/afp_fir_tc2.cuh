@@ -88,11 +88,11 @@ struct Tc2Params {
 
 typedef void (*tc2_kern_t)(const Tc2Params);
 
-__host__ __device__ constexpr int tc2_n_cores(int n_chunks) { return 8 * (n_chunks + 1) - 1; }
+__host__ __device__ constexpr int tc2_n_cores(int n_chunks, int U = 1) { return 8 * U * (n_chunks + 1) - U; }
 constexpr int TC2_STAGE_STRIDE = 9;                                  // granules per staged row: 8 + 1 (odd: conflict-free)
 constexpr int TC2_STAGE_BYTES = TC2_EPIS * 32 * TC2_STAGE_STRIDE * 16;  // one 32-row tile per epilogue warp
-__host__ __device__ constexpr int tc2_smem_bytes(int n_chunks, bool stage = false) {
-    return 2 * TC2_TILE_BYTES + 2 * tc2_n_cores(n_chunks) * 128 + 256 + (stage ? TC2_STAGE_BYTES : 0);
+__host__ __device__ constexpr int tc2_smem_bytes(int n_chunks, bool stage = false, int U = 1) {
+    return 2 * TC2_TILE_BYTES + 2 * tc2_n_cores(n_chunks, U) * 128 + 256 + (stage ? TC2_STAGE_BYTES : 0);
 }
 
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
@@ -114,18 +114,32 @@ __host__ __device__ constexpr uint32_t tc2_idesc(int n) { return (1u << 4) | ((u
 // Host side: the Hankel core array of a filter.  C_q[jj][e] = hp[8 q + jj + e], hp[t] = h[t - (R-1)]; every tap
 // h = hi + lo * 2^-11 with hi = fp16(h), lo = fp16((h - hi) * 2^11).  Layout: hi core q in slot 2 q, lo core q in
 // slot 2 q + 1, 64 halves each.  Returns the chunk count D + 1.
+//
+// U = 2 / 4: the polyphase interpolator  out[U n + p] = sum_k h[U k + p] x[n - k]  (zero-stuff by U, FIR at the high rate,
+// only the non-zero products) as the SAME Toeplitz form with wider rows: a row of R input samples makes U R consecutive
+// output samples, column c = U j + p, and the tap that joins element i of row m - d (sample R (m-d) + R-1 - i) to column c of
+// row m is  h[U (R d + j + i - (R-1)) + p] = g[U R d + U i + c],  g[t] = h[t - U (R-1)].  A core (8 columns x 8 elements)
+// again depends on one index only,  C_q[jj][e] = g[8 q + jj + U e]  with q = 8 U d + U (i / 8) + c / 8:  the next core in
+// K is U cores on, the next 8 columns one core on, 128 columns (16 cores) per instruction, 64 U columns per row in U / 2
+// passes.  One 64-sample window serves all U phases - the loaders do not change.  Layout: all hi cores, then all lo cores.
 template <class VEC>
-inline int tc2_build_cores(const double* taps, int n, VEC& w) {
-    const int D = (n + TC2_R - 2) / TC2_R, Q = 8 * (D + 2) - 1;
+inline int tc2_build_cores(const double* taps, int n, VEC& w, int U = 1) {
+    const int D = (n - 1 + (TC2_R - 1) * U) / (TC2_R * U), Q = tc2_n_cores(D + 1, U);
     w.assign((size_t)2 * Q * 64, __float2half_rn(0.f));
     for (int q = 0; q < Q; ++q)
         for (int jj = 0; jj < 8; ++jj)
             for (int e = 0; e < 8; ++e) {
-                const int k = 8 * q + jj + e - (TC2_R - 1);
+                const int k = 8 * q + jj + U * e - U * (TC2_R - 1);
                 const float hv = (k >= 0 && k < n) ? (float)taps[k] : 0.f;
                 const __half hi = __float2half_rn(hv);
-                w[(size_t)(2 * q) * 64 + jj * 8 + e] = hi;
-                w[(size_t)(2 * q + 1) * 64 + jj * 8 + e] = __float2half_rn((hv - __half2float(hi)) * 2048.0f);
+                const __half lo = __float2half_rn((hv - __half2float(hi)) * 2048.0f);
+                if (U == 1) {
+                    w[(size_t)(2 * q) * 64 + jj * 8 + e] = hi;
+                    w[(size_t)(2 * q + 1) * 64 + jj * 8 + e] = lo;
+                } else {
+                    w[(size_t)q * 64 + jj * 8 + e] = hi;
+                    w[(size_t)(Q + q) * 64 + jj * 8 + e] = lo;
+                }
             }
     return D + 1;
 }
@@ -235,7 +249,7 @@ struct RowTransposeSink {
     }
 };
 
-template <int EPI, bool GROUPED = false>
+template <int EPI, bool GROUPED = false, int U = 1>
 __global__ void __launch_bounds__(TC2_THREADS, 1)
 fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
     extern __shared__ __align__(128) unsigned char tc2_smem[];
@@ -246,9 +260,13 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(w_hi + 2 * P.n_cores * 128);
     uint64_t* win_early = bars;         // [2] step parity p: the rows the first chunks read are in place
     uint64_t* win_late = bars + 2;      // [2] ... and the rows only the later chunks read
-    uint64_t* mma_done = bars + 4;      // [2] accumulator set p final, window of the step read for the last time
-    uint64_t* acc_empty = bars + 6;     // [2] accumulator set p drained
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* mma_done = bars + 4;      // [2] step parity p: the window of the step has been read for the last time
+    uint64_t* acc_empty = bars + 6;     // [2] accumulator set drained
+    uint64_t* acc_full = bars + 8;      // [2] accumulator set final (U = 4: a step fills a set twice, 128 output columns at a time)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
+    static_assert(U == 1 || U == 2 || U == 4, "polyphase factors of the tensor kernel");
+    static_assert(!GROUPED || U == 1, "per-stream tap cores: U = 1 only");
+    constexpr int PASSES = U == 4 ? 2 : 1;   // accumulator fills per step
 
     constexpr int H = 16;               // history rows of a window (covers 1025 taps; shorter filters skip the oldest)
     const int n_steps = GROUPED ? P.steps_per_slot : (P.frames / TC2_STEP) * P.n_blocks;   // steps of one work item
@@ -260,7 +278,7 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
     if (tid == 32) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(&win_early[i], TC2_LOADERS / 2); mbar_init(&win_late[i], TC2_LOADERS / 2);   // the owning loader group's warps
-            mbar_init(&mma_done[i], 1); mbar_init(&acc_empty[i], TC2_EPIS);
+            mbar_init(&mma_done[i], 1); mbar_init(&acc_empty[i], TC2_EPIS); mbar_init(&acc_full[i], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -283,11 +301,17 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
         const uint64_t a_hi_d = umma_desc(smem_u32(tile_hi), TC2_A_LBO, TC2_PITCH), a_lo_d = umma_desc(smem_u32(tile_lo), TC2_A_LBO, TC2_PITCH);
         // B: the next core in K is the next index (256 B on); in N the wide product walks the slots (hi q, lo q, hi q+1, ...),
         // the narrow one the high cores only
-        const uint64_t w_wide_d = umma_desc(smem_u32(w_hi), 256, 128), w_hi_d = umma_desc(smem_u32(w_hi), 256, 256);
+        // U = 1.  B: the next core in K is the next index (256 B on); in N the wide product walks the slots (hi q, lo q, hi q+1,
+        // ...), the narrow one the high cores only.
+        // U = 2 / 4 (polyphase interpolator, file header of tc2_build_cores): all high cores, then all low cores; the next core
+        // in K is U cores on, in N one core on; 128 output columns per instruction.
+        const uint32_t lo_off = U == 1 ? 0u : (uint32_t)P.n_cores * 128u;
+        const uint64_t w_wide_d = U == 1 ? umma_desc(smem_u32(w_hi), 256, 128) : umma_desc(smem_u32(w_hi) + lo_off, U * 128, 128);
+        const uint64_t w_hi_d = U == 1 ? umma_desc(smem_u32(w_hi), 256, 256) : umma_desc(smem_u32(w_hi), U * 128, 128);
         const uint32_t top_a = (uint32_t)(a_hi_d >> 32), top_ww = (uint32_t)(w_wide_d >> 32), top_wh = (uint32_t)(w_hi_d >> 32);
         const uint32_t idesc_wide = tc2_idesc(2 * TC2_R), idesc = tc2_idesc(TC2_R);
         const int D = P.n_chunks - 1;
-        uint32_t kk = 0;                                       // steps issued by this CTA
+        uint32_t kk = 0, vk = 0;                               // steps / accumulator fills issued by this CTA
         int wpos = 8;
         long long t_acc = 0, t_dir = 0, t_stg = 0, t_iss = 0;  // cycles waiting for: accumulators, early rows, late rows; issuing
         const long long t_begin = clock64();
@@ -295,50 +319,71 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
             for (int k = 0; k < n_steps; ++k, ++kk) {
                 const uint32_t p = kk & 1u, ph = (kk >> 1) & 1u;
                 const Tc2Step st = tc2_step(wpos, k);
-                const long long c0 = clock64();
-                mbar_wait(&acc_empty[p], ph ^ 1u);             // (passes at once the first time round)
-                const long long c1 = clock64();
-                mbar_wait(&win_early[p], ph);
-                const long long c2 = clock64();
-                t_acc += c1 - c0; t_dir += c2 - c1;
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t acc_a = tmem_base + p * 256u, acc_b = acc_a + 128u;
                 bool late_seen = false;
-                bool first = true;
-                // Chunk order, the same for every step so that rounding does not depend on where a step ran:
-                // 8, D..9, 7..0 (what exists of it).  Chunk d reads window rows 16-d .. 23-d: the chunks >= 8 only history
-                // rows - a sliding step starts them while its new rows are still on their way.
-                for (int idx = 0; idx <= D; ++idx) {
-                    int d;
-                    if (D >= 8) d = idx == 0 ? 8 : (idx <= D - 8 ? D + 1 - idx : D - idx);
-                    else d = D - idx;
-                    const bool late = d <= 7;              // reads new rows (a first step publishes both barriers together)
-                    if (late && !late_seen) {
-                        const long long w0 = clock64();
-                        mbar_wait(&win_late[p], ph);
-                        t_stg += clock64() - w0;
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        late_seen = true;
-                    }
-                    if (elect_one()) {
-                        const uint32_t arow = (uint32_t)((st.pos + H - d) & (TC2_RING - 1));
-                        const uint32_t ah = (uint32_t)a_hi_d + arow, al = (uint32_t)a_lo_d + arow;
-                        const uint32_t ww = (uint32_t)w_wide_d + (uint32_t)(8 * d) * 16u, wh = (uint32_t)w_hi_d + (uint32_t)(8 * d) * 16u;
-#pragma unroll
-                        for (int ks = 0; ks < TC2_R / 16; ++ks) {
-                            const uint32_t ao = (uint32_t)(2 * ks * TC2_ROWS), wo = (uint32_t)(2 * ks) * 16u;
-                            const uint32_t f = (first && ks == 0) ? 0u : 1u;
-                            umma_f16(acc_a, ah + ao, top_a, ww + wo, top_ww, idesc_wide, f);   // x_hi * [W_hi | W_lo'] (interleaved by 8 columns)
-                            umma_f16(acc_b, al + ao, top_a, wh + wo, top_wh, idesc, f);        // x_lo' * W_hi
+#pragma unroll 1
+                for (int h = 0; h < PASSES; ++h, ++vk) {
+                    const uint32_t set = vk & 1u, aph = (vk >> 1) & 1u;
+                    const long long c0 = clock64();
+                    mbar_wait(&acc_empty[set], aph ^ 1u);      // (passes at once the first time round)
+                    const long long c1 = clock64();
+                    if (h == 0) mbar_wait(&win_early[p], ph);
+                    const long long c2 = clock64();
+                    t_acc += c1 - c0; t_dir += c2 - c1;
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t acc_a = tmem_base + set * 256u, acc_b = acc_a + 128u;
+                    bool first = true;
+                    // Chunk order, the same for every step so that rounding does not depend on where a step ran:
+                    // 8, D..9, 7..0 (what exists of it).  Chunk d reads window rows 16-d .. 23-d: the chunks >= 8 only history
+                    // rows - a sliding step starts them while its new rows are still on their way.
+                    for (int idx = 0; idx <= D; ++idx) {
+                        int d;
+                        if (D >= 8) d = idx == 0 ? 8 : (idx <= D - 8 ? D + 1 - idx : D - idx);
+                        else d = D - idx;
+                        const bool late = d <= 7;              // reads new rows (a first step publishes both barriers together)
+                        if (late && !late_seen) {
+                            const long long w0 = clock64();
+                            mbar_wait(&win_late[p], ph);
+                            t_stg += clock64() - w0;
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            late_seen = true;
                         }
+                        if (elect_one()) {
+                            const uint32_t arow = (uint32_t)((st.pos + H - d) & (TC2_RING - 1));
+                            const uint32_t ah = (uint32_t)a_hi_d + arow, al = (uint32_t)a_lo_d + arow;
+                            if (U == 1) {
+                                const uint32_t ww = (uint32_t)w_wide_d + (uint32_t)(8 * d) * 16u, wh = (uint32_t)w_hi_d + (uint32_t)(8 * d) * 16u;
+#pragma unroll
+                                for (int ks = 0; ks < TC2_R / 16; ++ks) {
+                                    const uint32_t ao = (uint32_t)(2 * ks * TC2_ROWS), wo = (uint32_t)(2 * ks) * 16u;
+                                    const uint32_t f = (first && ks == 0) ? 0u : 1u;
+                                    umma_f16(acc_a, ah + ao, top_a, ww + wo, top_ww, idesc_wide, f);   // x_hi * [W_hi | W_lo'] (interleaved by 8 columns)
+                                    umma_f16(acc_b, al + ao, top_a, wh + wo, top_wh, idesc, f);        // x_lo' * W_hi
+                                }
+                            } else {
+                                // core index of (chunk d, k-step ks, pass h): 8 U d + 2 U ks + 16 h; 8 descriptor units per core
+                                const uint32_t c0_ = (uint32_t)(8 * U * d + 16 * h) * 8u;
+                                const uint32_t wl = (uint32_t)w_wide_d + c0_, wh = (uint32_t)w_hi_d + c0_;
+#pragma unroll
+                                for (int ks = 0; ks < TC2_R / 16; ++ks) {
+                                    const uint32_t ao = (uint32_t)(2 * ks * TC2_ROWS), wo = (uint32_t)(2 * U * ks) * 8u;
+                                    const uint32_t f = (first && ks == 0) ? 0u : 1u;
+                                    umma_f16(acc_a, ah + ao, top_a, wh + wo, top_wh, idesc_wide, f);    // x_hi * W_hi   -> accumulator 0
+                                    umma_f16(acc_b, ah + ao, top_a, wl + wo, top_ww, idesc_wide, f);    // x_hi * W_lo'  -> accumulator 1
+                                    umma_f16(acc_b, al + ao, top_a, wh + wo, top_wh, idesc_wide, 1u);   // x_lo' * W_hi  -> accumulator 1
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        first = false;
+                    }
+                    if (!late_seen) { mbar_wait(&win_late[p], ph); late_seen = true; }
+                    if (elect_one()) {
+                        umma_commit(&acc_full[set]);
+                        if (h == PASSES - 1) umma_commit(&mma_done[p]);
                     }
                     __syncwarp();
-                    first = false;
+                    t_iss += clock64() - c2;
                 }
-                if (!late_seen) mbar_wait(&win_late[p], ph);
-                if (elect_one()) umma_commit(&mma_done[p]);
-                __syncwarp();
-                t_iss += clock64() - c2;
             }
         }
         if (P.prof && lane == 0) {
@@ -527,12 +572,13 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
         for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x) {
             const int s = GROUPED ? grp : grp * TC2_STREAMS + (m >> 3);
             for (int k = 0; k < n_steps; ++k, ++kk) {
+              if constexpr (U == 1) {
                 const uint32_t p = kk & 1u, ph = (kk >> 1) & 1u;
                 // first output sample of this thread's 32 within the call: slot m/8 runs through its own steps (GROUPED)
                 const int idx = ((GROUPED ? (m >> 3) * n_steps : 0) + k) * TC2_STEP + (m & 7) * TC2_R + 32 * half;
                 const int blk = idx / P.frames;
                 const long long r0 = P.prof ? clock64() : 0;
-                mbar_wait(&mma_done[p], ph);
+                mbar_wait(&acc_full[p], ph);
                 const long long r1 = P.prof ? clock64() : 0;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 // accumulator A columns 64 half .. +63 (this half's 32 output columns, hi*hi and hi*lo' interleaved by 8),
@@ -627,6 +673,65 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                     }
                 }
                 if (P.prof) { e_wait += r1 - r0; e_tmem += r2 - r1; e_store += clock64() - r1 - (r2 - r1); }
+              } else {
+                // Polyphase interpolator: a step fills an accumulator set PASSES times with 128 output columns; this thread owns
+                // row m and columns 64 half .. +63 of each fill = 64 consecutive output samples of its stream.
+                const int ti = k * TC2_STEP + (m & 7) * TC2_R;                  // first input sample of the row within the call
+                const int blk = ti / P.frames;
+                V.out = static_cast<unsigned char*>(P.out) + (long long)blk * P.out_block_stride * eb;
+                V.sample_base = P.sample_base + (unsigned long long)blk * (unsigned long long)(U * P.frames);
+                constexpr bool kWholeRow = EPI == epi_code(FMT_F32, DITHER_NONE);
+                constexpr int W = kWholeRow ? 32 : 16;                          // output samples per store pass
+#pragma unroll 1
+                for (int h = 0; h < PASSES; ++h) {
+                    const uint32_t vk = kk * PASSES + h, set = vk & 1u, aph = (vk >> 1) & 1u;
+                    const long long r0 = P.prof ? clock64() : 0;
+                    mbar_wait(&acc_full[set], aph);
+                    const long long r1 = P.prof ? clock64() : 0;
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t taddr = tmem_base + ((uint32_t)(32 * quarter) << 16) + set * 256u + (uint32_t)(64 * half);
+                    const long long o0 = (long long)U * (ti - blk * P.frames) + 128 * h + 64 * half;   // within the output block
+                    long long r2 = 0;
+#pragma unroll
+                    for (int f = 0; f < 64 / W; ++f) {
+                        const long long t0 = P.prof ? clock64() : 0;
+                        float y[W];
+#pragma unroll
+                        for (int g = 0; g < W / 16; ++g) {
+                            uint32_t a0[16], a1[16];
+                            asm volatile(
+                                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                                : "=r"(a0[0]), "=r"(a0[1]), "=r"(a0[2]), "=r"(a0[3]), "=r"(a0[4]), "=r"(a0[5]), "=r"(a0[6]), "=r"(a0[7]),
+                                  "=r"(a0[8]), "=r"(a0[9]), "=r"(a0[10]), "=r"(a0[11]), "=r"(a0[12]), "=r"(a0[13]), "=r"(a0[14]), "=r"(a0[15])
+                                : "r"(taddr + (uint32_t)(W * f + 16 * g)));
+                            asm volatile(
+                                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                                : "=r"(a1[0]), "=r"(a1[1]), "=r"(a1[2]), "=r"(a1[3]), "=r"(a1[4]), "=r"(a1[5]), "=r"(a1[6]), "=r"(a1[7]),
+                                  "=r"(a1[8]), "=r"(a1[9]), "=r"(a1[10]), "=r"(a1[11]), "=r"(a1[12]), "=r"(a1[13]), "=r"(a1[14]), "=r"(a1[15])
+                                : "r"(taddr + 128u + (uint32_t)(W * f + 16 * g)));
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                            for (int c = 0; c < 16; ++c)                               // y = acc0 + 2^-11 acc1
+                                y[16 * g + c] = __fmaf_rn(__uint_as_float(a1[c]), 4.8828125e-4f, __uint_as_float(a0[c]));
+                        }
+                        if (f == 64 / W - 1) {
+                            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&acc_empty[set]);
+                        }
+                        if (P.prof) r2 += clock64() - t0;
+                        if (!(P.prof && P.gain == 0.f)) {
+                            if (P.epi_stage && P.fast_out)
+                                store_row<W, EPI>(V, y, s, o0 + W * f, W, RowTransposeSink{stage_tile, s < P.n_streams});
+                            else
+                                store_row<W, EPI>(V, y, s, o0 + W * f, s < P.n_streams ? W : 0);
+                        }
+                    }
+                    if (P.prof) { e_wait += r1 - r0; e_tmem += r2; e_store += clock64() - r1 - r2; }
+                }
+              }
             }
             // (the epilogue warps have the slack for this; in the loaders it would delay the next group's first window)
             if (GROUPED) tc2_copy_history(P, grp, 1, TC2_STREAMS * n_steps * TC2_STEP, tid - 32 * (1 + TC2_LOADERS), 32 * TC2_EPIS);

@@ -100,20 +100,20 @@ def test_process_blocks_strided_views_and_int24():
 
 
 def test_process_blocks_falls_back_block_by_block_for_other_chains():
-    """A chain that is not one long U = 1 filter (here the 251-tap 4x interpolator) runs block by block behind the
-    same call."""
-    h = 4 * design.create_fir_filter(cutoff=[500, 8000], numtaps=251, window_type="kaiser", filter_type="bandpass",
-                                     samplerate=176400)
+    """A chain that is not one filter the tensor kernel takes (here a 3x interpolator: the kernel has the polyphase factors
+    2 and 4) runs block by block behind the same call."""
+    h = 3 * design.create_fir_filter(cutoff=[500, 8000], numtaps=251, window_type="kaiser", filter_type="bandpass",
+                                     samplerate=132300)
     S, B, nb = 6, 1024, 3
     x = noise(S, B * nb)
     xb = torch.from_numpy(blocks_of(x, B)).cuda()
-    with BatchFirEngine(h, n_streams=S, max_frames=B, upsample=4, chain="dac") as eng:
+    with BatchFirEngine(h, n_streams=S, max_frames=B, upsample=3, chain="dac") as eng:
         y_one = torch.stack([eng.process(xb[i]) for i in range(nb)]).cpu().numpy()
         eng.reset()
         y_multi = eng.process_blocks(xb).cpu().numpy()
         assert eng.stage_info()[-1]["kernel"] == 2
     np.testing.assert_array_equal(y_multi, y_one)
-    assert_parity(unblock(y_multi)[0], rc.polyphase_upsample_whole(h, x[0], 4).astype(np.float32), "C1 DAC chain")
+    assert_parity(unblock(y_multi)[0], rc.polyphase_upsample_whole(h, x[0], 3).astype(np.float32), "3x DAC chain")
 
 
 def test_small_and_full_scale_signals():
@@ -229,4 +229,45 @@ def test_short_filter_epilogues_bit_exact(fmt, dither, monkeypatch):
     code = {"f32": dq.FMT_F32, "i16": dq.FMT_I16, "i24": dq.FMT_I24_IN_I32, "i24_packed": dq.FMT_I24_PACKED}[fmt]
     # the per-block layout of packed samples is 3 bytes per sample: compare block by block through the oracle's own packing
     ref = dq.epilogue(yf, code, {"tpdf": dq.DITHER_TPDF, "rpdf": dq.DITHER_RPDF}[dither], 11, np.arange(S) + 5, 0)
+    np.testing.assert_array_equal(yq, ref)
+
+
+# Polyphase interpolators (U = 2 / 4) on the same kernel: wider Toeplitz rows (64 U output columns per 64-sample row), cores
+# C_q[jj][e] = g[8 q + jj + U e].  Phase lengths below / at / above a chunk boundary, one and several steps per group, a
+# ragged last stream group, block-by-block vs one multi-block call, and the quantised formats through the generic epilogue.
+@pytest.mark.parametrize("U,N,B,nb,S", [(2, 96, 512, 2, 5), (2, 251, 1024, 3, 37), (2, 501, 512, 5, 16), (2, 1001, 512, 4, 21),
+                                        (2, 129, 1536, 2, 3), (4, 251, 512, 3, 19), (4, 501, 1024, 2, 33), (4, 1001, 512, 5, 7),
+                                        (4, 160, 512, 1, 2), (2, 251, 512, 2, 148 * 16 + 9)])
+def test_polyphase_interpolator_on_tensor_kernel(U, N, B, nb, S):
+    h = U * design.create_fir_filter(cutoff=0.45 * 44100, numtaps=N, window_type="kaiser", samplerate=44100 * U)
+    x = noise(min(S, 48), B * nb, amp=0.3, seed=7 * N + U)
+    x = np.tile(x, ((S + x.shape[0] - 1) // x.shape[0], 1))[:S] * np.linspace(0.6, 1.0, S, dtype=np.float32)[:, None]
+    xb = torch.from_numpy(blocks_of(np.ascontiguousarray(x), B)).cuda()
+    with BatchFirEngine(h, n_streams=S, max_frames=B, upsample=U, chain="dac") as eng:
+        y_multi = unblock(eng.process_blocks(xb).cpu().numpy())
+        assert eng.stage_info()[-1]["kernel"] == 3 and eng.kernel_launches == 1
+        assert y_multi.shape == (S, U * B * nb)
+    with BatchFirEngine(h, n_streams=S, max_frames=B, upsample=U, chain="dac") as eng:
+        y_one = np.concatenate([eng.process(xb[i]).cpu().numpy() for i in range(nb)], axis=1)
+        assert eng.stage_info()[-1]["kernel"] == 3
+    np.testing.assert_array_equal(y_multi, y_one)
+    for s in sorted({0, 1, S // 2, S - 2, S - 1}):
+        assert_parity(y_multi[s], rc.polyphase_upsample_whole(h, x[s], U).astype(np.float32), f"U={U} N={N} B={B} s={s}")
+
+
+@pytest.mark.parametrize("U", [2, 4])
+@pytest.mark.parametrize("fmt,dither", [("i24", "tpdf"), ("i16", "none"), ("i24_packed", "tpdf"), ("f32", "rpdf")])
+def test_polyphase_epilogues_bit_exact(U, fmt, dither):
+    N, B, nb, S = 251, 512, 3, 20
+    h = U * design.create_fir_filter(cutoff=0.45 * 44100, numtaps=N, window_type="kaiser", samplerate=44100 * U)
+    x = noise(S, B * nb, amp=0.3, seed=5)
+    xb = torch.from_numpy(blocks_of(x, B)).cuda()
+    with BatchFirEngine(h, n_streams=S, max_frames=B, upsample=U, chain="dac") as eng:
+        yf = unblock(eng.process_blocks(xb).cpu().numpy())
+    with BatchFirEngine(h, n_streams=S, max_frames=B, upsample=U, chain="dac", out_format=fmt, dither=dither, seed=3,
+                        first_stream_id=11) as eng:
+        yq = unblock(eng.process_blocks(xb).cpu().numpy())
+        assert eng.stage_info()[-1]["kernel"] == 3
+    code = {"f32": dq.FMT_F32, "i16": dq.FMT_I16, "i24": dq.FMT_I24_IN_I32, "i24_packed": dq.FMT_I24_PACKED}[fmt]
+    ref = dq.epilogue(yf, code, {"tpdf": dq.DITHER_TPDF, "rpdf": dq.DITHER_RPDF, "none": dq.DITHER_NONE}[dither], 3, np.arange(S) + 11, 0)
     np.testing.assert_array_equal(yq, ref)
