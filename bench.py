@@ -395,18 +395,20 @@ def kernel_names(info):
             3: "afp::fir_tc2_kernel (tcgen05 / TMEM Toeplitz FIR, split FP16, resident Hankel tap cores)"}.get(k, str(k))
 
 
-def tensor_block(n_taps, samples_per_s, peaks_run, peaks_file):
-    """MMA work the split-FP16 kernel issues for `samples_per_s` outputs of an n_taps filter: 3 products (hi*hi and hi*lo as one
-    N=128 instruction, lo*hi as an N=64 one) over ceil-padded 64-sample Toeplitz chunks; against the tensor roofs measured in
-    this run."""
-    n_chunks = (n_taps + 62) // 64 + 1
-    issued = 3.0 * 2.0 * n_chunks * 64 * samples_per_s / 1e12
-    out = {"kind": "tcgen05.mma kind::f16, M=128 K=16, FP32 accumulators in TMEM, split FP16 (hi + lo*2^-11): x_hi*[W_hi|W_lo] as one N=128 "
-                   "instruction + x_lo*W_hi as an N=64 one per chunk and k-step",
-           "issued_tflops": round(issued, 1), "issued_over_algorithmic": round(3.0 * n_chunks * 64 / n_taps, 3)}
+def tensor_block(n_taps, samples_per_s, peaks_run, peaks_file, upsample=1):
+    """MMA work the split-FP16 kernel issues for `samples_per_s` outputs of an n_taps filter: 3 products over ceil-padded
+    Toeplitz chunks (U = 1: hi*hi and hi*lo as one N=128 instruction, lo*hi as an N=64 one; polyphase U = 2 / 4: three N=128
+    instructions over 64 U-column rows); against the tensor roofs measured in this run."""
+    U = upsample
+    n_chunks = (n_taps - 1 + 63 * U) // (64 * U) + 1
+    issued = 3.0 * 2.0 * n_chunks * 64 * samples_per_s / 1e12          # per OUTPUT sample, the same expression for every U
+    kind = ("x_hi*[W_hi|W_lo] as one N=128 instruction + x_lo*W_hi as an N=64 one per chunk and k-step" if U == 1 else
+            f"polyphase {U}x: 64-sample rows make {64 * U} output columns, three N=128 instructions per chunk, k-step and 128 columns")
+    out = {"kind": "tcgen05.mma kind::f16, M=128 K=16, FP32 accumulators in TMEM, split FP16 (hi + lo*2^-11): " + kind,
+           "issued_tflops": round(issued, 1), "issued_over_algorithmic": round(3.0 * n_chunks * 64 / (-(-n_taps // U)), 3)}
     if peaks_run:
-        # roof of the kernel's own instruction mix: 2/3 of the flop at the N=128 rate, 1/3 at the N=64 rate
-        mix = 3.0 / (2.0 / peaks_run["n128"][0] + 1.0 / peaks_run["n64"][0])
+        # roof of the kernel's own instruction mix: U = 1: 2/3 of the flop at the N=128 rate, 1/3 at the N=64 rate
+        mix = 3.0 / (2.0 / peaks_run["n128"][0] + 1.0 / peaks_run["n64"][0]) if U == 1 else peaks_run["n128"][0]
         out["measured_roof_n64_tflops"] = round(peaks_run["n64"][0], 1)
         out["measured_roof_n128_tflops"] = round(peaks_run["n128"][0], 1)
         out["measured_roof_n256_tflops"] = round(peaks_run["n256"][0], 1)
@@ -438,13 +440,19 @@ def roofline_for(eng, n_taps_exec, upsample, out_bytes, samples_per_s, ms_per_la
          "hbm": {"achieved_gbs": round(gbs, 1), "peak_gbs": hbm_peak, "frac": round(gbs / hbm_peak, 4), "peak_source": hbm_src}}
     if info.get("kernel") in (1, 3):
         bf16 = peaks_file.get("bf16_tflops", 1590.0)
-        r.update({"bound": "tensor", "achieved": round(tf, 2), "peak": bf16, "unit": "TFLOP/s", "frac": round(tf / bf16, 4),
-                  "peak_source": ("MEASURED_PEAKS.json bf16_tflops (cuBLAS burst; kind::f16 runs at the bf16 rate)" if "bf16_tflops" in peaks_file
-                                  else "fallback 1590 TFLOP/s"),
-                  "note": "achieved counts the ALGORITHMIC 2N flop per output sample; the split-precision Toeplitz form issues "
-                          "issued_over_algorithmic x that on the tensor pipe (see tensor)"})
+        tensor_src = ("MEASURED_PEAKS.json bf16_tflops (cuBLAS burst; kind::f16 runs at the bf16 rate)" if "bf16_tflops" in peaks_file
+                      else "fallback 1590 TFLOP/s")
+        if hbm_peak * 1e9 / byts < bf16 * 1e12 / flop:      # the lower roof in samples/s: short filters on the tensor kernel are HBM work
+            r.update({"bound": "hbm", "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(gbs / hbm_peak, 4),
+                      "peak_source": hbm_src,
+                      "tensor_roof": {"achieved_tflops": round(tf, 2), "peak_tflops": bf16, "frac": round(tf / bf16, 4), "peak_source": tensor_src}})
+        else:
+            r.update({"bound": "tensor", "achieved": round(tf, 2), "peak": bf16, "unit": "TFLOP/s", "frac": round(tf / bf16, 4),
+                      "peak_source": tensor_src,
+                      "note": "achieved counts the ALGORITHMIC 2N flop per output sample; the split-precision Toeplitz form issues "
+                              "issued_over_algorithmic x that on the tensor pipe (see tensor)"})
         if info.get("kernel") == 3:
-            r["tensor"] = tensor_block(n_taps_exec, samples_per_s, peaks_run, peaks_file)
+            r["tensor"] = tensor_block(n_taps_exec, samples_per_s, peaks_run, peaks_file, upsample)
         r["fp32_fma_equiv"] = {"speedup_over_fma_roof": round(tf / fma_peak, 3), "fma_roof_tflops": round(fma_peak, 2),
                                "note": "north-star framing (>= 70 % of the FP32-FMA roof for >= 251 taps): the same work on the "
                                        "FFMA2 kernels cannot exceed 1.0; a speed-up, not a roofline fraction"}
@@ -592,14 +600,54 @@ def c5_sweep(D, cpu, hbm_peak_gbs, fma_peak, iters=8):
                 row = {"taps": n_taps, "upsample": up, "streams_total": total, "streams_per_gpu": count, "frames": B,
                        "gsamples_s": round(gs, 1), "tflops": round(gs * flop / 1e3, 1), "alg_gbs": round(gs * byts, 0), "bound": bound,
                        "frac": round(gs / (min(roof_fma, roof_hbm) * D.world), 3), "kernel": info["kernel"], "tile": info["tile_taps"]}
+                row["hbm_frac"] = round(gs / (roof_hbm * D.world), 3)
                 if info["kernel"] in (1, 3):
-                    row["bound"] = "tensor (frac = speed-up over the FP32-FMA roof)"
+                    row["bound"] = "tensor (frac = speed-up over the FP32-FMA roof; hbm_frac = share of the HBM roof)"
                 if (n_taps, up) in cpu_rate:
                     c = cpu_rate[(n_taps, up)]
                     row["cpu_msamples_s"] = c["value"]
                     row["cpu_cores"] = c["cores"]
                     row["gpu_over_cpu"] = round(gs * 1e3 / c["value"], 0)
                 out.append(row)
+            # the same filter in the streaming form of the headline: 16 consecutive 512-frame blocks per call (afp_process_blocks)
+            total, nb, Bs = 16384, 16, 512
+            first, count = partition_streams(total, D.world, D.rank)
+            ms = 0.0
+            info = {"kernel": None, "tile_taps": None}
+            if count > 0:
+                eng = BatchFirEngine(h, n_streams=count, max_frames=Bs, upsample=up, device=D.local, first_stream_id=first)
+                xb = 0.1 * torch.randn(nb, count, Bs, device=D.dev)
+                yb = torch.empty(nb, count, Bs * up, device=D.dev)
+                for i in range(2):
+                    eng.process_blocks(xb, yb)
+            D.barrier()
+            if count > 0:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(max(iters // 2, 3)):
+                    eng.process_blocks(xb, yb)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / max(iters // 2, 3)
+                info = eng.stage_info()[-1]
+                eng.close()
+                del xb, yb
+            ms = D.max(ms)
+            gs = total * Bs * nb * up / ms / 1e6
+            flop, byts = 2.0 * -(-n_taps // up), 4.0 / up + 4.0
+            roof_fma, roof_hbm = fma_peak * 1e3 / flop, hbm_peak_gbs / byts
+            row = {"taps": n_taps, "upsample": up, "streams_total": total, "streams_per_gpu": count, "frames": Bs, "blocks_per_call": nb,
+                   "gsamples_s": round(gs, 1), "tflops": round(gs * flop / 1e3, 1), "alg_gbs": round(gs * byts, 0),
+                   "bound": "hbm" if roof_hbm < roof_fma else "fp32_fma", "frac": round(gs / (min(roof_fma, roof_hbm) * D.world), 3),
+                   "hbm_frac": round(gs / (roof_hbm * D.world), 3), "kernel": info["kernel"], "tile": info["tile_taps"]}
+            if info["kernel"] in (1, 3):
+                row["bound"] = "tensor (frac = speed-up over the FP32-FMA roof; hbm_frac = share of the HBM roof)"
+            if (n_taps, up) in cpu_rate:
+                c = cpu_rate[(n_taps, up)]
+                row["cpu_msamples_s"] = c["value"]
+                row["cpu_cores"] = c["cores"]
+                row["gpu_over_cpu"] = round(gs * 1e3 / c["value"], 0)
+            out.append(row)
     return out
 
 
