@@ -1675,7 +1675,8 @@ int afp_process_blocks(afp_ctx* c, const float* in, int64_t in_pitch, int64_t in
         // one launch for all the blocks: the CTA that owns a stream group walks its blocks with the window in
         // shared memory; the carried history is read once and written once
         bool done = false;
-        if ((s->U == 1 || ((s->U == 2 || s->U == 4) && c->group_of_stream.empty())) && c->decim == 1) {
+        // (the collapsed reference chain has its decimation folded into the base-rate filter: the stage itself runs with decim 1)
+        if ((s->U == 1 || ((s->U == 2 || s->U == 4) && c->group_of_stream.empty())) && (c->decim == 1 || s == &c->fused)) {
             auto launch = c->group_of_stream.empty() ? launch_stage_tc2 : launch_stage_tc2_grouped;
             rc = launch(c, *s, in, in_pitch, in_block_stride, out, out_pitch / unit, out_block_stride / unit, frames, n_blocks,
                         c->cfg.out_format, c->cfg.dither, c->out_samples, 0, S, st, &done);

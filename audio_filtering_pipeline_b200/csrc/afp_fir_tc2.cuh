@@ -45,7 +45,7 @@ namespace afp {
 
 constexpr int TC2_R = 64;                  // samples per row
 constexpr int TC2_STREAMS = 16;            // streams per work item (M = 128 = 16 x 8 rows)
-constexpr int TC2_ROWS = 41;               // rows per stream tile: a ring of 32, its first 8 repeated, + 1 (row pitch 41 x 16 B = 16 mod 128: conflict-free loader stores)
+constexpr int TC2_ROWS = 41;               // rows per stream tile (16 history rows): a ring of 32, its first 8 repeated, + 1 (row pitch 41 x 16 B = 16 mod 128: conflict-free loader stores)
 constexpr int TC2_STEP = 8 * TC2_R;        // new samples per stream and step
 constexpr int TC2_LOADERS = 16, TC2_EPIS = 8;           // warps (loaders: a warp keeps ~4 128-bit loads in flight whatever it issues - bench/microbench/stream_mlp.cu - so HBM reads scale with the number of loading warps)
 constexpr int TC2_THREADS = 32 * (1 + TC2_LOADERS + TC2_EPIS);
@@ -91,9 +91,16 @@ typedef void (*tc2_kern_t)(const Tc2Params);
 __host__ __device__ constexpr int tc2_n_cores(int n_chunks, int U = 1) { return 8 * U * (n_chunks + 1) - U; }
 constexpr int TC2_STAGE_STRIDE = 9;                                  // granules per staged row: 8 + 1 (odd: conflict-free)
 constexpr int TC2_STAGE_BYTES = TC2_EPIS * 32 * TC2_STAGE_STRIDE * 16;  // one 32-row tile per epilogue warp
+// History rows of a window: 16 cover 1025 taps per phase; filters of up to 8 chunks beyond the first (513 taps per phase -
+// every polyphase case) keep 8, which shrinks the stream tile from 41 to 33 rows (a ring of 24) and makes room for the
+// epilogue's staging tiles beside the larger polyphase core arrays.
+__host__ __device__ constexpr int tc2_hist_rows(int n_chunks) { return n_chunks - 1 <= 8 ? 8 : 16; }
+__host__ __device__ constexpr int tc2_tile_rows(int n_chunks) { return tc2_hist_rows(n_chunks) + 16 + 9; }     // ring + 8 repeated + 1
+__host__ __device__ constexpr int tc2_tile_bytes(int n_chunks) { return TC2_STREAMS * (TC2_R / 8) * tc2_tile_rows(n_chunks) * 16; }
 __host__ __device__ constexpr int tc2_smem_bytes(int n_chunks, bool stage = false, int U = 1) {
-    return 2 * TC2_TILE_BYTES + 2 * tc2_n_cores(n_chunks, U) * 128 + 256 + (stage ? TC2_STAGE_BYTES : 0);
+    return 2 * tc2_tile_bytes(n_chunks) + 2 * tc2_n_cores(n_chunks, U) * 128 + 256 + (stage ? TC2_STAGE_BYTES : 0);
 }
+static_assert(tc2_tile_bytes(17) == TC2_TILE_BYTES, "16 history rows: the 41-row tile");
 
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
                                          uint32_t accumulate) {
@@ -165,13 +172,13 @@ __device__ __forceinline__ void tc2_split4(const float4& v, uint2& hi, uint2& lo
 // and of that only the rows its MMAs read (chunk d reads window rows 16 - d .. 23 - d: a 251-tap filter 12 rows, not 24).
 // (The first version walked three fixed positions of a 40-row tile and reloaded all 24 rows on every third step; the
 // probe counters showed the MMA warp waiting for exactly those reloads: 6.1 of 8.0 kclk per step at 51 taps.)
-constexpr int TC2_RING = 32;
 struct Tc2Step { int pos; bool fresh; };
 // Window start of the next step given the previous step's: +8 inside a group; a new group starts 24 rows on, so that
 // its eight OLDEST rows are the ring rows the previous step's window does not cover - they can be written while that step's
 // MMAs still run (long filters only read them; the other sixteen rows wait for those MMAs).  `w` starts at 8.
-__device__ __forceinline__ Tc2Step tc2_step(int& w, int k) {
-    w = (w + (k == 0 ? 24 : 8)) & (TC2_RING - 1);
+__device__ __forceinline__ Tc2Step tc2_step(int& w, int k, int H) {      // (ring of H + 16 rows, window of H + 8)
+    w += k == 0 ? H + 8 : 8;
+    if (w >= H + 16) w -= H + 16;
     Tc2Step st;
     st.pos = w;
     st.fresh = k == 0;
@@ -255,8 +262,10 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
     extern __shared__ __align__(128) unsigned char tc2_smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned char* tile_hi = tc2_smem;
-    unsigned char* tile_lo = tile_hi + TC2_TILE_BYTES;
-    unsigned char* w_hi = tile_lo + TC2_TILE_BYTES;       // core slots: [hi q | lo q], 256 B per index
+    const int H = tc2_hist_rows(P.n_chunks);   // history rows of a window (16 cover 1025 taps per phase; up to 513: 8)
+    const int RING = H + 16, ROWS = RING + 9, A_LBO = ROWS * 16, PITCH = (TC2_R / 8) * A_LBO, TILE = TC2_STREAMS * PITCH;
+    unsigned char* tile_lo = tile_hi + TILE;
+    unsigned char* w_hi = tile_lo + TILE;       // core slots: [hi q | lo q], 256 B per index
     uint64_t* bars = reinterpret_cast<uint64_t*>(w_hi + 2 * P.n_cores * 128);
     uint64_t* win_early = bars;         // [2] step parity p: the rows the first chunks read are in place
     uint64_t* win_late = bars + 2;      // [2] ... and the rows only the later chunks read
@@ -268,7 +277,6 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
     static_assert(!GROUPED || U == 1, "per-stream tap cores: U = 1 only");
     constexpr int PASSES = U == 4 ? 2 : 1;   // accumulator fills per step
 
-    constexpr int H = 16;               // history rows of a window (covers 1025 taps; shorter filters skip the oldest)
     const int n_steps = GROUPED ? P.steps_per_slot : (P.frames / TC2_STEP) * P.n_blocks;   // steps of one work item
 
     if (warp == 0) {
@@ -298,7 +306,7 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
     // more than the epilogue gained: 553 -> 461 Gsamples/s at 51 taps.  25 warps compile to 72 registers each.)
     if (warp_u == 0) {
         // ================= MMA issuer: one elected lane, operands warp-uniform =================
-        const uint64_t a_hi_d = umma_desc(smem_u32(tile_hi), TC2_A_LBO, TC2_PITCH), a_lo_d = umma_desc(smem_u32(tile_lo), TC2_A_LBO, TC2_PITCH);
+        const uint64_t a_hi_d = umma_desc(smem_u32(tile_hi), A_LBO, PITCH), a_lo_d = umma_desc(smem_u32(tile_lo), A_LBO, PITCH);
         // B: the next core in K is the next index (256 B on); in N the wide product walks the slots (hi q, lo q, hi q+1, ...),
         // the narrow one the high cores only
         // U = 1.  B: the next core in K is the next index (256 B on); in N the wide product walks the slots (hi q, lo q, hi q+1,
@@ -318,7 +326,7 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
         for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x) {
             for (int k = 0; k < n_steps; ++k, ++kk) {
                 const uint32_t p = kk & 1u, ph = (kk >> 1) & 1u;
-                const Tc2Step st = tc2_step(wpos, k);
+                const Tc2Step st = tc2_step(wpos, k, H);
                 bool late_seen = false;
 #pragma unroll 1
                 for (int h = 0; h < PASSES; ++h, ++vk) {
@@ -348,13 +356,13 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                             late_seen = true;
                         }
                         if (elect_one()) {
-                            const uint32_t arow = (uint32_t)((st.pos + H - d) & (TC2_RING - 1));
+                            const uint32_t arow = (uint32_t)(st.pos + H - d >= RING ? st.pos + H - d - RING : st.pos + H - d);
                             const uint32_t ah = (uint32_t)a_hi_d + arow, al = (uint32_t)a_lo_d + arow;
                             if (U == 1) {
                                 const uint32_t ww = (uint32_t)w_wide_d + (uint32_t)(8 * d) * 16u, wh = (uint32_t)w_hi_d + (uint32_t)(8 * d) * 16u;
 #pragma unroll
                                 for (int ks = 0; ks < TC2_R / 16; ++ks) {
-                                    const uint32_t ao = (uint32_t)(2 * ks * TC2_ROWS), wo = (uint32_t)(2 * ks) * 16u;
+                                    const uint32_t ao = (uint32_t)(2 * ks * ROWS), wo = (uint32_t)(2 * ks) * 16u;
                                     const uint32_t f = (first && ks == 0) ? 0u : 1u;
                                     umma_f16(acc_a, ah + ao, top_a, ww + wo, top_ww, idesc_wide, f);   // x_hi * [W_hi | W_lo'] (interleaved by 8 columns)
                                     umma_f16(acc_b, al + ao, top_a, wh + wo, top_wh, idesc, f);        // x_lo' * W_hi
@@ -365,7 +373,7 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                                 const uint32_t wl = (uint32_t)w_wide_d + c0_, wh = (uint32_t)w_hi_d + c0_;
 #pragma unroll
                                 for (int ks = 0; ks < TC2_R / 16; ++ks) {
-                                    const uint32_t ao = (uint32_t)(2 * ks * TC2_ROWS), wo = (uint32_t)(2 * U * ks) * 8u;
+                                    const uint32_t ao = (uint32_t)(2 * ks * ROWS), wo = (uint32_t)(2 * U * ks) * 8u;
                                     const uint32_t f = (first && ks == 0) ? 0u : 1u;
                                     umma_f16(acc_a, ah + ao, top_a, wh + wo, top_wh, idesc_wide, f);    // x_hi * W_hi   -> accumulator 0
                                     umma_f16(acc_b, ah + ao, top_a, wl + wo, top_ww, idesc_wide, f);    // x_hi * W_lo'  -> accumulator 1
@@ -433,18 +441,18 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
             const int fs = 2 * lg + sh;
             const int grp_next = grp + gridDim.x;
             auto fresh_fetch_next = [&](int u) -> float4 {
-                return u < 4 ? fetch_of(grp_next, 0, 4 * u + fs, 16 + prow, pf4) : fetch_of(grp_next, 0, 4 * (u - 4) + fs, 8 + prow, pf4);
+                return u < 4 ? fetch_of(grp_next, 0, 4 * u + fs, H + prow, pf4) : fetch_of(grp_next, 0, 4 * (u - 4) + fs, H - 8 + prow, pf4);
             };
             auto place = [&](int pos, int sl, int wrow, int f4, const float4& v) {
                 uint2 hi, lo;
                 tc2_split4(v, hi, lo, amax);
-                const int row = (pos + wrow) & (TC2_RING - 1);
-                const int off = sl * TC2_PITCH + (7 - (f4 >> 1)) * TC2_A_LBO + row * 16 + ((f4 & 1) ? 0 : 8);
+                const int row = pos + wrow >= RING ? pos + wrow - RING : pos + wrow;
+                const int off = sl * PITCH + (7 - (f4 >> 1)) * A_LBO + row * 16 + ((f4 & 1) ? 0 : 8);
                 *reinterpret_cast<uint2*>(tile_hi + off) = hi;
                 *reinterpret_cast<uint2*>(tile_lo + off) = lo;
                 if (row < 8) {                             // rows 0..7 are repeated after row 31
-                    *reinterpret_cast<uint2*>(tile_hi + off + TC2_RING * 16) = hi;
-                    *reinterpret_cast<uint2*>(tile_lo + off + TC2_RING * 16) = lo;
+                    *reinterpret_cast<uint2*>(tile_hi + off + RING * 16) = hi;
+                    *reinterpret_cast<uint2*>(tile_lo + off + RING * 16) = lo;
                 }
             };
             auto publish = [&](uint64_t* bar) {
@@ -458,7 +466,7 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
             auto next_loads = [&](int kn) {
                 if (kn < n_steps) {
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) v[u] = fetch(kn, 2 * u + sh, 16 + prow, pf4);
+                    for (int u = 0; u < 8; ++u) v[u] = fetch(kn, 2 * u + sh, H + prow, pf4);
                 } else if (grp_next < P.n_groups && D < 9) {
 #pragma unroll
                     for (int u = 0; u < 8; ++u) v[u] = fresh_fetch_next(u);
@@ -478,7 +486,7 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
             // previous own step (next_loads), so they travel while the other group works.
             for (int k = 0; k < n_steps; ++k, ++kk) {
                 const uint32_t p = kk & 1u;
-                const Tc2Step st = tc2_step(wpos, k);
+                const Tc2Step st = tc2_step(wpos, k, H);
                 if (st.fresh) {
                     // First step of a group: the window rows its MMAs read, [16 - D, 24), in batches of 8 rows.  Both loader
                     // groups work on it (a thread takes one float4 position of every second stream), the two newest batches
@@ -503,8 +511,8 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                     if (!pre_fresh) {
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            v[u] = fetch(k, 4 * u + fs, 16 + prow, pf4);
-                            v[4 + u] = fetch(k, 4 * u + fs, 8 + prow, pf4);
+                            v[u] = fetch(k, 4 * u + fs, H + prow, pf4);
+                            v[4 + u] = fetch(k, 4 * u + fs, H - 8 + prow, pf4);
                         }
                     }
                     pre_fresh = false;
@@ -518,8 +526,8 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                     const int kn = (int)p == lg ? k + 2 : k + 1;
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        place(st.pos, 4 * u + fs, 16 + prow, pf4, v[u]);
-                        place(st.pos, 4 * u + fs, 8 + prow, pf4, v[4 + u]);
+                        place(st.pos, 4 * u + fs, H + prow, pf4, v[u]);
+                        place(st.pos, 4 * u + fs, H - 8 + prow, pf4, v[4 + u]);
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     asm volatile("bar.sync 1, %0;" ::"r"(32 * TC2_LOADERS) : "memory");
@@ -543,7 +551,7 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                     if (lane == 0) mbar_arrive(&win_early[p]);
                     const long long q2 = P.prof ? clock64() : 0;
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) place(st.pos, 2 * u + sh, 16 + prow, pf4, v[u]);
+                    for (int u = 0; u < 8; ++u) place(st.pos, 2 * u + sh, H + prow, pf4, v[u]);
                     publish(&win_late[p]);
                     if (P.prof) { t_ld += q1 - q0; t_slot += q2 - q1; t_place += clock64() - q2; }
                     next_loads(k + 2);

@@ -73,12 +73,14 @@ def c1_sweep(n, fs=44100, phase=0.0):
     return (0.1 * scipy.signal.chirp(t, 20.0, n / fs, 20000.0, method="logarithmic", phi=phase)).astype(np.float32)
 
 
-def test_c1_full_ten_second_sweep_431_blocks():
+def test_c1_full_ten_second_sweep_431_blocks(monkeypatch):
     """C1 as BASELINE.json states it: 251-tap Kaiser band-pass designed at 176.4 kHz, 44.1 kHz mono, 4x up-sample ->
     FIR -> [::4], 1024-frame blocks, the whole 10 s logarithmic sweep = 431 blocks (last one zero padded), TPDF ->
     int24.  (a) float output of stream 0 against the oracle chain; (b) the int24 run is bit-identical to the numpy
-    Philox statement over all 441 344 samples (the dither counter crosses 431 block boundaries); (c) a second engine fed
-    one block at a time, with its state saved at block 200 and restored into a fresh engine, gives the same bits."""
+    Philox statement over all 441 344 samples (the dither counter crosses 431 block boundaries); (c) the run cut at block
+    200, its state saved and restored into a fresh engine, gives the same bits - on the tensor kernel (multi-block calls of the
+    collapsed 95-tap chain) and, fed one block at a time, on the FFMA2 kernel (which a single 1024-frame block of a filter
+    this short selects; the two kernels agree to the float tolerance, not to the bit, so each is compared with itself)."""
     fs, U, B = 44100, 4, 1024
     h = design.create_fir_filter(cutoff=[500, 8000], numtaps=251, window_type="kaiser", filter_type="bandpass", samplerate=fs * U)
     h_up = design.design_upsampler(U, fs)
@@ -99,12 +101,23 @@ def test_c1_full_ten_second_sweep_431_blocks():
         yq = np.concatenate(list(eq.process_blocks(xb).cpu().numpy()), axis=1)
     np.testing.assert_array_equal(yq, dq.epilogue(yf, dq.FMT_I24_IN_I32, dq.DITHER_TPDF, 2024, np.arange(S), 0))
     with BatchFirEngine(h, out_format="i24", dither="tpdf", seed=2024, **kw) as e1:
+        first = list(e1.process_blocks(xb[:200]).cpu().numpy())
+        blob = e1.get_state()
+    with BatchFirEngine(h, out_format="i24", dither="tpdf", seed=2024, **kw) as e2:
+        e2.set_state(blob)
+        rest = list(e2.process_blocks(xb[200:]).cpu().numpy())
+    np.testing.assert_array_equal(np.concatenate(first + rest, axis=1), yq)
+    monkeypatch.setenv("AFP_NO_TC2", "1")
+    with BatchFirEngine(h, out_format="i24", dither="tpdf", seed=2024, **kw) as e0:
+        yq0 = np.concatenate(list(e0.process_blocks(xb).cpu().numpy()), axis=1)
+    assert np.abs(yq0.astype(np.int64) - yq).max() <= 1                     # the two kernels: at most one code apart
+    with BatchFirEngine(h, out_format="i24", dither="tpdf", seed=2024, **kw) as e1:
         first = [e1.process(xb[i]).cpu().numpy() for i in range(200)]
         blob = e1.get_state()
     with BatchFirEngine(h, out_format="i24", dither="tpdf", seed=2024, **kw) as e2:
         e2.set_state(blob)
         rest = [e2.process(xb[i]).cpu().numpy() for i in range(200, nblk)]
-    np.testing.assert_array_equal(np.concatenate(first + rest, axis=1), yq)
+    np.testing.assert_array_equal(np.concatenate(first + rest, axis=1), yq0)
 
 
 def test_dither_counter_past_2_to_32_samples():
