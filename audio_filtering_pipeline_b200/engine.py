@@ -217,9 +217,10 @@ class BatchFirEngine:
 
     def process_blocks(self, x, out=None):
         """``n`` consecutive blocks on device tensors: ``x`` float32 cuda [n, S, frames] (unit frame stride) ->
-        [n, S, out_cols].  Bit-identical to ``n`` calls of :meth:`process`; a chain that is one long U = 1 filter
-        runs as a single launch that keeps [history | block] in shared memory from block to block
-        (afp_process_blocks).  Asynchronous on torch's current stream."""
+        [n, S, out_cols].  The result of ``n`` calls of :meth:`process` (to the bit when both run on the same kernel,
+        see include/afp.h); a chain that is one filter - U = 1, the collapsed reference chain, or a 2x / 4x polyphase
+        interpolator - runs as a single tensor-core launch that keeps [history | block] in shared memory from block
+        to block (afp_process_blocks).  Asynchronous on torch's current stream."""
         import torch
         if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 3 or x.shape[1] != self.n_streams:
             raise ValueError("x must be a float32 CUDA tensor of shape [n_blocks, n_streams, frames]")

@@ -171,11 +171,14 @@ int afp_process(afp_ctx* ctx, const float* in_dev, int64_t in_pitch, void* out_d
                 int32_t frames, void* cuda_stream);
 /* n_blocks consecutive blocks (the buffers of n_blocks consecutive callbacks) in one call: block b of stream s
  * starts at in_dev[b*in_block_stride + s*in_pitch] / out_dev[b*out_block_stride + s*out_pitch] (strides in
- * elements, bytes for AFP_FMT_I24_PACKED).  Results are bit-identical to n_blocks afp_process calls.  For a chain
- * that is a single long U = 1 filter (>= 176 taps; the collapsed reference chain included) with blocks of a multiple
- * of 512 frames this is ONE launch: the CTA that owns 16 streams walks their blocks with [history | block] resident
- * in shared memory, the carried history (the reference's sliding input_buffer, stream_process.py:45-46,97-98)
- * is read once and written once.  Every other chain runs block by block. */
+ * elements, bytes for AFP_FMT_I24_PACKED).  The results equal those of n_blocks afp_process calls - to the bit when
+ * both forms run on the same kernel (always from 112 taps up; a shorter filter takes the tensor kernel only in calls of
+ * >= 8 x 512 frames per stream and the packed-FFMA2 kernel otherwise: the two agree to ~1e-7, not to the bit).  For a
+ * chain that is a single filter - U = 1 from 48 taps (the collapsed reference chain included), or a polyphase
+ * interpolator with U = 2 / 4 from 40 taps per phase - with blocks of a multiple of 512 frames this is ONE launch: the
+ * CTA that owns 16 streams walks their blocks with [history | block] resident in shared memory, the carried history
+ * (the reference's sliding input_buffer, stream_process.py:45-46,97-98) is read once and written once.  Every other
+ * chain runs block by block. */
 int afp_process_blocks(afp_ctx* ctx, const float* in_dev, int64_t in_pitch, int64_t in_block_stride, void* out_dev,
                        int64_t out_pitch, int64_t out_block_stride, int32_t frames, int32_t n_blocks, void* cuda_stream);
 /* The tensor path for long filters splits every sample into two FP16 numbers and therefore needs |x| <= 65504
