@@ -596,8 +596,8 @@ int launch_stage_tc2_grouped(afp_ctx* c, Stage& s, const float* in, long long in
     P.fast_out = (aligned16(out) && (out_pitch * eb) % 16 == 0 && (out_bstride * eb) % 16 == 0) ? 1 : 0;
     P.seed = c->cfg.seed; P.sample_base = sample_base; P.stream_id0 = c->cfg.first_stream_id + s0;
     P.gain = 1.0f; P.dither_lsb = std::ldexp(1.0f, -(c->dither_bits - 1));
-    P.epi_stage = afp::tc2_smem_bytes(s.tc2_chunks, true) <= kMaxSmem && !env_flag("AFP_TC2_NO_STAGE") ? 1 : 0;
-    const int smem = afp::tc2_smem_bytes(s.tc2_chunks, P.epi_stage != 0);
+    P.epi_stage = afp::tc2_smem_bytes(s.tc2_chunks, true, 1, true) <= kMaxSmem && !env_flag("AFP_TC2_NO_STAGE") ? 1 : 0;
+    const int smem = afp::tc2_smem_bytes(s.tc2_chunks, P.epi_stage != 0, 1, true);
     if (smem > kMaxSmem) return AFP_OK;
     const int grid = ns < c->n_sm ? ns : c->n_sm;
     afp_kernel_tc2_grouped()<<<grid, afp::TC2_THREADS, smem, stream>>>(P);

@@ -97,8 +97,10 @@ constexpr int TC2_STAGE_BYTES = TC2_EPIS * 32 * TC2_STAGE_STRIDE * 16;  // one 3
 __host__ __device__ constexpr int tc2_hist_rows(int n_chunks) { return n_chunks - 1 <= 8 ? 8 : 16; }
 __host__ __device__ constexpr int tc2_tile_rows(int n_chunks) { return tc2_hist_rows(n_chunks) + 16 + 9; }     // ring + 8 repeated + 1
 __host__ __device__ constexpr int tc2_tile_bytes(int n_chunks) { return TC2_STREAMS * (TC2_R / 8) * tc2_tile_rows(n_chunks) * 16; }
-__host__ __device__ constexpr int tc2_smem_bytes(int n_chunks, bool stage = false, int U = 1) {
-    return 2 * tc2_tile_bytes(n_chunks) + 2 * tc2_n_cores(n_chunks, U) * 128 + 256 + (stage ? TC2_STAGE_BYTES : 0);
+__host__ __device__ constexpr int tc2_smem_bytes(int n_chunks, bool stage = false, int U = 1, bool grouped = false) {
+    // (the per-stream-filter instantiation keeps the 16-row geometry as a compile-time constant: its loaders have no
+    // registers to spare for a runtime one - 170 vs 134 Gsamples/s on C3 with 4096 gain sets)
+    return 2 * (grouped ? TC2_TILE_BYTES : tc2_tile_bytes(n_chunks)) + 2 * tc2_n_cores(n_chunks, U) * 128 + 256 + (stage ? TC2_STAGE_BYTES : 0);
 }
 static_assert(tc2_tile_bytes(17) == TC2_TILE_BYTES, "16 history rows: the 41-row tile");
 
@@ -262,7 +264,7 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
     extern __shared__ __align__(128) unsigned char tc2_smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned char* tile_hi = tc2_smem;
-    const int H = tc2_hist_rows(P.n_chunks);   // history rows of a window (16 cover 1025 taps per phase; up to 513: 8)
+    const int H = GROUPED ? 16 : tc2_hist_rows(P.n_chunks);   // history rows of a window (16 cover 1025 taps per phase; up to 513: 8)
     const int RING = H + 16, ROWS = RING + 9, A_LBO = ROWS * 16, PITCH = (TC2_R / 8) * A_LBO, TILE = TC2_STREAMS * PITCH;
     unsigned char* tile_lo = tile_hi + TILE;
     unsigned char* w_hi = tile_lo + TILE;       // core slots: [hi q | lo q], 256 B per index
