@@ -105,3 +105,67 @@ def test_spectrum_kernel_formulation_equals_rfft(n):
     assert np.abs(lin_g - lin_r).max() <= 1e-5 * lin_r.max()
     strong = ref >= ref.max() - 60
     assert np.abs(got[strong] - ref[strong]).max() <= 0.01
+
+
+# ---- split-FP16 tensor kernel (csrc/afp_fir_tc2.cuh): the Toeplitz / Hankel-core form, U = 1 and polyphase ----------------
+def _hankel_cores(h, U):
+    """tc2_build_cores in numpy: C_q[jj][e] = g[8 q + jj + U e], g[t] = h[t - 63 U]; D + 1 chunks."""
+    n, R = len(h), 64
+    D = (n - 1 + (R - 1) * U) // (R * U)
+    Q = 8 * U * (D + 2) - U
+    q, jj, e = np.meshgrid(np.arange(Q), np.arange(8), np.arange(8), indexing="ij")
+    k = 8 * q + jj + U * e - U * (R - 1)
+    return np.where((k >= 0) & (k < n), h[np.clip(k, 0, n - 1)], 0.0), D
+
+
+def _tensor_form(h, x, U):
+    """What the kernel's MMAs compute, written with the same indices: rows of 64 input samples stored reversed, chunk d joins
+    row m - d to row m through the core array only (B descriptor: core 8 U d + U (i / 8) + c / 8, element (c % 8, i % 8))."""
+    R = 64
+    cores, D = _hankel_cores(h, U)
+    rows = len(x) // R
+    xr = np.concatenate([np.zeros(D * R), x]).reshape(D + rows, R)[:, ::-1]        # row r of the padded signal, element i = sample R-1-i
+    i = np.arange(R)
+    c = np.arange(R * U)
+    out = np.zeros((rows, R * U))
+    for d in range(D + 1):
+        qi = (8 * U * d + U * (i[:, None] // 8) + c[None, :] // 8)                    # [i, c] core index
+        B = cores[qi, c[None, :] % 8, i[:, None] % 8]                                # W_d[i][c]
+        out += xr[D - d: D - d + rows] @ B
+    return out.reshape(-1)
+
+
+@pytest.mark.parametrize("U,n", [(1, 51), (1, 64), (1, 65), (1, 251), (1, 1001), (1, 1025), (2, 96), (2, 251), (2, 1001), (4, 160),
+                                 (4, 251), (4, 1001), (4, 2049)])
+def test_hankel_core_form_equals_the_polyphase_fir(U, n):
+    """One array of 8 x 8 cores indexed by 8 U d + U (i/8) + c/8 reproduces  out[U m + p] = sum_k h[U k + p] x[m - k]
+    (scipy.signal.upfirdn) for every chunk, k-step and column group - the identity behind the resident tap cores, the
+    N = 128 walk over [hi | lo] slots and the polyphase form (64 U output columns per 64-sample row)."""
+    from scipy import signal
+    rng = np.random.default_rng(n * 8 + U)
+    h = rng.standard_normal(n) / n
+    x = rng.standard_normal(64 * 24)
+    ref = signal.upfirdn(h, x, up=U)[: len(x) * U]
+    np.testing.assert_allclose(_tensor_form(h, x, U), ref, rtol=0, atol=1e-12)
+    cores, D = _hankel_cores(h, U)
+    assert D + 1 <= 17 or n > 1025 * U              # the kernel's limit: 17 chunks = 1025 taps per phase
+    assert cores.shape[0] == 8 * U * (D + 2) - U    # tc2_n_cores
+
+
+def test_fp16_split_keeps_22_bits():
+    """x = hi + lo 2^-11 with hi = fp16(x), lo = fp16((x - hi) 2^11): three products (hi*hi, hi*lo, lo*hi) leave a relative
+    error of ~2^-22 per term - what the kernel's 1e-8 absolute error at audio levels rests on."""
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-1, 1, 4096).astype(np.float32)
+    w = (rng.standard_normal(4096) / 64).astype(np.float32)
+
+    def split(v):
+        hi = v.astype(np.float16)
+        lo = ((v - hi.astype(np.float32)) * np.float32(2048)).astype(np.float16)
+        return hi.astype(np.float64), lo.astype(np.float64)
+
+    xh, xl = split(x)
+    wh, wl = split(w)
+    approx = xh * wh + (xh * wl + xl * wh) / 2048.0
+    exact = x.astype(np.float64) * w.astype(np.float64)
+    assert np.abs(approx - exact).max() <= 2.0 ** -21 * np.abs(exact).max()
