@@ -258,10 +258,11 @@ int build_stage(afp_ctx* c, Stage& s, int kind, int U, const double* taps, int n
     const int tc_min = std::getenv("AFP_TC_MIN_TAPS") ? std::atoi(std::getenv("AFP_TC_MIN_TAPS")) : 400;
     const int tc2_min = std::getenv("AFP_TC_MIN_TAPS") ? std::atoi(std::getenv("AFP_TC_MIN_TAPS")) : 48;
     const bool tc_any = U == 1 && n_sub == 1 && !env_flag("AFP_NO_TC");
-    // Polyphase interpolators (U = 2 / 4) run on the same kernel with wider Toeplitz rows (tc2_build_cores): from 40 taps per
-    // phase up (below, the FFMA2 row kernel is already at 0.7-0.9 of the HBM roof).
+    // Polyphase interpolators (U = 2 / 4) run on the same kernel with wider Toeplitz rows (tc2_build_cores).  Crossovers
+    // against the FFMA2 row kernel, one 1024-frame block of 65536 streams per launch (bench/quick_perf.py): U = 2: 63 taps
+    // 638 vs 719 Gsamples/s, 79 taps 635 vs 566; U = 4: 101 taps 958 vs 916, 129 taps 959 vs 768.
     const bool tc2_up = (U == 2 || U == 4) && n_sub == 1 && !env_flag("AFP_NO_TC") && !env_flag("AFP_NO_TC2_UP") &&
-                        n >= (std::getenv("AFP_TC_MIN_TAPS") ? std::atoi(std::getenv("AFP_TC_MIN_TAPS")) : 40 * U);
+                        n >= (std::getenv("AFP_TC_MIN_TAPS") ? std::atoi(std::getenv("AFP_TC_MIN_TAPS")) : (U == 2 ? 72 : 96));
     const bool tc1_ok = tc_any && n >= tc_min, tc2_ok = (tc_any && n >= tc2_min || tc2_up) && !env_flag("AFP_NO_TC2");
     const bool tc_ok = tc1_ok || tc2_ok;
     // History length = padded taps per phase.  A multiple of 16 (every tile size divides it, so the two
