@@ -1060,6 +1060,8 @@ int afp_create(const afp_config* cfg, afp_ctx** out_ctx) {
             if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, split-FP16 tensor path)");
         }
     }
+    e = cudaFuncSetAttribute((const void*)afp_kernel_tc2(afp::epi_code(afp::FMT_F32, afp::DITHER_RPDF), 1), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, split-FP16 tensor path, float dither)");
     e = cudaFuncSetAttribute((const void*)afp_kernel_tc2_grouped(), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, split-FP16 tensor path, grouped)");
     for (int variant : {afp::AGC_FAST, afp::AGC_EXACT, afp::AGC_CHECKED, afp::AGC_PROBE_F32}) {

@@ -9,6 +9,7 @@ afp::tc2_kern_t afp_kernel_tc2(int epi, int up) {
     if (up == 4) return epi == kEpiF32 ? (tc2_kern_t)fir_tc2_kernel<kEpiF32, false, 4> : (tc2_kern_t)fir_tc2_kernel<EPI_GENERIC, false, 4>;
     if (up != 1) return nullptr;
     switch (epi) {
+        case epi_code(FMT_F32, DITHER_RPDF): return (tc2_kern_t)fir_tc2_kernel<epi_code(FMT_F32, DITHER_RPDF)>;   // C1: the reference's float dither
         case kEpiF32: return (tc2_kern_t)fir_tc2_kernel<kEpiF32>;
         case kEpiI24T: return (tc2_kern_t)fir_tc2_kernel<kEpiI24T>;
         case kEpiI16T: return (tc2_kern_t)fir_tc2_kernel<kEpiI16T>;
