@@ -1,5 +1,6 @@
 // Tensor-core FIR, second form: split-FP16 operands, Hankel tap cores resident in shared memory, consecutive
-// blocks of a stream group processed by one CTA (afp_process_blocks).  Long U = 1 filters (400..1025 taps).
+// blocks of a stream group processed by one CTA (afp_process_blocks).  U = 1 filters of 48..1025 taps and 2x / 4x polyphase
+// interpolators of up to 1025 taps per phase (tc2_build_cores).
 //
 // Same Toeplitz blocking as afp_fir_tc.cuh - rows of R = 64 samples, y[R m + j] = sum_d sum_i X[m-d][i] W_d[i][j],
 // the A operand of chunk d being the one sample tile moved up d rows through the descriptor start address -
@@ -11,14 +12,13 @@
 //     which turns the tap block into a Hankel matrix,  W'_d[i][j] = hp[R d + i + j],  hp[t] = h[t - (R-1)].
 //     In the K-major core-matrix layout a core (8 rows j x 16 bytes of i) of a Hankel matrix depends on
 //     (i0 + j0) only, so ONE array of cores  C_q[jj][e] = hp[8 q + jj + e]  serves every chunk, k-step and
-//     column group: the B descriptor of (chunk d, k-step ks) starts at core 8 d + 2 ks with leading and
-//     stride byte offsets both 128.  1001 taps -> 143 cores x 128 B = 18 KB (+ the same for the low parts),
-//     loaded once per CTA.
+//     column group: the B descriptor of (chunk d, k-step ks) starts at core index 8 d + 2 ks.  1001 taps -> 143
+//     core indices x (128 B high part + 128 B low part) = 36 KB, loaded once per CTA.
 //  2. FP16 split instead of TF32 split.  x = hi + lo * 2^-11 with hi = fp16(x), lo = fp16((x - hi) * 2^11),
 //     the same for the taps: 11 + 11 significant bits per operand, exactly what the 3xTF32 split keeps, but
 //     kind::f16 runs at twice the rate (K = 16 per instruction at the cost of tf32's K = 8) and a sample
-//     needs 4 bytes of shared memory (hi + lo) instead of 8, which is what makes room for two window
-//     positions (below).  Products  hi*hi and hi*lo' come out of ONE N = 128 instruction: the core array holds the
+//     needs 4 bytes of shared memory (hi + lo) instead of 8, which is what makes room for the ring of window rows
+//     (below).  Products  hi*hi and hi*lo' come out of ONE N = 128 instruction: the core array holds the
 //     high and the low core of every index side by side (slot 2q / 2q + 1), so a B descriptor that walks the slots
 //     one by one (stride 128 B) sees [hi core q | lo core q | hi core q+1 | ...] - accumulator A, column 16 g + c =
 //     x_hi * W_hi column 8 g + c, column 16 g + 8 + c = x_hi * W_lo' of the same column.  lo'*hi is an N = 64
@@ -27,14 +27,21 @@
 //     8 KB + 6 KB = 112 clk per chunk and k-step where three N = 64 instructions took 144.  Range: |x| < 65504
 //     (audio is +-1); a larger sample sets the context's range flag and the call reports it.
 //  3. The CTA keeps a stream group for all the blocks of the call.  A step = 16 streams x 8 rows (512
-//     samples); its window [H history rows | 8 new rows] slides over a ring of 32 tile rows (tc2_step), so the
+//     samples); its window [H history rows | 8 new rows] slides over a ring of H + 16 tile rows (tc2_step; H = 16, or 8
+//     for filters of up to 513 taps per phase), so the
 //     loader warps bring in only the 8 new rows of step k+1 while the tensor pipe works on step k and the epilogue
 //     warps drain step k-1 from TMEM (two accumulator sets).  History is read from the carried buffer only for the
 //     first step of a call and written once at its end; in between the "history" is the previous blocks' input,
 //     still in shared memory.
 //
+//  4. Warps: 1 MMA issuer, 16 loaders (two groups of 8 alternate steps), 8 epilogue.  A persistent CTA reads HBM at a rate set
+//     by the number of LOADING WARPS - a warp sustains ~4 128-bit loads whatever it issues (bench/microbench/stream_mlp.cu:
+//     4 / 8 / 16 warps read 3.0 / 5.1 / 6.6 TB/s) - so 16 warps x 8 loads replaced 8 x 16 (51 taps: 456 -> 553 Gsamples/s).
+//     25 warps leave 72 registers per thread, which shapes the epilogue (16 columns at a time for the quantised formats).
+//
 // Cost model (measured): an M = 128, K = 16 MMA takes max(pipe, operand bytes / 128 B/clk): N = 64 48 clk, N = 128
-// 64 clk;  a step is n_chunks x 4 k-steps x (64 + 48) clk.  1001 taps: 17 x 4 x 112 = 7.6 kclk per 8192 samples.
+// 64 clk;  a U = 1 step is n_chunks x 4 k-steps x (64 + 48) clk: 1001 taps 17 x 4 x 112 = 7.6 kclk per 8192 samples; a
+// polyphase step n_chunks x 4 x 3 x 64 clk per 128 output columns: 1001 taps at 2x 9 x 768 = 6.9 kclk per 16384 samples.
 #pragma once
 #include <cstdint>
 #include <cuda_fp16.h>
@@ -167,17 +174,16 @@ __device__ __forceinline__ void tc2_split4(const float4& v, uint2& hi, uint2& lo
 }
 
 // Where the window of a step lives - the same function in the MMA and the loader role.
-// A window is 24 rows [16 history | 8 new].  The stream tile is a RING of 32 rows (physical rows 32..39 repeat rows 0..7, so
-// the eight consecutive rows an MMA reads never wrap): step k of a stream group has its window at ring rows 8 k .. 8 k + 23
-// (mod 32) and writes only its 8 NEW rows, into the eight rows that are not part of the previous step's window - the oldest
-// rows of the step before that, free once that step's MMAs are done.  Only the first step of a group loads a whole window,
-// and of that only the rows its MMAs read (chunk d reads window rows 16 - d .. 23 - d: a 251-tap filter 12 rows, not 24).
+// A window is H + 8 rows [H history | 8 new], H = 16 or 8 (tc2_hist_rows).  The stream tile is a RING of H + 16 rows (the
+// physical rows after it repeat rows 0..7, so the eight consecutive rows an MMA reads never wrap): step k of a stream group
+// has its window at ring rows 8 k .. 8 k + H + 7 (mod H + 16) and writes only its 8 NEW rows, into the eight rows that are not
+// part of the previous step's window - the oldest rows of the step before that, free once that step's MMAs are done.  Only
+// the first step of a group loads a whole window (chunk d reads window rows H - d .. H + 7 - d).
 // (The first version walked three fixed positions of a 40-row tile and reloaded all 24 rows on every third step; the
 // probe counters showed the MMA warp waiting for exactly those reloads: 6.1 of 8.0 kclk per step at 51 taps.)
 struct Tc2Step { int pos; bool fresh; };
-// Window start of the next step given the previous step's: +8 inside a group; a new group starts 24 rows on, so that
-// its eight OLDEST rows are the ring rows the previous step's window does not cover - they can be written while that step's
-// MMAs still run (long filters only read them; the other sixteen rows wait for those MMAs).  `w` starts at 8.
+// Window start of the next step given the previous step's: +8 inside a group; a new group starts a whole window (H + 8
+// rows) on, so that its eight OLDEST rows are the ring rows the previous step's window does not cover.  `w` starts at 8.
 __device__ __forceinline__ Tc2Step tc2_step(int& w, int k, int H) {      // (ring of H + 16 rows, window of H + 8)
     w += k == 0 ? H + 8 : 8;
     if (w >= H + 16) w -= H + 16;
