@@ -443,13 +443,40 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                 }
                 return __ldg(reinterpret_cast<const float4*>(src));
             };
+            // One filter set per batch: a thread's loads of one batch share row, column, block and frame - ONE address
+            // computation (an integer division by the block length among it), then a stream pitch per load.  (Written as
+            // eight fetch_of calls the compiler repeats the division per load: ~30 instructions each.)
+            struct Loc { const float* base; long long pitch; };          // base == nullptr: before the carried samples - zeros
+            auto locate = [&](int k, int wrow, int f4) -> Loc {
+                const int t = k * TC2_STEP - H * TC2_R + wrow * TC2_R + f4 * 4;
+                if (t < -P.hist_len) return Loc{nullptr, 0};
+                if (t < 0) return Loc{P.hist_in + (P.hist_len + t), P.hist_pitch};
+                const int b_ = t / P.frames, f = t - b_ * P.frames;
+                return Loc{P.in + (long long)b_ * P.in_block_stride + f, P.in_pitch};
+            };
+            auto fetch_at = [&](const Loc& L, int g, int sl) -> float4 {
+                const int s = g * TC2_STREAMS + sl;
+                return (L.base && s < P.n_streams) ? __ldg(reinterpret_cast<const float4*>(L.base + (long long)s * L.pitch))
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+            };
             auto fetch = [&](int k, int sl, int wrow, int f4) -> float4 { return fetch_of(grp, k, sl, wrow, f4); };
             // a first window is loaded by both groups: this thread's streams there are fs + 4 u; its share of the two newest
             // batches: rows 16.. in v[0..3], rows 8.. in v[4..7]
             const int fs = 2 * lg + sh;
             const int grp_next = grp + gridDim.x;
-            auto fresh_fetch_next = [&](int u) -> float4 {
-                return u < 4 ? fetch_of(grp_next, 0, 4 * u + fs, H + prow, pf4) : fetch_of(grp_next, 0, 4 * (u - 4) + fs, H - 8 + prow, pf4);
+            // the two newest batches of group g's first window into v (rows H.. in v[0..3], rows H-8.. in v[4..7])
+            auto fresh_fetch_all = [&](int g) {
+                if (GROUPED) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        v[u] = fetch_of(g, 0, 4 * u + fs, H + prow, pf4);
+                        v[4 + u] = fetch_of(g, 0, 4 * u + fs, H - 8 + prow, pf4);
+                    }
+                } else {
+                    const Loc a = locate(0, H + prow, pf4), b = locate(0, H - 8 + prow, pf4);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { v[u] = fetch_at(a, g, 4 * u + fs); v[4 + u] = fetch_at(b, g, 4 * u + fs); }
+                }
             };
             auto place = [&](int pos, int sl, int wrow, int f4, const float4& v) {
                 uint2 hi, lo;
@@ -473,11 +500,16 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
             // its share of the next stream group's first window, which then finds its two newest batches on their way.
             auto next_loads = [&](int kn) {
                 if (kn < n_steps) {
+                    if (GROUPED) {
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) v[u] = fetch(kn, 2 * u + sh, H + prow, pf4);
+                        for (int u = 0; u < 8; ++u) v[u] = fetch(kn, 2 * u + sh, H + prow, pf4);
+                    } else {
+                        const Loc a = locate(kn, H + prow, pf4);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) v[u] = fetch_at(a, grp, 2 * u + sh);
+                    }
                 } else if (grp_next < P.n_groups && D < 9) {
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) v[u] = fresh_fetch_next(u);
+                    fresh_fetch_all(grp_next);
                     pre_fresh = true;
                 }
             };
@@ -509,20 +541,20 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                     if (D >= 9) {
                         // the oldest batch lies outside the previous step's window: free once step kk-2 is done
                         // (its loads use the registers a prefetched window would sit in: next_loads prefetches for D < 9 only)
+                        if (GROUPED) {
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) v[u] = fetch(k, 4 * u + fs, prow, pf4);
+                            for (int u = 0; u < 4; ++u) v[u] = fetch(k, 4 * u + fs, prow, pf4);
+                        } else {
+                            const Loc a = locate(k, prow, pf4);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) v[u] = fetch_at(a, grp, 4 * u + fs);
+                        }
                         if ((int)p == lg && kk >= 2) mbar_wait(&mma_done[p], ((kk - 2) >> 1) & 1u);
                         asm volatile("bar.sync 2, %0;" ::"r"(32 * TC2_LOADERS) : "memory");
 #pragma unroll
                         for (int u = 0; u < 4; ++u) place(st.pos, 4 * u + fs, prow, pf4, v[u]);
                     }
-                    if (!pre_fresh) {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            v[u] = fetch(k, 4 * u + fs, H + prow, pf4);
-                            v[4 + u] = fetch(k, 4 * u + fs, H - 8 + prow, pf4);
-                        }
-                    }
+                    if (!pre_fresh) fresh_fetch_all(grp);
                     pre_fresh = false;
                     if ((int)p != lg && kk >= 1) mbar_wait(&mma_done[p ^ 1u], ((kk - 1) >> 1) & 1u);
                     asm volatile("bar.sync 3, %0;" ::"r"(32 * TC2_LOADERS) : "memory");
