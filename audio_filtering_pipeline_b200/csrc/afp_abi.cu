@@ -261,8 +261,8 @@ int build_stage(afp_ctx* c, Stage& s, int kind, int U, const double* taps, int n
     // Polyphase interpolators (U = 2 / 4) run on the same kernel with wider Toeplitz rows (tc2_build_cores).  Crossovers
     // against the FFMA2 row kernel, one 1024-frame block of 65536 streams per launch (bench/quick_perf.py): U = 2: 63 taps
     // 638 vs 719 Gsamples/s, 79 taps 635 vs 566; U = 4: 101 taps 958 vs 916, 129 taps 959 vs 768.
-    const bool tc2_up = (U == 2 || U == 4) && n_sub == 1 && !env_flag("AFP_NO_TC") && !env_flag("AFP_NO_TC2_UP") &&
-                        n >= (std::getenv("AFP_TC_MIN_TAPS") ? std::atoi(std::getenv("AFP_TC_MIN_TAPS")) : (U == 2 ? 72 : 96));
+    const bool tc2_up = U >= 2 && U <= 4 && n_sub == 1 && !env_flag("AFP_NO_TC") && !env_flag("AFP_NO_TC2_UP") &&
+                        n >= (std::getenv("AFP_TC_MIN_TAPS") ? std::atoi(std::getenv("AFP_TC_MIN_TAPS")) : (U == 2 ? 72 : (U == 3 ? 84 : 96)));
     const bool tc1_ok = tc_any && n >= tc_min, tc2_ok = (tc_any && n >= tc2_min || tc2_up) && !env_flag("AFP_NO_TC2");
     const bool tc_ok = tc1_ok || tc2_ok;
     // History length = padded taps per phase.  A multiple of 16 (every tile size divides it, so the two
@@ -532,7 +532,7 @@ int launch_stage_tc2(afp_ctx* c, Stage& s, const float* in, long long in_pitch, 
                      long long out_pitch, long long out_bstride, int frames, int n_blocks, int fmt, int dither,
                      unsigned long long sample_base, int s0, int ns, cudaStream_t stream, bool* done) {
     *done = false;
-    if (!s.tc2_w || (s.U != 1 && s.U != 2 && s.U != 4) || env_flag("AFP_NO_TC2")) return AFP_OK;
+    if (!s.tc2_w || s.U < 1 || s.U > 4 || env_flag("AFP_NO_TC2")) return AFP_OK;
     if (!c->group_of_stream.empty()) return AFP_OK;   // per-group filters: launch_stage_tc2_grouped / the row-pair kernel
     if (frames < afp::TC2_STEP || frames % afp::TC2_STEP != 0 || n_blocks < 1) return AFP_OK;
     if ((long long)frames * n_blocks > (1 << 30)) return AFP_OK;
@@ -1055,7 +1055,7 @@ int afp_create(const afp_config* cfg, afp_ctx** out_ctx) {
             if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, grouped kernel)");
         }
     for (int epi : kAllEpi) {
-        for (int up : {1, 2, 4}) {
+        for (int up : {1, 2, 3, 4}) {
             e = cudaFuncSetAttribute((const void*)afp_kernel_tc2(epi, up), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
             if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaFuncSetAttribute(max dynamic smem, split-FP16 tensor path)");
         }
@@ -1679,7 +1679,7 @@ int afp_process_blocks(afp_ctx* c, const float* in, int64_t in_pitch, int64_t in
         // shared memory; the carried history is read once and written once
         bool done = false;
         // (the collapsed reference chain has its decimation folded into the base-rate filter: the stage itself runs with decim 1)
-        if ((s->U == 1 || ((s->U == 2 || s->U == 4) && c->group_of_stream.empty())) && (c->decim == 1 || s == &c->fused)) {
+        if ((s->U == 1 || (s->U >= 2 && s->U <= 4 && c->group_of_stream.empty())) && (c->decim == 1 || s == &c->fused)) {
             auto launch = c->group_of_stream.empty() ? launch_stage_tc2 : launch_stage_tc2_grouped;
             rc = launch(c, *s, in, in_pitch, in_block_stride, out, out_pitch / unit, out_block_stride / unit, frames, n_blocks,
                         c->cfg.out_format, c->cfg.dither, c->out_samples, 0, S, st, &done);

@@ -131,13 +131,13 @@ __host__ __device__ constexpr uint32_t tc2_idesc(int n) { return (1u << 4) | ((u
 // h = hi + lo * 2^-11 with hi = fp16(h), lo = fp16((h - hi) * 2^11).  Layout: hi core q in slot 2 q, lo core q in
 // slot 2 q + 1, 64 halves each.  Returns the chunk count D + 1.
 //
-// U = 2 / 4: the polyphase interpolator  out[U n + p] = sum_k h[U k + p] x[n - k]  (zero-stuff by U, FIR at the high rate,
+// U = 2 / 3 / 4: the polyphase interpolator  out[U n + p] = sum_k h[U k + p] x[n - k]  (zero-stuff by U, FIR at the high rate,
 // only the non-zero products) as the SAME Toeplitz form with wider rows: a row of R input samples makes U R consecutive
 // output samples, column c = U j + p, and the tap that joins element i of row m - d (sample R (m-d) + R-1 - i) to column c of
 // row m is  h[U (R d + j + i - (R-1)) + p] = g[U R d + U i + c],  g[t] = h[t - U (R-1)].  A core (8 columns x 8 elements)
 // again depends on one index only,  C_q[jj][e] = g[8 q + jj + U e]  with q = 8 U d + U (i / 8) + c / 8:  the next core in
-// K is U cores on, the next 8 columns one core on, 128 columns (16 cores) per instruction, 64 U columns per row in U / 2
-// passes.  One 64-sample window serves all U phases - the loaders do not change.  Layout: all hi cores, then all lo cores.
+// K is U cores on, the next 8 columns one core on, 128 columns (16 cores) per instruction, 64 U columns per row in passes
+// of 128 (3x: 128 + 64).  One 64-sample window serves all U phases - the loaders do not change.  Layout: all hi cores, then all lo cores.
 template <class VEC>
 inline int tc2_build_cores(const double* taps, int n, VEC& w, int U = 1) {
     const int D = (n - 1 + (TC2_R - 1) * U) / (TC2_R * U), Q = tc2_n_cores(D + 1, U);
@@ -281,9 +281,9 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
     uint64_t* acc_empty = bars + 6;     // [2] accumulator set drained
     uint64_t* acc_full = bars + 8;      // [2] accumulator set final (U = 4: a step fills a set twice, 128 output columns at a time)
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
-    static_assert(U == 1 || U == 2 || U == 4, "polyphase factors of the tensor kernel");
+    static_assert(U >= 1 && U <= 4, "polyphase factors of the tensor kernel");
     static_assert(!GROUPED || U == 1, "per-stream tap cores: U = 1 only");
-    constexpr int PASSES = U == 4 ? 2 : 1;   // accumulator fills per step
+    constexpr int PASSES = U >= 3 ? 2 : 1;   // accumulator fills per step: 128 output columns each (U = 3: 128 + 64)
 
     const int n_steps = GROUPED ? P.steps_per_slot : (P.frames / TC2_STEP) * P.n_blocks;   // steps of one work item
 
@@ -379,13 +379,14 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                                 // core index of (chunk d, k-step ks, pass h): 8 U d + 2 U ks + 16 h; 8 descriptor units per core
                                 const uint32_t c0_ = (uint32_t)(8 * U * d + 16 * h) * 8u;
                                 const uint32_t wl = (uint32_t)w_wide_d + c0_, wh = (uint32_t)w_hi_d + c0_;
+                                const uint32_t idesc_p = (U == 3 && h == 1) ? idesc : idesc_wide;   // 3x: the second pass has 64 columns
 #pragma unroll
                                 for (int ks = 0; ks < TC2_R / 16; ++ks) {
                                     const uint32_t ao = (uint32_t)(2 * ks * ROWS), wo = (uint32_t)(2 * U * ks) * 8u;
                                     const uint32_t f = (first && ks == 0) ? 0u : 1u;
-                                    umma_f16(acc_a, ah + ao, top_a, wh + wo, top_wh, idesc_wide, f);    // x_hi * W_hi   -> accumulator 0
-                                    umma_f16(acc_b, ah + ao, top_a, wl + wo, top_ww, idesc_wide, f);    // x_hi * W_lo'  -> accumulator 1
-                                    umma_f16(acc_b, al + ao, top_a, wh + wo, top_wh, idesc_wide, 1u);   // x_lo' * W_hi  -> accumulator 1
+                                    umma_f16(acc_a, ah + ao, top_a, wh + wo, top_wh, idesc_p, f);    // x_hi * W_hi   -> accumulator 0
+                                    umma_f16(acc_b, ah + ao, top_a, wl + wo, top_ww, idesc_p, f);    // x_hi * W_lo'  -> accumulator 1
+                                    umma_f16(acc_b, al + ao, top_a, wh + wo, top_wh, idesc_p, 1u);   // x_lo' * W_hi  -> accumulator 1
                                 }
                             }
                         }
@@ -737,11 +738,14 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                     mbar_wait(&acc_full[set], aph);
                     const long long r1 = P.prof ? clock64() : 0;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t taddr = tmem_base + ((uint32_t)(32 * quarter) << 16) + set * 256u + (uint32_t)(64 * half);
-                    const long long o0 = (long long)U * (ti - blk * P.frames) + 128 * h + 64 * half;   // within the output block
+                    const int cols_half = (U == 3 && h == 1) ? 32 : 64;       // this thread's columns of the fill (3x: 128 + 64 columns)
+                    const int nf = cols_half / W;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(32 * quarter) << 16) + set * 256u + (uint32_t)(cols_half * half);
+                    const long long o0 = (long long)U * (ti - blk * P.frames) + 128 * h + cols_half * half;   // within the output block
                     long long r2 = 0;
 #pragma unroll
                     for (int f = 0; f < 64 / W; ++f) {
+                        if (U == 3 && f >= nf) break;
                         const long long t0 = P.prof ? clock64() : 0;
                         float y[W];
 #pragma unroll
@@ -764,7 +768,7 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
                             for (int c = 0; c < 16; ++c)                               // y = acc0 + 2^-11 acc1
                                 y[16 * g + c] = __fmaf_rn(__uint_as_float(a1[c]), 4.8828125e-4f, __uint_as_float(a0[c]));
                         }
-                        if (f == 64 / W - 1) {
+                        if (f == nf - 1) {
                             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&acc_empty[set]);

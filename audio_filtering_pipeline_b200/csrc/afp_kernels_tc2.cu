@@ -4,8 +4,9 @@
 
 afp::tc2_kern_t afp_kernel_tc2(int epi, int up) {
     using namespace afp;
-    // polyphase interpolators (U = 2 / 4): plain float output specialised, everything else through the generic epilogue
+    // polyphase interpolators (U = 2 / 3 / 4): plain float output specialised, everything else through the generic epilogue
     if (up == 2) return epi == kEpiF32 ? (tc2_kern_t)fir_tc2_kernel<kEpiF32, false, 2> : (tc2_kern_t)fir_tc2_kernel<EPI_GENERIC, false, 2>;
+    if (up == 3) return epi == kEpiF32 ? (tc2_kern_t)fir_tc2_kernel<kEpiF32, false, 3> : (tc2_kern_t)fir_tc2_kernel<EPI_GENERIC, false, 3>;
     if (up == 4) return epi == kEpiF32 ? (tc2_kern_t)fir_tc2_kernel<kEpiF32, false, 4> : (tc2_kern_t)fir_tc2_kernel<EPI_GENERIC, false, 4>;
     if (up != 1) return nullptr;
     switch (epi) {

@@ -218,7 +218,7 @@ class BatchFirEngine:
     def process_blocks(self, x, out=None):
         """``n`` consecutive blocks on device tensors: ``x`` float32 cuda [n, S, frames] (unit frame stride) ->
         [n, S, out_cols].  The result of ``n`` calls of :meth:`process` (to the bit when both run on the same kernel,
-        see include/afp.h); a chain that is one filter - U = 1, the collapsed reference chain, or a 2x / 4x polyphase
+        see include/afp.h); a chain that is one filter - U = 1, the collapsed reference chain, or a 2x / 3x / 4x polyphase
         interpolator - runs as a single tensor-core launch that keeps [history | block] in shared memory from block
         to block (afp_process_blocks).  Asynchronous on torch's current stream."""
         import torch

@@ -48,6 +48,7 @@ int main(int argc, char** argv) {
     P.epi_stage = (!getenv("NOSTAGE") && afp::tc2_smem_bytes(n_chunks, true, U) <= 227 * 1024) ? 1 : 0;
     const int smem = afp::tc2_smem_bytes(n_chunks, P.epi_stage != 0, U);
     auto kern = U == 2 ? afp::fir_tc2_kernel<afp::epi_code(afp::FMT_F32, afp::DITHER_NONE), false, 2>
+                : U == 3 ? afp::fir_tc2_kernel<afp::epi_code(afp::FMT_F32, afp::DITHER_NONE), false, 3>
                 : U == 4 ? afp::fir_tc2_kernel<afp::epi_code(afp::FMT_F32, afp::DITHER_NONE), false, 4>
                 : getenv("P24") ? afp::fir_tc2_kernel<afp::epi_code(afp::FMT_I24_PACKED, afp::DITHER_TPDF)>
                 : getenv("I24") ? afp::fir_tc2_kernel<afp::epi_code(afp::FMT_I24_IN_I32, afp::DITHER_TPDF)> : afp::fir_tc2_kernel<afp::epi_code(afp::FMT_F32, afp::DITHER_NONE)>;
@@ -96,7 +97,7 @@ int main(int argc, char** argv) {
         ld += o[6]; slot += o[7]; place += o[8]; ew += o[9]; et += o[10]; es += o[11];
         tmax = std::max(tmax, o[0]);
     }
-    const double mma_clk = U == 1 ? (64.0 + 48.0) * n_chunks * 4 : 3 * 64.0 * n_chunks * 4 * (U / 2);   // U = 1: N = 128 + N = 64 per chunk and k-step; else 3 x N = 128 per pass
+    const double mma_clk = U == 1 ? (64.0 + 48.0) * n_chunks * 4 : 3 * 64.0 * n_chunks * 4 * (U / 2) + (U == 3 ? 3 * 48.0 * n_chunks * 4 : 0);   // U = 1: N = 128 + N = 64 per chunk and k-step; else 3 x N = 128 per pass
     printf("{\"taps\": %d, \"streams\": %d, \"frames\": %d, \"blocks\": %d, \"ms\": %.4f, \"gsamples_s\": %.1f, \"sm_mhz_from_clk\": %.0f, "
            "\"clk_per_step\": %.0f, \"model_mma_clk_per_step\": %.0f, \"wait_acc\": %.0f, \"wait_window\": %.0f, \"wait_shared_rows\": %.0f, \"issue\": %.0f, "
            "\"loader_load\": %.0f, \"loader_wait_slot\": %.0f, \"loader_split_store\": %.0f, \"epi_wait_mma\": %.0f, \"epi_tmem\": %.0f, \"epi_store\": %.0f}\n",

@@ -175,7 +175,7 @@ int afp_process(afp_ctx* ctx, const float* in_dev, int64_t in_pitch, void* out_d
  * both forms run on the same kernel (always from 112 taps up; a shorter filter takes the tensor kernel only in calls of
  * >= 8 x 512 frames per stream and the packed-FFMA2 kernel otherwise: the two agree to ~1e-7, not to the bit).  For a
  * chain that is a single filter - U = 1 from 48 taps (the collapsed reference chain included), or a polyphase
- * interpolator with U = 2 (from 72 taps) / 4 (from 96 taps) - with blocks of a multiple of 512 frames this is ONE launch: the
+ * interpolator with U = 2 / 3 / 4 (from 72 / 84 / 96 taps) - with blocks of a multiple of 512 frames this is ONE launch: the
  * CTA that owns 16 streams walks their blocks with [history | block] resident in shared memory, the carried history
  * (the reference's sliding input_buffer, stream_process.py:45-46,97-98) is read once and written once.  Every other
  * chain runs block by block. */

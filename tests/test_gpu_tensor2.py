@@ -100,20 +100,20 @@ def test_process_blocks_strided_views_and_int24():
 
 
 def test_process_blocks_falls_back_block_by_block_for_other_chains():
-    """A chain that is not one filter the tensor kernel takes (here a 3x interpolator: the kernel has the polyphase factors
-    2 and 4) runs block by block behind the same call."""
-    h = 3 * design.create_fir_filter(cutoff=[500, 8000], numtaps=251, window_type="kaiser", filter_type="bandpass",
-                                     samplerate=132300)
-    S, B, nb = 6, 1024, 3
+    """A call the tensor kernel does not take (here blocks of 1000 frames: it wants multiples of 512) runs block by block on
+    the FFMA2 kernels behind the same entry point."""
+    h = 4 * design.create_fir_filter(cutoff=[500, 8000], numtaps=251, window_type="kaiser", filter_type="bandpass",
+                                     samplerate=176400)
+    S, B, nb = 6, 1000, 3
     x = noise(S, B * nb)
     xb = torch.from_numpy(blocks_of(x, B)).cuda()
-    with BatchFirEngine(h, n_streams=S, max_frames=B, upsample=3, chain="dac") as eng:
+    with BatchFirEngine(h, n_streams=S, max_frames=B, upsample=4, chain="dac") as eng:
         y_one = torch.stack([eng.process(xb[i]) for i in range(nb)]).cpu().numpy()
         eng.reset()
         y_multi = eng.process_blocks(xb).cpu().numpy()
         assert eng.stage_info()[-1]["kernel"] == 2
     np.testing.assert_array_equal(y_multi, y_one)
-    assert_parity(unblock(y_multi)[0], rc.polyphase_upsample_whole(h, x[0], 3).astype(np.float32), "3x DAC chain")
+    assert_parity(unblock(y_multi)[0], rc.polyphase_upsample_whole(h, x[0], 4).astype(np.float32), "4x DAC chain, 1000-frame blocks")
 
 
 def test_small_and_full_scale_signals():
@@ -232,12 +232,14 @@ def test_short_filter_epilogues_bit_exact(fmt, dither, monkeypatch):
     np.testing.assert_array_equal(yq, ref)
 
 
-# Polyphase interpolators (U = 2 / 4) on the same kernel: wider Toeplitz rows (64 U output columns per 64-sample row), cores
+# Polyphase interpolators (U = 2 / 3 / 4) on the same kernel: wider Toeplitz rows (64 U output columns per 64-sample row), cores
 # C_q[jj][e] = g[8 q + jj + U e].  Phase lengths below / at / above a chunk boundary, one and several steps per group, a
 # ragged last stream group, block-by-block vs one multi-block call, and the quantised formats through the generic epilogue.
 @pytest.mark.parametrize("U,N,B,nb,S", [(2, 96, 512, 2, 5), (2, 251, 1024, 3, 37), (2, 501, 512, 5, 16), (2, 1001, 512, 4, 21),
                                         (2, 129, 1536, 2, 3), (4, 251, 512, 3, 19), (4, 501, 1024, 2, 33), (4, 1001, 512, 5, 7),
-                                        (4, 160, 512, 1, 2), (2, 251, 512, 2, 148 * 16 + 9)])
+                                        (4, 160, 512, 1, 2), (2, 251, 512, 2, 148 * 16 + 9),
+                                        (3, 90, 512, 2, 5), (3, 251, 1024, 3, 37), (3, 577, 512, 4, 18), (3, 1001, 1536, 2, 9),
+                                        (3, 192, 512, 1, 16)])
 def test_polyphase_interpolator_on_tensor_kernel(U, N, B, nb, S):
     h = U * design.create_fir_filter(cutoff=0.45 * 44100, numtaps=N, window_type="kaiser", samplerate=44100 * U)
     x = noise(min(S, 48), B * nb, amp=0.3, seed=7 * N + U)
@@ -255,7 +257,7 @@ def test_polyphase_interpolator_on_tensor_kernel(U, N, B, nb, S):
         assert_parity(y_multi[s], rc.polyphase_upsample_whole(h, x[s], U).astype(np.float32), f"U={U} N={N} B={B} s={s}")
 
 
-@pytest.mark.parametrize("U", [2, 4])
+@pytest.mark.parametrize("U", [2, 3, 4])
 @pytest.mark.parametrize("fmt,dither", [("i24", "tpdf"), ("i16", "none"), ("i24_packed", "tpdf"), ("f32", "rpdf")])
 def test_polyphase_epilogues_bit_exact(U, fmt, dither):
     N, B, nb, S = 251, 512, 3, 20

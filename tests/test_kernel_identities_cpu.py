@@ -135,7 +135,7 @@ def _tensor_form(h, x, U):
     return out.reshape(-1)
 
 
-@pytest.mark.parametrize("U,n", [(1, 51), (1, 64), (1, 65), (1, 251), (1, 1001), (1, 1025), (2, 96), (2, 251), (2, 1001), (4, 160),
+@pytest.mark.parametrize("U,n", [(1, 51), (1, 64), (1, 65), (1, 251), (1, 1001), (1, 1025), (2, 96), (2, 251), (2, 1001), (3, 90), (3, 251), (3, 1001), (4, 160),
                                  (4, 251), (4, 1001), (4, 2049)])
 def test_hankel_core_form_equals_the_polyphase_fir(U, n):
     """One array of 8 x 8 cores indexed by 8 U d + U (i/8) + c/8 reproduces  out[U m + p] = sum_k h[U k + p] x[m - k]
