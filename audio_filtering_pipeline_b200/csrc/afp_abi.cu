@@ -68,7 +68,7 @@ struct Stage {
     int tc_chunks[2] = {0, 0};
     // split-FP16 tensor kernel (afp_fir_tc2.cuh): Hankel tap cores [2][n_cores][8][8] halves, chunk count D + 1
     void* tc2_w = nullptr;
-    int tc2_cores = 0, tc2_chunks = 0;     // (U = 2 / 4: the polyphase form of the same kernel)
+    int tc2_cores = 0, tc2_chunks = 0;     // (U = 2 .. 4: the polyphase form of the same kernel)
     int last_kernel = 0;           // 0 = row-pair FFMA2, 1 = tcgen05 (3xTF32), 2 = single-row FFMA2, 3 = tcgen05 (split FP16)
     int last_T = 0;                // tile of the last launch (the single-row kernel picks its own)
     // per-launch host work of the single-row kernel that only depends on the stage: its tap-table image
@@ -258,9 +258,9 @@ int build_stage(afp_ctx* c, Stage& s, int kind, int U, const double* taps, int n
     const int tc_min = std::getenv("AFP_TC_MIN_TAPS") ? std::atoi(std::getenv("AFP_TC_MIN_TAPS")) : 400;
     const int tc2_min = std::getenv("AFP_TC_MIN_TAPS") ? std::atoi(std::getenv("AFP_TC_MIN_TAPS")) : 48;
     const bool tc_any = U == 1 && n_sub == 1 && !env_flag("AFP_NO_TC");
-    // Polyphase interpolators (U = 2 / 4) run on the same kernel with wider Toeplitz rows (tc2_build_cores).  Crossovers
+    // Polyphase interpolators (U = 2 .. 4) run on the same kernel with wider Toeplitz rows (tc2_build_cores).  Crossovers
     // against the FFMA2 row kernel, one 1024-frame block of 65536 streams per launch (bench/quick_perf.py): U = 2: 63 taps
-    // 638 vs 719 Gsamples/s, 79 taps 635 vs 566; U = 4: 101 taps 958 vs 916, 129 taps 959 vs 768.
+    // 638 vs 719 Gsamples/s, 79 taps 635 vs 566; U = 4: 101 taps 958 vs 916, 129 taps 959 vs 768; U = 3: 51 taps 834 vs 978, 101 taps 828 vs 684.
     const bool tc2_up = U >= 2 && U <= 4 && n_sub == 1 && !env_flag("AFP_NO_TC") && !env_flag("AFP_NO_TC2_UP") &&
                         n >= (std::getenv("AFP_TC_MIN_TAPS") ? std::atoi(std::getenv("AFP_TC_MIN_TAPS")) : (U == 2 ? 72 : (U == 3 ? 84 : 96)));
     const bool tc1_ok = tc_any && n >= tc_min, tc2_ok = (tc_any && n >= tc2_min || tc2_up) && !env_flag("AFP_NO_TC2");

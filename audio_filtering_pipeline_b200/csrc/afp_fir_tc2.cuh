@@ -1,5 +1,5 @@
 // Tensor-core FIR, second form: split-FP16 operands, Hankel tap cores resident in shared memory, consecutive
-// blocks of a stream group processed by one CTA (afp_process_blocks).  U = 1 filters of 48..1025 taps and 2x / 4x polyphase
+// blocks of a stream group processed by one CTA (afp_process_blocks).  U = 1 filters of 48..1025 taps and 2x .. 4x polyphase
 // interpolators of up to 1025 taps per phase (tc2_build_cores).
 //
 // Same Toeplitz blocking as afp_fir_tc.cuh - rows of R = 64 samples, y[R m + j] = sum_d sum_i X[m-d][i] W_d[i][j],
@@ -319,7 +319,7 @@ fir_tc2_kernel(const __grid_constant__ Tc2Params P) {
         // the narrow one the high cores only
         // U = 1.  B: the next core in K is the next index (256 B on); in N the wide product walks the slots (hi q, lo q, hi q+1,
         // ...), the narrow one the high cores only.
-        // U = 2 / 4 (polyphase interpolator, file header of tc2_build_cores): all high cores, then all low cores; the next core
+        // U = 2 .. 4 (polyphase interpolator, file header of tc2_build_cores): all high cores, then all low cores; the next core
         // in K is U cores on, in N one core on; 128 output columns per instruction.
         const uint32_t lo_off = U == 1 ? 0u : (uint32_t)P.n_cores * 128u;
         const uint64_t w_wide_d = U == 1 ? umma_desc(smem_u32(w_hi), 256, 128) : umma_desc(smem_u32(w_hi) + lo_off, U * 128, 128);
