@@ -334,7 +334,8 @@ _PROBE_CACHE = {}
 
 def pcie_probe(D, in_bytes, out_bytes, target_mib=384):
     """Concurrent pinned H2D + D2H copies in the byte ratio of an e2e step (the larger side `target_mib` MiB), on two streams,
-    all ranks at once.  Returns the seconds this pure copy pair needs per byte of step input (best of 5): the e2e ceiling."""
+    all ranks at once, six pairs back to back per timing.  Returns the seconds this pure copy pair needs per byte of step input
+    (best of 6 over two copy granularities): the e2e ceiling."""
     torch = D.torch
     key = round(out_bytes / in_bytes, 3)
     if key in _PROBE_CACHE:
@@ -346,17 +347,25 @@ def pcie_probe(D, in_bytes, out_bytes, target_mib=384):
     d_in, d_out = torch.empty(n_in, dtype=torch.float32, device=D.dev), torch.zeros(n_out, dtype=torch.float32, device=D.dev)
     s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
     best = None
-    for rep in range(6):
-        D.barrier()
-        t0 = time.perf_counter()
-        with torch.cuda.stream(s1):
-            d_in.copy_(h_in, non_blocking=True)
-        with torch.cuda.stream(s2):
-            h_out.copy_(d_out, non_blocking=True)
-        torch.cuda.synchronize()
-        dt = D.max(time.perf_counter() - t0)
-        if rep and (best is None or dt < best):
-            best = dt
+    pairs = 6      # back to back per timing, like the steps of the e2e leg: ranks drift apart and share the host links as they do there
+    # two forms, the faster one is the ceiling: whole buffers (best on one GPU), and 16 pieces per direction - the granularity of
+    # the engine's own pipeline, one block of all streams per copy (best when several ranks share the host links)
+    for pieces in (1, 16):
+        for rep in range(4):
+            D.barrier()
+            t0 = time.perf_counter()
+            for _ in range(pairs):
+                for c in range(pieces):
+                    a0, a1 = n_in * c // pieces, n_in * (c + 1) // pieces
+                    b0, b1 = n_out * c // pieces, n_out * (c + 1) // pieces
+                    with torch.cuda.stream(s1):
+                        d_in[a0:a1].copy_(h_in[a0:a1], non_blocking=True)
+                    with torch.cuda.stream(s2):
+                        h_out[b0:b1].copy_(d_out[b0:b1], non_blocking=True)
+            torch.cuda.synchronize()
+            dt = D.max(time.perf_counter() - t0) / pairs
+            if rep and (best is None or dt < best):
+                best = dt
     res = {"s_per_in_byte": best / (n_in * 4), "h2d_gbs": n_in * 4 / best / 1e9, "d2h_gbs": n_out * 4 / best / 1e9}
     _PROBE_CACHE[key] = res
     del h_in, h_out, d_in, d_out
@@ -381,7 +390,7 @@ def e2e_leg(D, eng, hx, hy, steps, in_bytes, out_bytes, samples_per_step, probe=
            "h2d_gbs": round(in_bytes * steps / te / 1e9, 1), "d2h_gbs": round(out_bytes * steps / te / 1e9, 1)}
     if probe:
         pr = pcie_probe(D, in_bytes, out_bytes)
-        out["ceiling"] = (f"bare concurrent pinned H2D + D2H copies in this step's byte ratio, all {D.world} ranks at once, best of 5: "
+        out["ceiling"] = (f"bare concurrent pinned H2D + D2H copies in this step's byte ratio, all {D.world} ranks at once, six pairs back to back, whole buffers or 16 pieces, best of 6: "
                           f"{pr['h2d_gbs']:.1f} GB/s in + {pr['d2h_gbs']:.1f} GB/s out per rank")
         out["ceiling_value"] = round(samples_per_step * D.world / (pr["s_per_in_byte"] * in_bytes) / 1e6, 2)
         out["frac"] = round(val / out["ceiling_value"], 3)
