@@ -542,7 +542,7 @@ def config_points(D, args, cpu, fma_peak, peaks_run, peaks_file):
         roof["launches_per_step"] = launches
         hx, hy = PinnedArray((NB, S, B), np.float32), PinnedArray((NB, S, cols), np.float32)
         hx.a[...] = x.cpu().numpy()
-        e2e = e2e_leg(D, eng, hx.a, hy.a, 3, S * B * NB * 4, n_out * 4, n_out)
+        e2e = e2e_leg(D, eng, hx.a, hy.a, 6, S * B * NB * 4, n_out * 4, n_out)
         hx.free(); hy.free()
         stage = eng.stage_info()
         eng.close()
