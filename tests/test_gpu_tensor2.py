@@ -136,6 +136,25 @@ def test_small_and_full_scale_signals():
         assert np.abs(y[s] - ref).max() <= 4e-6 * np.abs(ref).max() + 1e-9, f"signal {s}: split precision lost"
 
 
+@pytest.mark.parametrize("U", [2, 3, 4])
+def test_polyphase_full_scale_signals(U):
+    """The same worst case through the polyphase form: full-scale sines and a square wave into a 1001-tap U-times interpolator
+    (gain U), plus -120 dBFS noise."""
+    fs = 44100.0
+    h = U * design.create_fir_filter(cutoff=0.45 * fs, numtaps=1001, window_type="kaiser", samplerate=fs * U)
+    n = 512 * 5
+    t = np.arange(n) / fs
+    x = np.stack([0.999 * np.sin(2 * np.pi * 997.0 * t), 0.999 * np.sin(2 * np.pi * 15000.0 * t),
+                  1e-6 * np.random.default_rng(1).standard_normal(n), 0.999 * np.sign(np.sin(2 * np.pi * 50.0 * t))]).astype(np.float32)
+    with BatchFirEngine(h, n_streams=4, max_frames=512, upsample=U, chain="dac") as eng:
+        y = unblock(eng.process_blocks(torch.from_numpy(blocks_of(x, 512)).cuda()).cpu().numpy())
+        assert eng.stage_info()[-1]["kernel"] == 3
+    for s in range(4):
+        ref = rc.polyphase_upsample_whole(h, x[s], U)
+        assert_parity(y[s], ref.astype(np.float32), f"U={U} signal {s}")
+        assert np.abs(y[s] - ref).max() <= 4e-6 * np.abs(ref).max() + 1e-9, f"U={U} signal {s}: split precision lost"
+
+
 def test_state_roundtrip_across_process_blocks():
     h = taps_for(1001)
     S, B = 24, 512
