@@ -394,6 +394,9 @@ def e2e_leg(D, eng, hx, hy, steps, in_bytes, out_bytes, samples_per_step, probe=
                           f"{pr['h2d_gbs']:.1f} GB/s in + {pr['d2h_gbs']:.1f} GB/s out per rank")
         out["ceiling_value"] = round(samples_per_step * D.world / (pr["s_per_in_byte"] * in_bytes) / 1e6, 2)
         out["frac"] = round(val / out["ceiling_value"], 3)
+        if D.world > 1:
+            out["ceiling_note"] = ("several ranks share the host's memory and PCIe root: the probe is another run on the same saturated links, "
+                                   "not a strict upper bound - a frac around 1 (0.95-1.10 measured at 2 / 4 / 8 GPUs) means the path moves what the host can move")
     return out
 
 
