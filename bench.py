@@ -420,7 +420,8 @@ def tensor_block(n_taps, samples_per_s, peaks_run, peaks_file, upsample=1):
            "issued_tflops": round(issued, 1), "issued_over_algorithmic": round(3.0 * n_chunks * 64 / (-(-n_taps // U)), 3)}
     if peaks_run:
         # roof of the kernel's own instruction mix: U = 1: 2/3 of the flop at the N=128 rate, 1/3 at the N=64 rate
-        mix = 3.0 / (2.0 / peaks_run["n128"][0] + 1.0 / peaks_run["n64"][0]) if U == 1 else peaks_run["n128"][0]
+        # (3x polyphase: a 128- and a 64-column pass per row - the same 2 : 1 split; 2x / 4x: N=128 instructions only)
+        mix = 3.0 / (2.0 / peaks_run["n128"][0] + 1.0 / peaks_run["n64"][0]) if U in (1, 3) else peaks_run["n128"][0]
         out["measured_roof_n64_tflops"] = round(peaks_run["n64"][0], 1)
         out["measured_roof_n128_tflops"] = round(peaks_run["n128"][0], 1)
         out["measured_roof_n256_tflops"] = round(peaks_run["n256"][0], 1)
