@@ -253,7 +253,7 @@ int build_stage(afp_ctx* c, Stage& s, int kind, int U, const double* taps, int n
     // split-FP16 kernel (afp_fir_tc2.cuh) is bound by its loaders and epilogue, not by the MMAs, below ~400 taps - one
     // 1024-frame block per launch: 295 / 286 / 243 / 208 Gsamples/s at 51 / 101 / 251 / 385 taps (FFMA2: 388 / 243 / 123 /
     // 83); 16 blocks of 512 frames per launch: 494 / 424 / 325 at 51 / 251 / 449 taps.  So cores are built from 48 taps
-    // up and launch_stage_tc2 decides per call (>= 8 steps of 512 frames: from 48 taps, else from 112).  The 3xTF32
+    // up and launch_stage_tc2 decides per call (>= 8 steps of 512 frames: from 48 taps; >= 2 steps: from 60; one step: from 112).  The 3xTF32
     // kernel (afp_fir_tc.cuh, 256-frame blocks) only wins from 385 taps up.
     const int tc_min = std::getenv("AFP_TC_MIN_TAPS") ? std::atoi(std::getenv("AFP_TC_MIN_TAPS")) : 400;
     const int tc2_min = std::getenv("AFP_TC_MIN_TAPS") ? std::atoi(std::getenv("AFP_TC_MIN_TAPS")) : 48;
@@ -537,7 +537,12 @@ int launch_stage_tc2(afp_ctx* c, Stage& s, const float* in, long long in_pitch, 
     if (frames < afp::TC2_STEP || frames % afp::TC2_STEP != 0 || n_blocks < 1) return AFP_OK;
     if ((long long)frames * n_blocks > (1 << 30)) return AFP_OK;
     // short filters: only when a stream group's window start is amortised over enough steps (see build_stage)
-    if (!std::getenv("AFP_TC_MIN_TAPS") && s.U == 1 && s.n_taps < 112 && (long long)(frames / afp::TC2_STEP) * n_blocks < 8) return AFP_OK;
+    // (one 1024-frame block of 65536 streams per launch, tensor vs FFMA2 kernel: 51 taps 430 vs 464 Gsamples/s, 63 taps 429 vs 410,
+    // 79 taps 414 vs 351, 101 taps 410 vs 284; a single 512-frame step pays the whole window start)
+    {
+        const long long steps = (long long)(frames / afp::TC2_STEP) * n_blocks;
+        if (!std::getenv("AFP_TC_MIN_TAPS") && s.U == 1 && ((s.n_taps < 60 && steps < 8) || (s.n_taps < 112 && steps < 2))) return AFP_OK;
+    }
     const int eb = fmt == AFP_FMT_I16 ? 2 : (fmt == AFP_FMT_I24_PACKED ? 3 : 4);
     if (!aligned16(in) || in_pitch % 4 != 0 || in_bstride % 4 != 0 || s.hist_pitch % 4 != 0 || s.kq_pad % 8 != 0) return AFP_OK;
     if (s.tc2_chunks > 17 || s.kq_pad > 24 * afp::TC2_R) return AFP_OK;

@@ -172,8 +172,9 @@ int afp_process(afp_ctx* ctx, const float* in_dev, int64_t in_pitch, void* out_d
 /* n_blocks consecutive blocks (the buffers of n_blocks consecutive callbacks) in one call: block b of stream s
  * starts at in_dev[b*in_block_stride + s*in_pitch] / out_dev[b*out_block_stride + s*out_pitch] (strides in
  * elements, bytes for AFP_FMT_I24_PACKED).  The results equal those of n_blocks afp_process calls - to the bit when
- * both forms run on the same kernel (always from 112 taps up; a shorter filter takes the tensor kernel only in calls of
- * >= 8 x 512 frames per stream and the packed-FFMA2 kernel otherwise: the two agree to ~1e-7, not to the bit).  For a
+ * both forms run on the same kernel (always from 112 taps up; a shorter filter takes the tensor kernel in calls of
+ * >= 8 x 512 frames per stream, from 60 taps also in calls of >= 2 x 512 frames, and the packed-FFMA2 kernel otherwise:
+ * the two agree to ~1e-7, not to the bit).  For a
  * chain that is a single filter - U = 1 from 48 taps (the collapsed reference chain included), or a polyphase
  * interpolator with U = 2 / 3 / 4 (from 72 / 84 / 96 taps) - with blocks of a multiple of 512 frames this is ONE launch: the
  * CTA that owns 16 streams walks their blocks with [history | block] resident in shared memory, the carried history
